@@ -1,0 +1,124 @@
+/* tdm_b200.h — C ABI of libtdm_b200.so, the B200 (sm_100a) hot path of TinyDiffusionModels.
+ *
+ * The reference (LiamConnell/TinyDiffusionModels) has no FFI / plugin layer: its boundary is
+ * the Python surface of src/mnist.py and src/shakespeare.py.  Each entry point
+ * below therefore cites the reference *Python* function (file:line under /root/reference) whose
+ * device work it replaces; the ctypes binding that calls it lives in
+ * tinydiffusionmodels_b200/_lib.py and the reference-side stub is shown in INTEGRATION.md.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued asynchronously, never
+ *     synchronised, never allocates, and is CUDA-graph capturable;
+ *   - buffers are borrowed for the duration of the enqueued work, ownership never transfers;
+ *   - return value 0 = success, non-zero = error; tdm_last_error() gives a thread-local message;
+ *   - there is no CPU fallback: on a machine without an sm_100 GPU every compute call fails.
+ */
+#ifndef TDM_B200_H
+#define TDM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDM_OK 0
+#define TDM_ERR_ARG 1
+#define TDM_ERR_CUDA 2
+#define TDM_ERR_UNSUPPORTED 3
+
+/* ABI version of this header (bumped on any signature change). */
+int tdm_version(void);
+/* Thread-local description of the last non-zero return. Never NULL. */
+const char* tdm_last_error(void);
+/* Number of kernel launches this library has enqueued since load (bench.py's gpu_launches). */
+int64_t tdm_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Diffusion elementwise math
+ * ------------------------------------------------------------------------------------------- */
+
+/* q_sample: out[b,i] = sqrt_acp[t[b]] * x0[b,i] + sqrt_om_acp[t[b]] * noise[b,i]
+ * Replaces src/mnist.py:36-42 (inner = 784) and src/shakespeare.py:37-44 (inner = L*dim).
+ * fp32, bit-exact with the reference's mul/mul/add sequence (no FMA contraction).
+ * x0, noise, out: [batch, inner] contiguous fp32; t: [batch] int64 in [0, n_steps);
+ * sqrt_acp, sqrt_om_acp: [n_steps] fp32 schedule tables (src/mnist.py:32-33). */
+int tdm_q_sample(const float* x0, const float* noise, const int64_t* t, const float* sqrt_acp,
+                 const float* sqrt_om_acp, float* out, int64_t batch, int64_t inner, int n_steps,
+                 void* stream);
+
+/* q_sample with in-kernel Philox4x32-10 noise (training fast path, src/mnist.py:155-156).
+ * Writes the generated N(0,1) noise to noise_out (needed by the loss) and the diffused sample
+ * to out.  The noise for element i of sample b is the (i%4)-th normal of the Philox block
+ * counter = (i/4, sample_offset + b, stream_id, 0), key = seed.  See oracle/philox.py. */
+int tdm_q_sample_philox(const float* x0, const int64_t* t, const float* sqrt_acp,
+                        const float* sqrt_om_acp, float* noise_out, float* out, int64_t batch,
+                        int64_t inner, int n_steps, uint64_t seed, uint64_t sample_offset,
+                        uint32_t stream_id, void* stream);
+
+/* Reverse (ancestral) step, src/mnist.py:167-180 and src/shakespeare.py:343-352:
+ *   mean = (1/sqrt(alphas[t])) * (x - betas[t]/sqrt_om_acp[t] * eps)
+ *   out  = mean                       if t[0] == 0   (the reference branches on t[0] only)
+ *        = mean + sqrt(betas[t]) * z  otherwise
+ * z != NULL : injected-noise variant (parity tests), bit-exact with the reference op sequence.
+ * z == NULL : in-kernel Philox noise, counter = (i/4, sample_offset + b, step_id, 1).
+ * out may alias x.  All tensors [batch, inner] fp32; t [batch] int64. */
+int tdm_reverse_step(const float* x, const float* eps, const float* z, const int64_t* t,
+                     const float* betas, const float* alphas, const float* sqrt_om_acp, float* out,
+                     int64_t batch, int64_t inner, int n_steps, uint64_t seed,
+                     uint64_t sample_offset, uint32_t step_id, void* stream);
+
+/* Standard-normal fill with the library's Philox stream (x_T initialisation, src/mnist.py:190,
+ * src/shakespeare.py:382).  counter = (i/4, sample_offset + b, stream_id, 2). */
+int tdm_randn_philox(float* out, int64_t batch, int64_t inner, uint64_t seed,
+                     uint64_t sample_offset, uint32_t stream_id, void* stream);
+
+/* (clamp(x,-1,1)+1)/2, src/mnist.py:194. n elements fp32, out may alias x. */
+int tdm_to_unit_range(const float* x, float* out, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * MNIST UNet (src/mnist.py:45-87), bf16 tcgen05 implicit-GEMM convolutions, fp32 accumulate
+ * ------------------------------------------------------------------------------------------- */
+
+/* Number of fp32 parameters in the flat parameter vector (state_dict order, 181,473). */
+int64_t tdm_unet_param_count(void);
+/* Bytes of the packed bf16/fp32 weight image produced by tdm_unet_pack_weights. */
+int64_t tdm_unet_wpack_bytes(void);
+/* Bytes of activation workspace for a batch of `batch` images (forward only / with backward). */
+int64_t tdm_unet_workspace_bytes(int64_t batch, int for_backward);
+
+/* Convert the flat fp32 parameter vector (reference state_dict order: rb1.conv1.weight,
+ * rb1.conv1.bias, rb1.conv2.weight, ..., out.weight, out.bias; conv weights OIHW) into the
+ * kernel-side packed image (bf16 [tap][Cin/8][Cout][8] planes + fp32 biases). */
+int tdm_unet_pack_weights(const float* flat_params, void* wpack, void* stream);
+
+/* The workspace must be zero-filled once after allocation (guard rows), then may be reused
+ * for the same batch size; zero it again before using it with a different batch size. */
+
+/* Test/debug aid: workspace layout for `batch` as 14 int64 written to HOST memory:
+ * {tiles28, tiles14, plane_stride28, plane_stride14, off_t1, off_cat, off_p1, off_t2, off_s2,
+ *  off_h2, off_t3, off_t4, off_s4, total_bytes}.  Activation tensor [C][pos] lives at
+ * off + (c/8)*plane_stride + (HALO + pos)*16 + (c%8)*2 with pos(b,y,x) = b*S + (y+1)*(W+1) + x,
+ * S = (W+1)^2, HALO = 32 (W=28) or 16 (W=14). */
+int tdm_unet_debug_layout(int64_t batch, int64_t* host_out14);
+
+/* SimpleUNet.forward(x, t) (src/mnist.py:76-87).  x: [batch,1,28,28] fp32, t: [batch] int64,
+ * eps_out: [batch,1,28,28] fp32. */
+int tdm_unet_forward(const void* wpack, const float* x, const int64_t* t, float* eps_out,
+                     void* workspace, int64_t workspace_bytes, int64_t batch, void* stream);
+
+/* One fused p_sample (src/mnist.py:167-180): UNet forward with the reverse-step update applied
+ * in the last convolution's epilogue, so eps never reaches HBM.  z / Philox semantics as in
+ * tdm_reverse_step.  x_out may alias x_in: the only kernel that reads neighbours of x (rb1.conv1)
+ * has retired before the last kernel overwrites it, and that kernel reads x at its own pixel only. */
+int tdm_unet_p_sample(const void* wpack, const float* x_in, const int64_t* t, const float* z,
+                      const float* betas, const float* alphas, const float* sqrt_om_acp,
+                      float* x_out, void* workspace, int64_t workspace_bytes, int64_t batch,
+                      int n_steps, uint64_t seed, uint64_t sample_offset, uint32_t step_id,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDM_B200_H */

@@ -1,0 +1,236 @@
+// elementwise.cu — the HBM-bound diffusion math: q_sample, the reverse (ancestral) step, Philox
+// normal fill and the final [-1,1] -> [0,1] map.  One pass over memory each, 128-bit accesses,
+// schedule coefficients gathered per sample from the reference's fp32 tables.
+//
+// Bit-exactness: the injected-noise variants restate the reference's separate mul / sub / add /
+// div / sqrt ATen ops with the *_rn intrinsics so nvcc cannot contract them into FMAs
+// (contraction moves q_sample by up to 4.8e-7).
+#include "common.cuh"
+#include "diffusion_math.cuh"
+
+namespace tdm {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;  // float4s per thread -> 64 B in flight per stream per thread
+
+__device__ __forceinline__ float4 ldg4(const float* p) {
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ float4 ldcs4(const float* p) {
+    return __ldcs(reinterpret_cast<const float4*>(p));  // streaming: read once
+}
+__device__ __forceinline__ void stcs4(float* p, float4 v) {
+    __stcs(reinterpret_cast<float4*>(p), v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// q_sample (src/mnist.py:36-42, src/shakespeare.py:37-44)
+// ---------------------------------------------------------------------------------------------
+template <bool kPhilox>
+__global__ void __launch_bounds__(kThreads)
+q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
+                const int64_t* __restrict__ t, const float* __restrict__ sqrt_acp,
+                const float* __restrict__ sqrt_om, float* __restrict__ noise_out,
+                float* __restrict__ out, int64_t total4, uint32_t inner4, uint64_t seed,
+                uint64_t sample_offset, uint32_t stream_id) {
+    const int64_t base = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+    float4 xv[kUnroll], nv[kUnroll];
+    float ca[kUnroll], cb[kUnroll];
+    int64_t idx[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        idx[u] = base + (int64_t)u * kThreads;
+        if (idx[u] < total4) {
+            xv[u] = ldcs4(x0 + idx[u] * 4);
+            const int64_t b = idx[u] / inner4;
+            const int64_t tb = __ldg(t + b);
+            ca[u] = __ldg(sqrt_acp + tb);
+            cb[u] = __ldg(sqrt_om + tb);
+            if constexpr (kPhilox) {
+                const uint32_t quad = (uint32_t)(idx[u] - b * inner4);
+                nv[u] = philox_normal4(seed, sample_offset + (uint64_t)b, quad, stream_id,
+                                       kDomainQSample);
+            } else {
+                nv[u] = ldcs4(noise + idx[u] * 4);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        if (idx[u] < total4) {
+            float4 o;
+            o.x = __fadd_rn(__fmul_rn(ca[u], xv[u].x), __fmul_rn(cb[u], nv[u].x));
+            o.y = __fadd_rn(__fmul_rn(ca[u], xv[u].y), __fmul_rn(cb[u], nv[u].y));
+            o.z = __fadd_rn(__fmul_rn(ca[u], xv[u].z), __fmul_rn(cb[u], nv[u].z));
+            o.w = __fadd_rn(__fmul_rn(ca[u], xv[u].w), __fmul_rn(cb[u], nv[u].w));
+            stcs4(out + idx[u] * 4, o);
+            if constexpr (kPhilox) stcs4(noise_out + idx[u] * 4, nv[u]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// reverse step (src/mnist.py:167-180, src/shakespeare.py:343-352)
+// ---------------------------------------------------------------------------------------------
+template <bool kPhilox>
+__global__ void __launch_bounds__(kThreads)
+reverse_step_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                    const float* __restrict__ z, const int64_t* __restrict__ t,
+                    const float* __restrict__ betas, const float* __restrict__ alphas,
+                    const float* __restrict__ sqrt_om, float* __restrict__ out, int64_t total4,
+                    uint32_t inner4, uint64_t seed, uint64_t sample_offset, uint32_t step_id) {
+    // the reference decides "last step" from t[0] for the whole batch (src/mnist.py:176)
+    const bool add_noise = __ldg(t) != 0;
+    const int64_t base = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+    float4 xv[kUnroll], ev[kUnroll], zv[kUnroll];
+    StepCoef c[kUnroll];
+    int64_t idx[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        idx[u] = base + (int64_t)u * kThreads;
+        if (idx[u] < total4) {
+            xv[u] = ldcs4(x + idx[u] * 4);
+            ev[u] = ldcs4(eps + idx[u] * 4);
+            const int64_t b = idx[u] / inner4;
+            c[u] = step_coef(__ldg(t + b), betas, alphas, sqrt_om);
+            if constexpr (kPhilox) {
+                const uint32_t quad = (uint32_t)(idx[u] - b * inner4);
+                zv[u] = add_noise ? philox_normal4(seed, sample_offset + (uint64_t)b, quad, step_id,
+                                                   kDomainReverse)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                zv[u] = add_noise ? ldcs4(z + idx[u] * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        if (idx[u] < total4) {
+            float4 o;
+            o.x = rstep1(c[u], xv[u].x, ev[u].x, zv[u].x, add_noise);
+            o.y = rstep1(c[u], xv[u].y, ev[u].y, zv[u].y, add_noise);
+            o.z = rstep1(c[u], xv[u].z, ev[u].z, zv[u].z, add_noise);
+            o.w = rstep1(c[u], xv[u].w, ev[u].w, zv[u].w, add_noise);
+            stcs4(out + idx[u] * 4, o);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+randn_kernel(float* __restrict__ out, int64_t total4, uint32_t inner4, uint64_t seed,
+             uint64_t sample_offset, uint32_t stream_id) {
+    const int64_t base = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        const int64_t idx = base + (int64_t)u * kThreads;
+        if (idx < total4) {
+            const int64_t b = idx / inner4;
+            const uint32_t quad = (uint32_t)(idx - b * inner4);
+            stcs4(out + idx * 4,
+                  philox_normal4(seed, sample_offset + (uint64_t)b, quad, stream_id, kDomainInit));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+unit_range_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
+    // (clamp(x,-1,1) + 1) / 2 with the reference's op order (src/mnist.py:194)
+    int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        float4 v = ldcs4(x + i);
+        v.x = __fdiv_rn(__fadd_rn(fminf(fmaxf(v.x, -1.f), 1.f), 1.f), 2.f);
+        v.y = __fdiv_rn(__fadd_rn(fminf(fmaxf(v.y, -1.f), 1.f), 1.f), 2.f);
+        v.z = __fdiv_rn(__fadd_rn(fminf(fmaxf(v.z, -1.f), 1.f), 1.f), 2.f);
+        v.w = __fdiv_rn(__fadd_rn(fminf(fmaxf(v.w, -1.f), 1.f), 1.f), 2.f);
+        stcs4(out + i, v);
+    } else {
+        for (; i < n; ++i) out[i] = __fdiv_rn(__fadd_rn(fminf(fmaxf(x[i], -1.f), 1.f), 1.f), 2.f);
+    }
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline unsigned grid_for(int64_t total4) {
+    return (unsigned)((total4 + (int64_t)kThreads * kUnroll - 1) / ((int64_t)kThreads * kUnroll));
+}
+
+}  // namespace tdm
+
+using namespace tdm;
+
+extern "C" int tdm_q_sample(const float* x0, const float* noise, const int64_t* t,
+                            const float* sqrt_acp, const float* sqrt_om_acp, float* out,
+                            int64_t batch, int64_t inner, int n_steps, void* stream) {
+    TDM_CHECK_ARG(x0 && noise && t && sqrt_acp && sqrt_om_acp && out, "tdm_q_sample: null pointer");
+    TDM_CHECK_ARG(batch >= 0 && inner > 0 && n_steps > 0, "tdm_q_sample: bad sizes");
+    TDM_CHECK_ARG(inner % 4 == 0, "tdm_q_sample: inner (%lld) must be a multiple of 4", (long long)inner);
+    TDM_CHECK_ARG(aligned16(x0) && aligned16(noise) && aligned16(out), "tdm_q_sample: 16-byte alignment required");
+    if (batch == 0) return TDM_OK;
+    const int64_t total4 = batch * inner / 4;
+    q_sample_kernel<false><<<grid_for(total4), kThreads, 0, (cudaStream_t)stream>>>(
+        x0, noise, t, sqrt_acp, sqrt_om_acp, nullptr, out, total4, (uint32_t)(inner / 4), 0, 0, 0);
+    TDM_CHECK_LAUNCH("tdm_q_sample");
+    return TDM_OK;
+}
+
+extern "C" int tdm_q_sample_philox(const float* x0, const int64_t* t, const float* sqrt_acp,
+                                   const float* sqrt_om_acp, float* noise_out, float* out,
+                                   int64_t batch, int64_t inner, int n_steps, uint64_t seed,
+                                   uint64_t sample_offset, uint32_t stream_id, void* stream) {
+    TDM_CHECK_ARG(x0 && t && sqrt_acp && sqrt_om_acp && noise_out && out, "tdm_q_sample_philox: null pointer");
+    TDM_CHECK_ARG(batch >= 0 && inner > 0 && n_steps > 0, "tdm_q_sample_philox: bad sizes");
+    TDM_CHECK_ARG(inner % 4 == 0, "tdm_q_sample_philox: inner must be a multiple of 4");
+    TDM_CHECK_ARG(aligned16(x0) && aligned16(noise_out) && aligned16(out), "tdm_q_sample_philox: 16-byte alignment required");
+    if (batch == 0) return TDM_OK;
+    const int64_t total4 = batch * inner / 4;
+    q_sample_kernel<true><<<grid_for(total4), kThreads, 0, (cudaStream_t)stream>>>(
+        x0, nullptr, t, sqrt_acp, sqrt_om_acp, noise_out, out, total4, (uint32_t)(inner / 4), seed,
+        sample_offset, stream_id);
+    TDM_CHECK_LAUNCH("tdm_q_sample_philox");
+    return TDM_OK;
+}
+
+extern "C" int tdm_reverse_step(const float* x, const float* eps, const float* z, const int64_t* t,
+                                const float* betas, const float* alphas, const float* sqrt_om_acp,
+                                float* out, int64_t batch, int64_t inner, int n_steps, uint64_t seed,
+                                uint64_t sample_offset, uint32_t step_id, void* stream) {
+    TDM_CHECK_ARG(x && eps && t && betas && alphas && sqrt_om_acp && out, "tdm_reverse_step: null pointer");
+    TDM_CHECK_ARG(batch >= 0 && inner > 0 && n_steps > 0, "tdm_reverse_step: bad sizes");
+    TDM_CHECK_ARG(inner % 4 == 0, "tdm_reverse_step: inner must be a multiple of 4");
+    TDM_CHECK_ARG(aligned16(x) && aligned16(eps) && aligned16(out) && (!z || aligned16(z)),
+                  "tdm_reverse_step: 16-byte alignment required");
+    if (batch == 0) return TDM_OK;
+    const int64_t total4 = batch * inner / 4;
+    if (z)
+        reverse_step_kernel<false><<<grid_for(total4), kThreads, 0, (cudaStream_t)stream>>>(
+            x, eps, z, t, betas, alphas, sqrt_om_acp, out, total4, (uint32_t)(inner / 4), 0, 0, 0);
+    else
+        reverse_step_kernel<true><<<grid_for(total4), kThreads, 0, (cudaStream_t)stream>>>(
+            x, eps, nullptr, t, betas, alphas, sqrt_om_acp, out, total4, (uint32_t)(inner / 4), seed,
+            sample_offset, step_id);
+    TDM_CHECK_LAUNCH("tdm_reverse_step");
+    return TDM_OK;
+}
+
+extern "C" int tdm_randn_philox(float* out, int64_t batch, int64_t inner, uint64_t seed,
+                                uint64_t sample_offset, uint32_t stream_id, void* stream) {
+    TDM_CHECK_ARG(out, "tdm_randn_philox: null pointer");
+    TDM_CHECK_ARG(batch >= 0 && inner > 0 && inner % 4 == 0, "tdm_randn_philox: inner must be a positive multiple of 4");
+    TDM_CHECK_ARG(aligned16(out), "tdm_randn_philox: 16-byte alignment required");
+    if (batch == 0) return TDM_OK;
+    const int64_t total4 = batch * inner / 4;
+    randn_kernel<<<grid_for(total4), kThreads, 0, (cudaStream_t)stream>>>(
+        out, total4, (uint32_t)(inner / 4), seed, sample_offset, stream_id);
+    TDM_CHECK_LAUNCH("tdm_randn_philox");
+    return TDM_OK;
+}
+
+extern "C" int tdm_to_unit_range(const float* x, float* out, int64_t n, void* stream) {
+    TDM_CHECK_ARG(x && out && n >= 0, "tdm_to_unit_range: bad arguments");
+    TDM_CHECK_ARG(aligned16(x) && aligned16(out), "tdm_to_unit_range: 16-byte alignment required");
+    if (n == 0) return TDM_OK;
+    const int64_t nthreads = (n + 3) / 4;
+    unit_range_kernel<<<(unsigned)((nthreads + kThreads - 1) / kThreads), kThreads, 0,
+                        (cudaStream_t)stream>>>(x, out, n);
+    TDM_CHECK_LAUNCH("tdm_to_unit_range");
+    return TDM_OK;
+}

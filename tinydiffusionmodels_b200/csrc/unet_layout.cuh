@@ -1,0 +1,94 @@
+// unet_layout.cuh — activation / weight layouts of the MNIST UNet kernels.
+//
+// "Plane" activation layout.  All images of a batch at one resolution are flattened into one
+// position axis with a shared zero pad column per row and a shared zero pad row per image:
+//     pos(b, y, x) = b*S + (y+1)*Wp + x,   Wp = W+1,   S = (H+1)*Wp
+// so that every 3x3 tap is a constant position offset (ky-1)*Wp + (kx-1) and zero padding
+// (src/mnist.py:48-49, padding=1) falls out of the pad positions being stored as zeros.
+// Channels are stored in groups of 8 bf16 (16 bytes): tensor[plane = c/8][pos][c%8].  A plane
+// is a dense array of 16-byte rows, which is exactly the un-swizzled K-major core-matrix layout
+// tcgen05.mma reads, with the tap offset applied as a start-address shift.
+// Each plane has HALO guard rows on both sides (zeros, never written) so a tile's halo read
+// never leaves the allocation.
+#pragma once
+#include <cstdint>
+
+namespace tdm {
+
+constexpr int kTile = 128;  // positions per MMA tile (UMMA M)
+
+template <int W_>
+struct Geo {
+    static constexpr int W = W_, H = W_;
+    static constexpr int Wp = W_ + 1;
+    static constexpr int S = (W_ + 1) * (W_ + 1);
+    static constexpr int HALO = (W_ == 28) ? 32 : 16;  // >= Wp + 1
+    static constexpr int RT = kTile + 2 * HALO;        // smem rows per plane per tile
+    static_assert(HALO >= Wp + 1, "halo must cover the largest tap offset");
+};
+
+__host__ __device__ inline int64_t num_tiles(int64_t batch, int S) {
+    return (batch * S + kTile - 1) / kTile;
+}
+// rows allocated per plane
+__host__ __device__ inline int64_t plane_rows(int64_t batch, int S, int halo) {
+    return num_tiles(batch, S) * kTile + 2 * halo;
+}
+
+// ---- flat fp32 parameter vector (reference state_dict order) -----------------
+namespace P {
+constexpr int rb1_c1w = 0;                       // [32,1,3,3]
+constexpr int rb1_c1b = rb1_c1w + 288;           // [32]
+constexpr int rb1_c2w = rb1_c1b + 32;            // [32,32,3,3]
+constexpr int rb1_c2b = rb1_c2w + 9216;
+constexpr int rb1_tw = rb1_c2b + 32;             // [32,1]
+constexpr int rb1_tb = rb1_tw + 32;
+constexpr int rb1_sw = rb1_tb + 32;              // [32,1,1,1]
+constexpr int rb1_sb = rb1_sw + 32;
+constexpr int rb2_c1w = rb1_sb + 32;             // [64,32,3,3]
+constexpr int rb2_c1b = rb2_c1w + 18432;
+constexpr int rb2_c2w = rb2_c1b + 64;            // [64,64,3,3]
+constexpr int rb2_c2b = rb2_c2w + 36864;
+constexpr int rb2_tw = rb2_c2b + 64;
+constexpr int rb2_tb = rb2_tw + 64;
+constexpr int rb2_sw = rb2_tb + 64;              // [64,32,1,1]
+constexpr int rb2_sb = rb2_sw + 2048;
+constexpr int rb3_c1w = rb2_sb + 64;             // [64,64,3,3]
+constexpr int rb3_c1b = rb3_c1w + 36864;
+constexpr int rb3_c2w = rb3_c1b + 64;
+constexpr int rb3_c2b = rb3_c2w + 36864;
+constexpr int rb3_tw = rb3_c2b + 64;
+constexpr int rb3_tb = rb3_tw + 64;
+constexpr int rb4_c1w = rb3_tb + 64;             // [32,96,3,3]
+constexpr int rb4_c1b = rb4_c1w + 27648;
+constexpr int rb4_c2w = rb4_c1b + 32;            // [32,32,3,3]
+constexpr int rb4_c2b = rb4_c2w + 9216;
+constexpr int rb4_tw = rb4_c2b + 32;
+constexpr int rb4_tb = rb4_tw + 32;
+constexpr int rb4_sw = rb4_tb + 32;              // [32,96,1,1]
+constexpr int rb4_sb = rb4_sw + 3072;
+constexpr int out_w = rb4_sb + 32;               // [1,32,1,1]
+constexpr int out_b = out_w + 32;                // [1]
+constexpr int count = out_b + 1;
+static_assert(count == 181473, "SimpleUNet has 181,473 parameters");
+}  // namespace P
+
+// ---- packed weight image: bf16 [tap][Cin/8][Cout][8] per tensor-core conv, then fp32 copy -------
+namespace WP {
+constexpr int64_t conv_bytes(int cin, int cout) { return 9LL * cin * cout * 2; }
+constexpr int64_t skip_bytes(int cin, int cout) { return 1LL * cin * cout * 2; }
+constexpr int64_t rb1_c2 = 0;
+constexpr int64_t rb2_c1 = rb1_c2 + conv_bytes(32, 32);
+constexpr int64_t rb2_sk = rb2_c1 + conv_bytes(32, 64);   // must directly follow rb2_c1
+constexpr int64_t rb2_c2 = rb2_sk + skip_bytes(32, 64);
+constexpr int64_t rb3_c1 = rb2_c2 + conv_bytes(64, 64);
+constexpr int64_t rb3_c2 = rb3_c1 + conv_bytes(64, 64);
+constexpr int64_t rb4_c1 = rb3_c2 + conv_bytes(64, 64);
+constexpr int64_t rb4_sk = rb4_c1 + conv_bytes(96, 32);   // must directly follow rb4_c1
+constexpr int64_t rb4_c2 = rb4_sk + skip_bytes(96, 32);
+constexpr int64_t bf16_end = rb4_c2 + conv_bytes(32, 32);
+constexpr int64_t flat = (bf16_end + 255) / 256 * 256;     // fp32 copy of the flat parameters
+constexpr int64_t total = (flat + 4LL * P::count + 255) / 256 * 256;
+}  // namespace WP
+
+}  // namespace tdm

@@ -1,0 +1,159 @@
+"""Device-side state of the MNIST UNet: flat fp32 parameters, packed bf16 weights, workspace.
+
+The kernels consume one *flat* fp32 parameter vector in the reference's ``state_dict`` order
+ — the same buffer the optimizer and the gradient all-reduce operate on — plus a
+packed bf16 image of the convolution weights that ``tdm_unet_pack_weights`` derives from it.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .schedule import Schedule, schedule_on
+
+# (name, shape) in reference state_dict order (src/mnist.py:45-87)
+def _param_spec() -> list[tuple[str, tuple[int, ...]]]:
+    spec: list[tuple[str, tuple[int, ...]]] = []
+    for name, cin, cout in (("rb1", 1, 32), ("rb2", 32, 64), ("rb3", 64, 64), ("rb4", 96, 32)):
+        spec += [
+            (f"{name}.conv1.weight", (cout, cin, 3, 3)), (f"{name}.conv1.bias", (cout,)),
+            (f"{name}.conv2.weight", (cout, cout, 3, 3)), (f"{name}.conv2.bias", (cout,)),
+            (f"{name}.time_emb.weight", (cout, 1)), (f"{name}.time_emb.bias", (cout,)),
+        ]
+        if cin != cout:
+            spec += [(f"{name}.skip.weight", (cout, cin, 1, 1)), (f"{name}.skip.bias", (cout,))]
+    spec += [("out.weight", (1, 32, 1, 1)), ("out.bias", (1,))]
+    return spec
+
+
+PARAM_SPEC = _param_spec()
+PARAM_COUNT = sum(int(torch.Size(s).numel()) for _, s in PARAM_SPEC)
+assert PARAM_COUNT == 181_473
+
+
+def flatten_state_dict(sd: dict, device=None) -> torch.Tensor:
+    """Reference-format state_dict -> flat fp32 vector in PARAM_SPEC order (validates shapes)."""
+    parts = []
+    for name, shape in PARAM_SPEC:
+        if name not in sd:
+            raise KeyError(f"state_dict is missing {name!r}")
+        p = sd[name]
+        if tuple(p.shape) != shape:
+            raise ValueError(f"{name}: expected shape {shape}, got {tuple(p.shape)}")
+        parts.append(p.detach().reshape(-1).to(dtype=torch.float32, device=device))
+    return torch.cat(parts)
+
+
+def unflatten(flat: torch.Tensor) -> dict:
+    """Views of the flat vector under the reference's state_dict keys."""
+    out, off = {}, 0
+    for name, shape in PARAM_SPEC:
+        n = int(torch.Size(shape).numel())
+        out[name] = flat[off:off + n].view(shape)
+        off += n
+    return out
+
+
+class UNetEngine:
+    """Owns the packed weights and the activation workspace for batches up to ``max_batch``."""
+
+    def __init__(self, device, max_batch: int):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.TdmError("UNetEngine needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.load()
+        if self.lib.tdm_unet_param_count() != PARAM_COUNT:
+            raise _lib.TdmError("library/param-spec mismatch")
+        self.max_batch = int(max_batch)
+        self.wpack = torch.zeros(self.lib.tdm_unet_wpack_bytes(), dtype=torch.uint8, device=self.device)
+        self.ws_bytes = int(self.lib.tdm_unet_workspace_bytes(self.max_batch, 0))
+        # zero-filled once: guard rows and the never-written pad positions of the concat buffer
+        self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        self._ws_batch = None  # the plane strides depend on the batch: re-zero when it changes
+        self.sched: Schedule = schedule_on(self.device)
+        self._packed_from = None
+
+    # -- weights ---------------------------------------------------------------------------
+    def load_flat(self, flat: torch.Tensor) -> None:
+        if flat.numel() != PARAM_COUNT or flat.dtype != torch.float32 or not flat.is_cuda:
+            raise ValueError("flat params must be a CUDA fp32 vector of 181,473 elements")
+        flat = flat.contiguous()
+        _lib.check(self.lib.tdm_unet_pack_weights(flat.data_ptr(), self.wpack.data_ptr(),
+                                                  _lib.stream_ptr(self.device)), "tdm_unet_pack_weights")
+        self._packed_from = (flat.data_ptr(), flat._version)
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.load_flat(flatten_state_dict(sd, self.device))
+
+    def ensure_packed(self, flat: torch.Tensor) -> None:
+        if self._packed_from != (flat.data_ptr(), flat._version):
+            self.load_flat(flat)
+
+    # -- compute ---------------------------------------------------------------------------
+    def _prep(self, batch: int) -> None:
+        if batch > self.max_batch:
+            raise ValueError(f"batch {batch} exceeds engine capacity {self.max_batch}")
+        if self._ws_batch != batch:
+            # a different batch lays the planes out differently; stale data would sit in pad slots
+            if self._ws_batch is not None:
+                self.ws.zero_()
+            self._ws_batch = batch
+
+    def forward(self, x: torch.Tensor, t: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """eps = SimpleUNet(x, t) (src/mnist.py:76-87). x (B,1,28,28) fp32, t (B,) int64."""
+        b = x.shape[0]
+        self._prep(b)
+        x = x.contiguous()
+        t = t.to(torch.int64).contiguous()
+        out = torch.empty_like(x) if out is None else out
+        _lib.check(self.lib.tdm_unet_forward(self.wpack.data_ptr(), x.data_ptr(), t.data_ptr(),
+                                             out.data_ptr(), self.ws.data_ptr(), self.ws_bytes, b,
+                                             _lib.stream_ptr(self.device)), "tdm_unet_forward")
+        return out
+
+    def p_sample(self, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor | None = None,
+                 out: torch.Tensor | None = None, *, seed: int = 0, sample_offset: int = 0,
+                 step_id: int = 0) -> torch.Tensor:
+        """One fused reverse step (src/mnist.py:167-180); ``out`` may be ``x`` itself."""
+        b = x.shape[0]
+        self._prep(b)
+        x = x.contiguous()
+        t = t.to(torch.int64).contiguous()
+        out = torch.empty_like(x) if out is None else out
+        s = self.sched
+        _lib.check(self.lib.tdm_unet_p_sample(
+            self.wpack.data_ptr(), x.data_ptr(), t.data_ptr(), _lib.ptr(z), s.betas.data_ptr(),
+            s.alphas.data_ptr(), s.sqrt_one_minus_alphas_cumprod.data_ptr(), out.data_ptr(),
+            self.ws.data_ptr(), self.ws_bytes, b, s.timesteps, seed, sample_offset, step_id,
+            _lib.stream_ptr(self.device)), "tdm_unet_p_sample")
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# test/debug aid: read an intermediate activation back out of the plane layout
+# ---------------------------------------------------------------------------------------------
+_WS_NAMES = ("t1", "cat", "p1", "t2", "s2", "h2", "t3", "t4", "s4")
+_WS_GEOM = {"t1": (28, 32), "cat": (28, 96), "p1": (14, 32), "t2": (14, 64), "s2": (14, 64),
+            "h2": (14, 64), "t3": (14, 64), "t4": (28, 32), "s4": (28, 32)}
+
+
+def read_activation(engine: UNetEngine, name: str, batch: int) -> torch.Tensor:
+    """Decode workspace buffer ``name`` into a (B, C, H, W) fp32 tensor (pads dropped)."""
+    import ctypes
+
+    arr = (ctypes.c_int64 * 14)()
+    _lib.check(engine.lib.tdm_unet_debug_layout(batch, arr), "tdm_unet_debug_layout")
+    v = list(arr)
+    ps = {28: v[2], 14: v[3]}
+    off = dict(zip(_WS_NAMES, v[4:13]))[name]
+    w, c = _WS_GEOM[name]
+    halo = 32 if w == 28 else 16
+    wp, s = w + 1, (w + 1) * (w + 1)
+    rows = ps[w] // 16
+    raw = engine.ws[off: off + (c // 8) * ps[w]].view(torch.bfloat16).view(c // 8, rows, 8)
+    b = torch.arange(batch, device=raw.device).view(-1, 1, 1)
+    y = torch.arange(w, device=raw.device).view(1, -1, 1)
+    x = torch.arange(w, device=raw.device).view(1, 1, -1)
+    pos = (b * s + (y + 1) * wp + x + halo).reshape(-1)
+    g = raw[:, pos, :]                                  # (C/8, B*H*W, 8)
+    return g.permute(1, 0, 2).reshape(batch, w, w, c).permute(0, 3, 1, 2).float().contiguous()
