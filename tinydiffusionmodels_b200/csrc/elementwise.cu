@@ -160,11 +160,11 @@ using namespace tdm;
 extern "C" int tdm_q_sample(const float* x0, const float* noise, const int64_t* t,
                             const float* sqrt_acp, const float* sqrt_om_acp, float* out,
                             int64_t batch, int64_t inner, int n_steps, void* stream) {
+    if (batch == 0) return TDM_OK;
     TDM_CHECK_ARG(x0 && noise && t && sqrt_acp && sqrt_om_acp && out, "tdm_q_sample: null pointer");
     TDM_CHECK_ARG(batch >= 0 && inner > 0 && n_steps > 0, "tdm_q_sample: bad sizes");
     TDM_CHECK_ARG(inner % 4 == 0, "tdm_q_sample: inner (%lld) must be a multiple of 4", (long long)inner);
     TDM_CHECK_ARG(aligned16(x0) && aligned16(noise) && aligned16(out), "tdm_q_sample: 16-byte alignment required");
-    if (batch == 0) return TDM_OK;
     const int64_t total4 = batch * inner / 4;
     q_sample_kernel<false><<<grid_for(total4), kThreads, 0, (cudaStream_t)stream>>>(
         x0, noise, t, sqrt_acp, sqrt_om_acp, nullptr, out, total4, (uint32_t)(inner / 4), 0, 0, 0);
@@ -176,11 +176,11 @@ extern "C" int tdm_q_sample_philox(const float* x0, const int64_t* t, const floa
                                    const float* sqrt_om_acp, float* noise_out, float* out,
                                    int64_t batch, int64_t inner, int n_steps, uint64_t seed,
                                    uint64_t sample_offset, uint32_t stream_id, void* stream) {
+    if (batch == 0) return TDM_OK;
     TDM_CHECK_ARG(x0 && t && sqrt_acp && sqrt_om_acp && noise_out && out, "tdm_q_sample_philox: null pointer");
     TDM_CHECK_ARG(batch >= 0 && inner > 0 && n_steps > 0, "tdm_q_sample_philox: bad sizes");
     TDM_CHECK_ARG(inner % 4 == 0, "tdm_q_sample_philox: inner must be a multiple of 4");
     TDM_CHECK_ARG(aligned16(x0) && aligned16(noise_out) && aligned16(out), "tdm_q_sample_philox: 16-byte alignment required");
-    if (batch == 0) return TDM_OK;
     const int64_t total4 = batch * inner / 4;
     q_sample_kernel<true><<<grid_for(total4), kThreads, 0, (cudaStream_t)stream>>>(
         x0, nullptr, t, sqrt_acp, sqrt_om_acp, noise_out, out, total4, (uint32_t)(inner / 4), seed,
@@ -193,12 +193,12 @@ extern "C" int tdm_reverse_step(const float* x, const float* eps, const float* z
                                 const float* betas, const float* alphas, const float* sqrt_om_acp,
                                 float* out, int64_t batch, int64_t inner, int n_steps, uint64_t seed,
                                 uint64_t sample_offset, uint32_t step_id, void* stream) {
+    if (batch == 0) return TDM_OK;
     TDM_CHECK_ARG(x && eps && t && betas && alphas && sqrt_om_acp && out, "tdm_reverse_step: null pointer");
     TDM_CHECK_ARG(batch >= 0 && inner > 0 && n_steps > 0, "tdm_reverse_step: bad sizes");
     TDM_CHECK_ARG(inner % 4 == 0, "tdm_reverse_step: inner must be a multiple of 4");
     TDM_CHECK_ARG(aligned16(x) && aligned16(eps) && aligned16(out) && (!z || aligned16(z)),
                   "tdm_reverse_step: 16-byte alignment required");
-    if (batch == 0) return TDM_OK;
     const int64_t total4 = batch * inner / 4;
     if (z)
         reverse_step_kernel<false><<<grid_for(total4), kThreads, 0, (cudaStream_t)stream>>>(
@@ -213,10 +213,10 @@ extern "C" int tdm_reverse_step(const float* x, const float* eps, const float* z
 
 extern "C" int tdm_randn_philox(float* out, int64_t batch, int64_t inner, uint64_t seed,
                                 uint64_t sample_offset, uint32_t stream_id, void* stream) {
+    if (batch == 0) return TDM_OK;
     TDM_CHECK_ARG(out, "tdm_randn_philox: null pointer");
     TDM_CHECK_ARG(batch >= 0 && inner > 0 && inner % 4 == 0, "tdm_randn_philox: inner must be a positive multiple of 4");
     TDM_CHECK_ARG(aligned16(out), "tdm_randn_philox: 16-byte alignment required");
-    if (batch == 0) return TDM_OK;
     const int64_t total4 = batch * inner / 4;
     randn_kernel<<<grid_for(total4), kThreads, 0, (cudaStream_t)stream>>>(
         out, total4, (uint32_t)(inner / 4), seed, sample_offset, stream_id);
@@ -225,6 +225,7 @@ extern "C" int tdm_randn_philox(float* out, int64_t batch, int64_t inner, uint64
 }
 
 extern "C" int tdm_to_unit_range(const float* x, float* out, int64_t n, void* stream) {
+    if (n == 0) return TDM_OK;
     TDM_CHECK_ARG(x && out && n >= 0, "tdm_to_unit_range: bad arguments");
     TDM_CHECK_ARG(aligned16(x) && aligned16(out), "tdm_to_unit_range: 16-byte alignment required");
     if (n == 0) return TDM_OK;
