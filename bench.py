@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py — MNIST DDPM samples/sec (T=1000) on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload sample|train]
+
+A *step* is one complete T=1000 reverse-sampling trajectory (src/mnist.py:190-194) of a batch of
+`--batch` images per GPU: x_T -> 1000 x fused p_sample -> (clamp+1)/2.  Weak scaling: every rank
+samples its own `--batch` images (global sample index = rank*batch + b keys the Philox noise, so
+the union over ranks is independent of N), no data-path collective.
+
+`value`  : samples/s with x_T already resident in HBM when the clock starts (device-timed).
+`e2e`    : samples/s through the public host API: x_T copied from pinned host memory, the final
+           [0,1] images copied back to pinned host memory, both inside the timed region.
+`roofline`: the dominant kernel (rb4.conv1, 96->32 @28x28 + its 1x1 skip GEMM) — algorithmic
+           FLOPs per launch / its CUDA-event duration, against MEASURED_PEAKS.json.
+`cpu_baseline`: the oracle port of the reference's p_sample on the host cores (bounded sample).
+`--impl reference`: the same oracle port as the reference arm (CPU, all host threads).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+T_STEPS = 1000
+METRIC = "mnist_ddpm_samples_per_sec_T1000"
+UNIT = "samples/s"
+FLOPS_PER_IMAGE_STEP = 129_002_880
+
+
+def _peaks() -> tuple[dict, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return json.loads(p.read_text()), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines: list[str] = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [c.strip() for c in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port of the reference's p_sample on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_reverse_steps(batch: int, n_reverse_steps: int, warm: int = 2) -> tuple[float, int]:
+    """Seconds per reverse step of the CPU oracle (fp32, all host threads) at `batch`."""
+    import torch
+    from oracle import ddpm_oracle as O
+    from tests.helpers import random_unet_state_dict
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = random_unet_state_dict(0)
+    tab = O.make_tables()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, 1, 28, 28, generator=g)
+    with torch.no_grad():
+        for i in range(warm):
+            t = torch.full((batch,), T_STEPS - 1 - i, dtype=torch.long)
+            x = O.mnist_p_sample(sd, x, t, torch.randn_like(x), tab)
+        t0 = time.perf_counter()
+        for i in range(n_reverse_steps):
+            t = torch.full((batch,), T_STEPS - 1 - warm - i, dtype=torch.long)
+            x = O.mnist_p_sample(sd, x, t, torch.randn_like(x), tab)
+        dt = time.perf_counter() - t0
+    return dt / n_reverse_steps, cores
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 64  # BASELINE.json configs[0]: the reference's own CPU-runnable case
+    per_step = 10  # reverse steps timed per bench "step" (bounded sample of the 1000)
+    for _ in range(args.warmup):
+        cpu_reverse_steps(batch, 2, warm=1)
+    t0 = time.perf_counter()
+    secs = []
+    cores = 1
+    for _ in range(args.steps):
+        s, cores = cpu_reverse_steps(batch, per_step, warm=1)
+        secs.append(s)
+    wall = time.perf_counter() - t0
+    sec_per_rstep = sum(secs) / len(secs)
+    value = batch / (sec_per_rstep * T_STEPS)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "MNIST DDPM UNet 28x28x1 T=1000 reverse sampling, batch 64, random-init weights (CPU, oracle port of src/mnist.py:167-194)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} of {T_STEPS} reverse steps at batch {batch} per bench step, x1000/{per_step} extrapolated"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path for the product arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from tinydiffusionmodels_b200 import _lib, ops
+    from tinydiffusionmodels_b200.mnist import SimpleUNet, sample_loop
+    from tinydiffusionmodels_b200.unet_engine import UNetEngine
+
+    torch.manual_seed(0)
+    model = SimpleUNet().to(dev).eval()       # random-init weights of the reference architecture
+    B = args.batch
+    seed = 20260101
+    offset = rank * B                          # global sample index of this rank's first image
+    eng = model.engine(B)
+    lib = _lib.load()
+
+    # ---- one captured reverse step, replayed T times per trajectory -------------------------
+    x = torch.empty(B, 1, 28, 28, device=dev)
+    t_buf = torch.empty(B, dtype=torch.int64, device=dev)
+    out01 = torch.empty_like(x)
+    host_in = torch.randn(B, 1, 28, 28).pin_memory()
+    host_out = torch.empty(B, 1, 28, 28).pin_memory()
+
+    def one_step():
+        eng.p_sample(x, t_buf, None, out=x, seed=seed, sample_offset=offset)
+        _lib.check(lib.tdm_timestep_advance(t_buf.data_ptr(), B, -1, _lib.stream_ptr(dev)), "advance")
+
+    t_buf.fill_(T_STEPS - 1)
+    x.normal_()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        one_step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    n0 = _lib.launch_count()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        one_step()
+    launches_per_replay = _lib.launch_count() - n0
+
+    def trajectory_device():
+        """x_T drawn on the device (Philox), T reverse steps, map to [0,1]."""
+        _lib.check(lib.tdm_randn_philox(x.data_ptr(), B, 784, seed, offset, 0, _lib.stream_ptr(dev)), "randn")
+        t_buf.fill_(T_STEPS - 1)
+        for _ in range(T_STEPS):
+            graph.replay()
+        _lib.check(lib.tdm_to_unit_range(x.data_ptr(), out01.data_ptr(), x.numel(), _lib.stream_ptr(dev)), "unit")
+
+    def trajectory_e2e():
+        """Host x_T -> device, T reverse steps, [0,1] images -> host."""
+        x.copy_(host_in, non_blocking=True)
+        t_buf.fill_(T_STEPS - 1)
+        for _ in range(T_STEPS):
+            graph.replay()
+        _lib.check(lib.tdm_to_unit_range(x.data_ptr(), out01.data_ptr(), x.numel(), _lib.stream_ptr(dev)), "unit")
+        host_out.copy_(out01, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps: int) -> float:
+        """Max-over-ranks device milliseconds for `steps` calls of fn."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        barrier()
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(args.warmup):
+        trajectory_device()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n_before = _lib.launch_count()
+    ms = timed(trajectory_device, args.steps)
+    direct_launches = _lib.launch_count() - n_before
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms * 1e-3)
+
+    trajectory_e2e()  # warm the pinned-copy path
+    ms_e2e = timed(trajectory_e2e, max(1, min(args.steps, 3)))
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_value = world * B * e2e_steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel: live CUDA events between the nine launches --------
+    per_kernel = []
+    t_buf.fill_(500)
+    for i in range(8):
+        per_kernel.append(eng.profile_p_sample(x, t_buf, seed=seed))
+    per_kernel = per_kernel[2:]
+    kms = [statistics.mean(k[i] for k in per_kernel) for i in range(9)]
+    names = UNetEngine.KERNEL_NAMES
+    flops = UNetEngine.KERNEL_FLOPS_PER_IMAGE
+    top = max(range(9), key=lambda i: kms[i])
+    peaks, peak_src = _peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    achieved_tf = flops[top] * B / (kms[top] * 1e-3) / 1e12
+    step_ms_sum = sum(kms)
+    roofline = {
+        "bound": "tensor", "kernel": names[top], "achieved": achieved_tf, "peak": peak_tf,
+        "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+        "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
+        "kernel_ms": {n: round(v, 4) for n, v in zip(names, kms)},
+        "kernel_share_of_step": round(kms[top] / step_ms_sum, 4),
+        "whole_unet_tflops": FLOPS_PER_IMAGE_STEP * B / (step_ms_sum * 1e-3) / 1e12,
+    }
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline on this box's host cores (bounded sample) ----------------------------
+    sec_per_rstep, cores = cpu_reverse_steps(64, 20, warm=3)
+    cpu_value = 64 / (sec_per_rstep * T_STEPS)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {
+            "workload": f"MNIST DDPM UNet 28x28x1, T={T_STEPS} reverse sampling, {B} samples per GPU "
+                        f"({world * B} total), random-init weights, Philox noise in-kernel",
+            "samples_per_gpu": B, "T": T_STEPS,
+            "l2": f"working set {eng.ws_bytes / 2**20:.0f} MiB of activations per step > 126 MB L2",
+            "accumulate": "fp32", "activations": "bf16",
+        },
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 784 * 4,
+                "d2h_bytes_per_step": B * 784 * 4, "steps": e2e_steps},
+        "gpu_launches": int(direct_launches + launches_per_replay * T_STEPS * args.steps),
+        "roofline": roofline,
+        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "20 of 1000 reverse steps at batch 64 (oracle port of src/mnist.py:167-180), extrapolated x50"},
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--batch", type=int, default=4096, help="samples per GPU per step")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -62,12 +62,17 @@ int tdm_q_sample_philox(const float* x0, const int64_t* t, const float* sqrt_acp
  *   out  = mean                       if t[0] == 0   (the reference branches on t[0] only)
  *        = mean + sqrt(betas[t]) * z  otherwise
  * z != NULL : injected-noise variant (parity tests), bit-exact with the reference op sequence.
- * z == NULL : in-kernel Philox noise, counter = (i/4, sample_offset + b, step_id, 1).
+ * z == NULL : in-kernel Philox noise, counter = (i/4, sample_offset + b, step_id + t[b], 1):
+ *             the timestep itself keys the noise, so one captured launch serves every step.
  * out may alias x.  All tensors [batch, inner] fp32; t [batch] int64. */
 int tdm_reverse_step(const float* x, const float* eps, const float* z, const int64_t* t,
                      const float* betas, const float* alphas, const float* sqrt_om_acp, float* out,
                      int64_t batch, int64_t inner, int n_steps, uint64_t seed,
                      uint64_t sample_offset, uint32_t step_id, void* stream);
+
+/* t[b] += delta for b < batch (device-side loop counter of the captured sampling step;
+ * replaces the per-step torch.full of src/mnist.py:192). */
+int tdm_timestep_advance(int64_t* t, int64_t batch, int64_t delta, void* stream);
 
 /* Standard-normal fill with the library's Philox stream (x_T initialisation, src/mnist.py:190,
  * src/shakespeare.py:382).  counter = (i/4, sample_offset + b, stream_id, 2). */
@@ -117,6 +122,15 @@ int tdm_unet_p_sample(const void* wpack, const float* x_in, const int64_t* t, co
                       float* x_out, void* workspace, int64_t workspace_bytes, int64_t batch,
                       int n_steps, uint64_t seed, uint64_t sample_offset, uint32_t step_id,
                       void* stream);
+
+/* Measurement aid (bench.py roofline): one fused p_sample with CUDA events recorded on `stream`
+ * between its nine launches; SYNCHRONISES on the last event and writes the nine per-kernel
+ * durations in milliseconds to host_ms9 (order: rb1.conv1, rb1.conv2, avgpool, rb2.conv1,
+ * rb2.conv2, rb3.conv1, rb3.conv2, rb4.conv1, rb4.conv2+out+step). Philox noise. */
+int tdm_unet_profile_p_sample(const void* wpack, const float* x_in, const int64_t* t,
+                              const float* betas, const float* alphas, const float* sqrt_om_acp,
+                              float* x_out, void* workspace, int64_t workspace_bytes, int64_t batch,
+                              uint64_t seed, float* host_ms9, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,13 @@
+"""``python -m src.mnist --train/--sample`` — the reference's MNIST entry point, B200-native.
+
+Thin alias of tinydiffusionmodels_b200.mnist so that code written against the reference
+(``from src.mnist import SimpleUNet, q_sample, p_sample, sample, train``) keeps working.
+"""
+from tinydiffusionmodels_b200.mnist import (  # noqa: F401
+    ResidualBlock, SimpleUNet, alphas, alphas_cumprod, betas, linear_beta_schedule, main, p_sample,
+    q_sample, sample, sample_images, sample_loop, sqrt_alphas_cumprod,
+    sqrt_one_minus_alphas_cumprod, timesteps, train,
+)
+
+if __name__ == "__main__":
+    main()

@@ -25,6 +25,7 @@ SIGNATURES: dict[str, tuple] = {
     "tdm_q_sample": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, _P]),
     "tdm_q_sample_philox": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_uint64, c_uint64, c_uint32, _P]),
     "tdm_reverse_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_uint64, c_uint64, c_uint32, _P]),
+    "tdm_timestep_advance": (c_int, [_P, c_int64, c_int64, _P]),
     "tdm_randn_philox": (c_int, [_P, c_int64, c_int64, c_uint64, c_uint64, c_uint32, _P]),
     "tdm_to_unit_range": (c_int, [_P, _P, c_int64, _P]),
     "tdm_unet_param_count": (c_int64, []),
@@ -34,6 +35,7 @@ SIGNATURES: dict[str, tuple] = {
     "tdm_unet_pack_weights": (c_int, [_P, _P, _P]),
     "tdm_unet_forward": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P]),
     "tdm_unet_p_sample": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_uint64, c_uint64, c_uint32, _P]),
+    "tdm_unet_profile_p_sample": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, ctypes.POINTER(c_float), _P]),
 }
 
 

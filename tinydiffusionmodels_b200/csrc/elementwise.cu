@@ -92,11 +92,12 @@ reverse_step_kernel(const float* __restrict__ x, const float* __restrict__ eps,
             xv[u] = ldcs4(x + idx[u] * 4);
             ev[u] = ldcs4(eps + idx[u] * 4);
             const int64_t b = idx[u] / inner4;
-            c[u] = step_coef(__ldg(t + b), betas, alphas, sqrt_om);
+            const int64_t tb = __ldg(t + b);
+            c[u] = step_coef(tb, betas, alphas, sqrt_om);
             if constexpr (kPhilox) {
                 const uint32_t quad = (uint32_t)(idx[u] - b * inner4);
-                zv[u] = add_noise ? philox_normal4(seed, sample_offset + (uint64_t)b, quad, step_id,
-                                                   kDomainReverse)
+                zv[u] = add_noise ? philox_normal4(seed, sample_offset + (uint64_t)b, quad,
+                                                   step_id + (uint32_t)tb, kDomainReverse)
                                   : make_float4(0.f, 0.f, 0.f, 0.f);
             } else {
                 zv[u] = add_noise ? ldcs4(z + idx[u] * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -146,6 +147,11 @@ unit_range_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t 
     } else {
         for (; i < n; ++i) out[i] = __fdiv_rn(__fadd_rn(fminf(fmaxf(x[i], -1.f), 1.f), 1.f), 2.f);
     }
+}
+
+__global__ void add_i64_kernel(int64_t* __restrict__ t, int64_t n, int64_t delta) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) t[i] += delta;
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -233,5 +239,13 @@ extern "C" int tdm_to_unit_range(const float* x, float* out, int64_t n, void* st
     unit_range_kernel<<<(unsigned)((nthreads + kThreads - 1) / kThreads), kThreads, 0,
                         (cudaStream_t)stream>>>(x, out, n);
     TDM_CHECK_LAUNCH("tdm_to_unit_range");
+    return TDM_OK;
+}
+
+extern "C" int tdm_timestep_advance(int64_t* t, int64_t batch, int64_t delta, void* stream) {
+    if (batch == 0) return TDM_OK;
+    TDM_CHECK_ARG(t && batch > 0, "tdm_timestep_advance: bad arguments");
+    add_i64_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(t, batch, delta);
+    TDM_CHECK_LAUNCH("tdm_timestep_advance");
     return TDM_OK;
 }

@@ -482,7 +482,8 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const ConvArgs a) {
                     const int64_t oi = (int64_t)b * 784 + y * 28 + c;
                     if (a.fuse_step) {
                         const bool add_noise = __ldg(a.t) != 0;  // src/mnist.py:176
-                        const StepCoef sc = step_coef(__ldg(a.t + b), a.betas, a.alphas, a.sqrt_om);
+                        const int64_t tb = __ldg(a.t + b);
+                        const StepCoef sc = step_coef(tb, a.betas, a.alphas, a.sqrt_om);
                         float zz = 0.f;
                         if (add_noise) {
                             if (a.z) {
@@ -490,7 +491,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const ConvArgs a) {
                             } else {
                                 const int e = y * 28 + c;
                                 const float4 n4 = philox_normal4(a.seed, a.sample_offset + (uint64_t)b,
-                                                                 (uint32_t)(e >> 2), a.step_id, kDomainReverse);
+                                                                 (uint32_t)(e >> 2), a.step_id + (uint32_t)tb, kDomainReverse);
                                 const int k = e & 3;
                                 zz = k == 0 ? n4.x : k == 1 ? n4.y : k == 2 ? n4.z : n4.w;
                             }
@@ -540,6 +541,13 @@ struct StepArgs {
     uint32_t step_id = 0;
 };
 
+// optional per-kernel timing (bench.py's roofline): events recorded between the nine launches
+static thread_local cudaEvent_t* g_prof = nullptr;
+#define TDM_PROF(i)                                   \
+    do {                                              \
+        if (g_prof) cudaEventRecord(g_prof[i], st);   \
+    } while (0)
+
 static int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float* fout,
                              uint8_t* ws, int64_t ws_bytes, int64_t batch, const StepArgs& sa,
                              cudaStream_t st) {
@@ -556,9 +564,11 @@ static int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t
     int rc;
 
     // k1
+    TDM_PROF(0);
     rb1_conv1_kernel<<<nt28, 128, 0, st>>>(x, t, fp, ws + L.t1, L.ps28, B);
     TDM_CHECK_LAUNCH("rb1_conv1");
 
+    TDM_PROF(1);
     ConvArgs a{};
     a.t = t;
     a.batch = B;
@@ -569,10 +579,12 @@ static int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t
     if ((rc = launch_conv<28, 32, 32, EPI_RES_X, false>(a, st, "rb1_conv2"))) return rc;
 
     // k3: pool h1 -> p1
+    TDM_PROF(2);
     avgpool_kernel<<<dim3(nt14, 4), 128, 0, st>>>(ws + L.cat + 8 * L.ps28, L.ps28, ws + L.p1, L.ps14, B);
     TDM_CHECK_LAUNCH("avgpool");
 
     // k4: rb2.conv1 (+skip) -> t2, s2
+    TDM_PROF(3);
     a = ConvArgs{}; a.t = t; a.batch = B; a.nt = nt14;
     a.in = ws + L.p1; a.in_ps = L.ps14; a.w = wp + WP::rb2_c1; a.bias = fp + P::rb2_c1b;
     a.tw = fp + P::rb2_tw; a.tb = fp + P::rb2_tb; a.sbias = fp + P::rb2_sb;
@@ -580,24 +592,28 @@ static int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t
     if ((rc = launch_conv<14, 32, 64, EPI_CONV1, true>(a, st, "rb2_conv1"))) return rc;
 
     // k5: rb2.conv2 + s2 -> h2
+    TDM_PROF(4);
     a = ConvArgs{}; a.t = t; a.batch = B; a.nt = nt14;
     a.in = ws + L.t2; a.in_ps = L.ps14; a.w = wp + WP::rb2_c2; a.bias = fp + P::rb2_c2b;
     a.res = ws + L.s2; a.res_ps = L.ps14; a.out = ws + L.h2; a.out_ps = L.ps14;
     if ((rc = launch_conv<14, 64, 64, EPI_RES, false>(a, st, "rb2_conv2"))) return rc;
 
     // k6: rb3.conv1 -> t3
+    TDM_PROF(5);
     a = ConvArgs{}; a.t = t; a.batch = B; a.nt = nt14;
     a.in = ws + L.h2; a.in_ps = L.ps14; a.w = wp + WP::rb3_c1; a.bias = fp + P::rb3_c1b;
     a.tw = fp + P::rb3_tw; a.tb = fp + P::rb3_tb; a.out = ws + L.t3; a.out_ps = L.ps14;
     if ((rc = launch_conv<14, 64, 64, EPI_CONV1, false>(a, st, "rb3_conv1"))) return rc;
 
     // k7: rb3.conv2 + h2 -> upsampled into cat planes 0..7
+    TDM_PROF(6);
     a = ConvArgs{}; a.t = t; a.batch = B; a.nt = nt14;
     a.in = ws + L.t3; a.in_ps = L.ps14; a.w = wp + WP::rb3_c2; a.bias = fp + P::rb3_c2b;
     a.res = ws + L.h2; a.res_ps = L.ps14; a.out = ws + L.cat; a.out_ps = L.ps28;
     if ((rc = launch_conv<14, 64, 64, EPI_RES_UP, false>(a, st, "rb3_conv2"))) return rc;
 
     // k8: rb4.conv1 (+skip) -> t4, s4
+    TDM_PROF(7);
     a = ConvArgs{}; a.t = t; a.batch = B; a.nt = nt28;
     a.in = ws + L.cat; a.in_ps = L.ps28; a.w = wp + WP::rb4_c1; a.bias = fp + P::rb4_c1b;
     a.tw = fp + P::rb4_tw; a.tb = fp + P::rb4_tb; a.sbias = fp + P::rb4_sb;
@@ -605,6 +621,7 @@ static int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t
     if ((rc = launch_conv<28, 96, 32, EPI_CONV1, true>(a, st, "rb4_conv1"))) return rc;
 
     // k9: rb4.conv2 + s4, out conv, optional reverse step
+    TDM_PROF(8);
     a = ConvArgs{}; a.t = t; a.batch = B; a.nt = nt28;
     a.in = ws + L.t4; a.in_ps = L.ps28; a.w = wp + WP::rb4_c2; a.bias = fp + P::rb4_c2b;
     a.res = ws + L.s4; a.res_ps = L.ps28; a.aux_w = fp + P::out_w; a.aux_b = fp + P::out_b;
@@ -612,6 +629,7 @@ static int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t
     a.fuse_step = sa.fuse_step; a.z = sa.z; a.betas = sa.betas; a.alphas = sa.alphas;
     a.sqrt_om = sa.sqrt_om; a.seed = sa.seed; a.sample_offset = sa.sample_offset; a.step_id = sa.step_id;
     if ((rc = launch_conv<28, 32, 32, EPI_FINAL, false>(a, st, "rb4_conv2"))) return rc;
+    TDM_PROF(9);
     return TDM_OK;
 }
 
@@ -665,4 +683,33 @@ extern "C" int tdm_unet_p_sample(const void* wpack, const float* x_in, const int
     return unet_forward_impl(reinterpret_cast<const uint8_t*>(wpack), x_in, t, x_out,
                              reinterpret_cast<uint8_t*>(workspace), workspace_bytes, batch, sa,
                              (cudaStream_t)stream);
+}
+
+extern "C" int tdm_unet_profile_p_sample(const void* wpack, const float* x_in, const int64_t* t,
+                                         const float* betas, const float* alphas,
+                                         const float* sqrt_om_acp, float* x_out, void* workspace,
+                                         int64_t workspace_bytes, int64_t batch, uint64_t seed,
+                                         float* host_ms9, void* stream) {
+    TDM_CHECK_ARG(host_ms9, "tdm_unet_profile_p_sample: null output");
+    cudaEvent_t ev[10];
+    for (int i = 0; i < 10; ++i) TDM_CHECK_CUDA(cudaEventCreate(&ev[i]));
+    StepArgs sa;
+    sa.fuse_step = 1; sa.betas = betas; sa.alphas = alphas; sa.sqrt_om = sqrt_om_acp; sa.seed = seed;
+    g_prof = ev;
+    const int rc = unet_forward_impl(reinterpret_cast<const uint8_t*>(wpack), x_in, t, x_out,
+                                     reinterpret_cast<uint8_t*>(workspace), workspace_bytes, batch, sa,
+                                     (cudaStream_t)stream);
+    g_prof = nullptr;
+    int ret = rc;
+    if (rc == TDM_OK) {
+        cudaError_t e = cudaEventSynchronize(ev[9]);
+        if (e != cudaSuccess) {
+            set_error("tdm_unet_profile_p_sample: %s", cudaGetErrorString(e));
+            ret = TDM_ERR_CUDA;
+        } else {
+            for (int i = 0; i < 9; ++i) cudaEventElapsedTime(&host_ms9[i], ev[i], ev[i + 1]);
+        }
+    }
+    for (int i = 0; i < 10; ++i) cudaEventDestroy(ev[i]);
+    return ret;
 }

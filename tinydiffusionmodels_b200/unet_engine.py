@@ -128,6 +128,27 @@ class UNetEngine:
             _lib.stream_ptr(self.device)), "tdm_unet_p_sample")
         return out
 
+    KERNEL_NAMES = ("rb1_conv1", "rb1_conv2", "avgpool", "rb2_conv1", "rb2_conv2", "rb3_conv1",
+                    "rb3_conv2", "rb4_conv1", "rb4_conv2_out_step")
+    # algorithmic FLOPs per image of each launch (1x1 skips counted with the
+    # conv1 kernel that computes them, the out conv with rb4.conv2)
+    KERNEL_FLOPS_PER_IMAGE = (451_584, 14_450_688 + 50_176, 0, 7_225_344 + 802_816, 14_450_688, 14_450_688,
+                              14_450_688, 43_352_064 + 4_816_896, 14_450_688 + 50_176)
+
+    def profile_p_sample(self, x: torch.Tensor, t: torch.Tensor, seed: int = 0) -> list[float]:
+        """Per-kernel milliseconds of one fused p_sample (CUDA events between the launches)."""
+        import ctypes
+
+        b = x.shape[0]
+        self._prep(b)
+        ms = (ctypes.c_float * 9)()
+        s = self.sched
+        _lib.check(self.lib.tdm_unet_profile_p_sample(
+            self.wpack.data_ptr(), x.data_ptr(), t.data_ptr(), s.betas.data_ptr(), s.alphas.data_ptr(),
+            s.sqrt_one_minus_alphas_cumprod.data_ptr(), x.data_ptr(), self.ws.data_ptr(), self.ws_bytes,
+            b, seed, ms, _lib.stream_ptr(self.device)), "tdm_unet_profile_p_sample")
+        return list(ms)
+
 
 # ---------------------------------------------------------------------------------------------
 # test/debug aid: read an intermediate activation back out of the plane layout
