@@ -1,0 +1,169 @@
+"""Pin the CPU oracle (oracle/) to outputs of the real reference.
+
+The reference's own tests hold no golden vectors for the hot path, so the pins are
+vectors recorded by running the unmodified reference (tests/golden/make_golden.py).  CPU only.
+"""
+import types
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ddpm_oracle as O
+from oracle import philox as PX
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+@pytest.fixture(scope="module")
+def gm():
+    return torch.load(GOLD / "mnist_golden.pt", weights_only=False)
+
+
+@pytest.fixture(scope="module")
+def gt():
+    return torch.load(GOLD / "text_golden.pt", weights_only=False)
+
+
+def test_tables_bit_exact(gm):
+    tab = O.make_tables()
+    for k, v in gm["tables"].items():
+        assert torch.equal(tab[k], v), k
+
+
+def test_mnist_q_sample_bit_exact(gm):
+    assert torch.equal(O.q_sample(gm["x"], gm["t"], gm["noise"], gm["tables"]), gm["q_sample"])
+
+
+def test_unet_forward(gm):
+    out = O.unet_forward(gm["state_dict"], gm["x"], gm["t"])
+    torch.testing.assert_close(out, gm["unet"], rtol=0, atol=1e-6)
+
+
+def test_mnist_p_sample(gm):
+    sd, tab = gm["state_dict"], gm["tables"]
+    B = gm["x"].shape[0]
+    got = O.mnist_p_sample(sd, gm["x"], torch.full((B,), 700), gm["z"], tab)
+    torch.testing.assert_close(got, gm["p_sample_t700"], rtol=0, atol=1e-6)
+    got0 = O.mnist_p_sample(sd, gm["x"], torch.zeros(B, dtype=torch.long), None, tab)
+    torch.testing.assert_close(got0, gm["p_sample_t0"], rtol=0, atol=1e-6)
+
+
+def test_reverse_step_bit_exact_given_eps(gm):
+    # with the reference's own eps the elementwise restatement is bit-exact
+    sd, tab = gm["state_dict"], gm["tables"]
+    B = gm["x"].shape[0]
+    t = torch.full((B,), 700)
+    eps = O.unet_forward(sd, gm["x"], t)
+    a = O.reverse_step(gm["x"], eps, t, gm["z"], tab)
+    b = O.mnist_p_sample(sd, gm["x"], t, gm["z"], tab)
+    assert torch.equal(a, b)
+
+
+def test_short_trajectory(gm):
+    x = O.mnist_sample_loop(gm["state_dict"], gm["x"], gm["zs6"], gm["tables"], steps=6)
+    torch.testing.assert_close(x, gm["traj6"], rtol=0, atol=2e-5)
+    torch.testing.assert_close(O.to_unit_range(x), gm["unit_range"], rtol=0, atol=2e-5)
+
+
+def test_train_step_loss_grads_adamw(gm):
+    tr = gm["train"]
+    sd, tab = gm["state_dict"], gm["tables"]
+    loss, grads = O.mnist_loss_and_grads(sd, tr["x0"], tr["t"], gm["noise"], tab)
+    torch.testing.assert_close(loss, tr["loss"], rtol=1e-6, atol=0)
+    for k, n in tr["grad_norms"].items():
+        torch.testing.assert_close(grads[k].norm(), n, rtol=1e-4, atol=1e-9)
+    for k, g in tr["grads_small"].items():
+        torch.testing.assert_close(grads[k], g, rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(grads["rb4.conv1.weight"], tr["grad_rb4_conv1_w"], rtol=1e-4, atol=1e-7)
+    # AdamW, first step from zero moments
+    for k, want in tr["after_small"].items():
+        p, _, _ = O.adamw_step(sd[k], grads[k], torch.zeros_like(sd[k]), torch.zeros_like(sd[k]), 1)
+        torch.testing.assert_close(p, want, rtol=1e-5, atol=1e-7)
+    for k, n in tr["after_norms"].items():
+        p, _, _ = O.adamw_step(sd[k], grads[k], torch.zeros_like(sd[k]), torch.zeros_like(sd[k]), 1)
+        torch.testing.assert_close(p.norm(), n, rtol=1e-5, atol=0)
+
+
+def test_text_q_sample_and_transformer(gt):
+    tab = O.make_tables()
+    assert torch.equal(O.q_sample(gt["x"], gt["t"], gt["noise"], tab), gt["q_sample"])
+    out = O.transformer_forward(gt["model_sd"], gt["x"], gt["t"])
+    # the reference runs PyTorch's fused encoder fast path in eval mode; the op-by-op restatement
+    # differs from it by ~1e-6
+    torch.testing.assert_close(out, gt["transformer"], rtol=0, atol=2e-5)
+
+
+def test_text_p_sample(gt):
+    tab = O.make_tables()
+    B = gt["x"].shape[0]
+    got = O.text_p_sample(gt["model_sd"], gt["x"], torch.full((B,), 300), gt["z"], tab)
+    torch.testing.assert_close(got, gt["p_sample_t300"], rtol=0, atol=2e-5)
+    got0 = O.text_p_sample(gt["model_sd"], gt["x"], torch.zeros(B, dtype=torch.long), None, tab)
+    torch.testing.assert_close(got0, gt["p_sample_t0"], rtol=0, atol=2e-5)
+
+
+def test_rounding(gt):
+    w, b = gt["rounding_sd"]["decoder.weight"], gt["rounding_sd"]["decoder.bias"]
+    emb = gt["emb_sd"]["embeddings.weight"]
+    torch.testing.assert_close(O.learned_logits(gt["x"], w, b), gt["learned_logits"], rtol=0, atol=1e-6)
+    assert torch.equal(O.round_tokens(gt["x"], w=w, b=b), gt["learned_tokens"])
+    torch.testing.assert_close(O.cosine_logits(gt["x"], emb), gt["cosine_sims"], rtol=0, atol=1e-6)
+    assert torch.equal(O.round_tokens(gt["x"], emb=emb), gt["cosine_tokens"])
+
+
+def _guided_oracle(gt, learned: bool, temperature: float):
+    """guided_generate restated with the oracle's per-position mix (src/shakespeare.py:445-470)."""
+    table = gt["lm_table"]
+    w, b = gt["rounding_sd"]["decoder.weight"], gt["rounding_sd"]["decoder.bias"]
+    emb = gt["emb_sd"]["embeddings.weight"]
+    z = gt["x"]
+    B, L, _ = z.shape
+    ids = torch.full((B, 1), 2, dtype=torch.long)
+    for pos in range(L):
+        logits = table[ids] + 0.1 * torch.cumsum(table[ids], dim=1)
+        ar = logits[:, -1, :]
+        if learned:
+            nxt = O.guided_mix_step(ar, z[:, pos, :], 0.3, temperature, w=w, b=b)
+        else:
+            nxt = O.guided_mix_step(ar, z[:, pos, :], 0.3, temperature, emb=emb)
+        ids = torch.cat([ids, nxt[:, None]], dim=1)
+    return [" ".join(str(int(i)) for i in row) for row in ids[:, 1:]]
+
+
+def test_guided_generate(gt):
+    assert _guided_oracle(gt, True, 1.0) == gt["guided_learned"]
+    assert _guided_oracle(gt, False, 0.7) == gt["guided_cosine"]
+
+
+def test_philox_known_answers():
+    # Random123 kat_vectors, philox4x32-10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = PX.philox4x32_10(*[[c] for c in ctr], *key)
+        assert tuple(int(v[0]) for v in got) == want
+
+
+def test_philox_normals_are_standard():
+    z = PX.randn(256, 784, 3, 0, 17, PX.DOMAIN_REVERSE)
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01
+    assert np.isfinite(z).all()
+
+
+@pytest.mark.reference
+def test_oracle_matches_live_reference_unet():
+    """In the authoring container: the oracle against the live reference on fresh seeds."""
+    from tests.golden.make_golden import import_reference
+    ref, _ = import_reference()
+    torch.manual_seed(123)
+    model = ref.SimpleUNet().eval()
+    x = torch.randn(5, 1, 28, 28)
+    t = torch.randint(0, 1000, (5,))
+    with torch.no_grad():
+        want = model(x, t)
+    got = O.unet_forward(model.state_dict(), x, t)
+    torch.testing.assert_close(got, want, rtol=0, atol=1e-6)

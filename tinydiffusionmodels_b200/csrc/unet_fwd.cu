@@ -219,6 +219,8 @@ struct ConvArgs {
     int batch;
 };
 
+constexpr int kEpiGroups = 2;  // epilogue warp groups == TMEM accumulator stages
+
 template <int W, int CIN, int COUT, bool SKIPG>
 struct ConvCfg {
     using G = Geo<W>;
@@ -231,17 +233,18 @@ struct ConvCfg {
     static constexpr int AVAIL = MAX_SMEM - W_BYTES - PARAM_BYTES - 256;
     static constexpr int NSTAGE = (AVAIL / STAGE_BYTES) > 4 ? 4 : (AVAIL / STAGE_BYTES);
     static_assert(NSTAGE >= 2, "need at least two input stages");
-    static constexpr int NACC = 2;
+    static constexpr int NACC = kEpiGroups;
     static constexpr int ACC_COLS = SKIPG ? 2 * COUT : COUT;
     static constexpr int TMEM_COLS = (NACC * ACC_COLS <= 32) ? 32 : (NACC * ACC_COLS <= 64) ? 64
-                                   : (NACC * ACC_COLS <= 128) ? 128 : 256;
-    static_assert(NACC * ACC_COLS <= 256, "accumulators exceed the TMEM budget chosen here");
+                                   : (NACC * ACC_COLS <= 128) ? 128 : (NACC * ACC_COLS <= 256) ? 256 : 512;
+    static_assert(NACC * ACC_COLS <= 512, "accumulators exceed TMEM");
     static constexpr int SMEM_BYTES = W_BYTES + NSTAGE * STAGE_BYTES + PARAM_BYTES + 256;
-    static constexpr int THREADS = 192;
+    // warp 0 producer, warp 1 MMA issuer, then NACC groups of 4 epilogue warps
+    static constexpr int THREADS = 64 + 128 * NACC;
 };
 
 template <int W, int CIN, int COUT, int EPI, bool SKIPG>
-__global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const ConvArgs a) {
+__global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(const ConvArgs a) {
     using C = ConvCfg<W, CIN, COUT, SKIPG>;
     using G = Geo<W>;
     static_assert(COUT == 32 || COUT == 64, "COUT");
@@ -276,6 +279,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const ConvArgs a) {
         s_sbias[c] = SKIPG ? a.sbias[c] : 0.f;
         s_aux[c] = (EPI == EPI_RES_X || EPI == EPI_FINAL) ? a.aux_w[c] : 0.f;
         if (EPI == EPI_RES_X) s_aux[32 + c] = a.aux_b[c];
+        if (EPI == EPI_FINAL && c == 0) s_aux[32] = a.aux_b[0];
     }
     if (threadIdx.x == 0) {
         mbar_init(bar_w, 1);
@@ -365,12 +369,15 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const ConvArgs a) {
             }
         }
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        // ===== epilogue: group g = (warp-2)/4 owns accumulator stage g (tiles it = g, g+NACC, ..),
+        //       so the epilogues of consecutive tiles overlap; TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
-            const int acc = it % C::NACC;
-            const uint32_t aph = (it / C::NACC) & 1;
+        const int grp = (warp - 2) >> 2;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * C::ACC_COLS;
+        int n = 0;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < a.nt; tile += C::NACC * gridDim.x, ++n) {
+            const uint32_t aph = n & 1;
+            // ---- phase A: everything that does not need the accumulator (overlaps the MMAs) ----
             const int64_t pos = (int64_t)tile * kTile + q * 32 + lane;
             const int b = (int)(pos / G::S);
             const int rem = (int)(pos - (int64_t)b * G::S);
@@ -383,10 +390,42 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const ConvArgs a) {
             float xin = 0.f;
             if ((EPI == EPI_RES_X || EPI == EPI_FINAL) && valid && a.x)
                 xin = __ldg(a.x + (int64_t)b * 784 + y * 28 + c);
+            constexpr bool kHasRes = (EPI == EPI_RES || EPI == EPI_RES_UP || EPI == EPI_FINAL);
+            uint4 rv[kHasRes ? COUT / 8 : 1];
+            if constexpr (kHasRes) {
+#pragma unroll
+                for (int pl = 0; pl < COUT / 8; ++pl) {
+                    rv[pl] = make_uint4(0, 0, 0, 0);
+                    if (valid)  // residual planes share this kernel's position geometry
+                        rv[pl] = *reinterpret_cast<const uint4*>(a.res + pl * a.res_ps + (pos + G::HALO) * 16);
+                }
+            }
+            StepCoef sc{};
+            float zz = 0.f;
+            bool add_noise = false;
+            if constexpr (EPI == EPI_FINAL) {
+                if (a.fuse_step && valid) {
+                    add_noise = __ldg(a.t) != 0;  // src/mnist.py:176
+                    const int64_t tb = __ldg(a.t + b);
+                    sc = step_coef(tb, a.betas, a.alphas, a.sqrt_om);
+                    if (add_noise) {
+                        const int e = y * 28 + c;
+                        if (a.z) {
+                            zz = __ldg(a.z + (int64_t)b * 784 + e);
+                        } else {
+                            const float4 n4 = philox_normal4(a.seed, a.sample_offset + (uint64_t)b,
+                                                             (uint32_t)(e >> 2), a.step_id + (uint32_t)tb,
+                                                             kDomainReverse);
+                            const int k = e & 3;
+                            zz = k == 0 ? n4.x : k == 1 ? n4.y : k == 2 ? n4.z : n4.w;
+                        }
+                    }
+                }
+            }
 
-            mbar_wait(bar_accf + acc, aph);
+            // ---- phase B: drain the accumulator ----
+            mbar_wait(bar_accf + grp, aph);
             tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS;
             float dot = 0.f;
 
 #pragma unroll
@@ -400,7 +439,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const ConvArgs a) {
                     // all TMEM reads of this accumulator are done: hand it back to the MMA warp
                     tc_fence_before_sync();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_acce + acc);
+                    if (lane == 0) mbar_arrive(bar_acce + grp);
                 }
 #pragma unroll
                 for (int pj = 0; pj < 4; ++pj) {
@@ -424,12 +463,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const ConvArgs a) {
                             v[k] += fmaf(s_aux[ch], xin, s_aux[32 + ch]);
                         }
                     } else {
-                        // residual planes share the *input* geometry of this kernel
-                        uint4 rv = make_uint4(0, 0, 0, 0);
-                        if (valid)
-                            rv = *reinterpret_cast<const uint4*>(a.res + plane * a.res_ps +
-                                                                 (pos + G::HALO) * 16);
-                        const uint32_t* rw = &rv.x;
+                        const uint32_t* rw = &rv[plane].x;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const float2 f = unpack_bf16x2(rw[k]);
@@ -478,28 +512,9 @@ __global__ void __launch_bounds__(192, 1) conv3x3_tc_kernel(const ConvArgs a) {
             }
             if constexpr (EPI == EPI_FINAL) {
                 if (valid) {
-                    const float eps = dot + __ldg(a.aux_b);  // out conv bias (src/mnist.py:87)
+                    const float eps = dot + s_aux[32];  // out conv bias (src/mnist.py:87)
                     const int64_t oi = (int64_t)b * 784 + y * 28 + c;
-                    if (a.fuse_step) {
-                        const bool add_noise = __ldg(a.t) != 0;  // src/mnist.py:176
-                        const int64_t tb = __ldg(a.t + b);
-                        const StepCoef sc = step_coef(tb, a.betas, a.alphas, a.sqrt_om);
-                        float zz = 0.f;
-                        if (add_noise) {
-                            if (a.z) {
-                                zz = __ldg(a.z + oi);
-                            } else {
-                                const int e = y * 28 + c;
-                                const float4 n4 = philox_normal4(a.seed, a.sample_offset + (uint64_t)b,
-                                                                 (uint32_t)(e >> 2), a.step_id + (uint32_t)tb, kDomainReverse);
-                                const int k = e & 3;
-                                zz = k == 0 ? n4.x : k == 1 ? n4.y : k == 2 ? n4.z : n4.w;
-                            }
-                        }
-                        a.fout[oi] = rstep1(sc, xin, eps, zz, add_noise);
-                    } else {
-                        a.fout[oi] = eps;
-                    }
+                    a.fout[oi] = a.fuse_step ? rstep1(sc, xin, eps, zz, add_noise) : eps;
                 }
             }
         }
