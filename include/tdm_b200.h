@@ -123,6 +123,32 @@ int tdm_unet_p_sample(const void* wpack, const float* x_in, const int64_t* t, co
                       int n_steps, uint64_t seed, uint64_t sample_offset, uint32_t step_id,
                       void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Training step (src/mnist.py:153-159): forward that keeps what the backward needs, backward into
+ * one flat fp32 gradient vector (state_dict order), fused AdamW over the flat buffers.
+ * The workspace must be sized with tdm_unet_workspace_bytes(batch, 1).
+ * ------------------------------------------------------------------------------------------- */
+
+/* SimpleUNet.forward in training mode: as tdm_unet_forward, additionally storing ReLU masks and the
+ * last block's output in the workspace. */
+int tdm_unet_forward_train(const void* wpack, const float* x, const int64_t* t, float* eps_out,
+                           void* workspace, int64_t workspace_bytes, int64_t batch, void* stream);
+
+/* loss = mean((eps - noise)^2) (F.mse_loss, src/mnist.py:158) and d loss / d params.
+ * x, t: the inputs of the preceding tdm_unet_forward_train; eps: its output; noise: the target.
+ * flat_grad [181,473] and loss_out [1] are OVERWRITTEN (zeroed, then accumulated with atomics). */
+int tdm_unet_backward(const void* wpack, const float* x, const int64_t* t, const float* noise,
+                      const float* eps, float* flat_grad, float* loss_out, void* workspace,
+                      int64_t workspace_bytes, int64_t batch, void* stream);
+
+/* torch.optim.AdamW update (src/mnist.py:148,159) over flat fp32 buffers of n elements.
+ * grads are multiplied by grad_scale first (1/world_size after a sum all-reduce).
+ * step_dev: DEVICE pointer to the 1-based index of this update (kept on the device so a captured
+ * CUDA graph can be replayed; advance it with tdm_timestep_advance(step_dev, 1, +1, stream)). */
+int tdm_adamw_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay,
+                   float grad_scale, const int64_t* step_dev, void* stream);
+
 /* Measurement aid (bench.py roofline): one fused p_sample with CUDA events recorded on `stream`
  * between its nine launches; SYNCHRONISES on the last event and writes the nine per-kernel
  * durations in milliseconds to host_ms9 (order: rb1.conv1, rb1.conv2, avgpool, rb2.conv1,

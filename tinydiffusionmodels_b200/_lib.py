@@ -35,6 +35,9 @@ SIGNATURES: dict[str, tuple] = {
     "tdm_unet_pack_weights": (c_int, [_P, _P, _P]),
     "tdm_unet_forward": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P]),
     "tdm_unet_p_sample": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_uint64, c_uint64, c_uint32, _P]),
+    "tdm_unet_forward_train": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P]),
+    "tdm_unet_backward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P]),
+    "tdm_adamw_flat": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, _P, _P]),
     "tdm_unet_profile_p_sample": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, ctypes.POINTER(c_float), _P]),
 }
 

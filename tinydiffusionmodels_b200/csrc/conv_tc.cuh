@@ -1,0 +1,392 @@
+// conv_tc.cuh — the persistent warp-specialised tcgen05 implicit-GEMM convolution shared by the
+// UNet forward (unet_fwd.cu) and the data-gradient pass of the backward (unet_bwd.cu).
+//
+//   warp 0      producer: weights once, then one input tile (all channel planes, halo included)
+//               per iteration via 1-D bulk async copies into a ring of smem stages
+//   warp 1      one thread issues TAPS*CIN/16 tcgen05.mma (M=128 positions, N=COUT, K=16) per
+//               tile; the A operand of every tap is the same smem tile at a shifted row offset
+//   warps 2..   kEpiGroups groups of 4 epilogue warps; group g owns TMEM accumulator stage g
+#pragma once
+#include "common.cuh"
+#include "diffusion_math.cuh"
+#include "tc05.cuh"
+#include "unet_layout.cuh"
+
+namespace tdm {
+
+// ---------------------------------------------------------------------------------------------
+// tensor-core 3x3 convolution
+// ---------------------------------------------------------------------------------------------
+// EPI_PLAIN: out = acc (+ residual if given) — no bias, no ReLU: the data-gradient convolutions.
+enum : int { EPI_CONV1 = 0, EPI_RES = 1, EPI_RES_X = 2, EPI_RES_UP = 3, EPI_FINAL = 4, EPI_PLAIN = 5 };
+
+struct ConvArgs {
+    const uint8_t* in;     // input planes: row -HALO of plane 0
+    int64_t in_ps;         // plane stride (bytes)
+    const uint8_t* w;      // packed bf16 weights: conv, then (SKIPG) the 1x1 skip
+    const float* bias;     // [COUT] conv bias
+    const float* tw;       // [COUT] time_emb.weight   (EPI_CONV1)
+    const float* tb;       // [COUT] time_emb.bias     (EPI_CONV1)
+    const float* sbias;    // [COUT] skip bias         (SKIPG)
+    const int64_t* t;      // [B]
+    uint8_t* out;          // output planes
+    int64_t out_ps;
+    uint8_t* out2;         // skip output planes (SKIPG)
+    int64_t out2_ps;
+    const uint8_t* res;    // residual planes (EPI_RES / EPI_RES_UP / EPI_FINAL)
+    int64_t res_ps;
+    const float* x;        // [B,784] fp32: rb1 skip input (EPI_RES_X) or x_t (EPI_FINAL + step)
+    const float* aux_w;    // [32]: rb1.skip.weight (EPI_RES_X) or out.weight (EPI_FINAL)
+    const float* aux_b;    // [32] rb1.skip.bias / [1] out.bias
+    float* fout;           // EPI_FINAL: eps or x_{t-1}, [B,784] fp32
+    const float* z;        // injected noise or null (Philox)
+    const float* betas;
+    const float* alphas;
+    const float* sqrt_om;
+    uint64_t seed;
+    uint64_t sample_offset;
+    uint32_t step_id;
+    int fuse_step;
+    int nt;
+    int batch;
+    // training forward: ReLU masks, one uint32 per 32 channels per position: mask[chunk*mask_stride+pos]
+    uint32_t* mask;
+    int64_t mask_stride;
+};
+
+constexpr int kEpiGroups = 2;  // epilogue warp groups == TMEM accumulator stages
+
+template <int W, int CIN, int COUT, bool SKIPG, int TAPS = 9>
+struct ConvCfg {
+    using G = Geo<W>;
+    static constexpr int NPL = CIN / 8;
+    static constexpr int STAGE_BYTES = NPL * G::RT * 16;
+    static constexpr int WCONV_BYTES = TAPS * CIN * COUT * 2;
+    static constexpr int W_BYTES = WCONV_BYTES + (SKIPG ? CIN * COUT * 2 : 0);
+    static constexpr int PARAM_BYTES = 5 * 96 * 4;
+    static constexpr int MAX_SMEM = 227 * 1024;
+    static constexpr int AVAIL = MAX_SMEM - W_BYTES - PARAM_BYTES - 256;
+    static constexpr int NSTAGE = (AVAIL / STAGE_BYTES) > 4 ? 4 : (AVAIL / STAGE_BYTES);
+    static_assert(NSTAGE >= 2, "need at least two input stages");
+    static constexpr int NACC = kEpiGroups;
+    static constexpr int ACC_COLS = SKIPG ? 2 * COUT : COUT;
+    static constexpr int TMEM_COLS = (NACC * ACC_COLS <= 32) ? 32 : (NACC * ACC_COLS <= 64) ? 64
+                                   : (NACC * ACC_COLS <= 128) ? 128 : (NACC * ACC_COLS <= 256) ? 256 : 512;
+    static_assert(NACC * ACC_COLS <= 512, "accumulators exceed TMEM");
+    static constexpr int SMEM_BYTES = W_BYTES + NSTAGE * STAGE_BYTES + PARAM_BYTES + 256;
+    // warp 0 producer, warp 1 MMA issuer, then NACC groups of 4 epilogue warps
+    static constexpr int THREADS = 64 + 128 * NACC;
+};
+
+template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9>
+__global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(const ConvArgs a) {
+    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS>;
+    using G = Geo<W>;
+    static_assert(COUT == 32 || COUT == 64 || COUT == 96, "COUT");
+    static_assert(TAPS == 9 || TAPS == 1, "3x3 or 1x1");
+    static_assert(!SKIPG || COUT <= 64, "skip GEMM variant is forward-only");
+    static_assert(EPI != EPI_FINAL || COUT == 32, "final epilogue expects 32 channels");
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* s_w = smem;
+    uint8_t* s_in = smem + C::W_BYTES;
+    float* s_par = reinterpret_cast<float*>(s_in + C::NSTAGE * C::STAGE_BYTES);
+    float* s_bias = s_par;
+    float* s_tw = s_par + 96;
+    float* s_tb = s_par + 192;
+    float* s_sbias = s_par + 288;
+    float* s_aux = s_par + 384;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_par + 480);
+    uint64_t* bar_w = bars;
+    uint64_t* bar_full = bars + 1;
+    uint64_t* bar_empty = bar_full + C::NSTAGE;
+    uint64_t* bar_accf = bar_empty + C::NSTAGE;
+    uint64_t* bar_acce = bar_accf + C::NACC;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acce + C::NACC);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // ---- setup -----------------------------------------------------------------------------
+    if (threadIdx.x < COUT) {
+        const int c = threadIdx.x;
+        s_bias[c] = (EPI == EPI_PLAIN) ? 0.f : a.bias[c];
+        s_tw[c] = (EPI == EPI_CONV1) ? a.tw[c] : 0.f;
+        s_tb[c] = (EPI == EPI_CONV1) ? a.tb[c] : 0.f;
+        s_sbias[c] = SKIPG ? a.sbias[c] : 0.f;
+        s_aux[c] = (EPI == EPI_RES_X || EPI == EPI_FINAL) ? a.aux_w[c] : 0.f;
+        if (EPI == EPI_RES_X) s_aux[32 + c] = a.aux_b[c];
+        if (EPI == EPI_FINAL && c == 0) s_aux[32] = a.aux_b[0];
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(bar_w, 1);
+        for (int i = 0; i < C::NSTAGE; ++i) {
+            mbar_init(bar_full + i, 1);
+            mbar_init(bar_empty + i, 1);
+        }
+        for (int i = 0; i < C::NACC; ++i) {
+            mbar_init(bar_accf + i, 1);
+            mbar_init(bar_acce + i, 4);  // one arrival per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<C::TMEM_COLS>(s_tmem);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *s_tmem;
+
+    // ---- roles -----------------------------------------------------------------------------
+    if (warp == 0) {
+        // ===== producer: weights once, then one input tile per iteration =====
+        if (lane == 0) {
+            mbar_arrive_expect_tx(bar_w, C::W_BYTES);
+            constexpr int CH = 16384;
+            for (int off = 0; off < C::W_BYTES; off += CH) {
+                const int n = (C::W_BYTES - off) < CH ? (C::W_BYTES - off) : CH;
+                bulk_g2s(s_w + off, a.w + off, n, bar_w);
+            }
+        }
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
+            const int s = it % C::NSTAGE;
+            const uint32_t ph = (it / C::NSTAGE) & 1;
+            if (lane == 0) {
+                mbar_wait(bar_empty + s, ph ^ 1);
+                mbar_arrive_expect_tx(bar_full + s, C::STAGE_BYTES);
+            }
+            __syncwarp();
+            if (lane < C::NPL) {
+                bulk_g2s(s_in + s * C::STAGE_BYTES + lane * (G::RT * 16),
+                         a.in + lane * a.in_ps + (int64_t)tile * (kTile * 16), G::RT * 16,
+                         bar_full + s);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
+            mbar_wait(bar_w, 0);
+            const uint32_t w_addr = smem_u32(s_w);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
+                const int s = it % C::NSTAGE;
+                const uint32_t ph = (it / C::NSTAGE) & 1;
+                const int acc = it % C::NACC;
+                const uint32_t aph = (it / C::NACC) & 1;
+                mbar_wait(bar_acce + acc, aph ^ 1);
+                mbar_wait(bar_full + s, ph);
+                tc_fence_after_sync();
+                const uint32_t in_addr = smem_u32(s_in + s * C::STAGE_BYTES);
+                const uint32_t d = tmem_base + acc * C::ACC_COLS;
+#pragma unroll
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    const int off = (TAPS == 1) ? 0 : (tap / 3 - 1) * G::Wp + (tap % 3 - 1);
+#pragma unroll
+                    for (int ks = 0; ks < CIN / 16; ++ks) {
+                        const uint64_t ad = make_smem_desc(
+                            in_addr + (2 * ks) * (G::RT * 16) + (G::HALO + off) * 16, G::RT * 16, 128);
+                        const uint64_t bd = make_smem_desc(
+                            w_addr + ((tap * C::NPL + 2 * ks) * COUT) * 16, COUT * 16, 128);
+                        umma_bf16(d, ad, bd, idesc, (tap | ks) != 0);
+                    }
+                }
+                if constexpr (SKIPG) {
+#pragma unroll
+                    for (int ks = 0; ks < CIN / 16; ++ks) {
+                        const uint64_t ad = make_smem_desc(
+                            in_addr + (2 * ks) * (G::RT * 16) + G::HALO * 16, G::RT * 16, 128);
+                        const uint64_t bd = make_smem_desc(
+                            w_addr + C::WCONV_BYTES + ((2 * ks) * COUT) * 16, COUT * 16, 128);
+                        umma_bf16(d + COUT, ad, bd, idesc, ks != 0);
+                    }
+                }
+                umma_commit(bar_empty + s);   // smem stage reusable once these MMAs retire
+                umma_commit(bar_accf + acc);  // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue: group g = (warp-2)/4 owns accumulator stage g (tiles it = g, g+NACC, ..),
+        //       so the epilogues of consecutive tiles overlap; TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        const int grp = (warp - 2) >> 2;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * C::ACC_COLS;
+        int n = 0;
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < a.nt; tile += C::NACC * gridDim.x, ++n) {
+            const uint32_t aph = n & 1;
+            // ---- phase A: everything that does not need the accumulator (overlaps the MMAs) ----
+            const int64_t pos = (int64_t)tile * kTile + q * 32 + lane;
+            const int b = (int)(pos / G::S);
+            const int rem = (int)(pos - (int64_t)b * G::S);
+            const int r = rem / G::Wp, c = rem - r * G::Wp;
+            const bool valid = b < a.batch && r >= 1 && c < G::W;
+            const int y = r - 1;
+
+            float ts = 0.f;
+            if (EPI == EPI_CONV1 && valid) ts = (float)__ldg(a.t + b) / 1000.0f;
+            float xin = 0.f;
+            if ((EPI == EPI_RES_X || EPI == EPI_FINAL) && valid && a.x)
+                xin = __ldg(a.x + (int64_t)b * 784 + y * 28 + c);
+            constexpr bool kHasRes = (EPI == EPI_RES || EPI == EPI_RES_UP || EPI == EPI_FINAL || EPI == EPI_PLAIN);
+            uint4 rv[kHasRes ? COUT / 8 : 1];
+            if constexpr (kHasRes) {
+#pragma unroll
+                for (int pl = 0; pl < COUT / 8; ++pl) {
+                    rv[pl] = make_uint4(0, 0, 0, 0);
+                    if (valid && (EPI != EPI_PLAIN || a.res))  // residual planes share this geometry
+                        rv[pl] = *reinterpret_cast<const uint4*>(a.res + pl * a.res_ps + (pos + G::HALO) * 16);
+                }
+            }
+            StepCoef sc{};
+            float zz = 0.f;
+            bool add_noise = false;
+            if constexpr (EPI == EPI_FINAL) {
+                if (a.fuse_step && valid) {
+                    add_noise = __ldg(a.t) != 0;  // src/mnist.py:176
+                    const int64_t tb = __ldg(a.t + b);
+                    sc = step_coef(tb, a.betas, a.alphas, a.sqrt_om);
+                    if (add_noise) {
+                        const int e = y * 28 + c;
+                        if (a.z) {
+                            zz = __ldg(a.z + (int64_t)b * 784 + e);
+                        } else {
+                            const float4 n4 = philox_normal4(a.seed, a.sample_offset + (uint64_t)b,
+                                                             (uint32_t)(e >> 2), a.step_id + (uint32_t)tb,
+                                                             kDomainReverse);
+                            const int k = e & 3;
+                            zz = k == 0 ? n4.x : k == 1 ? n4.y : k == 2 ? n4.z : n4.w;
+                        }
+                    }
+                }
+            }
+
+            // ---- phase B: drain the accumulator ----
+            mbar_wait(bar_accf + grp, aph);
+            tc_fence_after_sync();
+            float dot = 0.f;
+
+#pragma unroll
+            for (int c0 = 0; c0 < COUT; c0 += 32) {
+                uint32_t r1[32];
+                uint32_t mbits = 0;
+                tmem_ld32(taddr + c0, r1);
+                uint32_t r2[32];
+                if constexpr (SKIPG) tmem_ld32(taddr + COUT + c0, r2);
+                tmem_ld_wait();
+                if (c0 + 32 >= COUT) {
+                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+                    tc_fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_acce + grp);
+                }
+#pragma unroll
+                for (int pj = 0; pj < 4; ++pj) {
+                    const int plane = c0 / 8 + pj;
+                    float v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int ch = c0 + pj * 8 + k;
+                        if constexpr (EPI == EPI_PLAIN) {
+                            v[k] = __uint_as_float(r1[pj * 8 + k]);
+                        } else {
+                            v[k] = fmaxf(__uint_as_float(r1[pj * 8 + k]) + s_bias[ch], 0.f);
+                            mbits |= (v[k] > 0.f ? 1u : 0u) << (pj * 8 + k);
+                        }
+                    }
+                    if constexpr (EPI == EPI_CONV1) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int ch = c0 + pj * 8 + k;
+                            v[k] += fmaf(s_tw[ch], ts, s_tb[ch]);
+                        }
+                    } else if constexpr (EPI == EPI_RES_X) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int ch = c0 + pj * 8 + k;
+                            v[k] += fmaf(s_aux[ch], xin, s_aux[32 + ch]);
+                        }
+                    } else {
+                        const uint32_t* rw = &rv[plane].x;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float2 f = unpack_bf16x2(rw[k]);
+                            v[2 * k] += f.x;
+                            v[2 * k + 1] += f.y;
+                        }
+                    }
+                    if constexpr (EPI == EPI_FINAL) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) dot = fmaf(s_aux[c0 + pj * 8 + k], v[k], dot);
+                    }
+                    if (EPI != EPI_FINAL || a.out) {
+                        uint4 o;
+                        o.x = valid ? pack_bf16x2(v[0], v[1]) : 0u;
+                        o.y = valid ? pack_bf16x2(v[2], v[3]) : 0u;
+                        o.z = valid ? pack_bf16x2(v[4], v[5]) : 0u;
+                        o.w = valid ? pack_bf16x2(v[6], v[7]) : 0u;
+                        if constexpr (EPI == EPI_RES_UP) {
+                            // nearest x2 upsample (src/mnist.py:83): one 14x14 pixel -> 2x2 block
+                            // of the 28x28 geometry; pad positions there keep their initial zeros.
+                            if (valid) {
+                                using GU = Geo<28>;
+                                const int64_t p00 = (int64_t)b * GU::S + (2 * y + 1) * GU::Wp + 2 * c;
+                                uint8_t* dst = a.out + plane * a.out_ps + (p00 + GU::HALO) * 16;
+                                *reinterpret_cast<uint4*>(dst) = o;
+                                *reinterpret_cast<uint4*>(dst + 16) = o;
+                                *reinterpret_cast<uint4*>(dst + GU::Wp * 16) = o;
+                                *reinterpret_cast<uint4*>(dst + GU::Wp * 16 + 16) = o;
+                            }
+                        } else {
+                            *reinterpret_cast<uint4*>(a.out + plane * a.out_ps + (pos + G::HALO) * 16) = o;
+                        }
+                    }
+                    if constexpr (SKIPG) {
+                        uint4 o2;
+                        uint32_t* ow = &o2.x;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int ch = c0 + pj * 8 + 2 * k;
+                            const float s0 = __uint_as_float(r2[pj * 8 + 2 * k]) + s_sbias[ch];
+                            const float s1 = __uint_as_float(r2[pj * 8 + 2 * k + 1]) + s_sbias[ch + 1];
+                            ow[k] = valid ? pack_bf16x2(s0, s1) : 0u;
+                        }
+                        *reinterpret_cast<uint4*>(a.out2 + plane * a.out2_ps + (pos + G::HALO) * 16) = o2;
+                    }
+                }
+                if (EPI != EPI_PLAIN && a.mask) a.mask[(c0 / 32) * a.mask_stride + pos] = valid ? mbits : 0u;
+            }
+            if constexpr (EPI == EPI_FINAL) {
+                if (valid) {
+                    const float eps = dot + s_aux[32];  // out conv bias (src/mnist.py:87)
+                    const int64_t oi = (int64_t)b * 784 + y * 28 + c;
+                    a.fout[oi] = a.fuse_step ? rstep1(sc, xin, eps, zz, add_noise) : eps;
+                }
+            }
+        }
+    }
+
+    // ---- teardown --------------------------------------------------------------------------
+    __syncwarp();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9>
+static int launch_conv(const ConvArgs& a, cudaStream_t st, const char* name) {
+    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS>;
+    auto kern = conv3x3_tc_kernel<W, CIN, COUT, EPI, SKIPG, TAPS>;
+    static bool configured = false;
+    if (!configured) {
+        TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured = true;
+    }
+    const int grid = a.nt < num_sms() ? a.nt : num_sms();
+    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(a);
+    TDM_CHECK_LAUNCH(name);
+    return TDM_OK;
+}
+
+
+}  // namespace tdm

@@ -1,0 +1,614 @@
+// unet_bwd.cu — backward pass and optimizer of the MNIST DDPM training step (src/mnist.py:153-159):
+//   loss = mse(model(q_sample(x0, t, noise), t), noise); loss.backward(); AdamW.step()
+//
+// Gradients flow through the same plane layout as the activations (bf16, fp32 accumulation):
+//   * data gradients   : conv3x3_tc_kernel (conv_tc.cuh) with transposed, tap-flipped weights
+//   * weight gradients : wgrad_tc_kernel below — per tile of 128 positions, TAPS*8 tcgen05.mma
+//                        with BOTH operands MN-major straight from the plane tiles (K = positions),
+//                        all taps accumulated in TMEM across the CTA's tiles, one atomic flush
+//   * ReLU masks / bias / time-embedding gradients: mask_reduce_kernel (elementwise, HBM-bound)
+//   * rb1.conv1 (Cin = 1), pooling / upsampling transposes, MSE gradient: small SIMT kernels
+// All parameter gradients land in ONE flat fp32 buffer in the reference's state_dict order — the
+// buffer the NCCL all-reduce and the fused AdamW operate on.
+#include "common.cuh"
+#include "conv_tc.cuh"
+#include "tc05.cuh"
+#include "unet_layout.cuh"
+#include "unet_ws.cuh"
+
+namespace tdm {
+
+// ---------------------------------------------------------------------------------------------
+// weight gradient on tensor cores
+//   dW[cg][cx][tap] += sum_pos G[pos][cg] * X[pos + off(tap)][cx]
+// A = G^T (M = cg, K = pos), B = X^T (N = cx, K = pos): in the plane layout [c/8][pos][8] the
+// channel index is the contiguous one, i.e. both operands are MN-major, un-swizzled:
+//   8 channels contiguous (16 B), 8 positions at 16 B stride (one 128 B core matrix),
+//   channel groups at SBO = plane stride, position groups at LBO = 128 B.
+// M = 64: TMEM row m lives in lane (m%16) + 32*(m/16); a second accumulator set is interleaved at
+// lane offset 16, so nine taps need only 5*CX columns.
+// ---------------------------------------------------------------------------------------------
+struct WgradArgs {
+    const uint8_t* g;   // gradient planes (row -HALO of plane 0), CG channels
+    int64_t g_ps;
+    const uint8_t* x;   // activation planes, CX channels
+    int64_t x_ps;
+    float* dw;          // [CG][CX][TAPS] fp32, accumulated with atomics
+    int nt;
+};
+
+template <int W, int CG, int CX, int TAPS>
+struct WgradCfg {
+    using G = Geo<W>;
+    static constexpr int GPL = CG / 8, XPL = CX / 8;
+    static constexpr int G_BYTES = GPL * kTile * 16;
+    static constexpr int X_BYTES = XPL * G::RT * 16;
+    static constexpr int STAGE_BYTES = G_BYTES + X_BYTES;
+    static_assert(CG == 64 || X_BYTES >= 8 * kTile * 16 - G_BYTES, "M=64 pad rows must stay inside the stage");
+    static constexpr int AVAIL = 227 * 1024 - 1024;
+    static constexpr int NSTAGE = (AVAIL / STAGE_BYTES) > 4 ? 4 : (AVAIL / STAGE_BYTES);
+    static_assert(NSTAGE >= 2, "stages");
+    static constexpr int NCOLS = (TAPS == 9 ? 5 : 1) * CX;
+    static constexpr int TMEM_COLS = NCOLS <= 32 ? 32 : NCOLS <= 64 ? 64 : NCOLS <= 128 ? 128 : NCOLS <= 256 ? 256 : 512;
+    static_assert(NCOLS <= 512, "TMEM");
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 512;
+    static constexpr int THREADS = 192;
+};
+
+template <int W, int CG, int CX, int TAPS>
+__global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const WgradArgs a) {
+    using C = WgradCfg<W, CG, CX, TAPS>;
+    using G = Geo<W>;
+    static_assert(CG == 32 || CG == 64, "CG");
+    static_assert(CX % 16 == 0 && CX <= 96, "CX");
+
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* s_in = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE_BYTES);
+    uint64_t* bar_full = bars;
+    uint64_t* bar_empty = bars + C::NSTAGE;
+    uint64_t* bar_done = bar_empty + C::NSTAGE;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_done + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C::NSTAGE; ++i) {
+            mbar_init(bar_full + i, 1);
+            mbar_init(bar_empty + i, 1);
+        }
+        mbar_init(bar_done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<C::TMEM_COLS>(s_tmem);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
+            const int s = it % C::NSTAGE;
+            const uint32_t ph = (it / C::NSTAGE) & 1;
+            if (lane == 0) {
+                mbar_wait(bar_empty + s, ph ^ 1);
+                mbar_arrive_expect_tx(bar_full + s, C::STAGE_BYTES);
+            }
+            __syncwarp();
+            uint8_t* st = s_in + s * C::STAGE_BYTES;
+            if (lane < C::GPL) {
+                bulk_g2s(st + lane * (kTile * 16),
+                         a.g + lane * a.g_ps + ((int64_t)tile * kTile + G::HALO) * 16, kTile * 16,
+                         bar_full + s);
+            } else if (lane >= 16 && lane < 16 + C::XPL) {
+                const int j = lane - 16;
+                bulk_g2s(st + C::G_BYTES + j * (G::RT * 16), a.x + j * a.x_ps + (int64_t)tile * (kTile * 16),
+                         G::RT * 16, bar_full + s);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(64, CX, 1, 1);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
+                const int s = it % C::NSTAGE;
+                const uint32_t ph = (it / C::NSTAGE) & 1;
+                mbar_wait(bar_full + s, ph);
+                tc_fence_after_sync();
+                const uint32_t g_addr = smem_u32(s_in + s * C::STAGE_BYTES);
+                const uint32_t x_addr = g_addr + C::G_BYTES;
+#pragma unroll
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    const int off = (TAPS == 1) ? 0 : (tap / 3 - 1) * G::Wp + (tap % 3 - 1);
+                    const uint32_t d = tmem_base + (tap < 5 ? tap * CX : ((16u << 16) + (tap - 5) * CX));
+#pragma unroll
+                    for (int ks = 0; ks < kTile / 16; ++ks) {
+                        const uint64_t ad = make_smem_desc(g_addr + ks * 256, 128, kTile * 16);
+                        const uint64_t bd = make_smem_desc(x_addr + (G::HALO + off + ks * 16) * 16, 128, G::RT * 16);
+                        umma_bf16(d, ad, bd, idesc, (it | ks) != 0);
+                    }
+                }
+                umma_commit(bar_empty + s);
+            }
+            if (it > 0) umma_commit(bar_done);
+        }
+    } else if ((int)blockIdx.x < a.nt) {
+        // ===== one final flush: TMEM -> atomics into the flat gradient =====
+        mbar_wait(bar_done, 0);
+        tc_fence_after_sync();
+        const int q = warp & 3;
+        const int m = q * 16 + (lane & 15);
+        const int upper = lane >> 4;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        constexpr int NSET = (TAPS == 9) ? 5 : 1;
+#pragma unroll
+        for (int ts = 0; ts < NSET; ++ts) {
+            const int tap = upper ? 5 + ts : ts;
+            const bool live = m < CG && tap < TAPS;
+#pragma unroll
+            for (int c0 = 0; c0 < CX; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + ts * CX + c0, r);
+                tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        atomicAdd(a.dw + ((int64_t)(m * CX + c0 + i) * TAPS + tap), __uint_as_float(r[i]));
+                }
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+template <int W, int CG, int CX, int TAPS>
+static int launch_wgrad(const WgradArgs& a, cudaStream_t st, const char* name) {
+    using C = WgradCfg<W, CG, CX, TAPS>;
+    auto kern = wgrad_tc_kernel<W, CG, CX, TAPS>;
+    static bool configured = false;
+    if (!configured) {
+        TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured = true;
+    }
+    const int grid = a.nt < num_sms() ? a.nt : num_sms();
+    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(a);
+    TDM_CHECK_LAUNCH(name);
+    return TDM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// elementwise pieces
+// ---------------------------------------------------------------------------------------------
+constexpr int kChunk = 1024;  // positions per block in the reducing elementwise kernels
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// MSE gradient + 1x1 output convolution backward.  blockDim = (32, 4): lane -> position, y -> plane.
+//   g = 2*(eps - noise)/n ; go4[c] = out.weight[c]*g ; d out.weight[c] += g*h4[c] ; d out.bias += g
+__global__ void __launch_bounds__(128)
+loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
+                 const uint8_t* __restrict__ h4, int64_t ps, const float* __restrict__ wo,
+                 uint8_t* __restrict__ go, float* __restrict__ d_wo, float* __restrict__ d_bo,
+                 float* __restrict__ loss, int batch, int64_t npos, float inv_n) {
+    using G = Geo<28>;
+    const int lane = threadIdx.x, j = threadIdx.y;
+    float w[8], acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        w[k] = __ldg(wo + j * 8 + k);
+        acc[k] = 0.f;
+    }
+    float lsum = 0.f, gsum = 0.f;
+    const int64_t base = (int64_t)blockIdx.x * kChunk;
+    for (int it = 0; it < kChunk / 32; ++it) {
+        const int64_t pos = base + it * 32 + lane;
+        if (pos >= npos) break;
+        const int b = (int)(pos / G::S);
+        const int rem = (int)(pos - (int64_t)b * G::S);
+        const int r = rem / G::Wp, c = rem - r * G::Wp;
+        const bool valid = b < batch && r >= 1 && c < G::W;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (valid) {
+            const int64_t i = (int64_t)b * 784 + (r - 1) * 28 + c;
+            const float d = __ldg(eps + i) - __ldg(noise + i);
+            const float g = 2.0f * d * inv_n;
+            const uint4 hv = *reinterpret_cast<const uint4*>(h4 + j * ps + (pos + G::HALO) * 16);
+            const uint32_t* hw = &hv.x;
+            uint32_t* ow = &o.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 h = unpack_bf16x2(hw[k]);
+                acc[2 * k] = fmaf(g, h.x, acc[2 * k]);
+                acc[2 * k + 1] = fmaf(g, h.y, acc[2 * k + 1]);
+                ow[k] = pack_bf16x2(w[2 * k] * g, w[2 * k + 1] * g);
+            }
+            if (j == 0) {
+                lsum = fmaf(d * inv_n, d, lsum);
+                gsum += g;
+            }
+        }
+        *reinterpret_cast<uint4*>(go + j * ps + (pos + G::HALO) * 16) = o;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float s = warp_sum(acc[k]);
+        if (lane == 0) atomicAdd(d_wo + j * 8 + k, s);
+    }
+    if (j == 0) {
+        lsum = warp_sum(lsum);
+        gsum = warp_sum(gsum);
+        if (lane == 0) {
+            atomicAdd(loss, lsum);
+            atomicAdd(d_bo, gsum);
+        }
+    }
+}
+
+// out = g (.) relu_mask, with the per-channel reductions the block needs:
+//   d_plain[c] += sum g[c]            (time_emb.bias or skip.bias gradient; nullable)
+//   d_ts[c]    += sum g[c]*t/1000     (time_emb.weight gradient; nullable)
+//   d_masked[c]+= sum g[c]*mask       (conv bias gradient; nullable)
+// blockDim = (32, CH/8).  `out` may alias `g`.
+__global__ void mask_reduce_kernel(const uint8_t* __restrict__ g, int64_t ps, int halo,
+                                   const uint32_t* __restrict__ mask, int64_t mask_stride,
+                                   uint8_t* __restrict__ out, const int64_t* __restrict__ t, int S,
+                                   int batch, int64_t npos, float* __restrict__ d_plain,
+                                   float* __restrict__ d_ts, float* __restrict__ d_masked) {
+    const int lane = threadIdx.x, j = threadIdx.y;
+    float sp[8], st[8], sm[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sp[k] = st[k] = sm[k] = 0.f;
+    const int64_t base = (int64_t)blockIdx.x * kChunk;
+    for (int it = 0; it < kChunk / 32; ++it) {
+        const int64_t pos = base + it * 32 + lane;
+        if (pos >= npos) break;
+        const uint4 gv = *reinterpret_cast<const uint4*>(g + j * ps + (pos + halo) * 16);
+        const uint32_t word = mask ? mask[(j >> 2) * mask_stride + pos] : 0xffffffffu;
+        const uint32_t bits = (word >> ((j & 3) * 8)) & 0xffu;
+        float ts = 0.f;
+        if (d_ts) {
+            const int b = (int)(pos / S);
+            ts = b < batch ? (float)__ldg(t + b) / 1000.0f : 0.f;
+        }
+        const uint32_t* gw = &gv.x;
+        uint4 o;
+        uint32_t* ow = &o.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = unpack_bf16x2(gw[k]);
+            const float m0 = (bits >> (2 * k)) & 1u ? f.x : 0.f;
+            const float m1 = (bits >> (2 * k + 1)) & 1u ? f.y : 0.f;
+            sp[2 * k] += f.x;
+            sp[2 * k + 1] += f.y;
+            st[2 * k] = fmaf(f.x, ts, st[2 * k]);
+            st[2 * k + 1] = fmaf(f.y, ts, st[2 * k + 1]);
+            sm[2 * k] += m0;
+            sm[2 * k + 1] += m1;
+            ow[k] = pack_bf16x2(m0, m1);
+        }
+        if (out) *reinterpret_cast<uint4*>(out + j * ps + (pos + halo) * 16) = o;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float a = warp_sum(sp[k]), b = warp_sum(st[k]), c = warp_sum(sm[k]);
+        if (lane == 0) {
+            if (d_plain) atomicAdd(d_plain + j * 8 + k, a);
+            if (d_ts) atomicAdd(d_ts + j * 8 + k, b);
+            if (d_masked) atomicAdd(d_masked + j * 8 + k, c);
+        }
+    }
+}
+
+// transpose of the nearest x2 upsample (src/mnist.py:83): 2x2 sum, 28-geometry -> 14-geometry
+__global__ void __launch_bounds__(128)
+upsample_bwd_kernel(const uint8_t* __restrict__ in, int64_t in_ps, uint8_t* __restrict__ out,
+                    int64_t out_ps, int batch) {
+    using GI = Geo<28>;
+    using GO = Geo<14>;
+    const int64_t pos = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int plane = blockIdx.y;
+    const int b = (int)(pos / GO::S);
+    const int rem = (int)(pos - (int64_t)b * GO::S);
+    const int r = rem / GO::Wp, c = rem - r * GO::Wp;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (b < batch && r >= 1 && c < GO::W) {
+        const int64_t p00 = (int64_t)b * GI::S + (2 * (r - 1) + 1) * GI::Wp + 2 * c;
+        const uint8_t* src = in + plane * in_ps + (p00 + GI::HALO) * 16;
+        const uint4 q0 = *reinterpret_cast<const uint4*>(src);
+        const uint4 q1 = *reinterpret_cast<const uint4*>(src + 16);
+        const uint4 q2 = *reinterpret_cast<const uint4*>(src + GI::Wp * 16);
+        const uint4 q3 = *reinterpret_cast<const uint4*>(src + GI::Wp * 16 + 16);
+        const uint32_t *a0 = &q0.x, *a1 = &q1.x, *a2 = &q2.x, *a3 = &q3.x;
+        uint32_t* ow = &o.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f0 = unpack_bf16x2(a0[k]), f1 = unpack_bf16x2(a1[k]);
+            const float2 f2 = unpack_bf16x2(a2[k]), f3 = unpack_bf16x2(a3[k]);
+            ow[k] = pack_bf16x2(f0.x + f1.x + f2.x + f3.x, f0.y + f1.y + f2.y + f3.y);
+        }
+    }
+    *reinterpret_cast<uint4*>(out + plane * out_ps + (pos + GO::HALO) * 16) = o;
+}
+
+// transpose of avg_pool2d(2) (src/mnist.py:80) added to the gradient h1 receives through the
+// concat: out[pos28] = a[pos28] + 0.25 * gp[pos14(y/2, x/2)]
+__global__ void __launch_bounds__(128)
+pool_bwd_add_kernel(const uint8_t* __restrict__ a, int64_t a_ps, const uint8_t* __restrict__ gp,
+                    int64_t gp_ps, uint8_t* __restrict__ out, int64_t out_ps, int batch) {
+    using G28 = Geo<28>;
+    using G14 = Geo<14>;
+    const int64_t pos = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int plane = blockIdx.y;
+    const int b = (int)(pos / G28::S);
+    const int rem = (int)(pos - (int64_t)b * G28::S);
+    const int r = rem / G28::Wp, c = rem - r * G28::Wp;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (b < batch && r >= 1 && c < G28::W) {
+        const int y = r - 1;
+        const int64_t p14 = (int64_t)b * G14::S + (y / 2 + 1) * G14::Wp + c / 2;
+        const uint4 av = *reinterpret_cast<const uint4*>(a + plane * a_ps + (pos + G28::HALO) * 16);
+        const uint4 gv = *reinterpret_cast<const uint4*>(gp + plane * gp_ps + (p14 + G14::HALO) * 16);
+        const uint32_t *aw = &av.x, *gw = &gv.x;
+        uint32_t* ow = &o.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = unpack_bf16x2(aw[k]), h = unpack_bf16x2(gw[k]);
+            ow[k] = pack_bf16x2(fmaf(0.25f, h.x, f.x), fmaf(0.25f, h.y, f.y));
+        }
+    }
+    *reinterpret_cast<uint4*>(out + plane * out_ps + (pos + G28::HALO) * 16) = o;
+}
+
+// rb1.conv1 (Cin = 1) and rb1.skip (1x1, Cin = 1) weight gradients:
+//   dW1[co][tap] += sum gc[pos][co] * x[pos + off(tap)]      dWs[co] += sum go[pos][co] * x[pos]
+// block = 320 threads: 288 (co, tap) pairs + 32 skip channels, over chunks of 128 positions.
+__global__ void __launch_bounds__(320)
+rb1_wgrad_kernel(const uint8_t* __restrict__ gc, const uint8_t* __restrict__ go, int64_t ps,
+                 const float* __restrict__ x, float* __restrict__ d_w1, float* __restrict__ d_ws,
+                 int batch, int nt) {
+    using G = Geo<28>;
+    __shared__ float s_gc[128][33], s_go[128][33], s_x[128][9];
+    const int tid = threadIdx.x;
+    float acc = 0.f;
+    for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+        __syncthreads();
+        for (int i = tid; i < 128 * 4; i += 320) {
+            const int p = i & 127, j = i >> 7;
+            const int64_t pos = (int64_t)tile * 128 + p;
+            const uint4 v = *reinterpret_cast<const uint4*>(gc + j * ps + (pos + G::HALO) * 16);
+            const uint4 u = *reinterpret_cast<const uint4*>(go + j * ps + (pos + G::HALO) * 16);
+            const uint32_t *vw = &v.x, *uw = &u.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = unpack_bf16x2(vw[k]), h = unpack_bf16x2(uw[k]);
+                s_gc[p][j * 8 + 2 * k] = f.x;
+                s_gc[p][j * 8 + 2 * k + 1] = f.y;
+                s_go[p][j * 8 + 2 * k] = h.x;
+                s_go[p][j * 8 + 2 * k + 1] = h.y;
+            }
+        }
+        for (int i = tid; i < 128 * 9; i += 320) {
+            const int p = i / 9, tap = i - p * 9;
+            const int64_t pos = (int64_t)tile * 128 + p;
+            const int b = (int)(pos / G::S);
+            const int rem = (int)(pos - (int64_t)b * G::S);
+            const int r = rem / G::Wp, c = rem - r * G::Wp;
+            float v = 0.f;
+            if (b < batch && r >= 1 && c < G::W) {
+                const int yy = r - 1 + tap / 3 - 1, xx = c + tap % 3 - 1;
+                if (yy >= 0 && yy < 28 && xx >= 0 && xx < 28) v = __ldg(x + (int64_t)b * 784 + yy * 28 + xx);
+            }
+            s_x[p][tap] = v;
+        }
+        __syncthreads();
+        if (tid < 288) {
+            const int co = tid / 9, tap = tid - co * 9;
+#pragma unroll 8
+            for (int p = 0; p < 128; ++p) acc = fmaf(s_gc[p][co], s_x[p][tap], acc);
+        } else {
+            const int co = tid - 288;
+#pragma unroll 8
+            for (int p = 0; p < 128; ++p) acc = fmaf(s_go[p][co], s_x[p][4], acc);
+        }
+    }
+    if (tid < 288) atomicAdd(d_w1 + tid, acc);
+    else atomicAdd(d_ws + (tid - 288), acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused AdamW over the flat buffers — torch.optim.AdamW's update (decoupled weight decay):
+//   p *= 1 - lr*wd; m = lerp(m, g, 1-b1); v = b2*v + (1-b2)*g*g;
+//   p -= (lr / (1-b1^k)) * m / (sqrt(v)/sqrt(1-b2^k) + eps)
+// `step` lives on the device (1-based k of THIS update) so a captured graph can be replayed.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+             float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
+             float grad_scale, const int64_t* __restrict__ step) {
+    __shared__ float s_c[2];
+    if (threadIdx.x == 0) {
+        const double k = (double)*step;
+        s_c[0] = (float)((double)lr / (1.0 - pow((double)b1, k)));   // step size
+        s_c[1] = (float)sqrt(1.0 - pow((double)b2, k));               // sqrt(bias_correction2)
+    }
+    __syncthreads();
+    const float step_size = s_c[0], sbc2 = s_c[1];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float gi = g[i] * grad_scale;
+    float pi = p[i] * (1.0f - lr * wd);
+    const float mi = m[i] + (gi - m[i]) * (1.0f - b1);
+    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    const float denom = sqrtf(vi) / sbc2 + eps;
+    pi -= step_size * (mi / denom);
+    p[i] = pi;
+    m[i] = mi;
+    v[i] = vi;
+}
+
+// ---------------------------------------------------------------------------------------------
+// orchestration
+// ---------------------------------------------------------------------------------------------
+static int mask_reduce(const uint8_t* g, int64_t ps, int halo, const uint32_t* mask, int64_t mstride,
+                       uint8_t* out, int ch, const int64_t* t, int S, int batch, int64_t npos,
+                       float* d_plain, float* d_ts, float* d_masked, cudaStream_t st) {
+    const unsigned grid = (unsigned)((npos + kChunk - 1) / kChunk);
+    mask_reduce_kernel<<<grid, dim3(32, ch / 8), 0, st>>>(g, ps, halo, mask, mstride, out, t, S, batch,
+                                                          npos, d_plain, d_ts, d_masked);
+    TDM_CHECK_LAUNCH("mask_reduce");
+    return TDM_OK;
+}
+
+static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* t, const float* noise,
+                              const float* eps, float* dflat, float* loss, uint8_t* ws,
+                              int64_t ws_bytes, int64_t batch, cudaStream_t st) {
+    TDM_CHECK_ARG(wp && x && t && noise && eps && dflat && loss && ws, "unet_backward: null pointer");
+    TDM_CHECK_ARG(batch > 0 && batch <= (1 << 20), "unet_backward: batch out of range");
+    const UNetWs L = make_ws(batch, true);
+    TDM_CHECK_ARG(ws_bytes >= L.total, "unet_backward: workspace too small (%lld < %lld)",
+                  (long long)ws_bytes, (long long)L.total);
+    const float* fp = reinterpret_cast<const float*>(wp + WP::flat);
+    const int B = (int)batch;
+    const int nt28 = (int)L.nt28, nt14 = (int)L.nt14;
+    const int H28 = Geo<28>::HALO, H14 = Geo<14>::HALO, S28 = Geo<28>::S, S14 = Geo<14>::S;
+    auto M = [&](int64_t off) { return reinterpret_cast<const uint32_t*>(ws + off); };
+    int rc;
+    ConvArgs c{};
+    WgradArgs w{};
+
+    TDM_CHECK_CUDA(cudaMemsetAsync(dflat, 0, sizeof(float) * P::count, st));
+    TDM_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
+
+    // ---- loss and out conv ---------------------------------------------------------------
+    loss_grad_kernel<<<(unsigned)((L.np28 + kChunk - 1) / kChunk), dim3(32, 4), 0, st>>>(
+        eps, noise, ws + L.h4, L.ps28, fp + P::out_w, ws + L.go28, dflat + P::out_w, dflat + P::out_b,
+        loss, B, L.np28, 1.0f / (float)(batch * 784));
+    TDM_CHECK_LAUNCH("loss_grad");
+
+    // ---- rb4: x_in = cat (96), h = t4, g_out = go28 ----------------------------------------
+    if ((rc = mask_reduce(ws + L.go28, L.ps28, H28, M(L.m2_4), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
+                          dflat + P::rb4_sb, nullptr, dflat + P::rb4_c2b, st))) return rc;
+    w = WgradArgs{ws + L.gc28, L.ps28, ws + L.t4, L.ps28, dflat + P::rb4_c2w, nt28};
+    if ((rc = launch_wgrad<28, 32, 32, 9>(w, st, "wgrad_rb4_c2"))) return rc;
+    c = ConvArgs{}; c.t = t; c.batch = B; c.nt = nt28;
+    c.in = ws + L.gc28; c.in_ps = L.ps28; c.w = wp + WP::d_rb4_c2; c.out = ws + L.gh28; c.out_ps = L.ps28;
+    if ((rc = launch_conv<28, 32, 32, EPI_PLAIN, false>(c, st, "dgrad_rb4_c2"))) return rc;
+    if ((rc = mask_reduce(ws + L.gh28, L.ps28, H28, M(L.m1_4), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
+                          dflat + P::rb4_tb, dflat + P::rb4_tw, dflat + P::rb4_c1b, st))) return rc;
+    w = WgradArgs{ws + L.gc28, L.ps28, ws + L.cat, L.ps28, dflat + P::rb4_c1w, nt28};
+    if ((rc = launch_wgrad<28, 32, 96, 9>(w, st, "wgrad_rb4_c1"))) return rc;
+    w = WgradArgs{ws + L.go28, L.ps28, ws + L.cat, L.ps28, dflat + P::rb4_sw, nt28};
+    if ((rc = launch_wgrad<28, 32, 96, 1>(w, st, "wgrad_rb4_skip"))) return rc;
+    c = ConvArgs{}; c.t = t; c.batch = B; c.nt = nt28;
+    c.in = ws + L.gc28; c.in_ps = L.ps28; c.w = wp + WP::d_rb4_c1; c.out = ws + L.gcat; c.out_ps = L.ps28;
+    if ((rc = launch_conv<28, 32, 96, EPI_PLAIN, false>(c, st, "dgrad_rb4_c1"))) return rc;
+    c.in = ws + L.go28; c.w = wp + WP::d_rb4_sk; c.res = ws + L.gcat; c.res_ps = L.ps28;
+    if ((rc = launch_conv<28, 32, 96, EPI_PLAIN, false, 1>(c, st, "dgrad_rb4_skip"))) return rc;
+
+    // ---- through the concat: channels 0..63 -> up(h3)^T -> g_out of rb3 ---------------------
+    upsample_bwd_kernel<<<dim3(nt14, 8), 128, 0, st>>>(ws + L.gcat, L.ps28, ws + L.go14a, L.ps14, B);
+    TDM_CHECK_LAUNCH("upsample_bwd");
+
+    // ---- rb3: x_in = h2, h = t3, identity skip, g_out = go14a -------------------------------
+    if ((rc = mask_reduce(ws + L.go14a, L.ps14, H14, M(L.m2_3), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
+                          nullptr, nullptr, dflat + P::rb3_c2b, st))) return rc;
+    w = WgradArgs{ws + L.gc14, L.ps14, ws + L.t3, L.ps14, dflat + P::rb3_c2w, nt14};
+    if ((rc = launch_wgrad<14, 64, 64, 9>(w, st, "wgrad_rb3_c2"))) return rc;
+    c = ConvArgs{}; c.t = t; c.batch = B; c.nt = nt14;
+    c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb3_c2; c.out = ws + L.gh14; c.out_ps = L.ps14;
+    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false>(c, st, "dgrad_rb3_c2"))) return rc;
+    if ((rc = mask_reduce(ws + L.gh14, L.ps14, H14, M(L.m1_3), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
+                          dflat + P::rb3_tb, dflat + P::rb3_tw, dflat + P::rb3_c1b, st))) return rc;
+    w = WgradArgs{ws + L.gc14, L.ps14, ws + L.h2, L.ps14, dflat + P::rb3_c1w, nt14};
+    if ((rc = launch_wgrad<14, 64, 64, 9>(w, st, "wgrad_rb3_c1"))) return rc;
+    c = ConvArgs{}; c.t = t; c.batch = B; c.nt = nt14;
+    c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb3_c1; c.res = ws + L.go14a; c.res_ps = L.ps14;
+    c.out = ws + L.go14b; c.out_ps = L.ps14;   // g_out of rb2
+    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false>(c, st, "dgrad_rb3_c1"))) return rc;
+
+    // ---- rb2: x_in = p1 (32), h = t2, skip 32->64, g_out = go14b ----------------------------
+    if ((rc = mask_reduce(ws + L.go14b, L.ps14, H14, M(L.m2_2), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
+                          dflat + P::rb2_sb, nullptr, dflat + P::rb2_c2b, st))) return rc;
+    w = WgradArgs{ws + L.gc14, L.ps14, ws + L.t2, L.ps14, dflat + P::rb2_c2w, nt14};
+    if ((rc = launch_wgrad<14, 64, 64, 9>(w, st, "wgrad_rb2_c2"))) return rc;
+    c = ConvArgs{}; c.t = t; c.batch = B; c.nt = nt14;
+    c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb2_c2; c.out = ws + L.gh14; c.out_ps = L.ps14;
+    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false>(c, st, "dgrad_rb2_c2"))) return rc;
+    if ((rc = mask_reduce(ws + L.gh14, L.ps14, H14, M(L.m1_2), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
+                          dflat + P::rb2_tb, dflat + P::rb2_tw, dflat + P::rb2_c1b, st))) return rc;
+    w = WgradArgs{ws + L.gc14, L.ps14, ws + L.p1, L.ps14, dflat + P::rb2_c1w, nt14};
+    if ((rc = launch_wgrad<14, 64, 32, 9>(w, st, "wgrad_rb2_c1"))) return rc;
+    w = WgradArgs{ws + L.go14b, L.ps14, ws + L.p1, L.ps14, dflat + P::rb2_sw, nt14};
+    if ((rc = launch_wgrad<14, 64, 32, 1>(w, st, "wgrad_rb2_skip"))) return rc;
+    c = ConvArgs{}; c.t = t; c.batch = B; c.nt = nt14;
+    c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb2_c1; c.out = ws + L.gp1; c.out_ps = L.ps14;
+    if ((rc = launch_conv<14, 64, 32, EPI_PLAIN, false>(c, st, "dgrad_rb2_c1"))) return rc;
+    c.in = ws + L.go14b; c.w = wp + WP::d_rb2_sk; c.res = ws + L.gp1; c.res_ps = L.ps14;
+    if ((rc = launch_conv<14, 64, 32, EPI_PLAIN, false, 1>(c, st, "dgrad_rb2_skip"))) return rc;
+
+    // ---- h1 receives: concat channels 64..95 + avg-pool transpose of g_p1 -------------------
+    pool_bwd_add_kernel<<<dim3(nt28, 4), 128, 0, st>>>(ws + L.gcat + 8 * L.ps28, L.ps28, ws + L.gp1, L.ps14,
+                                                      ws + L.go28, L.ps28, B);
+    TDM_CHECK_LAUNCH("pool_bwd_add");
+
+    // ---- rb1: x_in = x (1 channel), h = t1, skip 1->32, g_out = go28 ------------------------
+    if ((rc = mask_reduce(ws + L.go28, L.ps28, H28, M(L.m2_1), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
+                          dflat + P::rb1_sb, nullptr, dflat + P::rb1_c2b, st))) return rc;
+    w = WgradArgs{ws + L.gc28, L.ps28, ws + L.t1, L.ps28, dflat + P::rb1_c2w, nt28};
+    if ((rc = launch_wgrad<28, 32, 32, 9>(w, st, "wgrad_rb1_c2"))) return rc;
+    c = ConvArgs{}; c.t = t; c.batch = B; c.nt = nt28;
+    c.in = ws + L.gc28; c.in_ps = L.ps28; c.w = wp + WP::d_rb1_c2; c.out = ws + L.gh28; c.out_ps = L.ps28;
+    if ((rc = launch_conv<28, 32, 32, EPI_PLAIN, false>(c, st, "dgrad_rb1_c2"))) return rc;
+    if ((rc = mask_reduce(ws + L.gh28, L.ps28, H28, M(L.m1_1), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
+                          dflat + P::rb1_tb, dflat + P::rb1_tw, dflat + P::rb1_c1b, st))) return rc;
+    {
+        const int grid = nt28 < 4 * num_sms() ? nt28 : 4 * num_sms();
+        rb1_wgrad_kernel<<<grid, 320, 0, st>>>(ws + L.gc28, ws + L.go28, L.ps28, x, dflat + P::rb1_c1w,
+                                               dflat + P::rb1_sw, B, nt28);
+        TDM_CHECK_LAUNCH("rb1_wgrad");
+    }
+    return TDM_OK;
+}
+
+}  // namespace tdm
+
+using namespace tdm;
+
+extern "C" int tdm_unet_forward_train(const void* wpack, const float* x, const int64_t* t,
+                                      float* eps_out, void* workspace, int64_t workspace_bytes,
+                                      int64_t batch, void* stream) {
+    StepArgs sa;
+    sa.train = 1;
+    return unet_forward_impl(reinterpret_cast<const uint8_t*>(wpack), x, t, eps_out,
+                             reinterpret_cast<uint8_t*>(workspace), workspace_bytes, batch, sa,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int tdm_unet_backward(const void* wpack, const float* x, const int64_t* t, const float* noise,
+                                 const float* eps, float* flat_grad, float* loss_out, void* workspace,
+                                 int64_t workspace_bytes, int64_t batch, void* stream) {
+    return unet_backward_impl(reinterpret_cast<const uint8_t*>(wpack), x, t, noise, eps, flat_grad,
+                              loss_out, reinterpret_cast<uint8_t*>(workspace), workspace_bytes, batch,
+                              (cudaStream_t)stream);
+}
+
+extern "C" int tdm_adamw_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                              int64_t n, float lr, float beta1, float beta2, float eps,
+                              float weight_decay, float grad_scale, const int64_t* step_dev,
+                              void* stream) {
+    TDM_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && step_dev && n >= 0, "tdm_adamw_flat: bad arguments");
+    if (n == 0) return TDM_OK;
+    adamw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step_dev);
+    TDM_CHECK_LAUNCH("tdm_adamw_flat");
+    return TDM_OK;
+}

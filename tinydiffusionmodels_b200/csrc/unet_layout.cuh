@@ -86,7 +86,19 @@ constexpr int64_t rb3_c2 = rb3_c1 + conv_bytes(64, 64);
 constexpr int64_t rb4_c1 = rb3_c2 + conv_bytes(64, 64);
 constexpr int64_t rb4_sk = rb4_c1 + conv_bytes(96, 32);   // must directly follow rb4_c1
 constexpr int64_t rb4_c2 = rb4_sk + skip_bytes(96, 32);
-constexpr int64_t bf16_end = rb4_c2 + conv_bytes(32, 32);
+constexpr int64_t fwd_end = rb4_c2 + conv_bytes(32, 32);
+// data-gradient convolutions: weights transposed (Cin<->Cout) and tap-flipped, same plane format
+// [tap][Cin'/8][Cout'][8] with Cin' = forward Cout, Cout' = forward Cin
+constexpr int64_t d_rb1_c2 = fwd_end;                               // 32 -> 32
+constexpr int64_t d_rb2_c2 = d_rb1_c2 + conv_bytes(32, 32);         // 64 -> 64
+constexpr int64_t d_rb2_c1 = d_rb2_c2 + conv_bytes(64, 64);         // 64 -> 32
+constexpr int64_t d_rb2_sk = d_rb2_c1 + conv_bytes(64, 32);         // 64 -> 32 (1x1)
+constexpr int64_t d_rb3_c2 = d_rb2_sk + skip_bytes(64, 32);         // 64 -> 64
+constexpr int64_t d_rb3_c1 = d_rb3_c2 + conv_bytes(64, 64);         // 64 -> 64
+constexpr int64_t d_rb4_c2 = d_rb3_c1 + conv_bytes(64, 64);         // 32 -> 32
+constexpr int64_t d_rb4_c1 = d_rb4_c2 + conv_bytes(32, 32);         // 32 -> 96
+constexpr int64_t d_rb4_sk = d_rb4_c1 + conv_bytes(32, 96);         // 32 -> 96 (1x1)
+constexpr int64_t bf16_end = d_rb4_sk + skip_bytes(32, 96);
 constexpr int64_t flat = (bf16_end + 255) / 256 * 256;     // fp32 copy of the flat parameters
 constexpr int64_t total = (flat + 4LL * P::count + 255) / 256 * 256;
 }  // namespace WP

@@ -1,0 +1,192 @@
+"""Training step of the MNIST DDPM on B200 (reference: src/mnist.py:148-160).
+
+``UNetTrainer.step(x0)`` is the whole inner loop body of the reference's ``train`` as device work:
+t ~ U{0..T-1}, noise ~ N(0,I) (Philox, in-kernel), q_sample, UNet forward (keeping ReLU masks),
+MSE, backward into ONE flat gradient buffer, optional NCCL all-reduce of that buffer (data
+parallel), fused AdamW on the flat master parameters, weight re-pack.  Nothing synchronises the
+host; the loss comes back as a device scalar.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .schedule import schedule_on
+from .unet_engine import PARAM_COUNT
+
+
+class TrainEngine:
+    """Workspace + packed weights for forward-with-saves and backward at a fixed max batch."""
+
+    def __init__(self, device, max_batch: int):
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.TdmError("training needs a CUDA device (no CPU fallback)")
+        self.lib = _lib.load()
+        self.max_batch = int(max_batch)
+        self.wpack = torch.zeros(self.lib.tdm_unet_wpack_bytes(), dtype=torch.uint8, device=self.device)
+        self.ws_bytes = int(self.lib.tdm_unet_workspace_bytes(self.max_batch, 1))
+        self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        self._ws_batch = None
+
+    def _prep(self, batch: int) -> None:
+        if batch > self.max_batch:
+            raise ValueError(f"batch {batch} exceeds engine capacity {self.max_batch}")
+        if self._ws_batch != batch:
+            if self._ws_batch is not None:
+                self.ws.zero_()
+            self._ws_batch = batch
+
+    def pack(self, flat: torch.Tensor) -> None:
+        _lib.check(self.lib.tdm_unet_pack_weights(flat.data_ptr(), self.wpack.data_ptr(),
+                                                  _lib.stream_ptr(self.device)), "tdm_unet_pack_weights")
+
+    def forward(self, x: torch.Tensor, t: torch.Tensor, eps_out: torch.Tensor) -> torch.Tensor:
+        b = x.shape[0]
+        self._prep(b)
+        _lib.check(self.lib.tdm_unet_forward_train(self.wpack.data_ptr(), x.data_ptr(), t.data_ptr(),
+                                                   eps_out.data_ptr(), self.ws.data_ptr(), self.ws_bytes, b,
+                                                   _lib.stream_ptr(self.device)), "tdm_unet_forward_train")
+        return eps_out
+
+    def backward(self, x, t, noise, eps, flat_grad, loss_out) -> None:
+        b = x.shape[0]
+        _lib.check(self.lib.tdm_unet_backward(self.wpack.data_ptr(), x.data_ptr(), t.data_ptr(),
+                                              noise.data_ptr(), eps.data_ptr(), flat_grad.data_ptr(),
+                                              loss_out.data_ptr(), self.ws.data_ptr(), self.ws_bytes, b,
+                                              _lib.stream_ptr(self.device)), "tdm_unet_backward")
+
+
+def loss_and_flat_grad(model, x_noisy: torch.Tensor, t: torch.Tensor, noise: torch.Tensor):
+    """(loss, flat gradient) of F.mse_loss(model(x_noisy, t), noise) through the CUDA kernels."""
+    flat = model.flat_params()
+    eng = TrainEngine(flat.device, x_noisy.shape[0])
+    eng.pack(flat)
+    x_noisy = x_noisy.float().contiguous()
+    noise = noise.float().contiguous()
+    t = t.to(torch.int64).contiguous()
+    eps = torch.empty_like(x_noisy)
+    eng.forward(x_noisy, t, eps)
+    g = torch.empty(PARAM_COUNT, device=flat.device, dtype=torch.float32)
+    loss = torch.empty(1, device=flat.device, dtype=torch.float32)
+    eng.backward(x_noisy, t, noise, eps, g, loss)
+    return loss[0], g, eps
+
+
+class UNetTrainer:
+    """AdamW training of a SimpleUNet with the reference's hyper-parameters
+    (torch.optim.AdamW(lr): betas (0.9, 0.999), eps 1e-8, weight_decay 0.01)."""
+
+    def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
+                 weight_decay: float = 0.01, max_batch: int = 128, seed: int | None = None,
+                 process_group=None):
+        self.model = model
+        self.flat = model.flat_params()
+        dev = self.flat.device
+        self.device = dev
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.grad = model.flat_grads()
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.step_dev = torch.ones(1, dtype=torch.int64, device=dev)   # 1-based index of the next update
+        self.engine = TrainEngine(dev, max_batch)
+        self.engine.pack(self.flat)
+        self.sched = schedule_on(dev)
+        self.seed = int(torch.randint(0, 2**62, (), dtype=torch.int64)) if seed is None else seed
+        self.iteration = 0
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+            self.rank = torch.distributed.get_rank(process_group)
+        else:
+            self.rank = 0
+        self.loss = torch.zeros(1, device=dev)
+        self._bufs = {}
+
+    def _buffers(self, b: int):
+        if b not in self._bufs:
+            dev = self.device
+            self._bufs[b] = (torch.empty(b, 1, 28, 28, device=dev), torch.empty(b, 1, 28, 28, device=dev),
+                             torch.empty(b, 1, 28, 28, device=dev))
+        return self._bufs[b]
+
+    def step(self, x0: torch.Tensor, t: torch.Tensor | None = None, noise: torch.Tensor | None = None) -> torch.Tensor:
+        """One optimizer step on the batch ``x0`` (B,1,28,28) in [-1,1]. Returns the loss (device)."""
+        lib = self.engine.lib
+        st = _lib.stream_ptr(self.device)
+        b = x0.shape[0]
+        x0 = x0.float().contiguous()
+        x_noisy, noise_buf, eps = self._buffers(b)
+        s = self.sched
+        if t is None:
+            t = torch.randint(0, s.timesteps, (b,), device=self.device)       # src/mnist.py:154
+        t = t.to(torch.int64).contiguous()
+        offset = (self.iteration * self.world + self.rank) * b                  # distinct noise per rank/step
+        if noise is None:
+            _lib.check(lib.tdm_q_sample_philox(x0.data_ptr(), t.data_ptr(), s.sqrt_alphas_cumprod.data_ptr(),
+                                               s.sqrt_one_minus_alphas_cumprod.data_ptr(), noise_buf.data_ptr(),
+                                               x_noisy.data_ptr(), b, 784, s.timesteps, self.seed, offset, 0, st),
+                       "tdm_q_sample_philox")
+            noise = noise_buf
+        else:
+            noise = noise.float().contiguous()
+            _lib.check(lib.tdm_q_sample(x0.data_ptr(), noise.data_ptr(), t.data_ptr(),
+                                        s.sqrt_alphas_cumprod.data_ptr(),
+                                        s.sqrt_one_minus_alphas_cumprod.data_ptr(), x_noisy.data_ptr(), b, 784,
+                                        s.timesteps, st), "tdm_q_sample")
+        self.engine.forward(x_noisy, t, eps)
+        self.engine.backward(x_noisy, t, noise, eps, self.grad, self.loss)
+        scale = 1.0
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grad, group=self.pg)            # NCCL sum over NVLink
+            scale = 1.0 / self.world
+        _lib.check(lib.tdm_adamw_flat(self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(),
+                                      self.v.data_ptr(), PARAM_COUNT, self.lr, self.betas[0], self.betas[1],
+                                      self.eps, self.wd, scale, self.step_dev.data_ptr(), st), "tdm_adamw_flat")
+        _lib.check(lib.tdm_timestep_advance(self.step_dev.data_ptr(), 1, 1, st), "tdm_timestep_advance")
+        self.engine.pack(self.flat)
+        self.iteration += 1
+        return self.loss[0].clone()   # the buffer is overwritten by the next step
+
+
+class _UNetFn(torch.autograd.Function):
+    """Autograd bridge so ``loss = F.mse_loss(model(x, t), noise); loss.backward()`` written against
+    the reference keeps working: forward keeps the masks, backward turns d(loss)/d(eps) into
+    parameter gradients with the same kernels (via the identity  dL/dθ = J^T · g_eps)."""
+
+    @staticmethod
+    def forward(ctx, model, x, t, *params):
+        flat = model.flat_params()
+        eng = TrainEngine(flat.device, x.shape[0])
+        eng.pack(flat)
+        x = x.float().contiguous()
+        t = t.to(torch.int64).contiguous()
+        eps = torch.empty_like(x)
+        eng.forward(x, t, eps)
+        ctx.model, ctx.eng = model, eng
+        ctx.save_for_backward(x, t, eps)
+        return eps
+
+    @staticmethod
+    def backward(ctx, g_eps):
+        x, t, eps = ctx.saved_tensors
+        model, eng = ctx.model, ctx.eng
+        b = x.shape[0]
+        # tdm_unet_backward differentiates mean((eps - noise)^2): g = 2 (eps - noise) / n.
+        # Choosing noise = eps - g_eps * n / 2 makes that equal the incoming gradient.
+        n = float(b * 784)
+        noise = (eps - g_eps.float().contiguous() * (n / 2.0)).contiguous()
+        g = torch.empty(PARAM_COUNT, device=x.device, dtype=torch.float32)
+        loss = torch.empty(1, device=x.device, dtype=torch.float32)
+        eng.backward(x, t, noise, eps, g, loss)
+        grads, off = [], 0
+        for p in model.parameters():
+            k = p.numel()
+            grads.append(g[off:off + k].view(p.shape))
+            off += k
+        return (None, None, None, *grads)
+
+
+def unet_autograd_forward(model, x, t):
+    return _UNetFn.apply(model, x, t, *model.parameters())
