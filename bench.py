@@ -286,6 +286,9 @@ def run_ours(args) -> None:
         "whole_unet_tflops": FLOPS_PER_IMAGE_STEP * B / (step_ms_sum * 1e-3) / 1e12,
     }
 
+    # ---- secondary metric: UNet train images/s (BASELINE.json configs[1]), data-parallel ------
+    train = bench_train(dev, rank, world, args.train_batch, barrier)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -313,10 +316,75 @@ def run_ours(args) -> None:
         "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": "20 of 1000 reverse steps at batch 64 (oracle port of src/mnist.py:167-180), extrapolated x50"},
         "clocks": clocks,
+        "train": train,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_train(dev, rank, world, batch, barrier, steps: int = 30, warmup: int = 5) -> dict:
+    """UNet DDPM training step (src/mnist.py:153-159) on synthetic U(-1,1) images, `batch` per GPU,
+    gradients all-reduced over NCCL when world > 1.  Device-resident and host-fed variants."""
+    import torch
+    import torch.distributed as dist
+
+    from tinydiffusionmodels_b200 import _lib
+    from tinydiffusionmodels_b200.mnist import SimpleUNet
+    from tinydiffusionmodels_b200.unet_train import UNetTrainer
+
+    torch.manual_seed(0)
+    model = SimpleUNet().to(dev)
+    trainer = UNetTrainer(model, lr=1e-3, max_batch=batch, seed=7)
+    g = torch.Generator(device=dev).manual_seed(rank)
+    x_dev = torch.rand(batch, 1, 28, 28, device=dev, generator=g) * 2 - 1
+    x_host = (torch.rand(batch, 1, 28, 28) * 2 - 1).pin_memory()
+    loss_host = torch.zeros(1).pin_memory()
+
+    def run(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def step_dev():
+        trainer.step(x_dev)
+
+    def step_e2e():
+        loss = trainer.step(x_host.to(dev, non_blocking=True))
+        loss_host.copy_(loss, non_blocking=True)
+
+    for _ in range(warmup):
+        step_dev()
+    n0 = _lib.launch_count()
+    ms = run(step_dev, steps)
+    step_e2e()
+    ms_e2e = run(step_e2e, steps)
+    # launches per step are counted from one eager (non-graph) step of the same trainer
+    trainer.use_graph = False
+    n0 = _lib.launch_count()
+    trainer.step(x_dev)
+    launches = _lib.launch_count() - n0
+    flops = 386_506_496 * batch   # fwd+bwd per image (SURVEY.md §8d)
+    return {
+        "metric": "unet_train_images_per_sec", "unit": "images/s",
+        "value": world * batch * steps / (ms * 1e-3),
+        "e2e": {"value": world * batch * steps / (ms_e2e * 1e-3), "unit": "images/s",
+                "h2d_bytes_per_step": batch * 784 * 4, "d2h_bytes_per_step": 4},
+        "ms_per_step": ms / steps, "steps": steps, "batch_per_gpu": batch, "global_batch": world * batch,
+        "dtype": "bf16 (fp32 master weights, AdamW moments and accumulation)",
+        "tflops_per_gpu": flops / (ms / steps * 1e-3) / 1e12,
+        "gpu_launches_per_step": int(launches),
+        "allreduce_bytes_per_step": 181_473 * 4 if world > 1 else 0,
+        "final_loss": float(trainer.loss.item()),
+    }
 
 
 def main():
@@ -326,6 +394,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=4096, help="samples per GPU per step")
+    ap.add_argument("--train-batch", type=int, default=512, help="training images per GPU per step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -51,11 +51,13 @@ int tdm_q_sample(const float* x0, const float* noise, const int64_t* t, const fl
 /* q_sample with in-kernel Philox4x32-10 noise (training fast path, src/mnist.py:155-156).
  * Writes the generated N(0,1) noise to noise_out (needed by the loss) and the diffused sample
  * to out.  The noise for element i of sample b is the (i%4)-th normal of the Philox block
- * counter = (i/4, sample_offset + b, stream_id, 0), key = seed.  See oracle/philox.py. */
+ * counter = (i/4, sample_offset + b, stream_id + *stream_id_dev, 0), key = seed (oracle/philox.py).
+ * stream_id_dev (nullable DEVICE int64) lets a captured CUDA graph draw fresh noise per replay:
+ * the trainer points it at its on-device step counter. */
 int tdm_q_sample_philox(const float* x0, const int64_t* t, const float* sqrt_acp,
                         const float* sqrt_om_acp, float* noise_out, float* out, int64_t batch,
                         int64_t inner, int n_steps, uint64_t seed, uint64_t sample_offset,
-                        uint32_t stream_id, void* stream);
+                        uint32_t stream_id, const int64_t* stream_id_dev, void* stream);
 
 /* Reverse (ancestral) step, src/mnist.py:167-180 and src/shakespeare.py:343-352:
  *   mean = (1/sqrt(alphas[t])) * (x - betas[t]/sqrt_om_acp[t] * eps)

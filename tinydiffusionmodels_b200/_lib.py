@@ -23,7 +23,7 @@ SIGNATURES: dict[str, tuple] = {
     "tdm_last_error": (c_char_p, []),
     "tdm_launch_count": (c_int64, []),
     "tdm_q_sample": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, _P]),
-    "tdm_q_sample_philox": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_uint64, c_uint64, c_uint32, _P]),
+    "tdm_q_sample_philox": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_uint64, c_uint64, c_uint32, _P, _P]),
     "tdm_reverse_step": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_uint64, c_uint64, c_uint32, _P]),
     "tdm_timestep_advance": (c_int, [_P, c_int64, c_int64, _P]),
     "tdm_randn_philox": (c_int, [_P, c_int64, c_int64, c_uint64, c_uint64, c_uint32, _P]),

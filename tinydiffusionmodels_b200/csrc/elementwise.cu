@@ -32,8 +32,9 @@ q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
                 const int64_t* __restrict__ t, const float* __restrict__ sqrt_acp,
                 const float* __restrict__ sqrt_om, float* __restrict__ noise_out,
                 float* __restrict__ out, int64_t total4, uint32_t inner4, uint64_t seed,
-                uint64_t sample_offset, uint32_t stream_id) {
+                uint64_t sample_offset, uint32_t stream_id, const int64_t* __restrict__ stream_dev) {
     const int64_t base = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+    if (kPhilox && stream_dev) stream_id += (uint32_t)__ldg(stream_dev);
     float4 xv[kUnroll], nv[kUnroll];
     float ca[kUnroll], cb[kUnroll];
     int64_t idx[kUnroll];
@@ -173,7 +174,7 @@ extern "C" int tdm_q_sample(const float* x0, const float* noise, const int64_t* 
     TDM_CHECK_ARG(aligned16(x0) && aligned16(noise) && aligned16(out), "tdm_q_sample: 16-byte alignment required");
     const int64_t total4 = batch * inner / 4;
     q_sample_kernel<false><<<grid_for(total4), kThreads, 0, (cudaStream_t)stream>>>(
-        x0, noise, t, sqrt_acp, sqrt_om_acp, nullptr, out, total4, (uint32_t)(inner / 4), 0, 0, 0);
+        x0, noise, t, sqrt_acp, sqrt_om_acp, nullptr, out, total4, (uint32_t)(inner / 4), 0, 0, 0, nullptr);
     TDM_CHECK_LAUNCH("tdm_q_sample");
     return TDM_OK;
 }
@@ -181,7 +182,8 @@ extern "C" int tdm_q_sample(const float* x0, const float* noise, const int64_t* 
 extern "C" int tdm_q_sample_philox(const float* x0, const int64_t* t, const float* sqrt_acp,
                                    const float* sqrt_om_acp, float* noise_out, float* out,
                                    int64_t batch, int64_t inner, int n_steps, uint64_t seed,
-                                   uint64_t sample_offset, uint32_t stream_id, void* stream) {
+                                   uint64_t sample_offset, uint32_t stream_id,
+                                   const int64_t* stream_id_dev, void* stream) {
     if (batch == 0) return TDM_OK;
     TDM_CHECK_ARG(x0 && t && sqrt_acp && sqrt_om_acp && noise_out && out, "tdm_q_sample_philox: null pointer");
     TDM_CHECK_ARG(batch >= 0 && inner > 0 && n_steps > 0, "tdm_q_sample_philox: bad sizes");
@@ -190,7 +192,7 @@ extern "C" int tdm_q_sample_philox(const float* x0, const int64_t* t, const floa
     const int64_t total4 = batch * inner / 4;
     q_sample_kernel<true><<<grid_for(total4), kThreads, 0, (cudaStream_t)stream>>>(
         x0, nullptr, t, sqrt_acp, sqrt_om_acp, noise_out, out, total4, (uint32_t)(inner / 4), seed,
-        sample_offset, stream_id);
+        sample_offset, stream_id, stream_id_dev);
     TDM_CHECK_LAUNCH("tdm_q_sample_philox");
     return TDM_OK;
 }

@@ -55,7 +55,7 @@ def q_sample(x_start: torch.Tensor, t: torch.Tensor, noise: torch.Tensor | None 
                                            sched.sqrt_alphas_cumprod.data_ptr(),
                                            sched.sqrt_one_minus_alphas_cumprod.data_ptr(),
                                            n.data_ptr(), out.data_ptr(), b, inner, sched.timesteps,
-                                           seed, sample_offset, stream_id, st), "tdm_q_sample_philox")
+                                           seed, sample_offset, stream_id, None, st), "tdm_q_sample_philox")
     return (out, n) if return_noise else out
 
 

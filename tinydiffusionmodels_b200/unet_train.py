@@ -79,7 +79,7 @@ class UNetTrainer:
 
     def __init__(self, model, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.01, max_batch: int = 128, seed: int | None = None,
-                 process_group=None):
+                 process_group=None, use_graph: bool = True):
         self.model = model
         self.flat = model.flat_params()
         dev = self.flat.device
@@ -103,6 +103,8 @@ class UNetTrainer:
             self.rank = 0
         self.loss = torch.zeros(1, device=dev)
         self._bufs = {}
+        self._graph_cache = {}
+        self.use_graph = use_graph
 
     def _buffers(self, b: int):
         if b not in self._bufs:
@@ -111,41 +113,86 @@ class UNetTrainer:
                              torch.empty(b, 1, 28, 28, device=dev))
         return self._bufs[b]
 
-    def step(self, x0: torch.Tensor, t: torch.Tensor | None = None, noise: torch.Tensor | None = None) -> torch.Tensor:
-        """One optimizer step on the batch ``x0`` (B,1,28,28) in [-1,1]. Returns the loss (device)."""
+    # -- device work of one step, split at the (optional) gradient exchange --------------------
+    def _fwd_bwd(self, x0, t, noise, b):
         lib = self.engine.lib
         st = _lib.stream_ptr(self.device)
-        b = x0.shape[0]
-        x0 = x0.float().contiguous()
         x_noisy, noise_buf, eps = self._buffers(b)
         s = self.sched
-        if t is None:
-            t = torch.randint(0, s.timesteps, (b,), device=self.device)       # src/mnist.py:154
-        t = t.to(torch.int64).contiguous()
-        offset = (self.iteration * self.world + self.rank) * b                  # distinct noise per rank/step
         if noise is None:
+            # Philox stream = on-device step counter, sample index = rank*b + row: fresh noise every
+            # step and rank, and the launch arguments never change (graph-replayable)
             _lib.check(lib.tdm_q_sample_philox(x0.data_ptr(), t.data_ptr(), s.sqrt_alphas_cumprod.data_ptr(),
                                                s.sqrt_one_minus_alphas_cumprod.data_ptr(), noise_buf.data_ptr(),
-                                               x_noisy.data_ptr(), b, 784, s.timesteps, self.seed, offset, 0, st),
+                                               x_noisy.data_ptr(), b, 784, s.timesteps, self.seed,
+                                               self.rank * b, 0, self.step_dev.data_ptr(), st),
                        "tdm_q_sample_philox")
             noise = noise_buf
         else:
-            noise = noise.float().contiguous()
             _lib.check(lib.tdm_q_sample(x0.data_ptr(), noise.data_ptr(), t.data_ptr(),
                                         s.sqrt_alphas_cumprod.data_ptr(),
                                         s.sqrt_one_minus_alphas_cumprod.data_ptr(), x_noisy.data_ptr(), b, 784,
                                         s.timesteps, st), "tdm_q_sample")
         self.engine.forward(x_noisy, t, eps)
         self.engine.backward(x_noisy, t, noise, eps, self.grad, self.loss)
-        scale = 1.0
-        if self.world > 1:
-            torch.distributed.all_reduce(self.grad, group=self.pg)            # NCCL sum over NVLink
-            scale = 1.0 / self.world
+
+    def _update(self):
+        lib = self.engine.lib
+        st = _lib.stream_ptr(self.device)
         _lib.check(lib.tdm_adamw_flat(self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(),
                                       self.v.data_ptr(), PARAM_COUNT, self.lr, self.betas[0], self.betas[1],
-                                      self.eps, self.wd, scale, self.step_dev.data_ptr(), st), "tdm_adamw_flat")
+                                      self.eps, self.wd, 1.0 / self.world, self.step_dev.data_ptr(), st),
+                   "tdm_adamw_flat")
         _lib.check(lib.tdm_timestep_advance(self.step_dev.data_ptr(), 1, 1, st), "tdm_timestep_advance")
         self.engine.pack(self.flat)
+
+    def _exchange(self):
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grad, group=self.pg)   # NCCL sum of the 726 KB flat buffer
+
+    def _graphs(self, b: int):
+        """Two captured graphs per batch size: [q_sample, forward, backward] and [AdamW, re-pack];
+        the gradient all-reduce (if any) runs between them on the same stream."""
+        if b not in self._graph_cache:
+            dev = self.device
+            x_s = torch.zeros(b, 1, 28, 28, device=dev)
+            t_s = torch.zeros(b, dtype=torch.int64, device=dev)
+            keep = (self.flat.clone(), self.m.clone(), self.v.clone(), self.step_dev.clone())
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):       # warm-up outside capture (lazy attribute setup)
+                self._fwd_bwd(x_s, t_s, None, b)
+                self._update()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            self.flat.copy_(keep[0]); self.m.copy_(keep[1]); self.v.copy_(keep[2]); self.step_dev.copy_(keep[3])
+            self.engine.pack(self.flat)
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._fwd_bwd(x_s, t_s, None, b)
+            with torch.cuda.graph(g2):
+                self._update()
+            self._graph_cache[b] = (g1, g2, x_s, t_s)
+        return self._graph_cache[b]
+
+    def step(self, x0: torch.Tensor, t: torch.Tensor | None = None, noise: torch.Tensor | None = None) -> torch.Tensor:
+        """One optimizer step on the batch ``x0`` (B,1,28,28) in [-1,1]. Returns the loss (device scalar)."""
+        b = x0.shape[0]
+        if t is None:
+            t = torch.randint(0, self.sched.timesteps, (b,), device=self.device)   # src/mnist.py:154
+        if self.use_graph and noise is None:
+            g1, g2, x_s, t_s = self._graphs(b)
+            x_s.copy_(x0, non_blocking=True)
+            t_s.copy_(t, non_blocking=True)
+            g1.replay()
+            self._exchange()
+            g2.replay()
+        else:
+            x0 = x0.float().contiguous()
+            t = t.to(torch.int64).contiguous()
+            noise = None if noise is None else noise.float().contiguous()
+            self._fwd_bwd(x0, t, noise, b)
+            self._exchange()
+            self._update()
         self.iteration += 1
         return self.loss[0].clone()   # the buffer is overwritten by the next step
 
