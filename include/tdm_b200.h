@@ -151,6 +151,63 @@ int tdm_adamw_flat(float* params, const float* grads, float* exp_avg, float* exp
                    float lr, float beta1, float beta2, float eps, float weight_decay,
                    float grad_scale, const int64_t* step_dev, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Shakespeare embedding-space sampler (src/shakespeare.py): TinyTransformer denoiser, reverse step,
+ * rounding.  Supported shapes: seq_len 64 or 128, width 256 or 2048 (4 heads, FFN 2048, post-LN,
+ * ReLU — the nn.TransformerEncoderLayer defaults the reference uses, src/shakespeare.py:108-111).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Row-major fp32 weight [n][k] (nn.Linear.weight) -> bf16 planes [k/8][n_padded][8]; rows >= n are
+ * zero.  n_padded must be a multiple of 256 for use as a GEMM / rounding operand. */
+int tdm_pack_linear(const float* w, int n, int k, int n_padded, void* out_planes, void* stream);
+
+int64_t tdm_text_workspace_bytes(int64_t batch, int seq_len, int dim);
+
+/* Put x_t (batch, seq_len, dim) fp32 into the workspace as the sampler state and prepare the first
+ * GEMM operand x + time_emb(t/1000) (src/shakespeare.py:116-118). */
+int tdm_text_load_state(const float* x_rows, const int64_t* t, const float* time_w, const float* time_b,
+                        void* workspace, int64_t workspace_bytes, int64_t batch, int seq_len, int dim,
+                        void* stream);
+
+/* Copy out of the workspace as (batch, seq_len, dim) fp32: which = 0 the state x, which = 1 the
+ * denoiser output of the last tdm_text_forward. */
+int tdm_text_read(const void* workspace, int64_t workspace_bytes, int which, float* out_rows,
+                  int64_t batch, int seq_len, int dim, void* stream);
+
+/* TinyTransformer.forward (src/shakespeare.py:115-120, eval mode) on the loaded state.
+ * host_ptrs: HOST array of DEVICE pointers, 12 per encoder layer in this order —
+ *   in_proj_weight*, in_proj_bias, out_proj.weight*, out_proj.bias, linear1.weight*, linear1.bias,
+ *   linear2.weight*, linear2.bias, norm1.weight, norm1.bias, norm2.weight, norm2.bias
+ * (* = packed with tdm_pack_linear; the rest fp32 vectors) — followed by time_emb.weight [dim] and
+ * time_emb.bias [dim] (fp32). */
+int tdm_text_forward(const void* const* host_ptrs, int depth, void* workspace, int64_t workspace_bytes,
+                     const int64_t* t, int64_t batch, int seq_len, int dim, void* stream);
+
+/* One reverse step (src/shakespeare.py:343-352) on the loaded state: forward as above with the
+ * update x_{t-1} = (x_t - beta_t/sqrt(1-acp_t) eps)/sqrt(alpha_t) + sqrt(beta_t) z and the next
+ * step's time embedding (t-1) fused into the last LayerNorm.  z_rows: injected noise (batch,
+ * seq_len, dim) or NULL for in-kernel Philox keyed like tdm_reverse_step (inner = seq_len*dim).
+ * After the call the state holds x_{t-1}; advance t with tdm_timestep_advance and call again. */
+int tdm_text_p_sample(const void* const* host_ptrs, int depth, void* workspace, int64_t workspace_bytes,
+                      const int64_t* t, const float* z_rows, const float* betas, const float* alphas,
+                      const float* sqrt_om_acp, int64_t batch, int seq_len, int dim, uint64_t seed,
+                      uint64_t sample_offset, uint32_t step_id, void* stream);
+
+int64_t tdm_round_workspace_bytes(int64_t rows, int dim, int64_t vocab);
+
+/* Rounding: out_idx[r] = argmax_v score(r, v) without materialising the (rows, vocab) logits.
+ *   learned (cosine=0): score = x_r . W_v + bias_v          (src/shakespeare.py:389-390, 451-454)
+ *   cosine  (cosine=1): score = x_r . E_v / (|x_r| |E_v|)   (src/shakespeare.py:398-401, 462-464);
+ *                       w_planes must hold the row-normalised embedding matrix, bias = NULL
+ *   guided (ar_logits != NULL, rows = batch): score = (1-alpha) ar[r][v]/T + alpha score/T
+ *                                                          (src/shakespeare.py:449-467)
+ * x_rows (rows, dim) fp32; w_planes from tdm_pack_linear with n_padded = vocab_padded;
+ * out_val (nullable) receives the winning score.  Ties go to the lowest index (torch.argmax). */
+int tdm_round_argmax(const float* x_rows, int64_t rows, int dim, const void* w_planes, int64_t vocab,
+                     int64_t vocab_padded, const float* bias, int cosine, const float* ar_logits,
+                     int64_t ar_ld, float alpha, float temperature, int64_t* out_idx, float* out_val,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
 /* Measurement aid (bench.py roofline): one fused p_sample with CUDA events recorded on `stream`
  * between its nine launches; SYNCHRONISES on the last event and writes the nine per-kernel
  * durations in milliseconds to host_ms9 (order: rb1.conv1, rb1.conv2, avgpool, rb2.conv1,

@@ -38,6 +38,14 @@ SIGNATURES: dict[str, tuple] = {
     "tdm_unet_forward_train": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P]),
     "tdm_unet_backward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P]),
     "tdm_adamw_flat": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, _P, _P]),
+    "tdm_pack_linear": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "tdm_text_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
+    "tdm_text_load_state": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, _P]),
+    "tdm_text_read": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, c_int, _P]),
+    "tdm_text_forward": (c_int, [ctypes.POINTER(_P), c_int, _P, c_int64, _P, c_int64, c_int, c_int, _P]),
+    "tdm_text_p_sample": (c_int, [ctypes.POINTER(_P), c_int, _P, c_int64, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_uint64, c_uint64, c_uint32, _P]),
+    "tdm_round_workspace_bytes": (c_int64, [c_int64, c_int, c_int64]),
+    "tdm_round_argmax": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int64, _P, c_int, _P, c_int64, c_float, c_float, _P, _P, _P, c_int64, _P]),
     "tdm_unet_profile_p_sample": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, ctypes.POINTER(c_float), _P]),
 }
 

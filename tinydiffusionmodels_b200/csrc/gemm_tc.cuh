@@ -1,0 +1,263 @@
+// gemm_tc.cuh — persistent warp-specialised tcgen05 GEMM for the text path:
+//     C[M, N] = A[M, K] · W[N, K]^T  (+ bias, fused epilogue)
+// Operands are bf16 "planes" — [K/8][rows][8], 16-byte rows — the same un-swizzled K-major
+// core-matrix layout the UNet kernels use, so a 128x64 A block or a 256x64 W block is eight
+// contiguous 1-D bulk async copies (no tensor maps).  Tile 128 x 256 x 64, 4 smem stages,
+// two TMEM accumulator stages (2 x 256 columns) each drained by its own group of 4 epilogue warps.
+//
+// Epilogues (thread = output row, all N columns of the tile in registers 32 at a time):
+//   GE_BF16    bias (+ReLU) -> bf16 planes                      (QKV, FFN1 of nn.TransformerEncoderLayer)
+//   GE_RES_F32 bias + fp32 residual -> fp32 planes (pre-LN)     (attention out-proj, FFN2)
+//   GE_ARGMAX  running (max, argmax) over N, optionally mixed with AR logits — the logits are
+//              never written (src/shakespeare.py:389-390, 398-401, 451-467)
+#pragma once
+#include "common.cuh"
+#include "tc05.cuh"
+
+namespace tdm {
+
+enum : int { GE_BF16 = 0, GE_RES_F32 = 1, GE_ARGMAX = 2 };
+
+constexpr int kBM = 128, kBN = 256, kBK = 64;
+constexpr int kGemmStages = 4;
+constexpr int kGemmStageA = kBM * kBK * 2;   // 16 KB
+constexpr int kGemmStageB = kBN * kBK * 2;   // 32 KB
+constexpr int kGemmStage = kGemmStageA + kGemmStageB;
+constexpr int kGemmSmem = kGemmStages * kGemmStage + 1024;
+constexpr int kGemmThreads = 64 + 2 * 128;
+
+struct GemmArgs {
+    const uint8_t* a;      // bf16 planes [K/8][a_rows][8]
+    int64_t a_ps;          // plane stride, bytes
+    const uint8_t* w;      // bf16 planes [K/8][Np][8]
+    int64_t w_ps;
+    const float* bias;     // [N] or null
+    int M;                 // valid rows
+    int Mp;                // rows rounded up to 128 (tiles)
+    int N;                 // columns, multiple of 256 (padded)
+    int n_valid;           // columns that exist (argmax ignores the padding)
+    int K;                 // multiple of 64
+    int relu;
+    uint8_t* out_bf16;     // GE_BF16: bf16 planes [N/8][Mp][8]
+    int64_t ob_ps;
+    const uint8_t* res;    // GE_RES_F32: fp32 planes [N/4][Mp][4]
+    int64_t res_ps;
+    uint8_t* out_f32;      // GE_RES_F32: fp32 planes
+    int64_t of_ps;
+    // GE_ARGMAX
+    const float* row_scale;  // [M] multiplies the dot product (cosine: 1/||x||), or null
+    const float* ar;         // [M][ar_ld] fp32 AR logits, or null
+    int64_t ar_ld;
+    float alpha, inv_temp;
+    float* part_val;         // [2*nsplit][Mp]
+    int64_t* part_idx;
+    int nsplit;              // work items per row tile (== N/256 for the plain epilogues)
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStage);
+    uint64_t* bar_full = bars;
+    uint64_t* bar_empty = bars + kGemmStages;
+    uint64_t* bar_accf = bar_empty + kGemmStages;
+    uint64_t* bar_acce = bar_accf + 2;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acce + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kGemmStages; ++i) {
+            mbar_init(bar_full + i, 1);
+            mbar_init(bar_empty + i, 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar_accf + i, 1);
+            mbar_init(bar_acce + i, 4);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<512>(s_tmem);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *s_tmem;
+
+    const int m_tiles = a.Mp / kBM;
+    const int n_tiles = a.N / kBN;
+    const int items = m_tiles * a.nsplit;
+    const int kblocks = a.K / kBK;
+
+    if (warp == 0) {
+        // ===== producer =====
+        int kit = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int mt = item / a.nsplit, sp = item - mt * a.nsplit;
+            const int n0 = (int)((int64_t)sp * n_tiles / a.nsplit), n1 = (int)((int64_t)(sp + 1) * n_tiles / a.nsplit);
+            for (int nt = n0; nt < n1; ++nt) {
+                for (int kb = 0; kb < kblocks; ++kb, ++kit) {
+                    const int s = kit % kGemmStages;
+                    const uint32_t ph = (kit / kGemmStages) & 1;
+                    if (lane == 0) {
+                        mbar_wait(bar_empty + s, ph ^ 1);
+                        mbar_arrive_expect_tx(bar_full + s, kGemmStage);
+                    }
+                    __syncwarp();
+                    uint8_t* st = smem + s * kGemmStage;
+                    if (lane < 8) {
+                        bulk_g2s(st + lane * (kBM * 16), a.a + (int64_t)(kb * 8 + lane) * a.a_ps + (int64_t)mt * (kBM * 16),
+                                 kBM * 16, bar_full + s);
+                    } else if (lane < 16) {
+                        const int j = lane - 8;
+                        bulk_g2s(st + kGemmStageA + j * (kBN * 16),
+                                 a.w + (int64_t)(kb * 8 + j) * a.w_ps + (int64_t)nt * (kBN * 16), kBN * 16, bar_full + s);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(kBM, kBN);
+            int kit = 0, it = 0;
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const int mt = item / a.nsplit, sp = item - mt * a.nsplit;
+                const int n0 = (int)((int64_t)sp * n_tiles / a.nsplit), n1 = (int)((int64_t)(sp + 1) * n_tiles / a.nsplit);
+                for (int nt = n0; nt < n1; ++nt, ++it) {
+                    const int acc = it & 1;
+                    const uint32_t aph = (it >> 1) & 1;
+                    mbar_wait(bar_acce + acc, aph ^ 1);
+                    const uint32_t d = tmem_base + acc * kBN;
+                    for (int kb = 0; kb < kblocks; ++kb, ++kit) {
+                        const int s = kit % kGemmStages;
+                        const uint32_t ph = (kit / kGemmStages) & 1;
+                        mbar_wait(bar_full + s, ph);
+                        tc_fence_after_sync();
+                        const uint32_t a_addr = smem_u32(smem + s * kGemmStage);
+                        const uint32_t b_addr = a_addr + kGemmStageA;
+#pragma unroll
+                        for (int ks = 0; ks < kBK / 16; ++ks) {
+                            const uint64_t ad = make_smem_desc(a_addr + (2 * ks) * (kBM * 16), kBM * 16, 128);
+                            const uint64_t bd = make_smem_desc(b_addr + (2 * ks) * (kBN * 16), kBN * 16, 128);
+                            umma_bf16(d, ad, bd, idesc, (kb | ks) != 0);
+                        }
+                        umma_commit(bar_empty + s);
+                    }
+                    umma_commit(bar_accf + acc);
+                }
+            }
+        }
+    } else {
+        // ===== epilogue groups =====
+        const int q = warp & 3;
+        const int grp = (warp - 2) >> 2;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * kBN;
+        int it = 0, n_mine = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int mt = item / a.nsplit, sp = item - mt * a.nsplit;
+            const int n0 = (int)((int64_t)sp * n_tiles / a.nsplit), n1 = (int)((int64_t)(sp + 1) * n_tiles / a.nsplit);
+            const int row = mt * kBM + q * 32 + lane;
+            const bool rvalid = row < a.M;
+            float best = -INFINITY;
+            int64_t best_i = INT64_MAX;
+            float rs = 1.f;
+            if (EPI == GE_ARGMAX && a.row_scale && rvalid) rs = __ldg(a.row_scale + row);
+            for (int nt = n0; nt < n1; ++nt, ++it) {
+                if ((it & 1) != grp) continue;
+                const uint32_t aph = (n_mine++) & 1;
+                mbar_wait(bar_accf + grp, aph);
+                tc_fence_after_sync();
+#pragma unroll 1
+                for (int c0 = 0; c0 < kBN; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld_wait();
+                    if (c0 + 32 == kBN) {
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_acce + grp);
+                    }
+                    const int nb = nt * kBN + c0;
+                    if constexpr (EPI == GE_BF16) {
+#pragma unroll
+                        for (int pj = 0; pj < 4; ++pj) {
+                            float v[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                v[k] = __uint_as_float(r[pj * 8 + k]) + (a.bias ? __ldg(a.bias + nb + pj * 8 + k) : 0.f);
+                                if (a.relu) v[k] = fmaxf(v[k], 0.f);
+                            }
+                            if (rvalid) {
+                                uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
+                                                     pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+                                *reinterpret_cast<uint4*>(a.out_bf16 + (int64_t)(nb / 8 + pj) * a.ob_ps + (int64_t)row * 16) = o;
+                            }
+                        }
+                    } else if constexpr (EPI == GE_RES_F32) {
+#pragma unroll
+                        for (int pj = 0; pj < 8; ++pj) {
+                            if (rvalid) {
+                                const int64_t pl = nb / 4 + pj;
+                                const float4 rv = *reinterpret_cast<const float4*>(a.res + pl * a.res_ps + (int64_t)row * 16);
+                                float4 o;
+                                o.x = __uint_as_float(r[pj * 4 + 0]) + __ldg(a.bias + nb + pj * 4 + 0) + rv.x;
+                                o.y = __uint_as_float(r[pj * 4 + 1]) + __ldg(a.bias + nb + pj * 4 + 1) + rv.y;
+                                o.z = __uint_as_float(r[pj * 4 + 2]) + __ldg(a.bias + nb + pj * 4 + 2) + rv.z;
+                                o.w = __uint_as_float(r[pj * 4 + 3]) + __ldg(a.bias + nb + pj * 4 + 3) + rv.w;
+                                *reinterpret_cast<float4*>(a.out_f32 + pl * a.of_ps + (int64_t)row * 16) = o;
+                            }
+                        }
+                    } else {
+                        if (rvalid) {
+                            const float* arow = a.ar ? a.ar + (int64_t)row * a.ar_ld : nullptr;
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) {
+                                const int n = nb + k;
+                                if (n < a.n_valid) {
+                                    float v = __uint_as_float(r[k]) * rs + (a.bias ? __ldg(a.bias + n) : 0.f);
+                                    if (arow) {
+                                        // src/shakespeare.py:449-466: both logit sets divided by the
+                                        // temperature, then mixed (1-alpha)*ar + alpha*diff
+                                        v = (1.0f - a.alpha) * (__ldg(arow + n) * a.inv_temp) + a.alpha * (v * a.inv_temp);
+                                    }
+                                    if (v > best) {   // strict: first (lowest) index wins ties, as torch.argmax
+                                        best = v;
+                                        best_i = n;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            if constexpr (EPI == GE_ARGMAX) {
+                const int64_t slot = (int64_t)(sp * 2 + grp) * a.Mp + row;
+                a.part_val[slot] = best;
+                a.part_idx[slot] = best_i;
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+template <int EPI>
+static int launch_gemm(const GemmArgs& a, cudaStream_t st, const char* name) {
+    auto kern = gemm_tc_kernel<EPI>;
+    static bool configured = false;
+    if (!configured) {
+        TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        configured = true;
+    }
+    TDM_CHECK_ARG(a.Mp % kBM == 0 && a.N % kBN == 0 && a.K % kBK == 0 && a.K > 0 && a.nsplit > 0,
+                  "%s: bad GEMM shape M=%d Mp=%d N=%d K=%d", name, a.M, a.Mp, a.N, a.K);
+    const int items = (a.Mp / kBM) * a.nsplit;
+    const int grid = items < num_sms() ? items : num_sms();
+    kern<<<grid, kGemmThreads, kGemmSmem, st>>>(a);
+    TDM_CHECK_LAUNCH(name);
+    return TDM_OK;
+}
+
+}  // namespace tdm

@@ -1,0 +1,329 @@
+"""Shakespeare embedding-space text diffusion on B200 — host mirror of the reference's
+``src/shakespeare.py`` for the *sampling* paths named by the north star:
+
+* ``q_sample`` / ``p_sample``                      (ref src/shakespeare.py:37-44, 343-352)
+* ``TinyTransformer.forward`` (eval)               (ref :105-120)  -> tcgen05 GEMMs + attention
+* ``sample`` / ``sample_diffusion_embeddings``     (ref :355-426)  -> graph-replayed reverse loop,
+                                                                      fused rounding GEMM + argmax
+* ``guided_generate``                              (ref :429-470)  -> fused diff-logit GEMM + AR mix + argmax
+* ``LearnedEmbedding`` / ``LearnedRounding``       (ref :46-102)   parameter containers (weight ABI)
+
+Text *training* (ref :122-341) is outside this build's hot path: the modules raise
+instead of silently running PyTorch kernels.  The base LM inside ``guided_generate`` is third
+party (transformers) and stays a torch module.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+from pathlib import Path
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .schedule import linear_beta_schedule, make_schedule  # noqa: F401
+from .text_engine import Rounder, TextEngine
+from .utils import get_samples_dir, load_checkpoint, save_samples
+
+HF_TOKEN = os.getenv("HF_TOKEN")
+T = 1_000
+_tables = make_schedule(T)
+betas = _tables.betas
+alphas = _tables.alphas
+alphas_cumprod = _tables.alphas_cumprod
+sqrt_alphas_cumprod = _tables.sqrt_alphas_cumprod
+sqrt_one_minus_alphas_cumprod = _tables.sqrt_one_minus_alphas_cumprod
+
+
+def _fresh_seed() -> int:
+    return int(torch.randint(0, 2**62, (), dtype=torch.int64))
+
+
+def q_sample(x0: torch.Tensor, t: torch.Tensor, noise=None):
+    if noise is None:
+        return ops.q_sample(x0, t, None, seed=_fresh_seed())
+    return ops.q_sample(x0, t, noise)
+
+
+class LearnedEmbedding(nn.Module):
+    """nn.Embedding(V, dim) under the reference's key ``embeddings.weight`` (ref :46-84)."""
+
+    def __init__(self, vocab_size, embed_dim, pretrained_embeddings=None):
+        super().__init__()
+        self.vocab_size = vocab_size
+        self.embed_dim = embed_dim
+        self.embeddings = nn.Embedding(vocab_size, embed_dim)
+        with torch.no_grad():
+            if pretrained_embeddings is None:
+                nn.init.normal_(self.embeddings.weight, mean=0.0, std=0.02)
+            elif pretrained_embeddings.size(1) == embed_dim:
+                self.embeddings.weight.copy_(pretrained_embeddings)
+            else:
+                proj = nn.Linear(pretrained_embeddings.size(1), embed_dim, bias=False).to(pretrained_embeddings.device)
+                self.embeddings.weight.copy_(proj(pretrained_embeddings))
+
+    def forward(self, token_ids):
+        raise _lib.TdmError("embedding lookup belongs to text training, which this build does not accelerate")
+
+    def get_embedding_matrix(self):
+        return self.embeddings.weight
+
+
+class LearnedRounding(nn.Module):
+    """nn.Linear(dim, V) under the reference's keys ``decoder.weight/bias`` (ref :87-102).
+    Calling it materialises logits only for small problems; samplers use ``Rounder`` instead."""
+
+    def __init__(self, embed_dim, vocab_size):
+        super().__init__()
+        self.decoder = nn.Linear(embed_dim, vocab_size)
+
+    def forward(self, embeddings):
+        raise _lib.TdmError("LearnedRounding logits are never materialised here: use sample()/guided_generate(), "
+                            "which fuse the GEMM with the argmax")
+
+
+class TinyTransformer(nn.Module):
+    """Same parameters/keys as the reference's TinyTransformer; forward runs the CUDA engine."""
+
+    def __init__(self, dim, n_heads=4, depth=3, dropout=0.1):
+        super().__init__()
+        if n_heads != 4:
+            raise _lib.TdmError("the kernels implement the reference's 4-head configuration")
+        layer = nn.TransformerEncoderLayer(d_model=dim, nhead=n_heads, batch_first=True, dropout=dropout)
+        self.encoder = nn.TransformerEncoder(layer, num_layers=depth, enable_nested_tensor=False)
+        self.time_emb = nn.Linear(1, dim)
+        self.dropout = nn.Dropout(dropout)
+        self.dim = dim
+        self._engines: dict = {}
+
+    def _version(self) -> int:
+        return sum(p._version for p in self.parameters())
+
+    def engine(self, batch: int, seq_len: int) -> TextEngine:
+        p0 = next(self.parameters())
+        if not p0.is_cuda:
+            raise _lib.TdmError("TinyTransformer runs on CUDA only (no CPU fallback): call .to('cuda')")
+        key = (batch, seq_len, p0.device, self._version(), p0.data_ptr())
+        if key not in self._engines:
+            self._engines.clear()
+            self._engines[key] = TextEngine(self.state_dict(), p0.device, batch, seq_len)
+        return self._engines[key]
+
+    def forward(self, x: torch.Tensor, t: torch.Tensor):
+        if self.training or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+                             and x.requires_grad):
+            raise _lib.TdmError("TinyTransformer here is inference-only (eval + no_grad); text training is "
+                                "outside this build's hot path")
+        return self.engine(x.shape[0], x.shape[1]).forward(x, t)
+
+
+def p_sample(model, x, t):
+    """One reverse step with in-kernel Philox noise."""
+    return model.engine(x.shape[0], x.shape[1]).p_sample(x, t, None, seed=_fresh_seed())
+
+
+_rounders: dict = {}
+
+
+def _rounder(device) -> Rounder:
+    key = str(torch.device(device))
+    if key not in _rounders:
+        _rounders[key] = Rounder(device)
+    return _rounders[key]
+
+
+def round_to_tokens(x, rounding_fn, embedding_fn, use_learned_rounding=True, use_learned_embeddings=True):
+    """tokens = argmax over V (ref :387-401)."""
+    r = _rounder(x.device)
+    if use_learned_rounding:
+        return r.argmax(x, weight=rounding_fn.decoder.weight, bias=rounding_fn.decoder.bias)
+    emb = embedding_fn.get_embedding_matrix() if use_learned_embeddings else embedding_fn
+    return r.argmax(x, weight=emb, cosine=True)
+
+
+def sample_diffusion_embeddings(model, embed_dim, device, n, seq_len, seed=None, sample_offset=0):
+    """Pure diffusion embeddings z (n, seq_len, embed_dim) — the T-step loop of ref :418-426."""
+    seed = _fresh_seed() if seed is None else seed
+    model.eval()
+    x = ops.randn((n, seq_len, embed_dim), device, seed=seed, sample_offset=sample_offset, stream_id=0)
+    return model.engine(n, seq_len).sample_loop(x, seed=seed, sample_offset=sample_offset, steps=T)
+
+
+def sample(model, rounding_fn, embedding_fn, tokenizer, device, n_samples=4, seq_len=128,
+           use_learned_rounding=True, use_learned_embeddings=True, embed_dim=None):
+    model.eval()
+    samples_dir = get_samples_dir("samples")
+    with torch.no_grad():
+        if embed_dim is None:
+            embed_dim = embedding_fn.embed_dim if use_learned_embeddings else embedding_fn.shape[1]
+        x = sample_diffusion_embeddings(model, embed_dim, device, n_samples, seq_len)
+        tokens = round_to_tokens(x, rounding_fn, embedding_fn, use_learned_rounding, use_learned_embeddings)
+        texts = tokenizer.batch_decode(tokens, skip_special_tokens=True)
+        for i, text in enumerate(texts):
+            print(text)
+            if isinstance(samples_dir, str) and samples_dir.startswith("gs://"):
+                path = f"{samples_dir}/sample_{i}.txt"
+            else:
+                path = Path(samples_dir) / f"sample_{i}.txt"
+            save_samples(text, path)
+            print(f"✔ Wrote {path}")
+        return texts
+
+
+def guided_generate(base_lm, rounding_fn, tokenizer, embedding_fn, diff_z, alpha=0.5, max_len=128,
+                    temperature=1.0, use_learned_rounding=True, use_learned_embeddings=True):
+    """Greedy AR decoding steered by the diffusion embeddings (ref :429-470).  Per position the
+    diffusion logits, the (1-alpha)/alpha mix with the AR logits and the argmax are one kernel."""
+    device = diff_z.device
+    B, L, _ = diff_z.shape
+    r = _rounder(device)
+    start = tokenizer.bos_token_id or tokenizer.eos_token_id
+    input_ids = torch.full((B, L + 1), start, device=device, dtype=torch.long)   # preallocated, no per-step cat
+    if use_learned_rounding:
+        kw = dict(weight=rounding_fn.decoder.weight, bias=rounding_fn.decoder.bias, cosine=False)
+    else:
+        emb = embedding_fn.get_embedding_matrix() if use_learned_embeddings else embedding_fn
+        kw = dict(weight=emb, cosine=True)
+    with torch.no_grad():
+        for pos in range(L):
+            ar_logits = base_lm(input_ids[:, :pos + 1]).logits[:, -1, :]          # third-party LM forward
+            nxt = r.argmax(diff_z[:, pos, :], ar_logits=ar_logits, alpha=alpha, temperature=temperature, **kw)
+            input_ids[:, pos + 1] = nxt
+    return tokenizer.batch_decode(input_ids[:, 1:], skip_special_tokens=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# CLI — the reference's 22 flags (src/shakespeare.py:475-496) plus an offline path
+# ---------------------------------------------------------------------------------------------
+class _SyntheticTokenizer:
+    """Offline stand-in (no HF hub on the benchmark boxes): decodes ids as space-separated ints."""
+    bos_token_id = 2
+    eos_token_id = 1
+
+    def batch_decode(self, ids, skip_special_tokens=True):
+        return [" ".join(str(int(i)) for i in row) for row in ids]
+
+
+class _SyntheticLM(nn.Module):
+    """Random-init bigram LM standing in for google/gemma-2b-it when --synthetic is given."""
+
+    def __init__(self, vocab, dim=64):
+        super().__init__()
+        self.emb = nn.Embedding(vocab, dim)
+        self.out = nn.Linear(dim, vocab)
+
+    def get_input_embeddings(self):
+        return self.emb
+
+    def forward(self, input_ids):
+        import types
+        return types.SimpleNamespace(logits=self.out(self.emb(input_ids)))
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--train", action="store_true")
+    parser.add_argument("--sample", action="store_true", help="plain diffusion sample")
+    parser.add_argument("--guided_sample", action="store_true", help="AR + diffusion guidance")
+    parser.add_argument("--epochs", type=int, default=1)
+    parser.add_argument("--batch_size", type=int, default=32)
+    parser.add_argument("--seq_len", type=int, default=64)
+    parser.add_argument("--ckpt", type=str, default="gs://text-diffusion/diffusion/outputs/model/text-model.pth"
+                        if "AIP_MODEL_DIR" in os.environ else "text_ckpt.pth")
+    parser.add_argument("--model_id", type=str, default="google/gemma-2b-it")
+    parser.add_argument("--n", type=int, default=10)
+    parser.add_argument("--alpha", type=float, default=0.3)
+    parser.add_argument("--rounding_weight", type=float, default=1.0)
+    parser.add_argument("--use_cosine_fallback", action="store_true")
+    parser.add_argument("--use_learned_embeddings", action="store_true")
+    parser.add_argument("--embed_dim", type=int, default=None)
+    parser.add_argument("--init_from_pretrained", action="store_true")
+    parser.add_argument("--dropout", type=float, default=0.1)
+    parser.add_argument("--weight_decay", type=float, default=1e-4)
+    parser.add_argument("--patience", type=int, default=5)
+    parser.add_argument("--use_lr_scheduling", action="store_true", default=True)
+    parser.add_argument("--warmup_steps", type=int, default=100)
+    parser.add_argument("--val_split", type=float, default=0.1)
+    parser.add_argument("--lr", type=float, default=1e-4)
+    # additive: run without the HF hub (random-init stand-ins, synthetic vocabulary)
+    parser.add_argument("--synthetic", action="store_true", help="no HF downloads: synthetic tokenizer/LM")
+    parser.add_argument("--vocab_size", type=int, default=8192, help="vocabulary for --synthetic")
+    parser.add_argument("--seed", type=int, default=None)
+    args = parser.parse_args(argv)
+
+    if not torch.cuda.is_available():
+        raise _lib.TdmError("tinydiffusionmodels_b200 needs a CUDA (sm_100a) device; there is no CPU path")
+    device = "cuda"
+    print(f"Device: {device}")
+    if args.seed is not None:
+        torch.manual_seed(args.seed)
+    if args.train:
+        raise _lib.TdmError("text training is outside this build's hot path (SURVEY.md §8f); use the reference")
+
+    if args.synthetic:
+        tokenizer = _SyntheticTokenizer()
+        lm_model = _SyntheticLM(args.vocab_size).to(device).eval()
+    else:
+        from transformers import AutoModelForCausalLM, AutoTokenizer
+        tokenizer = AutoTokenizer.from_pretrained(args.model_id)
+        lm_model = AutoModelForCausalLM.from_pretrained(args.model_id).to(device).eval()
+    pretrained = lm_model.get_input_embeddings().weight.detach().to(device)
+    vocab_size, pretrained_dim = pretrained.shape
+
+    if args.use_learned_embeddings:
+        embed_dim = args.embed_dim if args.embed_dim is not None else pretrained_dim
+        embedding_fn = LearnedEmbedding(vocab_size, embed_dim, pretrained if args.init_from_pretrained else None).to(device)
+    else:
+        embed_dim = pretrained_dim
+        embedding_fn = pretrained
+    diff_model = TinyTransformer(embed_dim, dropout=args.dropout).to(device)
+    rounding_fn = LearnedRounding(embed_dim, vocab_size).to(device)
+
+    def load():
+        nonlocal embedding_fn
+        if not (args.synthetic and not os.path.exists(args.ckpt)):
+            ck = load_checkpoint(args.ckpt, device)
+            if isinstance(ck, dict) and "diffusion_model" in ck:
+                diff_model.load_state_dict(ck["diffusion_model"])
+                rounding_fn.load_state_dict(ck["rounding_fn"])
+                if args.use_learned_embeddings and "embedding_fn" in ck:
+                    embedding_fn.load_state_dict(ck["embedding_fn"])
+                elif args.use_learned_embeddings:
+                    print("Warning: Learned embeddings requested but not found in checkpoint. Using pre-trained fallback.")
+                    args.use_learned_embeddings = False
+                    embedding_fn = pretrained
+            else:
+                diff_model.load_state_dict(ck)
+                print("Warning: Using old checkpoint format. Falling back to pre-trained embeddings and cosine similarity.")
+                args.use_cosine_fallback = True
+                args.use_learned_embeddings = False
+                embedding_fn = pretrained
+        else:
+            print("--synthetic without a checkpoint: sampling from random-init weights")
+
+    if args.sample:
+        load()
+        sample(diff_model, rounding_fn, embedding_fn, tokenizer, device, args.n, args.seq_len,
+               use_learned_rounding=not args.use_cosine_fallback,
+               use_learned_embeddings=args.use_learned_embeddings, embed_dim=embed_dim)
+    if args.guided_sample:
+        load()
+        z = sample_diffusion_embeddings(diff_model, embed_dim, device, args.n, args.seq_len)
+        texts = guided_generate(lm_model, rounding_fn, tokenizer, embedding_fn, z, alpha=args.alpha,
+                                max_len=args.seq_len, use_learned_rounding=not args.use_cosine_fallback,
+                                use_learned_embeddings=args.use_learned_embeddings)
+        samples_dir = get_samples_dir("samples")
+        for i, text in enumerate(texts):
+            if isinstance(samples_dir, str) and samples_dir.startswith("gs://"):
+                path = f"{samples_dir}/guided_sample_{i}.txt"
+            else:
+                path = Path(samples_dir) / f"guided_sample_{i}.txt"
+            save_samples(text, path)
+            print(f"✔ Wrote {path}")
+    if not (args.train or args.sample or args.guided_sample):
+        print("Nothing to do. Try --train or --guided_sample.")
+
+
+if __name__ == "__main__":
+    main()
