@@ -144,7 +144,10 @@ def run_reference(args) -> None:
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "MNIST DDPM UNet 28x28x1 T=1000 reverse sampling, batch 64, random-init weights (CPU, oracle port of src/mnist.py:167-194)"},
+        "config": {"workload": f"MNIST DDPM UNet 28x28x1, T={T_STEPS} reverse sampling, {args.batch} samples per GPU "
+                               f"({args.gpus * args.batch} total), random-init weights",
+                   "samples_per_gpu": args.batch, "T": T_STEPS,
+                   "note": "reference arm: CPU fp32 oracle port of src/mnist.py:167-194 on a bounded sample of this workload"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{per_step} of {T_STEPS} reverse steps at batch {batch} per bench step, x1000/{per_step} extrapolated"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

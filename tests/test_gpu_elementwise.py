@@ -6,7 +6,6 @@ import torch
 from oracle import ddpm_oracle as O
 from oracle import philox as PX
 from tinydiffusionmodels_b200 import ops
-from tinydiffusionmodels_b200.schedule import make_schedule
 
 pytestmark = pytest.mark.gpu
 TAB = O.make_tables()
@@ -46,12 +45,6 @@ def test_reverse_step_mixed_t_follows_t0(cuda):
     t = torch.tensor([7, 0, 9])
     assert torch.equal(ops.reverse_step(x.to(cuda), e.to(cuda), t.to(cuda), z.to(cuda)).cpu(),
                        O.reverse_step(x, e, t, z, TAB))
-
-
-def test_schedule_tables_match_oracle():
-    s = make_schedule()
-    for k, v in TAB.items():
-        assert torch.equal(getattr(s, k), v), k
 
 
 def test_philox_randn_matches_numpy_oracle(cuda):
@@ -101,9 +94,3 @@ def test_empty_batch(cuda):
     x = torch.empty(0, 1, 28, 28, device=cuda)
     t = torch.empty(0, dtype=torch.long, device=cuda)
     assert ops.q_sample(x, t, x.clone()).shape == (0, 1, 28, 28)
-
-
-def test_cpu_tensor_is_an_error():
-    from tinydiffusionmodels_b200._lib import TdmError
-    with pytest.raises(TdmError):
-        ops.q_sample(torch.zeros(1, 4), torch.zeros(1, dtype=torch.long), torch.zeros(1, 4))
