@@ -106,8 +106,8 @@ int tdm_unet_pack_weights(const float* flat_params, void* wpack, void* stream);
 /* Test/debug aid: workspace layout for `batch` as 14 int64 written to HOST memory:
  * {tiles28, tiles14, plane_stride28, plane_stride14, off_t1, off_cat, off_p1, off_t2, off_s2,
  *  off_h2, off_t3, off_t4, off_s4, total_bytes}.  Activation tensor [C][pos] lives at
- * off + (c/8)*plane_stride + (HALO + pos)*16 + (c%8)*2 with pos(b,y,x) = b*S + (y+1)*(W+1) + x,
- * S = (W+1)^2, HALO = 32 (W=28) or 16 (W=14). */
+ * off + (c/8)*plane_stride + (GUARD + pos)*16 + (c%8)*2 with pos(b,y,x) = b*S + (y+1)*(W+1) + x,
+ * S = (W+1)^2, GUARD = 40 (W=28) or 24 (W=14). */
 int tdm_unet_debug_layout(int64_t batch, int64_t* host_out14);
 
 /* SimpleUNet.forward(x, t) (src/mnist.py:76-87).  x: [batch,1,28,28] fp32, t: [batch] int64,

@@ -3,9 +3,20 @@
 //
 //   warp 0      producer: weights once, then one input tile (all channel planes, halo included)
 //               per iteration via 1-D bulk async copies into a ring of smem stages
-//   warp 1      one thread issues TAPS*CIN/16 tcgen05.mma (M=128 positions, N=COUT, K=16) per
-//               tile; the A operand of every tap is the same smem tile at a shifted row offset
+//   warp 1      one thread issues the tcgen05.mma of a tile (M = 128 positions, K = 16 channels);
+//               the A operand of every tap is the same smem tile at a shifted row offset
 //   warps 2..   kEpiGroups groups of 4 epilogue warps; group g owns TMEM accumulator stage g
+//
+// Two MMA schedules:
+//   KXC = false  nine taps, N = COUT each:            D[p]            = sum_tap W_tap X[p + off(tap)]
+//   KXC = true   the three kx taps of a row share one MMA with N = 3*COUT (weights of kx = 0,1,2
+//                side by side), A shifted by (ky-1)*Wp only:
+//                                                      Y[q][kx]        = sum_ky W[ky][kx] X[q + (ky-1)Wp]
+//                and the epilogue finishes                out[p]      = Y[p-1][0] + Y[p][1] + Y[p+1][2]
+//                with two warp shuffles per channel (neighbour rows are neighbour lanes).  An MMA costs
+//                about 32 (A) + N/4 (B) + 15 cycles of shared-memory operand fetch whatever N is, so
+//                tripling N cuts the operand traffic per FLOP by ~2x.  Tiles overlap by
+//                two rows: tile t computes Y for rows [126t-1, 126t+127) and outputs [126t, 126t+126).
 #pragma once
 #include "common.cuh"
 #include "diffusion_math.cuh"
@@ -14,14 +25,11 @@
 
 namespace tdm {
 
-// ---------------------------------------------------------------------------------------------
-// tensor-core 3x3 convolution
-// ---------------------------------------------------------------------------------------------
 // EPI_PLAIN: out = acc (+ residual if given) — no bias, no ReLU: the data-gradient convolutions.
 enum : int { EPI_CONV1 = 0, EPI_RES = 1, EPI_RES_X = 2, EPI_RES_UP = 3, EPI_FINAL = 4, EPI_PLAIN = 5 };
 
 struct ConvArgs {
-    const uint8_t* in;     // input planes: row -HALO of plane 0
+    const uint8_t* in;     // input planes: row -GUARD of plane 0
     int64_t in_ps;         // plane stride (bytes)
     const uint8_t* w;      // packed bf16 weights: conv, then (SKIPG) the 1x1 skip
     const float* bias;     // [COUT] conv bias
@@ -33,7 +41,7 @@ struct ConvArgs {
     int64_t out_ps;
     uint8_t* out2;         // skip output planes (SKIPG)
     int64_t out2_ps;
-    const uint8_t* res;    // residual planes (EPI_RES / EPI_RES_UP / EPI_FINAL)
+    const uint8_t* res;    // residual planes (EPI_RES / EPI_RES_UP / EPI_FINAL / EPI_PLAIN)
     int64_t res_ps;
     const float* x;        // [B,784] fp32: rb1 skip input (EPI_RES_X) or x_t (EPI_FINAL + step)
     const float* aux_w;    // [32]: rb1.skip.weight (EPI_RES_X) or out.weight (EPI_FINAL)
@@ -47,7 +55,7 @@ struct ConvArgs {
     uint64_t sample_offset;
     uint32_t step_id;
     int fuse_step;
-    int nt;
+    int np;                // positions covered by the buffers (multiple of 128)
     int batch;
     // training forward: ReLU masks, one uint32 per 32 channels per position: mask[chunk*mask_stride+pos]
     uint32_t* mask;
@@ -56,7 +64,7 @@ struct ConvArgs {
 
 constexpr int kEpiGroups = 2;  // epilogue warp groups == TMEM accumulator stages
 
-template <int W, int CIN, int COUT, bool SKIPG, int TAPS = 9>
+template <int W, int CIN, int COUT, bool SKIPG, int TAPS, bool KXC>
 struct ConvCfg {
     using G = Geo<W>;
     static constexpr int NPL = CIN / 8;
@@ -64,28 +72,47 @@ struct ConvCfg {
     static constexpr int WCONV_BYTES = TAPS * CIN * COUT * 2;
     static constexpr int W_BYTES = WCONV_BYTES + (SKIPG ? CIN * COUT * 2 : 0);
     static constexpr int PARAM_BYTES = 5 * 96 * 4;
+    static constexpr int XCH_BYTES = KXC ? kEpiGroups * 4 * 2 * COUT * 4 : 0;
     static constexpr int MAX_SMEM = 227 * 1024;
-    static constexpr int AVAIL = MAX_SMEM - W_BYTES - PARAM_BYTES - 256;
+    static constexpr int AVAIL = MAX_SMEM - W_BYTES - PARAM_BYTES - XCH_BYTES - 256;
     static constexpr int NSTAGE = (AVAIL / STAGE_BYTES) > 4 ? 4 : (AVAIL / STAGE_BYTES);
     static_assert(NSTAGE >= 2, "need at least two input stages");
     static constexpr int NACC = kEpiGroups;
-    static constexpr int ACC_COLS = SKIPG ? 2 * COUT : COUT;
+    static constexpr int NMAIN = KXC ? 3 * COUT : COUT;            // columns of the conv accumulator
+    static constexpr int ACC_COLS = NMAIN + (SKIPG ? COUT : 0);
     static constexpr int TMEM_COLS = (NACC * ACC_COLS <= 32) ? 32 : (NACC * ACC_COLS <= 64) ? 64
                                    : (NACC * ACC_COLS <= 128) ? 128 : (NACC * ACC_COLS <= 256) ? 256 : 512;
     static_assert(NACC * ACC_COLS <= 512, "accumulators exceed TMEM");
-    static constexpr int SMEM_BYTES = W_BYTES + NSTAGE * STAGE_BYTES + PARAM_BYTES + 256;
+    static_assert(NMAIN <= 256 && NMAIN % 16 == 0, "UMMA N");
+    static constexpr int SMEM_BYTES = W_BYTES + NSTAGE * STAGE_BYTES + PARAM_BYTES + XCH_BYTES + 256;
     // warp 0 producer, warp 1 MMA issuer, then NACC groups of 4 epilogue warps
     static constexpr int THREADS = 64 + 128 * NACC;
+    // tile t: accumulator rows [t*TSTRIDE - ROW0, +128), output rows are tile rows [ROW0, 128-ROW0)
+    static constexpr int TSTRIDE = KXC ? 126 : 128;
+    static constexpr int ROW0 = KXC ? 1 : 0;
+    static constexpr int CW = KXC ? 16 : 32;   // channels per epilogue chunk
 };
 
-template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9>
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]) {
+    if constexpr (N == 16) tmem_ld16(taddr, r);
+    else tmem_ld32(taddr, r);
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, bool KXC = false>
 __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(const ConvArgs a) {
-    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS>;
+    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC>;
     using G = Geo<W>;
     static_assert(COUT == 32 || COUT == 64 || COUT == 96, "COUT");
     static_assert(TAPS == 9 || TAPS == 1, "3x3 or 1x1");
+    static_assert(!KXC || TAPS == 9, "kx-combining is a 3x3 schedule");
     static_assert(!SKIPG || COUT <= 64, "skip GEMM variant is forward-only");
     static_assert(EPI != EPI_FINAL || COUT == 32, "final epilogue expects 32 channels");
+    constexpr int CW = C::CW;
 
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* s_w = smem;
@@ -96,7 +123,8 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
     float* s_tb = s_par + 192;
     float* s_sbias = s_par + 288;
     float* s_aux = s_par + 384;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(s_par + 480);
+    float* s_xch = s_par + 480;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_xch) + C::XCH_BYTES);
     uint64_t* bar_w = bars;
     uint64_t* bar_full = bars + 1;
     uint64_t* bar_empty = bar_full + C::NSTAGE;
@@ -106,6 +134,7 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int nt = (a.np + C::TSTRIDE - 1) / C::TSTRIDE;
 
     // ---- setup -----------------------------------------------------------------------------
     if (threadIdx.x < COUT) {
@@ -148,7 +177,7 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
             }
         }
         int it = 0;
-        for (int tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; tile < nt; tile += gridDim.x, ++it) {
             const int s = it % C::NSTAGE;
             const uint32_t ph = (it / C::NSTAGE) & 1;
             if (lane == 0) {
@@ -157,19 +186,21 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
             }
             __syncwarp();
             if (lane < C::NPL) {
-                bulk_g2s(s_in + s * C::STAGE_BYTES + lane * (G::RT * 16),
-                         a.in + lane * a.in_ps + (int64_t)tile * (kTile * 16), G::RT * 16,
-                         bar_full + s);
+                // smem row 0 = global row tile*TSTRIDE - ROW0 - HALO; the buffer starts at row -GUARD
+                const int64_t row = (int64_t)tile * C::TSTRIDE - C::ROW0 - G::HALO + G::GUARD;
+                bulk_g2s(s_in + s * C::STAGE_BYTES + lane * (G::RT * 16), a.in + lane * a.in_ps + row * 16,
+                         G::RT * 16, bar_full + s);
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, COUT);
+            constexpr uint32_t idesc = make_idesc_bf16(128, C::NMAIN);
+            constexpr uint32_t idesc_skip = make_idesc_bf16(128, COUT);
             mbar_wait(bar_w, 0);
             const uint32_t w_addr = smem_u32(s_w);
             int it = 0;
-            for (int tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
+            for (int tile = blockIdx.x; tile < nt; tile += gridDim.x, ++it) {
                 const int s = it % C::NSTAGE;
                 const uint32_t ph = (it / C::NSTAGE) & 1;
                 const int acc = it % C::NACC;
@@ -179,16 +210,30 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
                 tc_fence_after_sync();
                 const uint32_t in_addr = smem_u32(s_in + s * C::STAGE_BYTES);
                 const uint32_t d = tmem_base + acc * C::ACC_COLS;
+                if constexpr (KXC) {
 #pragma unroll
-                for (int tap = 0; tap < TAPS; ++tap) {
-                    const int off = (TAPS == 1) ? 0 : (tap / 3 - 1) * G::Wp + (tap % 3 - 1);
+                    for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
-                    for (int ks = 0; ks < CIN / 16; ++ks) {
-                        const uint64_t ad = make_smem_desc(
-                            in_addr + (2 * ks) * (G::RT * 16) + (G::HALO + off) * 16, G::RT * 16, 128);
-                        const uint64_t bd = make_smem_desc(
-                            w_addr + ((tap * C::NPL + 2 * ks) * COUT) * 16, COUT * 16, 128);
-                        umma_bf16(d, ad, bd, idesc, (tap | ks) != 0);
+                        for (int ks = 0; ks < CIN / 16; ++ks) {
+                            const uint64_t ad = make_smem_desc(
+                                in_addr + (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp) * 16, G::RT * 16, 128);
+                            const uint64_t bd = make_smem_desc(
+                                w_addr + ((ky * C::NPL + 2 * ks) * 3 * COUT) * 16, 3 * COUT * 16, 128);
+                            umma_bf16(d, ad, bd, idesc, (ky | ks) != 0);
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int tap = 0; tap < TAPS; ++tap) {
+                        const int off = (TAPS == 1) ? 0 : (tap / 3 - 1) * G::Wp + (tap % 3 - 1);
+#pragma unroll
+                        for (int ks = 0; ks < CIN / 16; ++ks) {
+                            const uint64_t ad = make_smem_desc(
+                                in_addr + (2 * ks) * (G::RT * 16) + (G::HALO + off) * 16, G::RT * 16, 128);
+                            const uint64_t bd = make_smem_desc(
+                                w_addr + ((tap * C::NPL + 2 * ks) * COUT) * 16, COUT * 16, 128);
+                            umma_bf16(d, ad, bd, idesc, (tap | ks) != 0);
+                        }
                     }
                 }
                 if constexpr (SKIPG) {
@@ -198,7 +243,7 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
                             in_addr + (2 * ks) * (G::RT * 16) + G::HALO * 16, G::RT * 16, 128);
                         const uint64_t bd = make_smem_desc(
                             w_addr + C::WCONV_BYTES + ((2 * ks) * COUT) * 16, COUT * 16, 128);
-                        umma_bf16(d + COUT, ad, bd, idesc, ks != 0);
+                        umma_bf16(d + C::NMAIN, ad, bd, idesc_skip, ks != 0);
                     }
                 }
                 umma_commit(bar_empty + s);   // smem stage reusable once these MMAs retire
@@ -212,14 +257,16 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
         const int grp = (warp - 2) >> 2;
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * C::ACC_COLS;
         int n = 0;
-        for (int tile = blockIdx.x + grp * gridDim.x; tile < a.nt; tile += C::NACC * gridDim.x, ++n) {
+        for (int tile = blockIdx.x + grp * gridDim.x; tile < nt; tile += C::NACC * gridDim.x, ++n) {
             const uint32_t aph = n & 1;
             // ---- phase A: everything that does not need the accumulator (overlaps the MMAs) ----
-            const int64_t pos = (int64_t)tile * kTile + q * 32 + lane;
+            const int trow = q * 32 + lane;                                   // row inside the tile
+            const int64_t pos = (int64_t)tile * C::TSTRIDE - C::ROW0 + trow;  // global position
+            const bool owned = trow >= C::ROW0 && trow < 128 - C::ROW0 && pos < a.np;  // this tile outputs pos
             const int b = (int)(pos / G::S);
             const int rem = (int)(pos - (int64_t)b * G::S);
             const int r = rem / G::Wp, c = rem - r * G::Wp;
-            const bool valid = b < a.batch && r >= 1 && c < G::W;
+            const bool valid = owned && pos >= 0 && b < a.batch && r >= 1 && c < G::W;
             const int y = r - 1;
 
             float ts = 0.f;
@@ -234,7 +281,7 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
                 for (int pl = 0; pl < COUT / 8; ++pl) {
                     rv[pl] = make_uint4(0, 0, 0, 0);
                     if (valid && (EPI != EPI_PLAIN || a.res))  // residual planes share this geometry
-                        rv[pl] = *reinterpret_cast<const uint4*>(a.res + pl * a.res_ps + (pos + G::HALO) * 16);
+                        rv[pl] = *reinterpret_cast<const uint4*>(a.res + pl * a.res_ps + (pos + G::GUARD) * 16);
                 }
             }
             StepCoef sc{};
@@ -264,33 +311,83 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
             mbar_wait(bar_accf + grp, aph);
             tc_fence_after_sync();
             float dot = 0.f;
+            uint32_t mbits = 0;
 
 #pragma unroll
-            for (int c0 = 0; c0 < COUT; c0 += 32) {
-                uint32_t r1[32];
-                uint32_t mbits = 0;
-                tmem_ld32(taddr + c0, r1);
-                uint32_t r2[32];
-                if constexpr (SKIPG) tmem_ld32(taddr + COUT + c0, r2);
-                tmem_ld_wait();
-                if (c0 + 32 >= COUT) {
-                    // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-                    tc_fence_before_sync();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_acce + grp);
+            for (int c0 = 0; c0 < COUT; c0 += CW) {
+                float acc[CW];
+                uint32_t r2[CW];
+                if constexpr (KXC) {
+                    uint32_t d0[CW], d1[CW], d2[CW];
+                    tmem_ld_n<CW>(taddr + c0, d0);
+                    tmem_ld_n<CW>(taddr + COUT + c0, d1);
+                    tmem_ld_n<CW>(taddr + 2 * COUT + c0, d2);
+                    if constexpr (SKIPG) tmem_ld_n<CW>(taddr + 3 * COUT + c0, r2);
+                    tmem_ld_wait();
+                    if (c0 + CW >= COUT) {
+                        // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_acce + grp);
+                    }
+                    // rows p-1 / p+1 are lanes -1 / +1; across the warp boundary they come through smem.
+                    // Everything below is branch-free per channel (selects, broadcast loads): per-channel
+                    // `if (lane == 0)` patches compile to divergent branches and dominated the kernel.
+                    float4* xs = reinterpret_cast<float4*>(s_xch + ((grp * 4 + q) * 2) * COUT + c0);
+                    if (lane == 31) {
+#pragma unroll
+                        for (int k = 0; k < CW / 4; ++k)
+                            xs[k] = make_float4(__uint_as_float(d0[4 * k]), __uint_as_float(d0[4 * k + 1]),
+                                                __uint_as_float(d0[4 * k + 2]), __uint_as_float(d0[4 * k + 3]));
+                    }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int k = 0; k < CW / 4; ++k)
+                            xs[COUT / 4 + k] = make_float4(__uint_as_float(d2[4 * k]), __uint_as_float(d2[4 * k + 1]),
+                                                           __uint_as_float(d2[4 * k + 2]), __uint_as_float(d2[4 * k + 3]));
+                    }
+                    named_bar_sync(1 + grp, 128);
+                    // q == 0 / q == 3: tile rows 0 / 127 are never output rows, any finite value will do
+                    const float4* xprev = reinterpret_cast<const float4*>(s_xch + ((grp * 4 + (q > 0 ? q - 1 : 0)) * 2) * COUT + c0);
+                    const float4* xnext = reinterpret_cast<const float4*>(s_xch + ((grp * 4 + (q < 3 ? q + 1 : 3)) * 2 + 1) * COUT + c0);
+                    const bool first = lane == 0, last = lane == 31;
+#pragma unroll
+                    for (int k4 = 0; k4 < CW / 4; ++k4) {
+                        const float4 pu = xprev[k4], pd = xnext[k4];   // same address for all lanes: broadcast
+                        const float pus[4] = {pu.x, pu.y, pu.z, pu.w}, pds[4] = {pd.x, pd.y, pd.z, pd.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int k = 4 * k4 + j;
+                            const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(d0[k]), 1);
+                            const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[k]), 1);
+                            acc[k] = (first ? pus[j] : up) + __uint_as_float(d1[k]) + (last ? pds[j] : dn);
+                        }
+                    }
+                } else {
+                    uint32_t r1[CW];
+                    tmem_ld_n<CW>(taddr + c0, r1);
+                    if constexpr (SKIPG) tmem_ld_n<CW>(taddr + COUT + c0, r2);
+                    tmem_ld_wait();
+                    if (c0 + CW >= COUT) {
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_acce + grp);
+                    }
+#pragma unroll
+                    for (int k = 0; k < CW; ++k) acc[k] = __uint_as_float(r1[k]);
                 }
 #pragma unroll
-                for (int pj = 0; pj < 4; ++pj) {
+                for (int pj = 0; pj < CW / 8; ++pj) {
                     const int plane = c0 / 8 + pj;
                     float v[8];
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int ch = c0 + pj * 8 + k;
                         if constexpr (EPI == EPI_PLAIN) {
-                            v[k] = __uint_as_float(r1[pj * 8 + k]);
+                            v[k] = acc[pj * 8 + k];
                         } else {
-                            v[k] = fmaxf(__uint_as_float(r1[pj * 8 + k]) + s_bias[ch], 0.f);
-                            mbits |= (v[k] > 0.f ? 1u : 0u) << (pj * 8 + k);
+                            v[k] = fmaxf(acc[pj * 8 + k] + s_bias[ch], 0.f);
+                            mbits |= (v[k] > 0.f ? 1u : 0u) << (ch & 31);
                         }
                     }
                     if constexpr (EPI == EPI_CONV1) {
@@ -330,14 +427,14 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
                             if (valid) {
                                 using GU = Geo<28>;
                                 const int64_t p00 = (int64_t)b * GU::S + (2 * y + 1) * GU::Wp + 2 * c;
-                                uint8_t* dst = a.out + plane * a.out_ps + (p00 + GU::HALO) * 16;
+                                uint8_t* dst = a.out + plane * a.out_ps + (p00 + GU::GUARD) * 16;
                                 *reinterpret_cast<uint4*>(dst) = o;
                                 *reinterpret_cast<uint4*>(dst + 16) = o;
                                 *reinterpret_cast<uint4*>(dst + GU::Wp * 16) = o;
                                 *reinterpret_cast<uint4*>(dst + GU::Wp * 16 + 16) = o;
                             }
                         } else {
-                            *reinterpret_cast<uint4*>(a.out + plane * a.out_ps + (pos + G::HALO) * 16) = o;
+                            if (owned) *reinterpret_cast<uint4*>(a.out + plane * a.out_ps + (pos + G::GUARD) * 16) = o;
                         }
                     }
                     if constexpr (SKIPG) {
@@ -350,10 +447,13 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
                             const float s1 = __uint_as_float(r2[pj * 8 + 2 * k + 1]) + s_sbias[ch + 1];
                             ow[k] = valid ? pack_bf16x2(s0, s1) : 0u;
                         }
-                        *reinterpret_cast<uint4*>(a.out2 + plane * a.out2_ps + (pos + G::HALO) * 16) = o2;
+                        if (owned) *reinterpret_cast<uint4*>(a.out2 + plane * a.out2_ps + (pos + G::GUARD) * 16) = o2;
                     }
                 }
-                if (EPI != EPI_PLAIN && a.mask) a.mask[(c0 / 32) * a.mask_stride + pos] = valid ? mbits : 0u;
+                if ((c0 + CW) % 32 == 0) {
+                    if (EPI != EPI_PLAIN && a.mask && owned) a.mask[(c0 / 32) * a.mask_stride + pos] = valid ? mbits : 0u;
+                    mbits = 0;
+                }
             }
             if constexpr (EPI == EPI_FINAL) {
                 if (valid) {
@@ -373,20 +473,20 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
     if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
-template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9>
+template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, bool KXC = false>
 static int launch_conv(const ConvArgs& a, cudaStream_t st, const char* name) {
-    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS>;
-    auto kern = conv3x3_tc_kernel<W, CIN, COUT, EPI, SKIPG, TAPS>;
+    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC>;
+    auto kern = conv3x3_tc_kernel<W, CIN, COUT, EPI, SKIPG, TAPS, KXC>;
     static bool configured = false;
     if (!configured) {
         TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         configured = true;
     }
-    const int grid = a.nt < num_sms() ? a.nt : num_sms();
+    const int nt = (a.np + C::TSTRIDE - 1) / C::TSTRIDE;
+    const int grid = nt < num_sms() ? nt : num_sms();
     kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(a);
     TDM_CHECK_LAUNCH(name);
     return TDM_OK;
 }
-
 
 }  // namespace tdm

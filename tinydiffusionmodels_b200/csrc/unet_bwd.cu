@@ -99,11 +99,11 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const WgradArgs a) {
             uint8_t* st = s_in + s * C::STAGE_BYTES;
             if (lane < C::GPL) {
                 bulk_g2s(st + lane * (kTile * 16),
-                         a.g + lane * a.g_ps + ((int64_t)tile * kTile + G::HALO) * 16, kTile * 16,
+                         a.g + lane * a.g_ps + ((int64_t)tile * kTile + G::GUARD) * 16, kTile * 16,
                          bar_full + s);
             } else if (lane >= 16 && lane < 16 + C::XPL) {
                 const int j = lane - 16;
-                bulk_g2s(st + C::G_BYTES + j * (G::RT * 16), a.x + j * a.x_ps + (int64_t)tile * (kTile * 16),
+                bulk_g2s(st + C::G_BYTES + j * (G::RT * 16), a.x + j * a.x_ps + ((int64_t)tile * kTile - G::HALO + G::GUARD) * 16,
                          G::RT * 16, bar_full + s);
             }
         }
@@ -221,7 +221,7 @@ loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
             const int64_t i = (int64_t)b * 784 + (r - 1) * 28 + c;
             const float d = __ldg(eps + i) - __ldg(noise + i);
             const float g = 2.0f * d * inv_n;
-            const uint4 hv = *reinterpret_cast<const uint4*>(h4 + j * ps + (pos + G::HALO) * 16);
+            const uint4 hv = *reinterpret_cast<const uint4*>(h4 + j * ps + (pos + G::GUARD) * 16);
             const uint32_t* hw = &hv.x;
             uint32_t* ow = &o.x;
 #pragma unroll
@@ -236,7 +236,7 @@ loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
                 gsum += g;
             }
         }
-        *reinterpret_cast<uint4*>(go + j * ps + (pos + G::HALO) * 16) = o;
+        *reinterpret_cast<uint4*>(go + j * ps + (pos + G::GUARD) * 16) = o;
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -322,7 +322,7 @@ upsample_bwd_kernel(const uint8_t* __restrict__ in, int64_t in_ps, uint8_t* __re
     uint4 o = make_uint4(0, 0, 0, 0);
     if (b < batch && r >= 1 && c < GO::W) {
         const int64_t p00 = (int64_t)b * GI::S + (2 * (r - 1) + 1) * GI::Wp + 2 * c;
-        const uint8_t* src = in + plane * in_ps + (p00 + GI::HALO) * 16;
+        const uint8_t* src = in + plane * in_ps + (p00 + GI::GUARD) * 16;
         const uint4 q0 = *reinterpret_cast<const uint4*>(src);
         const uint4 q1 = *reinterpret_cast<const uint4*>(src + 16);
         const uint4 q2 = *reinterpret_cast<const uint4*>(src + GI::Wp * 16);
@@ -336,7 +336,7 @@ upsample_bwd_kernel(const uint8_t* __restrict__ in, int64_t in_ps, uint8_t* __re
             ow[k] = pack_bf16x2(f0.x + f1.x + f2.x + f3.x, f0.y + f1.y + f2.y + f3.y);
         }
     }
-    *reinterpret_cast<uint4*>(out + plane * out_ps + (pos + GO::HALO) * 16) = o;
+    *reinterpret_cast<uint4*>(out + plane * out_ps + (pos + GO::GUARD) * 16) = o;
 }
 
 // transpose of avg_pool2d(2) (src/mnist.py:80) added to the gradient h1 receives through the
@@ -355,8 +355,8 @@ pool_bwd_add_kernel(const uint8_t* __restrict__ a, int64_t a_ps, const uint8_t* 
     if (b < batch && r >= 1 && c < G28::W) {
         const int y = r - 1;
         const int64_t p14 = (int64_t)b * G14::S + (y / 2 + 1) * G14::Wp + c / 2;
-        const uint4 av = *reinterpret_cast<const uint4*>(a + plane * a_ps + (pos + G28::HALO) * 16);
-        const uint4 gv = *reinterpret_cast<const uint4*>(gp + plane * gp_ps + (p14 + G14::HALO) * 16);
+        const uint4 av = *reinterpret_cast<const uint4*>(a + plane * a_ps + (pos + G28::GUARD) * 16);
+        const uint4 gv = *reinterpret_cast<const uint4*>(gp + plane * gp_ps + (p14 + G14::GUARD) * 16);
         const uint32_t *aw = &av.x, *gw = &gv.x;
         uint32_t* ow = &o.x;
 #pragma unroll
@@ -365,7 +365,7 @@ pool_bwd_add_kernel(const uint8_t* __restrict__ a, int64_t a_ps, const uint8_t* 
             ow[k] = pack_bf16x2(fmaf(0.25f, h.x, f.x), fmaf(0.25f, h.y, f.y));
         }
     }
-    *reinterpret_cast<uint4*>(out + plane * out_ps + (pos + G28::HALO) * 16) = o;
+    *reinterpret_cast<uint4*>(out + plane * out_ps + (pos + G28::GUARD) * 16) = o;
 }
 
 // rb1.conv1 (Cin = 1) and rb1.skip (1x1, Cin = 1) weight gradients:
@@ -384,8 +384,8 @@ rb1_wgrad_kernel(const uint8_t* __restrict__ gc, const uint8_t* __restrict__ go,
         for (int i = tid; i < 128 * 4; i += 320) {
             const int p = i & 127, j = i >> 7;
             const int64_t pos = (int64_t)tile * 128 + p;
-            const uint4 v = *reinterpret_cast<const uint4*>(gc + j * ps + (pos + G::HALO) * 16);
-            const uint4 u = *reinterpret_cast<const uint4*>(go + j * ps + (pos + G::HALO) * 16);
+            const uint4 v = *reinterpret_cast<const uint4*>(gc + j * ps + (pos + G::GUARD) * 16);
+            const uint4 u = *reinterpret_cast<const uint4*>(go + j * ps + (pos + G::GUARD) * 16);
             const uint32_t *vw = &v.x, *uw = &u.x;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -479,7 +479,7 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     const float* fp = reinterpret_cast<const float*>(wp + WP::flat);
     const int B = (int)batch;
     const int nt28 = (int)L.nt28, nt14 = (int)L.nt14;
-    const int H28 = Geo<28>::HALO, H14 = Geo<14>::HALO, S28 = Geo<28>::S, S14 = Geo<14>::S;
+    const int H28 = Geo<28>::GUARD, H14 = Geo<14>::GUARD, S28 = Geo<28>::S, S14 = Geo<14>::S;
     auto M = [&](int64_t off) { return reinterpret_cast<const uint32_t*>(ws + off); };
     int rc;
     ConvArgs c{};
@@ -499,16 +499,16 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
                           dflat + P::rb4_sb, nullptr, dflat + P::rb4_c2b, st))) return rc;
     w = WgradArgs{ws + L.gc28, L.ps28, ws + L.t4, L.ps28, dflat + P::rb4_c2w, nt28};
     if ((rc = launch_wgrad<28, 32, 32, 9>(w, st, "wgrad_rb4_c2"))) return rc;
-    c = ConvArgs{}; c.t = t; c.batch = B; c.nt = nt28;
+    c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
     c.in = ws + L.gc28; c.in_ps = L.ps28; c.w = wp + WP::d_rb4_c2; c.out = ws + L.gh28; c.out_ps = L.ps28;
-    if ((rc = launch_conv<28, 32, 32, EPI_PLAIN, false>(c, st, "dgrad_rb4_c2"))) return rc;
+    if ((rc = launch_conv<28, 32, 32, EPI_PLAIN, false, 9, true>(c, st, "dgrad_rb4_c2"))) return rc;
     if ((rc = mask_reduce(ws + L.gh28, L.ps28, H28, M(L.m1_4), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
                           dflat + P::rb4_tb, dflat + P::rb4_tw, dflat + P::rb4_c1b, st))) return rc;
     w = WgradArgs{ws + L.gc28, L.ps28, ws + L.cat, L.ps28, dflat + P::rb4_c1w, nt28};
     if ((rc = launch_wgrad<28, 32, 96, 9>(w, st, "wgrad_rb4_c1"))) return rc;
     w = WgradArgs{ws + L.go28, L.ps28, ws + L.cat, L.ps28, dflat + P::rb4_sw, nt28};
     if ((rc = launch_wgrad<28, 32, 96, 1>(w, st, "wgrad_rb4_skip"))) return rc;
-    c = ConvArgs{}; c.t = t; c.batch = B; c.nt = nt28;
+    c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
     c.in = ws + L.gc28; c.in_ps = L.ps28; c.w = wp + WP::d_rb4_c1; c.out = ws + L.gcat; c.out_ps = L.ps28;
     if ((rc = launch_conv<28, 32, 96, EPI_PLAIN, false>(c, st, "dgrad_rb4_c1"))) return rc;
     c.in = ws + L.go28; c.w = wp + WP::d_rb4_sk; c.res = ws + L.gcat; c.res_ps = L.ps28;
@@ -523,35 +523,35 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
                           nullptr, nullptr, dflat + P::rb3_c2b, st))) return rc;
     w = WgradArgs{ws + L.gc14, L.ps14, ws + L.t3, L.ps14, dflat + P::rb3_c2w, nt14};
     if ((rc = launch_wgrad<14, 64, 64, 9>(w, st, "wgrad_rb3_c2"))) return rc;
-    c = ConvArgs{}; c.t = t; c.batch = B; c.nt = nt14;
+    c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
     c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb3_c2; c.out = ws + L.gh14; c.out_ps = L.ps14;
-    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false>(c, st, "dgrad_rb3_c2"))) return rc;
+    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false, 9, true>(c, st, "dgrad_rb3_c2"))) return rc;
     if ((rc = mask_reduce(ws + L.gh14, L.ps14, H14, M(L.m1_3), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
                           dflat + P::rb3_tb, dflat + P::rb3_tw, dflat + P::rb3_c1b, st))) return rc;
     w = WgradArgs{ws + L.gc14, L.ps14, ws + L.h2, L.ps14, dflat + P::rb3_c1w, nt14};
     if ((rc = launch_wgrad<14, 64, 64, 9>(w, st, "wgrad_rb3_c1"))) return rc;
-    c = ConvArgs{}; c.t = t; c.batch = B; c.nt = nt14;
+    c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
     c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb3_c1; c.res = ws + L.go14a; c.res_ps = L.ps14;
     c.out = ws + L.go14b; c.out_ps = L.ps14;   // g_out of rb2
-    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false>(c, st, "dgrad_rb3_c1"))) return rc;
+    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false, 9, true>(c, st, "dgrad_rb3_c1"))) return rc;
 
     // ---- rb2: x_in = p1 (32), h = t2, skip 32->64, g_out = go14b ----------------------------
     if ((rc = mask_reduce(ws + L.go14b, L.ps14, H14, M(L.m2_2), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
                           dflat + P::rb2_sb, nullptr, dflat + P::rb2_c2b, st))) return rc;
     w = WgradArgs{ws + L.gc14, L.ps14, ws + L.t2, L.ps14, dflat + P::rb2_c2w, nt14};
     if ((rc = launch_wgrad<14, 64, 64, 9>(w, st, "wgrad_rb2_c2"))) return rc;
-    c = ConvArgs{}; c.t = t; c.batch = B; c.nt = nt14;
+    c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
     c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb2_c2; c.out = ws + L.gh14; c.out_ps = L.ps14;
-    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false>(c, st, "dgrad_rb2_c2"))) return rc;
+    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false, 9, true>(c, st, "dgrad_rb2_c2"))) return rc;
     if ((rc = mask_reduce(ws + L.gh14, L.ps14, H14, M(L.m1_2), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
                           dflat + P::rb2_tb, dflat + P::rb2_tw, dflat + P::rb2_c1b, st))) return rc;
     w = WgradArgs{ws + L.gc14, L.ps14, ws + L.p1, L.ps14, dflat + P::rb2_c1w, nt14};
     if ((rc = launch_wgrad<14, 64, 32, 9>(w, st, "wgrad_rb2_c1"))) return rc;
     w = WgradArgs{ws + L.go14b, L.ps14, ws + L.p1, L.ps14, dflat + P::rb2_sw, nt14};
     if ((rc = launch_wgrad<14, 64, 32, 1>(w, st, "wgrad_rb2_skip"))) return rc;
-    c = ConvArgs{}; c.t = t; c.batch = B; c.nt = nt14;
+    c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
     c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb2_c1; c.out = ws + L.gp1; c.out_ps = L.ps14;
-    if ((rc = launch_conv<14, 64, 32, EPI_PLAIN, false>(c, st, "dgrad_rb2_c1"))) return rc;
+    if ((rc = launch_conv<14, 64, 32, EPI_PLAIN, false, 9, true>(c, st, "dgrad_rb2_c1"))) return rc;
     c.in = ws + L.go14b; c.w = wp + WP::d_rb2_sk; c.res = ws + L.gp1; c.res_ps = L.ps14;
     if ((rc = launch_conv<14, 64, 32, EPI_PLAIN, false, 1>(c, st, "dgrad_rb2_skip"))) return rc;
 
@@ -565,9 +565,9 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
                           dflat + P::rb1_sb, nullptr, dflat + P::rb1_c2b, st))) return rc;
     w = WgradArgs{ws + L.gc28, L.ps28, ws + L.t1, L.ps28, dflat + P::rb1_c2w, nt28};
     if ((rc = launch_wgrad<28, 32, 32, 9>(w, st, "wgrad_rb1_c2"))) return rc;
-    c = ConvArgs{}; c.t = t; c.batch = B; c.nt = nt28;
+    c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
     c.in = ws + L.gc28; c.in_ps = L.ps28; c.w = wp + WP::d_rb1_c2; c.out = ws + L.gh28; c.out_ps = L.ps28;
-    if ((rc = launch_conv<28, 32, 32, EPI_PLAIN, false>(c, st, "dgrad_rb1_c2"))) return rc;
+    if ((rc = launch_conv<28, 32, 32, EPI_PLAIN, false, 9, true>(c, st, "dgrad_rb1_c2"))) return rc;
     if ((rc = mask_reduce(ws + L.gh28, L.ps28, H28, M(L.m1_1), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
                           dflat + P::rb1_tb, dflat + P::rb1_tw, dflat + P::rb1_c1b, st))) return rc;
     {

@@ -34,34 +34,46 @@ struct PackJob {
     int64_t dst;   // byte offset into wpack
     int cin, cout, taps;  // of the FORWARD convolution
     int transpose;        // 1: emit the data-gradient image (channels swapped, taps flipped)
+    int kxc;              // 1: kx-combined image [ky][K/8][3*N][8] (n' = kx*N + n), else [tap][K/8][N][8]
 };
 constexpr int kPackJobs = 18;
 __constant__ PackJob c_jobs[kPackJobs] = {
-    {P::rb1_c2w, WP::rb1_c2, 32, 32, 9, 0}, {P::rb2_c1w, WP::rb2_c1, 32, 64, 9, 0},
-    {P::rb2_sw, WP::rb2_sk, 32, 64, 1, 0},  {P::rb2_c2w, WP::rb2_c2, 64, 64, 9, 0},
-    {P::rb3_c1w, WP::rb3_c1, 64, 64, 9, 0}, {P::rb3_c2w, WP::rb3_c2, 64, 64, 9, 0},
-    {P::rb4_c1w, WP::rb4_c1, 96, 32, 9, 0}, {P::rb4_sw, WP::rb4_sk, 96, 32, 1, 0},
-    {P::rb4_c2w, WP::rb4_c2, 32, 32, 9, 0},
-    {P::rb1_c2w, WP::d_rb1_c2, 32, 32, 9, 1}, {P::rb2_c2w, WP::d_rb2_c2, 64, 64, 9, 1},
-    {P::rb2_c1w, WP::d_rb2_c1, 32, 64, 9, 1}, {P::rb2_sw, WP::d_rb2_sk, 32, 64, 1, 1},
-    {P::rb3_c2w, WP::d_rb3_c2, 64, 64, 9, 1}, {P::rb3_c1w, WP::d_rb3_c1, 64, 64, 9, 1},
-    {P::rb4_c2w, WP::d_rb4_c2, 32, 32, 9, 1}, {P::rb4_c1w, WP::d_rb4_c1, 96, 32, 9, 1},
-    {P::rb4_sw, WP::d_rb4_sk, 96, 32, 1, 1}};
+    {P::rb1_c2w, WP::rb1_c2, 32, 32, 9, 0, 1}, {P::rb2_c1w, WP::rb2_c1, 32, 64, 9, 0, 1},
+    {P::rb2_sw, WP::rb2_sk, 32, 64, 1, 0, 0},  {P::rb2_c2w, WP::rb2_c2, 64, 64, 9, 0, 1},
+    {P::rb3_c1w, WP::rb3_c1, 64, 64, 9, 0, 1}, {P::rb3_c2w, WP::rb3_c2, 64, 64, 9, 0, 1},
+    {P::rb4_c1w, WP::rb4_c1, 96, 32, 9, 0, 1}, {P::rb4_sw, WP::rb4_sk, 96, 32, 1, 0, 0},
+    {P::rb4_c2w, WP::rb4_c2, 32, 32, 9, 0, 1},
+    {P::rb1_c2w, WP::d_rb1_c2, 32, 32, 9, 1, 1}, {P::rb2_c2w, WP::d_rb2_c2, 64, 64, 9, 1, 1},
+    {P::rb2_c1w, WP::d_rb2_c1, 32, 64, 9, 1, 1}, {P::rb2_sw, WP::d_rb2_sk, 32, 64, 1, 1, 0},
+    {P::rb3_c2w, WP::d_rb3_c2, 64, 64, 9, 1, 1}, {P::rb3_c1w, WP::d_rb3_c1, 64, 64, 9, 1, 1},
+    {P::rb4_c2w, WP::d_rb4_c2, 32, 32, 9, 1, 1}, {P::rb4_c1w, WP::d_rb4_c1, 96, 32, 9, 1, 0},
+    {P::rb4_sw, WP::d_rb4_sk, 96, 32, 1, 1, 0}};
 
 __global__ void pack_weights_kernel(const float* __restrict__ flat, uint8_t* __restrict__ wpack) {
     const PackJob j = c_jobs[blockIdx.y];
     const int n = j.taps * j.cin * j.cout;
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(wpack + j.dst);
-    // destination is [tap][K/8][N][8]: K = contraction channels, N = produced channels
+    // K = contraction channels, N = produced channels of the convolution this image feeds
     const int kch = j.transpose ? j.cout : j.cin;
     const int nch = j.transpose ? j.cin : j.cout;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int k = i & 7;
         int r = i >> 3;
-        const int nn = r % nch;
-        r /= nch;
-        const int cp = r % (kch / 8);
-        const int tap = r / (kch / 8);
+        int nn, cp, tap;
+        if (j.kxc) {
+            const int n3 = r % (3 * nch);
+            r /= 3 * nch;
+            cp = r % (kch / 8);
+            const int ky = r / (kch / 8);
+            const int kx = n3 / nch;
+            nn = n3 - kx * nch;
+            tap = ky * 3 + kx;
+        } else {
+            nn = r % nch;
+            r /= nch;
+            cp = r % (kch / 8);
+            tap = r / (kch / 8);
+        }
         const int kk = cp * 8 + k;
         const int co = j.transpose ? kk : nn;
         const int ci = j.transpose ? nn : kk;
@@ -128,7 +140,7 @@ rb1_conv1_kernel(const float* __restrict__ x, const int64_t* __restrict__ t,
     }
 #pragma unroll
     for (int p = 0; p < 4; ++p)
-        *reinterpret_cast<uint4*>(out + p * out_ps + (pos + G::HALO) * 16) = o[p];
+        *reinterpret_cast<uint4*>(out + p * out_ps + (pos + G::GUARD) * 16) = o[p];
     if (mask) mask[pos] = mbits;
 }
 
@@ -150,7 +162,7 @@ avgpool_kernel(const uint8_t* __restrict__ in, int64_t in_ps, uint8_t* __restric
     if (valid) {
         const int y = r - 1;
         const int64_t p00 = (int64_t)b * GI::S + (2 * y + 1) * GI::Wp + 2 * c;
-        const uint8_t* src = in + plane * in_ps + (p00 + GI::HALO) * 16;
+        const uint8_t* src = in + plane * in_ps + (p00 + GI::GUARD) * 16;
         const uint4 q0 = *reinterpret_cast<const uint4*>(src);
         const uint4 q1 = *reinterpret_cast<const uint4*>(src + 16);
         const uint4 q2 = *reinterpret_cast<const uint4*>(src + GI::Wp * 16);
@@ -165,7 +177,7 @@ avgpool_kernel(const uint8_t* __restrict__ in, int64_t in_ps, uint8_t* __restric
             ow[k] = pack_bf16x2((f0.x + f1.x + f2.x + f3.x) * 0.25f, (f0.y + f1.y + f2.y + f3.y) * 0.25f);
         }
     }
-    *reinterpret_cast<uint4*>(out + plane * out_ps + (pos + GO::HALO) * 16) = o;
+    *reinterpret_cast<uint4*>(out + plane * out_ps + (pos + GO::GUARD) * 16) = o;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -206,9 +218,9 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     // k2: rb1.conv2 -> h1 = cat planes 8..11
     a.in = ws + L.t1; a.in_ps = L.ps28; a.w = wp + WP::rb1_c2; a.bias = fp + P::rb1_c2b;
     a.out = ws + L.cat + 8 * L.ps28; a.out_ps = L.ps28;
-    a.x = x; a.aux_w = fp + P::rb1_sw; a.aux_b = fp + P::rb1_sb; a.nt = nt28;
+    a.x = x; a.aux_w = fp + P::rb1_sw; a.aux_b = fp + P::rb1_sb; a.np = (int)L.np28;
     a.mask = mk(L.m2_1); a.mask_stride = L.np28;
-    if ((rc = launch_conv<28, 32, 32, EPI_RES_X, false>(a, st, "rb1_conv2"))) return rc;
+    if ((rc = launch_conv<28, 32, 32, EPI_RES_X, false, 9, true>(a, st, "rb1_conv2"))) return rc;
 
     // k3: pool h1 -> p1
     TDM_PROF(2);
@@ -217,49 +229,49 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
 
     // k4: rb2.conv1 (+skip) -> t2, s2
     TDM_PROF(3);
-    a = ConvArgs{}; a.t = t; a.batch = B; a.nt = nt14;
+    a = ConvArgs{}; a.t = t; a.batch = B; a.np = (int)L.np14;
     a.in = ws + L.p1; a.in_ps = L.ps14; a.w = wp + WP::rb2_c1; a.bias = fp + P::rb2_c1b;
     a.tw = fp + P::rb2_tw; a.tb = fp + P::rb2_tb; a.sbias = fp + P::rb2_sb;
     a.out = ws + L.t2; a.out_ps = L.ps14; a.out2 = ws + L.s2; a.out2_ps = L.ps14;
     a.mask = mk(L.m1_2); a.mask_stride = L.np14;
-    if ((rc = launch_conv<14, 32, 64, EPI_CONV1, true>(a, st, "rb2_conv1"))) return rc;
+    if ((rc = launch_conv<14, 32, 64, EPI_CONV1, true, 9, true>(a, st, "rb2_conv1"))) return rc;
 
     // k5: rb2.conv2 + s2 -> h2
     TDM_PROF(4);
-    a = ConvArgs{}; a.t = t; a.batch = B; a.nt = nt14;
+    a = ConvArgs{}; a.t = t; a.batch = B; a.np = (int)L.np14;
     a.in = ws + L.t2; a.in_ps = L.ps14; a.w = wp + WP::rb2_c2; a.bias = fp + P::rb2_c2b;
     a.res = ws + L.s2; a.res_ps = L.ps14; a.out = ws + L.h2; a.out_ps = L.ps14;
     a.mask = mk(L.m2_2); a.mask_stride = L.np14;
-    if ((rc = launch_conv<14, 64, 64, EPI_RES, false>(a, st, "rb2_conv2"))) return rc;
+    if ((rc = launch_conv<14, 64, 64, EPI_RES, false, 9, true>(a, st, "rb2_conv2"))) return rc;
 
     // k6: rb3.conv1 -> t3
     TDM_PROF(5);
-    a = ConvArgs{}; a.t = t; a.batch = B; a.nt = nt14;
+    a = ConvArgs{}; a.t = t; a.batch = B; a.np = (int)L.np14;
     a.in = ws + L.h2; a.in_ps = L.ps14; a.w = wp + WP::rb3_c1; a.bias = fp + P::rb3_c1b;
     a.tw = fp + P::rb3_tw; a.tb = fp + P::rb3_tb; a.out = ws + L.t3; a.out_ps = L.ps14;
     a.mask = mk(L.m1_3); a.mask_stride = L.np14;
-    if ((rc = launch_conv<14, 64, 64, EPI_CONV1, false>(a, st, "rb3_conv1"))) return rc;
+    if ((rc = launch_conv<14, 64, 64, EPI_CONV1, false, 9, true>(a, st, "rb3_conv1"))) return rc;
 
     // k7: rb3.conv2 + h2 -> upsampled into cat planes 0..7
     TDM_PROF(6);
-    a = ConvArgs{}; a.t = t; a.batch = B; a.nt = nt14;
+    a = ConvArgs{}; a.t = t; a.batch = B; a.np = (int)L.np14;
     a.in = ws + L.t3; a.in_ps = L.ps14; a.w = wp + WP::rb3_c2; a.bias = fp + P::rb3_c2b;
     a.res = ws + L.h2; a.res_ps = L.ps14; a.out = ws + L.cat; a.out_ps = L.ps28;
     a.mask = mk(L.m2_3); a.mask_stride = L.np14;
-    if ((rc = launch_conv<14, 64, 64, EPI_RES_UP, false>(a, st, "rb3_conv2"))) return rc;
+    if ((rc = launch_conv<14, 64, 64, EPI_RES_UP, false, 9, true>(a, st, "rb3_conv2"))) return rc;
 
     // k8: rb4.conv1 (+skip) -> t4, s4
     TDM_PROF(7);
-    a = ConvArgs{}; a.t = t; a.batch = B; a.nt = nt28;
+    a = ConvArgs{}; a.t = t; a.batch = B; a.np = (int)L.np28;
     a.in = ws + L.cat; a.in_ps = L.ps28; a.w = wp + WP::rb4_c1; a.bias = fp + P::rb4_c1b;
     a.tw = fp + P::rb4_tw; a.tb = fp + P::rb4_tb; a.sbias = fp + P::rb4_sb;
     a.out = ws + L.t4; a.out_ps = L.ps28; a.out2 = ws + L.s4; a.out2_ps = L.ps28;
     a.mask = mk(L.m1_4); a.mask_stride = L.np28;
-    if ((rc = launch_conv<28, 96, 32, EPI_CONV1, true>(a, st, "rb4_conv1"))) return rc;
+    if ((rc = launch_conv<28, 96, 32, EPI_CONV1, true, 9, true>(a, st, "rb4_conv1"))) return rc;
 
     // k9: rb4.conv2 + s4, out conv, optional reverse step
     TDM_PROF(8);
-    a = ConvArgs{}; a.t = t; a.batch = B; a.nt = nt28;
+    a = ConvArgs{}; a.t = t; a.batch = B; a.np = (int)L.np28;
     a.in = ws + L.t4; a.in_ps = L.ps28; a.w = wp + WP::rb4_c2; a.bias = fp + P::rb4_c2b;
     a.res = ws + L.s4; a.res_ps = L.ps28; a.aux_w = fp + P::out_w; a.aux_b = fp + P::out_b;
     a.fout = fout; a.x = sa.fuse_step ? x : nullptr;
@@ -267,7 +279,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     if (sa.train) { a.out = ws + L.h4; a.out_ps = L.ps28; }
     a.fuse_step = sa.fuse_step; a.z = sa.z; a.betas = sa.betas; a.alphas = sa.alphas;
     a.sqrt_om = sa.sqrt_om; a.seed = sa.seed; a.sample_offset = sa.sample_offset; a.step_id = sa.step_id;
-    if ((rc = launch_conv<28, 32, 32, EPI_FINAL, false>(a, st, "rb4_conv2"))) return rc;
+    if ((rc = launch_conv<28, 32, 32, EPI_FINAL, false, 9, true>(a, st, "rb4_conv2"))) return rc;
     TDM_PROF(9);
     return TDM_OK;
 }

@@ -8,8 +8,8 @@
 // Channels are stored in groups of 8 bf16 (16 bytes): tensor[plane = c/8][pos][c%8].  A plane
 // is a dense array of 16-byte rows, which is exactly the un-swizzled K-major core-matrix layout
 // tcgen05.mma reads, with the tap offset applied as a start-address shift.
-// Each plane has HALO guard rows on both sides (zeros, never written) so a tile's halo read
-// never leaves the allocation.
+// Each plane has GUARD zero rows in front and TAIL zero rows behind (never written) so a tile's
+// halo read never leaves the allocation.
 #pragma once
 #include <cstdint>
 
@@ -24,15 +24,18 @@ struct Geo {
     static constexpr int S = (W_ + 1) * (W_ + 1);
     static constexpr int HALO = (W_ == 28) ? 32 : 16;  // >= Wp + 1
     static constexpr int RT = kTile + 2 * HALO;        // smem rows per plane per tile
+    static constexpr int GUARD = HALO + 8;             // zero rows in front of position 0 in HBM
+    static constexpr int TAIL = HALO + kTile;          // zero rows after the last tile (kx-combined
+                                                       // tiles overlap and may start up to 127 rows late)
     static_assert(HALO >= Wp + 1, "halo must cover the largest tap offset");
 };
 
 __host__ __device__ inline int64_t num_tiles(int64_t batch, int S) {
     return (batch * S + kTile - 1) / kTile;
 }
-// rows allocated per plane
+// rows allocated per plane: GUARD | nt*128 positions | TAIL
 __host__ __device__ inline int64_t plane_rows(int64_t batch, int S, int halo) {
-    return num_tiles(batch, S) * kTile + 2 * halo;
+    return num_tiles(batch, S) * kTile + (halo + 8) + (halo + kTile);
 }
 
 // ---- flat fp32 parameter vector (reference state_dict order) -----------------
