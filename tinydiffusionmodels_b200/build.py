@@ -27,6 +27,11 @@ NVCC_FLAGS = [
 ]
 
 
+def _flags() -> list[str]:
+    extra = os.environ.get("TDM_NVCC_DEFS", "").split()   # e.g. -DTDM_KXC_MASK=0x7f (schedule sweeps)
+    return NVCC_FLAGS + extra
+
+
 def _nvcc() -> str:
     for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and Path(cand).exists():
@@ -43,7 +48,7 @@ def _digest() -> str:
     for f in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [PKG.parent / "include" / "tdm_b200.h"]):
         h.update(f.name.encode())
         h.update(f.read_bytes())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(_flags()).encode())
     return h.hexdigest()
 
 
@@ -58,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(src: Path) -> tuple[Path, str]:
         obj = OBJ / (src.stem + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        cmd = [nvcc, *_flags(), "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src.name}:\n{r.stdout}\n{r.stderr}")

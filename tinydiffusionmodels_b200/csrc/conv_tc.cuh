@@ -5,7 +5,8 @@
 //               per iteration via 1-D bulk async copies into a ring of smem stages
 //   warp 1      one thread issues the tcgen05.mma of a tile (M = 128 positions, K = 16 channels);
 //               the A operand of every tap is the same smem tile at a shifted row offset
-//   warps 2..   kEpiGroups groups of 4 epilogue warps; group g owns TMEM accumulator stage g
+//   warps 2..   kEpiGroups groups of 8 epilogue warps; group g owns TMEM accumulator stage g; inside a
+//               group two warps share each TMEM lane quarter and take alternate 16-channel chunks
 //
 // Two MMA schedules:
 //   KXC = false  nine taps, N = COUT each:            D[p]            = sum_tap W_tap X[p + off(tap)]
@@ -62,7 +63,8 @@ struct ConvArgs {
     int64_t mask_stride;
 };
 
-constexpr int kEpiGroups = 2;  // epilogue warp groups == TMEM accumulator stages
+constexpr int kEpiGroups = 4;  // epilogue warp groups == TMEM accumulator stages (tiles in flight)
+constexpr int kHalves = 1;     // warps per TMEM lane quarter inside a group (2: alternate 16-channel chunks)
 
 template <int W, int CIN, int COUT, bool SKIPG, int TAPS, bool KXC>
 struct ConvCfg {
@@ -72,7 +74,7 @@ struct ConvCfg {
     static constexpr int WCONV_BYTES = TAPS * CIN * COUT * 2;
     static constexpr int W_BYTES = WCONV_BYTES + (SKIPG ? CIN * COUT * 2 : 0);
     static constexpr int PARAM_BYTES = 5 * 96 * 4;
-    static constexpr int XCH_BYTES = KXC ? kEpiGroups * 4 * 2 * COUT * 4 : 0;
+    static constexpr int XCH_BYTES = (KXC ? kEpiGroups * kHalves * 4 * 2 * COUT * 4 : 0) + kEpiGroups * 2 * 128 * 4;
     static constexpr int MAX_SMEM = 227 * 1024;
     static constexpr int AVAIL = MAX_SMEM - W_BYTES - PARAM_BYTES - XCH_BYTES - 256;
     static constexpr int NSTAGE = (AVAIL / STAGE_BYTES) > 4 ? 4 : (AVAIL / STAGE_BYTES);
@@ -85,12 +87,12 @@ struct ConvCfg {
     static_assert(NACC * ACC_COLS <= 512, "accumulators exceed TMEM");
     static_assert(NMAIN <= 256 && NMAIN % 16 == 0, "UMMA N");
     static constexpr int SMEM_BYTES = W_BYTES + NSTAGE * STAGE_BYTES + PARAM_BYTES + XCH_BYTES + 256;
-    // warp 0 producer, warp 1 MMA issuer, then NACC groups of 4 epilogue warps
-    static constexpr int THREADS = 64 + 128 * NACC;
+    // warp 0 producer, warp 1 MMA issuer, then NACC groups of 8 epilogue warps
+    static constexpr int THREADS = 64 + 128 * kHalves * NACC;
     // tile t: accumulator rows [t*TSTRIDE - ROW0, +128), output rows are tile rows [ROW0, 128-ROW0)
     static constexpr int TSTRIDE = KXC ? 126 : 128;
     static constexpr int ROW0 = KXC ? 1 : 0;
-    static constexpr int CW = KXC ? 16 : 32;   // channels per epilogue chunk
+    static constexpr int CW = 16;              // channels per epilogue chunk
 };
 
 template <int N>
@@ -104,7 +106,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 }
 
 template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, bool KXC = false>
-__global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(const ConvArgs a) {
+__global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups, 1) conv3x3_tc_kernel(const ConvArgs a) {
     using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC>;
     using G = Geo<W>;
     static_assert(COUT == 32 || COUT == 64 || COUT == 96, "COUT");
@@ -123,8 +125,9 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
     float* s_tb = s_par + 192;
     float* s_sbias = s_par + 288;
     float* s_aux = s_par + 384;
-    float* s_xch = s_par + 480;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_xch) + C::XCH_BYTES);
+    float* s_dot = s_par + 480;                       // [grp][tile parity][128] partial out-conv dots
+    float* s_xch = s_dot + kEpiGroups * 2 * 128;      // kx-combine boundary rows
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_dot) + C::XCH_BYTES);
     uint64_t* bar_w = bars;
     uint64_t* bar_full = bars + 1;
     uint64_t* bar_empty = bar_full + C::NSTAGE;
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
         }
         for (int i = 0; i < C::NACC; ++i) {
             mbar_init(bar_accf + i, 1);
-            mbar_init(bar_acce + i, 4);  // one arrival per epilogue warp
+            mbar_init(bar_acce + i, 4 * kHalves);  // one arrival per epilogue warp
         }
         mbar_fence_init();
     }
@@ -254,7 +257,8 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
         // ===== epilogue: group g = (warp-2)/4 owns accumulator stage g (tiles it = g, g+NACC, ..),
         //       so the epilogues of consecutive tiles overlap; TMEM lane quarter = warp % 4 =====
         const int q = warp & 3;
-        const int grp = (warp - 2) >> 2;
+        const int grp = (warp - 2) / (4 * kHalves);
+        const int half = ((warp - 2) >> 2) % kHalves;   // which alternate 16-channel chunks this warp owns
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * C::ACC_COLS;
         int n = 0;
         for (int tile = blockIdx.x + grp * gridDim.x; tile < nt; tile += C::NACC * gridDim.x, ++n) {
@@ -272,23 +276,25 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
             float ts = 0.f;
             if (EPI == EPI_CONV1 && valid) ts = (float)__ldg(a.t + b) / 1000.0f;
             float xin = 0.f;
-            if ((EPI == EPI_RES_X || EPI == EPI_FINAL) && valid && a.x)
+            if ((EPI == EPI_RES_X || (EPI == EPI_FINAL && half == 0)) && valid && a.x)
                 xin = __ldg(a.x + (int64_t)b * 784 + y * 28 + c);
             constexpr bool kHasRes = (EPI == EPI_RES || EPI == EPI_RES_UP || EPI == EPI_FINAL || EPI == EPI_PLAIN);
-            uint4 rv[kHasRes ? COUT / 8 : 1];
+            // residual planes of this warp's chunks only: local index i -> plane (i/2)*4 + half*2 + i%2
+            uint4 rv[kHasRes ? COUT / (8 * kHalves) : 1];
             if constexpr (kHasRes) {
 #pragma unroll
-                for (int pl = 0; pl < COUT / 8; ++pl) {
-                    rv[pl] = make_uint4(0, 0, 0, 0);
+                for (int i = 0; i < COUT / (8 * kHalves); ++i) {
+                    const int pl = (kHalves == 2) ? (i >> 1) * 4 + half * 2 + (i & 1) : i;
+                    rv[i] = make_uint4(0, 0, 0, 0);
                     if (valid && (EPI != EPI_PLAIN || a.res))  // residual planes share this geometry
-                        rv[pl] = *reinterpret_cast<const uint4*>(a.res + pl * a.res_ps + (pos + G::GUARD) * 16);
+                        rv[i] = *reinterpret_cast<const uint4*>(a.res + pl * a.res_ps + (pos + G::GUARD) * 16);
                 }
             }
             StepCoef sc{};
             float zz = 0.f;
             bool add_noise = false;
             if constexpr (EPI == EPI_FINAL) {
-                if (a.fuse_step && valid) {
+                if (a.fuse_step && valid && half == 0) {   // half 0 finishes the pixel
                     add_noise = __ldg(a.t) != 0;  // src/mnist.py:176
                     const int64_t tb = __ldg(a.t + b);
                     sc = step_coef(tb, a.betas, a.alphas, a.sqrt_om);
@@ -314,7 +320,9 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
             uint32_t mbits = 0;
 
 #pragma unroll
-            for (int c0 = 0; c0 < COUT; c0 += CW) {
+            for (int ci = 0; ci < COUT / (kHalves * CW); ++ci) {
+                const int c0 = (kHalves * ci + half) * CW;
+                const bool last_chunk = ci == COUT / (kHalves * CW) - 1;
                 float acc[CW];
                 uint32_t r2[CW];
                 if constexpr (KXC) {
@@ -324,7 +332,7 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
                     tmem_ld_n<CW>(taddr + 2 * COUT + c0, d2);
                     if constexpr (SKIPG) tmem_ld_n<CW>(taddr + 3 * COUT + c0, r2);
                     tmem_ld_wait();
-                    if (c0 + CW >= COUT) {
+                    if (last_chunk) {
                         // all TMEM reads of this accumulator are done: hand it back to the MMA warp
                         tc_fence_before_sync();
                         __syncwarp();
@@ -333,7 +341,7 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
                     // rows p-1 / p+1 are lanes -1 / +1; across the warp boundary they come through smem.
                     // Everything below is branch-free per channel (selects, broadcast loads): per-channel
                     // `if (lane == 0)` patches compile to divergent branches and dominated the kernel.
-                    float4* xs = reinterpret_cast<float4*>(s_xch + ((grp * 4 + q) * 2) * COUT + c0);
+                    float4* xs = reinterpret_cast<float4*>(s_xch + ((grp * 4 + q) * 2) * COUT + c0);   // per (group, quarter)
                     if (lane == 31) {
 #pragma unroll
                         for (int k = 0; k < CW / 4; ++k)
@@ -346,7 +354,7 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
                             xs[COUT / 4 + k] = make_float4(__uint_as_float(d2[4 * k]), __uint_as_float(d2[4 * k + 1]),
                                                            __uint_as_float(d2[4 * k + 2]), __uint_as_float(d2[4 * k + 3]));
                     }
-                    named_bar_sync(1 + grp, 128);
+                    named_bar_sync(1 + grp * kHalves + half, 128);   // the 4 warps (quarters) sharing this chunk
                     // q == 0 / q == 3: tile rows 0 / 127 are never output rows, any finite value will do
                     const float4* xprev = reinterpret_cast<const float4*>(s_xch + ((grp * 4 + (q > 0 ? q - 1 : 0)) * 2) * COUT + c0);
                     const float4* xnext = reinterpret_cast<const float4*>(s_xch + ((grp * 4 + (q < 3 ? q + 1 : 3)) * 2 + 1) * COUT + c0);
@@ -368,7 +376,7 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
                     tmem_ld_n<CW>(taddr + c0, r1);
                     if constexpr (SKIPG) tmem_ld_n<CW>(taddr + COUT + c0, r2);
                     tmem_ld_wait();
-                    if (c0 + CW >= COUT) {
+                    if (last_chunk) {
                         tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_acce + grp);
@@ -387,8 +395,11 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
                             v[k] = acc[pj * 8 + k];
                         } else {
                             v[k] = fmaxf(acc[pj * 8 + k] + s_bias[ch], 0.f);
-                            mbits |= (v[k] > 0.f ? 1u : 0u) << (ch & 31);
                         }
+                    }
+                    if (EPI != EPI_PLAIN && a.mask) {   // training only (uniform branch)
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) mbits |= (v[k] > 0.f ? 1u : 0u) << ((c0 + pj * 8 + k) & 31);
                     }
                     if constexpr (EPI == EPI_CONV1) {
 #pragma unroll
@@ -403,7 +414,7 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
                             v[k] += fmaf(s_aux[ch], xin, s_aux[32 + ch]);
                         }
                     } else {
-                        const uint32_t* rw = &rv[plane].x;
+                        const uint32_t* rw = &rv[ci * 2 + pj].x;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const float2 f = unpack_bf16x2(rw[k]);
@@ -450,13 +461,22 @@ __global__ void __launch_bounds__(64 + 128 * kEpiGroups, 1) conv3x3_tc_kernel(co
                         if (owned) *reinterpret_cast<uint4*>(a.out2 + plane * a.out2_ps + (pos + G::GUARD) * 16) = o2;
                     }
                 }
-                if ((c0 + CW) % 32 == 0) {
-                    if (EPI != EPI_PLAIN && a.mask && owned) a.mask[(c0 / 32) * a.mask_stride + pos] = valid ? mbits : 0u;
-                    mbits = 0;
+                if (EPI != EPI_PLAIN && a.mask && owned) {
+                    // one uint32 per 32 channels per position; this warp owns 16 of its bits
+                    uint16_t* m16 = reinterpret_cast<uint16_t*>(a.mask + (c0 / 32) * a.mask_stride + pos);
+                    m16[(c0 >> 4) & 1] = valid ? (uint16_t)(mbits >> (c0 & 16)) : (uint16_t)0;
                 }
+                mbits = 0;
             }
             if constexpr (EPI == EPI_FINAL) {
-                if (valid) {
+                // the two halves each hold a partial dot of the 1x1 out conv: half 1 hands its part over
+                if constexpr (kHalves == 2) {
+                    float* sd = s_dot + (grp * 2 + (n & 1)) * 128 + trow;
+                    if (half == 1) *sd = dot;
+                    named_bar_sync(9 + grp, 256);
+                    if (half == 0) dot += *sd;
+                }
+                if (half == 0 && valid) {
                     const float eps = dot + s_aux[32];  // out conv bias (src/mnist.py:87)
                     const int64_t oi = (int64_t)b * 784 + y * 28 + c;
                     a.fout[oi] = a.fuse_step ? rstep1(sc, xin, eps, zz, add_noise) : eps;

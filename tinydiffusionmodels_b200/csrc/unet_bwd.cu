@@ -501,7 +501,7 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = launch_wgrad<28, 32, 32, 9>(w, st, "wgrad_rb4_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
     c.in = ws + L.gc28; c.in_ps = L.ps28; c.w = wp + WP::d_rb4_c2; c.out = ws + L.gh28; c.out_ps = L.ps28;
-    if ((rc = launch_conv<28, 32, 32, EPI_PLAIN, false, 9, true>(c, st, "dgrad_rb4_c2"))) return rc;
+    if ((rc = launch_conv<28, 32, 32, EPI_PLAIN, false, 9, KX::rb4c2>(c, st, "dgrad_rb4_c2"))) return rc;
     if ((rc = mask_reduce(ws + L.gh28, L.ps28, H28, M(L.m1_4), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
                           dflat + P::rb4_tb, dflat + P::rb4_tw, dflat + P::rb4_c1b, st))) return rc;
     w = WgradArgs{ws + L.gc28, L.ps28, ws + L.cat, L.ps28, dflat + P::rb4_c1w, nt28};
@@ -525,7 +525,7 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = launch_wgrad<14, 64, 64, 9>(w, st, "wgrad_rb3_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
     c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb3_c2; c.out = ws + L.gh14; c.out_ps = L.ps14;
-    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false, 9, true>(c, st, "dgrad_rb3_c2"))) return rc;
+    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false, 9, KX::rb3c2>(c, st, "dgrad_rb3_c2"))) return rc;
     if ((rc = mask_reduce(ws + L.gh14, L.ps14, H14, M(L.m1_3), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
                           dflat + P::rb3_tb, dflat + P::rb3_tw, dflat + P::rb3_c1b, st))) return rc;
     w = WgradArgs{ws + L.gc14, L.ps14, ws + L.h2, L.ps14, dflat + P::rb3_c1w, nt14};
@@ -533,7 +533,7 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
     c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb3_c1; c.res = ws + L.go14a; c.res_ps = L.ps14;
     c.out = ws + L.go14b; c.out_ps = L.ps14;   // g_out of rb2
-    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false, 9, true>(c, st, "dgrad_rb3_c1"))) return rc;
+    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false, 9, KX::rb3c1>(c, st, "dgrad_rb3_c1"))) return rc;
 
     // ---- rb2: x_in = p1 (32), h = t2, skip 32->64, g_out = go14b ----------------------------
     if ((rc = mask_reduce(ws + L.go14b, L.ps14, H14, M(L.m2_2), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
@@ -542,7 +542,7 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = launch_wgrad<14, 64, 64, 9>(w, st, "wgrad_rb2_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
     c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb2_c2; c.out = ws + L.gh14; c.out_ps = L.ps14;
-    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false, 9, true>(c, st, "dgrad_rb2_c2"))) return rc;
+    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false, 9, KX::rb2c2>(c, st, "dgrad_rb2_c2"))) return rc;
     if ((rc = mask_reduce(ws + L.gh14, L.ps14, H14, M(L.m1_2), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
                           dflat + P::rb2_tb, dflat + P::rb2_tw, dflat + P::rb2_c1b, st))) return rc;
     w = WgradArgs{ws + L.gc14, L.ps14, ws + L.p1, L.ps14, dflat + P::rb2_c1w, nt14};
@@ -551,7 +551,7 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = launch_wgrad<14, 64, 32, 1>(w, st, "wgrad_rb2_skip"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
     c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb2_c1; c.out = ws + L.gp1; c.out_ps = L.ps14;
-    if ((rc = launch_conv<14, 64, 32, EPI_PLAIN, false, 9, true>(c, st, "dgrad_rb2_c1"))) return rc;
+    if ((rc = launch_conv<14, 64, 32, EPI_PLAIN, false, 9, KX::rb2c1>(c, st, "dgrad_rb2_c1"))) return rc;
     c.in = ws + L.go14b; c.w = wp + WP::d_rb2_sk; c.res = ws + L.gp1; c.res_ps = L.ps14;
     if ((rc = launch_conv<14, 64, 32, EPI_PLAIN, false, 1>(c, st, "dgrad_rb2_skip"))) return rc;
 
@@ -567,7 +567,7 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = launch_wgrad<28, 32, 32, 9>(w, st, "wgrad_rb1_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
     c.in = ws + L.gc28; c.in_ps = L.ps28; c.w = wp + WP::d_rb1_c2; c.out = ws + L.gh28; c.out_ps = L.ps28;
-    if ((rc = launch_conv<28, 32, 32, EPI_PLAIN, false, 9, true>(c, st, "dgrad_rb1_c2"))) return rc;
+    if ((rc = launch_conv<28, 32, 32, EPI_PLAIN, false, 9, KX::rb1c2>(c, st, "dgrad_rb1_c2"))) return rc;
     if ((rc = mask_reduce(ws + L.gh28, L.ps28, H28, M(L.m1_1), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
                           dflat + P::rb1_tb, dflat + P::rb1_tw, dflat + P::rb1_c1b, st))) return rc;
     {

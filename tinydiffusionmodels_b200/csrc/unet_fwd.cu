@@ -38,15 +38,16 @@ struct PackJob {
 };
 constexpr int kPackJobs = 18;
 __constant__ PackJob c_jobs[kPackJobs] = {
-    {P::rb1_c2w, WP::rb1_c2, 32, 32, 9, 0, 1}, {P::rb2_c1w, WP::rb2_c1, 32, 64, 9, 0, 1},
-    {P::rb2_sw, WP::rb2_sk, 32, 64, 1, 0, 0},  {P::rb2_c2w, WP::rb2_c2, 64, 64, 9, 0, 1},
-    {P::rb3_c1w, WP::rb3_c1, 64, 64, 9, 0, 1}, {P::rb3_c2w, WP::rb3_c2, 64, 64, 9, 0, 1},
-    {P::rb4_c1w, WP::rb4_c1, 96, 32, 9, 0, 1}, {P::rb4_sw, WP::rb4_sk, 96, 32, 1, 0, 0},
-    {P::rb4_c2w, WP::rb4_c2, 32, 32, 9, 0, 1},
-    {P::rb1_c2w, WP::d_rb1_c2, 32, 32, 9, 1, 1}, {P::rb2_c2w, WP::d_rb2_c2, 64, 64, 9, 1, 1},
-    {P::rb2_c1w, WP::d_rb2_c1, 32, 64, 9, 1, 1}, {P::rb2_sw, WP::d_rb2_sk, 32, 64, 1, 1, 0},
-    {P::rb3_c2w, WP::d_rb3_c2, 64, 64, 9, 1, 1}, {P::rb3_c1w, WP::d_rb3_c1, 64, 64, 9, 1, 1},
-    {P::rb4_c2w, WP::d_rb4_c2, 32, 32, 9, 1, 1}, {P::rb4_c1w, WP::d_rb4_c1, 96, 32, 9, 1, 0},
+    {P::rb1_c2w, WP::rb1_c2, 32, 32, 9, 0, KX::rb1c2}, {P::rb2_c1w, WP::rb2_c1, 32, 64, 9, 0, KX::rb2c1},
+    {P::rb2_sw, WP::rb2_sk, 32, 64, 1, 0, 0},          {P::rb2_c2w, WP::rb2_c2, 64, 64, 9, 0, KX::rb2c2},
+    {P::rb3_c1w, WP::rb3_c1, 64, 64, 9, 0, KX::rb3c1}, {P::rb3_c2w, WP::rb3_c2, 64, 64, 9, 0, KX::rb3c2},
+    {P::rb4_c1w, WP::rb4_c1, 96, 32, 9, 0, KX::rb4c1}, {P::rb4_sw, WP::rb4_sk, 96, 32, 1, 0, 0},
+    {P::rb4_c2w, WP::rb4_c2, 32, 32, 9, 0, KX::rb4c2},
+    // data-gradient images follow the schedule of the forward conv they transpose
+    {P::rb1_c2w, WP::d_rb1_c2, 32, 32, 9, 1, KX::rb1c2}, {P::rb2_c2w, WP::d_rb2_c2, 64, 64, 9, 1, KX::rb2c2},
+    {P::rb2_c1w, WP::d_rb2_c1, 32, 64, 9, 1, KX::rb2c1}, {P::rb2_sw, WP::d_rb2_sk, 32, 64, 1, 1, 0},
+    {P::rb3_c2w, WP::d_rb3_c2, 64, 64, 9, 1, KX::rb3c2}, {P::rb3_c1w, WP::d_rb3_c1, 64, 64, 9, 1, KX::rb3c1},
+    {P::rb4_c2w, WP::d_rb4_c2, 32, 32, 9, 1, KX::rb4c2}, {P::rb4_c1w, WP::d_rb4_c1, 96, 32, 9, 1, 0},
     {P::rb4_sw, WP::d_rb4_sk, 96, 32, 1, 1, 0}};
 
 __global__ void pack_weights_kernel(const float* __restrict__ flat, uint8_t* __restrict__ wpack) {
@@ -220,7 +221,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     a.out = ws + L.cat + 8 * L.ps28; a.out_ps = L.ps28;
     a.x = x; a.aux_w = fp + P::rb1_sw; a.aux_b = fp + P::rb1_sb; a.np = (int)L.np28;
     a.mask = mk(L.m2_1); a.mask_stride = L.np28;
-    if ((rc = launch_conv<28, 32, 32, EPI_RES_X, false, 9, true>(a, st, "rb1_conv2"))) return rc;
+    if ((rc = launch_conv<28, 32, 32, EPI_RES_X, false, 9, KX::rb1c2>(a, st, "rb1_conv2"))) return rc;
 
     // k3: pool h1 -> p1
     TDM_PROF(2);
@@ -234,7 +235,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     a.tw = fp + P::rb2_tw; a.tb = fp + P::rb2_tb; a.sbias = fp + P::rb2_sb;
     a.out = ws + L.t2; a.out_ps = L.ps14; a.out2 = ws + L.s2; a.out2_ps = L.ps14;
     a.mask = mk(L.m1_2); a.mask_stride = L.np14;
-    if ((rc = launch_conv<14, 32, 64, EPI_CONV1, true, 9, true>(a, st, "rb2_conv1"))) return rc;
+    if ((rc = launch_conv<14, 32, 64, EPI_CONV1, true, 9, KX::rb2c1>(a, st, "rb2_conv1"))) return rc;
 
     // k5: rb2.conv2 + s2 -> h2
     TDM_PROF(4);
@@ -242,7 +243,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     a.in = ws + L.t2; a.in_ps = L.ps14; a.w = wp + WP::rb2_c2; a.bias = fp + P::rb2_c2b;
     a.res = ws + L.s2; a.res_ps = L.ps14; a.out = ws + L.h2; a.out_ps = L.ps14;
     a.mask = mk(L.m2_2); a.mask_stride = L.np14;
-    if ((rc = launch_conv<14, 64, 64, EPI_RES, false, 9, true>(a, st, "rb2_conv2"))) return rc;
+    if ((rc = launch_conv<14, 64, 64, EPI_RES, false, 9, KX::rb2c2>(a, st, "rb2_conv2"))) return rc;
 
     // k6: rb3.conv1 -> t3
     TDM_PROF(5);
@@ -250,7 +251,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     a.in = ws + L.h2; a.in_ps = L.ps14; a.w = wp + WP::rb3_c1; a.bias = fp + P::rb3_c1b;
     a.tw = fp + P::rb3_tw; a.tb = fp + P::rb3_tb; a.out = ws + L.t3; a.out_ps = L.ps14;
     a.mask = mk(L.m1_3); a.mask_stride = L.np14;
-    if ((rc = launch_conv<14, 64, 64, EPI_CONV1, false, 9, true>(a, st, "rb3_conv1"))) return rc;
+    if ((rc = launch_conv<14, 64, 64, EPI_CONV1, false, 9, KX::rb3c1>(a, st, "rb3_conv1"))) return rc;
 
     // k7: rb3.conv2 + h2 -> upsampled into cat planes 0..7
     TDM_PROF(6);
@@ -258,7 +259,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     a.in = ws + L.t3; a.in_ps = L.ps14; a.w = wp + WP::rb3_c2; a.bias = fp + P::rb3_c2b;
     a.res = ws + L.h2; a.res_ps = L.ps14; a.out = ws + L.cat; a.out_ps = L.ps28;
     a.mask = mk(L.m2_3); a.mask_stride = L.np14;
-    if ((rc = launch_conv<14, 64, 64, EPI_RES_UP, false, 9, true>(a, st, "rb3_conv2"))) return rc;
+    if ((rc = launch_conv<14, 64, 64, EPI_RES_UP, false, 9, KX::rb3c2>(a, st, "rb3_conv2"))) return rc;
 
     // k8: rb4.conv1 (+skip) -> t4, s4
     TDM_PROF(7);
@@ -267,7 +268,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     a.tw = fp + P::rb4_tw; a.tb = fp + P::rb4_tb; a.sbias = fp + P::rb4_sb;
     a.out = ws + L.t4; a.out_ps = L.ps28; a.out2 = ws + L.s4; a.out2_ps = L.ps28;
     a.mask = mk(L.m1_4); a.mask_stride = L.np28;
-    if ((rc = launch_conv<28, 96, 32, EPI_CONV1, true, 9, true>(a, st, "rb4_conv1"))) return rc;
+    if ((rc = launch_conv<28, 96, 32, EPI_CONV1, true, 9, KX::rb4c1>(a, st, "rb4_conv1"))) return rc;
 
     // k9: rb4.conv2 + s4, out conv, optional reverse step
     TDM_PROF(8);
@@ -279,7 +280,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     if (sa.train) { a.out = ws + L.h4; a.out_ps = L.ps28; }
     a.fuse_step = sa.fuse_step; a.z = sa.z; a.betas = sa.betas; a.alphas = sa.alphas;
     a.sqrt_om = sa.sqrt_om; a.seed = sa.seed; a.sample_offset = sa.sample_offset; a.step_id = sa.step_id;
-    if ((rc = launch_conv<28, 32, 32, EPI_FINAL, false, 9, true>(a, st, "rb4_conv2"))) return rc;
+    if ((rc = launch_conv<28, 32, 32, EPI_FINAL, false, 9, KX::rb4c2>(a, st, "rb4_conv2"))) return rc;
     TDM_PROF(9);
     return TDM_OK;
 }

@@ -106,4 +106,20 @@ constexpr int64_t flat = (bf16_end + 255) / 256 * 256;     // fp32 copy of the f
 constexpr int64_t total = (flat + 4LL * P::count + 255) / 256 * 256;
 }  // namespace WP
 
+// ---- MMA schedule per 3x3 convolution (conv_tc.cuh): bit set = kx-combined (N = 3*Cout) ------------
+// Chosen from measurements on B200 (profiles/r01_kxc_sweep.txt): combining pays where the MMA count
+// dominates (rb4.conv1, K = 9*96); elsewhere the leaner nine-tap epilogue wins.
+#ifndef TDM_KXC_MASK
+#define TDM_KXC_MASK 0x20
+#endif
+namespace KX {
+constexpr bool rb1c2 = (TDM_KXC_MASK >> 0) & 1;
+constexpr bool rb2c1 = (TDM_KXC_MASK >> 1) & 1;
+constexpr bool rb2c2 = (TDM_KXC_MASK >> 2) & 1;
+constexpr bool rb3c1 = (TDM_KXC_MASK >> 3) & 1;
+constexpr bool rb3c2 = (TDM_KXC_MASK >> 4) & 1;
+constexpr bool rb4c1 = (TDM_KXC_MASK >> 5) & 1;
+constexpr bool rb4c2 = (TDM_KXC_MASK >> 6) & 1;
+}  // namespace KX
+
 }  // namespace tdm
