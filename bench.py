@@ -280,9 +280,15 @@ def run_ours(args) -> None:
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
     achieved_tf = flops[top] * B / (kms[top] * 1e-3) / 1e12
     step_ms_sum = sum(kms)
+    traffic = None
+    tfile = ROOT / "profiles" / "r01_traffic_rb4_conv1.json"
+    if tfile.exists():
+        tj = json.loads(tfile.read_text())
+        if tj.get("kernel") == names[top] and tj.get("batch") == B:
+            traffic = tj["dram_bytes_per_launch"]   # dram read+write of one launch, ncu --set full
     roofline = {
         "bound": "tensor", "kernel": names[top], "achieved": achieved_tf, "peak": peak_tf,
-        "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+        "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
         "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
         "kernel_ms": {n: round(v, 4) for n, v in zip(names, kms)},
         "kernel_share_of_step": round(kms[top] / step_ms_sum, 4),
@@ -291,6 +297,8 @@ def run_ours(args) -> None:
 
     # ---- secondary metric: UNet train images/s (BASELINE.json configs[1]), data-parallel ------
     train = bench_train(dev, rank, world, args.train_batch, barrier)
+    # ---- secondary metric: Shakespeare sampler sequences/s (BASELINE.json configs[3], [4]) -----
+    text = bench_text(dev, rank, world, args.text_batch, barrier) if not args.no_text else None
 
     if rank != 0:
         if world > 1:
@@ -320,6 +328,7 @@ def run_ours(args) -> None:
                          "sample": "20 of 1000 reverse steps at batch 64 (oracle port of src/mnist.py:167-180), extrapolated x50"},
         "clocks": clocks,
         "train": train,
+        "text": text,
     }
     print(json.dumps(line))
     if world > 1:
@@ -390,6 +399,84 @@ def bench_train(dev, rank, world, batch, barrier, steps: int = 30, warmup: int =
     }
 
 
+def bench_text(dev, rank, world, batch, barrier, rsteps: int = 100) -> dict:
+    """Shakespeare embedding-space sampler (src/shakespeare.py:355-426): TinyTransformer(256), L=64,
+    `batch` sequences per GPU.  Times `rsteps` graph-replayed reverse steps (of the T=1000 loop) and
+    the learned-rounding argmax at V=256,000; sequences/s = batch / (1000*step + rounding)."""
+    import torch
+    import torch.distributed as dist
+
+    from tinydiffusionmodels_b200 import _lib
+    from tinydiffusionmodels_b200.shakespeare import LearnedRounding, TinyTransformer
+    from tinydiffusionmodels_b200.text_engine import Rounder
+
+    torch.manual_seed(0)
+    dim, L, V = 256, 64, 256_000
+    model = TinyTransformer(dim).to(dev).eval()
+    eng = model.engine(batch, L)
+    x = torch.randn(batch, L, dim, device=dev)
+    t = torch.full((batch,), 999, device=dev, dtype=torch.int64)
+    eng.load_state(x, t)
+
+    def one():
+        eng.p_sample_inplace(t, None, seed=3, sample_offset=rank * batch)
+        _lib.check(eng.lib.tdm_timestep_advance(t.data_ptr(), batch, -1, _lib.stream_ptr(dev)), "advance")
+
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        one()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    n0 = _lib.launch_count()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        one()
+    launches = _lib.launch_count() - n0
+    t.fill_(999)
+    for _ in range(5):
+        g.replay()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(rsteps):
+        g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / rsteps
+    rf = LearnedRounding(dim, V).to(dev)
+    rounder = Rounder(dev)
+    z = eng.read(0)
+    rounder.argmax(z, weight=rf.decoder.weight, bias=rf.decoder.bias)
+    e0.record()
+    for _ in range(3):
+        rounder.argmax(z, weight=rf.decoder.weight, bias=rf.decoder.bias)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_round = e0.elapsed_time(e1) / 3
+    ar = torch.randn(batch, V, device=dev)
+    rounder.argmax(z[:, 0], weight=rf.decoder.weight, bias=rf.decoder.bias, ar_logits=ar, alpha=0.3)
+    e0.record()
+    for _ in range(3):
+        rounder.argmax(z[:, 0], weight=rf.decoder.weight, bias=rf.decoder.bias, ar_logits=ar, alpha=0.3)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_mix = e0.elapsed_time(e1) / 3
+    tot = torch.tensor([1000 * ms_step + ms_round], device=dev)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    flop_tok = 8_060_928
+    return {
+        "metric": "shakespeare_sequences_per_sec_T1000", "unit": "sequences/s",
+        "value": world * batch / (float(tot.item()) * 1e-3),
+        "config": {"workload": f"TinyTransformer(dim=256, depth 3, 4 heads), L=64, {batch} sequences per GPU, "
+                               f"T=1000 reverse steps + learned rounding argmax over V={V}; random-init weights"},
+        "ms_per_reverse_step": ms_step, "reverse_steps_timed": rsteps, "ms_rounding": ms_round,
+        "denoiser_tflops": flop_tok * L * batch / (ms_step * 1e-3) / 1e12,
+        "guided_mix_ms_per_position": ms_mix, "gpu_launches_per_reverse_step": int(launches),
+        "dtype": "bf16 (fp32 residual stream, LayerNorm, softmax, accumulation)",
+    }
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -398,6 +485,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--batch", type=int, default=4096, help="samples per GPU per step")
     ap.add_argument("--train-batch", type=int, default=512, help="training images per GPU per step")
+    ap.add_argument("--text-batch", type=int, default=512, help="text sequences per GPU (secondary metric)")
+    ap.add_argument("--no-text", action="store_true", help="skip the text secondary metric")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
