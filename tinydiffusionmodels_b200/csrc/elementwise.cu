@@ -10,12 +10,13 @@
 
 namespace tdm {
 
-constexpr int kThreads = 256;
+// One block = one sample x one chunk of kThreads*kUnroll float4s (grid = (batch, chunks)): the sample
+// index, its timestep and the schedule coefficients are block-uniform, so nothing per element needs an
+// integer division or an IEEE divide/sqrt.  A warp touches 512 contiguous bytes per access.
+constexpr int kThreads = 64;
 constexpr int kUnroll = 4;  // float4s per thread -> 64 B in flight per stream per thread
+constexpr int kChunk4 = kThreads * kUnroll;
 
-__device__ __forceinline__ float4 ldg4(const float* p) {
-    return __ldg(reinterpret_cast<const float4*>(p));
-}
 __device__ __forceinline__ float4 ldcs4(const float* p) {
     return __ldcs(reinterpret_cast<const float4*>(p));  // streaming: read once
 }
@@ -31,41 +32,35 @@ __global__ void __launch_bounds__(kThreads)
 q_sample_kernel(const float* __restrict__ x0, const float* __restrict__ noise,
                 const int64_t* __restrict__ t, const float* __restrict__ sqrt_acp,
                 const float* __restrict__ sqrt_om, float* __restrict__ noise_out,
-                float* __restrict__ out, int64_t total4, uint32_t inner4, uint64_t seed,
-                uint64_t sample_offset, uint32_t stream_id, const int64_t* __restrict__ stream_dev) {
-    const int64_t base = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+                float* __restrict__ out, uint32_t inner4, uint64_t seed, uint64_t sample_offset,
+                uint32_t stream_id, const int64_t* __restrict__ stream_dev) {
+    const int64_t b = blockIdx.x;
+    const uint32_t q0 = blockIdx.y * kChunk4 + threadIdx.x;
     if (kPhilox && stream_dev) stream_id += (uint32_t)__ldg(stream_dev);
+    const int64_t tb = __ldg(t + b);
+    const float ca = __ldg(sqrt_acp + tb), cb = __ldg(sqrt_om + tb);
+    const int64_t base = b * (int64_t)inner4;
     float4 xv[kUnroll], nv[kUnroll];
-    float ca[kUnroll], cb[kUnroll];
-    int64_t idx[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-        idx[u] = base + (int64_t)u * kThreads;
-        if (idx[u] < total4) {
-            xv[u] = ldcs4(x0 + idx[u] * 4);
-            const int64_t b = idx[u] / inner4;
-            const int64_t tb = __ldg(t + b);
-            ca[u] = __ldg(sqrt_acp + tb);
-            cb[u] = __ldg(sqrt_om + tb);
-            if constexpr (kPhilox) {
-                const uint32_t quad = (uint32_t)(idx[u] - b * inner4);
-                nv[u] = philox_normal4(seed, sample_offset + (uint64_t)b, quad, stream_id,
-                                       kDomainQSample);
-            } else {
-                nv[u] = ldcs4(noise + idx[u] * 4);
-            }
+        const uint32_t q = q0 + u * kThreads;
+        if (q < inner4) {
+            xv[u] = ldcs4(x0 + (base + q) * 4);
+            if constexpr (kPhilox) nv[u] = philox_normal4(seed, sample_offset + (uint64_t)b, q, stream_id, kDomainQSample);
+            else nv[u] = ldcs4(noise + (base + q) * 4);
         }
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-        if (idx[u] < total4) {
+        const uint32_t q = q0 + u * kThreads;
+        if (q < inner4) {
             float4 o;
-            o.x = __fadd_rn(__fmul_rn(ca[u], xv[u].x), __fmul_rn(cb[u], nv[u].x));
-            o.y = __fadd_rn(__fmul_rn(ca[u], xv[u].y), __fmul_rn(cb[u], nv[u].y));
-            o.z = __fadd_rn(__fmul_rn(ca[u], xv[u].z), __fmul_rn(cb[u], nv[u].z));
-            o.w = __fadd_rn(__fmul_rn(ca[u], xv[u].w), __fmul_rn(cb[u], nv[u].w));
-            stcs4(out + idx[u] * 4, o);
-            if constexpr (kPhilox) stcs4(noise_out + idx[u] * 4, nv[u]);
+            o.x = __fadd_rn(__fmul_rn(ca, xv[u].x), __fmul_rn(cb, nv[u].x));
+            o.y = __fadd_rn(__fmul_rn(ca, xv[u].y), __fmul_rn(cb, nv[u].y));
+            o.z = __fadd_rn(__fmul_rn(ca, xv[u].z), __fmul_rn(cb, nv[u].z));
+            o.w = __fadd_rn(__fmul_rn(ca, xv[u].w), __fmul_rn(cb, nv[u].w));
+            stcs4(out + (base + q) * 4, o);
+            if constexpr (kPhilox) stcs4(noise_out + (base + q) * 4, nv[u]);
         }
     }
 }
@@ -78,66 +73,63 @@ __global__ void __launch_bounds__(kThreads)
 reverse_step_kernel(const float* __restrict__ x, const float* __restrict__ eps,
                     const float* __restrict__ z, const int64_t* __restrict__ t,
                     const float* __restrict__ betas, const float* __restrict__ alphas,
-                    const float* __restrict__ sqrt_om, float* __restrict__ out, int64_t total4,
-                    uint32_t inner4, uint64_t seed, uint64_t sample_offset, uint32_t step_id) {
+                    const float* __restrict__ sqrt_om, float* __restrict__ out, uint32_t inner4,
+                    uint64_t seed, uint64_t sample_offset, uint32_t step_id) {
     // the reference decides "last step" from t[0] for the whole batch (src/mnist.py:176)
     const bool add_noise = __ldg(t) != 0;
-    const int64_t base = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+    const int64_t b = blockIdx.x;
+    const uint32_t q0 = blockIdx.y * kChunk4 + threadIdx.x;
+    const int64_t tb = __ldg(t + b);
+    const StepCoef c = step_coef(tb, betas, alphas, sqrt_om);   // block-uniform
+    const int64_t base = b * (int64_t)inner4;
     float4 xv[kUnroll], ev[kUnroll], zv[kUnroll];
-    StepCoef c[kUnroll];
-    int64_t idx[kUnroll];
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-        idx[u] = base + (int64_t)u * kThreads;
-        if (idx[u] < total4) {
-            xv[u] = ldcs4(x + idx[u] * 4);
-            ev[u] = ldcs4(eps + idx[u] * 4);
-            const int64_t b = idx[u] / inner4;
-            const int64_t tb = __ldg(t + b);
-            c[u] = step_coef(tb, betas, alphas, sqrt_om);
-            if constexpr (kPhilox) {
-                const uint32_t quad = (uint32_t)(idx[u] - b * inner4);
-                zv[u] = add_noise ? philox_normal4(seed, sample_offset + (uint64_t)b, quad,
-                                                   step_id + (uint32_t)tb, kDomainReverse)
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-            } else {
-                zv[u] = add_noise ? ldcs4(z + idx[u] * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t q = q0 + u * kThreads;
+        if (q < inner4) {
+            xv[u] = ldcs4(x + (base + q) * 4);
+            ev[u] = ldcs4(eps + (base + q) * 4);
+            zv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (add_noise) {
+                if constexpr (kPhilox)
+                    zv[u] = philox_normal4(seed, sample_offset + (uint64_t)b, q, step_id + (uint32_t)tb, kDomainReverse);
+                else
+                    zv[u] = ldcs4(z + (base + q) * 4);
             }
         }
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-        if (idx[u] < total4) {
+        const uint32_t q = q0 + u * kThreads;
+        if (q < inner4) {
             float4 o;
-            o.x = rstep1(c[u], xv[u].x, ev[u].x, zv[u].x, add_noise);
-            o.y = rstep1(c[u], xv[u].y, ev[u].y, zv[u].y, add_noise);
-            o.z = rstep1(c[u], xv[u].z, ev[u].z, zv[u].z, add_noise);
-            o.w = rstep1(c[u], xv[u].w, ev[u].w, zv[u].w, add_noise);
-            stcs4(out + idx[u] * 4, o);
+            o.x = rstep1(c, xv[u].x, ev[u].x, zv[u].x, add_noise);
+            o.y = rstep1(c, xv[u].y, ev[u].y, zv[u].y, add_noise);
+            o.z = rstep1(c, xv[u].z, ev[u].z, zv[u].z, add_noise);
+            o.w = rstep1(c, xv[u].w, ev[u].w, zv[u].w, add_noise);
+            stcs4(out + (base + q) * 4, o);
         }
     }
 }
 
 __global__ void __launch_bounds__(kThreads)
-randn_kernel(float* __restrict__ out, int64_t total4, uint32_t inner4, uint64_t seed,
-             uint64_t sample_offset, uint32_t stream_id) {
-    const int64_t base = (int64_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+randn_kernel(float* __restrict__ out, uint32_t inner4, uint64_t seed, uint64_t sample_offset,
+             uint32_t stream_id) {
+    const int64_t b = blockIdx.x;
+    const uint32_t q0 = blockIdx.y * kChunk4 + threadIdx.x;
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
-        const int64_t idx = base + (int64_t)u * kThreads;
-        if (idx < total4) {
-            const int64_t b = idx / inner4;
-            const uint32_t quad = (uint32_t)(idx - b * inner4);
-            stcs4(out + idx * 4,
-                  philox_normal4(seed, sample_offset + (uint64_t)b, quad, stream_id, kDomainInit));
-        }
+        const uint32_t q = q0 + u * kThreads;
+        if (q < inner4)
+            stcs4(out + (b * (int64_t)inner4 + q) * 4,
+                  philox_normal4(seed, sample_offset + (uint64_t)b, q, stream_id, kDomainInit));
     }
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(256)
 unit_range_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
     // (clamp(x,-1,1) + 1) / 2 with the reference's op order (src/mnist.py:194)
-    int64_t i = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 4;
+    int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
     if (i + 3 < n) {
         float4 v = ldcs4(x + i);
         v.x = __fdiv_rn(__fadd_rn(fminf(fmaxf(v.x, -1.f), 1.f), 1.f), 2.f);
@@ -156,9 +148,11 @@ __global__ void add_i64_kernel(int64_t* __restrict__ t, int64_t n, int64_t delta
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-static inline unsigned grid_for(int64_t total4) {
-    return (unsigned)((total4 + (int64_t)kThreads * kUnroll - 1) / ((int64_t)kThreads * kUnroll));
+static inline dim3 grid_for(int64_t batch, int64_t inner4) {
+    return dim3((unsigned)batch, (unsigned)((inner4 + kChunk4 - 1) / kChunk4));
 }
+#define TDM_CHECK_EW_SHAPE(who)                                                                          \
+    TDM_CHECK_ARG(batch <= 0x7fffffffLL && inner / 4 <= 65535LL * kChunk4, who ": tensor too large for one launch")
 
 }  // namespace tdm
 
@@ -172,9 +166,9 @@ extern "C" int tdm_q_sample(const float* x0, const float* noise, const int64_t* 
     TDM_CHECK_ARG(batch >= 0 && inner > 0 && n_steps > 0, "tdm_q_sample: bad sizes");
     TDM_CHECK_ARG(inner % 4 == 0, "tdm_q_sample: inner (%lld) must be a multiple of 4", (long long)inner);
     TDM_CHECK_ARG(aligned16(x0) && aligned16(noise) && aligned16(out), "tdm_q_sample: 16-byte alignment required");
-    const int64_t total4 = batch * inner / 4;
-    q_sample_kernel<false><<<grid_for(total4), kThreads, 0, (cudaStream_t)stream>>>(
-        x0, noise, t, sqrt_acp, sqrt_om_acp, nullptr, out, total4, (uint32_t)(inner / 4), 0, 0, 0, nullptr);
+    TDM_CHECK_EW_SHAPE("tdm_q_sample");
+    q_sample_kernel<false><<<grid_for(batch, inner / 4), kThreads, 0, (cudaStream_t)stream>>>(
+        x0, noise, t, sqrt_acp, sqrt_om_acp, nullptr, out, (uint32_t)(inner / 4), 0, 0, 0, nullptr);
     TDM_CHECK_LAUNCH("tdm_q_sample");
     return TDM_OK;
 }
@@ -189,9 +183,9 @@ extern "C" int tdm_q_sample_philox(const float* x0, const int64_t* t, const floa
     TDM_CHECK_ARG(batch >= 0 && inner > 0 && n_steps > 0, "tdm_q_sample_philox: bad sizes");
     TDM_CHECK_ARG(inner % 4 == 0, "tdm_q_sample_philox: inner must be a multiple of 4");
     TDM_CHECK_ARG(aligned16(x0) && aligned16(noise_out) && aligned16(out), "tdm_q_sample_philox: 16-byte alignment required");
-    const int64_t total4 = batch * inner / 4;
-    q_sample_kernel<true><<<grid_for(total4), kThreads, 0, (cudaStream_t)stream>>>(
-        x0, nullptr, t, sqrt_acp, sqrt_om_acp, noise_out, out, total4, (uint32_t)(inner / 4), seed,
+    TDM_CHECK_EW_SHAPE("tdm_q_sample_philox");
+    q_sample_kernel<true><<<grid_for(batch, inner / 4), kThreads, 0, (cudaStream_t)stream>>>(
+        x0, nullptr, t, sqrt_acp, sqrt_om_acp, noise_out, out, (uint32_t)(inner / 4), seed,
         sample_offset, stream_id, stream_id_dev);
     TDM_CHECK_LAUNCH("tdm_q_sample_philox");
     return TDM_OK;
@@ -207,13 +201,13 @@ extern "C" int tdm_reverse_step(const float* x, const float* eps, const float* z
     TDM_CHECK_ARG(inner % 4 == 0, "tdm_reverse_step: inner must be a multiple of 4");
     TDM_CHECK_ARG(aligned16(x) && aligned16(eps) && aligned16(out) && (!z || aligned16(z)),
                   "tdm_reverse_step: 16-byte alignment required");
-    const int64_t total4 = batch * inner / 4;
+    TDM_CHECK_EW_SHAPE("tdm_reverse_step");
     if (z)
-        reverse_step_kernel<false><<<grid_for(total4), kThreads, 0, (cudaStream_t)stream>>>(
-            x, eps, z, t, betas, alphas, sqrt_om_acp, out, total4, (uint32_t)(inner / 4), 0, 0, 0);
+        reverse_step_kernel<false><<<grid_for(batch, inner / 4), kThreads, 0, (cudaStream_t)stream>>>(
+            x, eps, z, t, betas, alphas, sqrt_om_acp, out, (uint32_t)(inner / 4), 0, 0, 0);
     else
-        reverse_step_kernel<true><<<grid_for(total4), kThreads, 0, (cudaStream_t)stream>>>(
-            x, eps, nullptr, t, betas, alphas, sqrt_om_acp, out, total4, (uint32_t)(inner / 4), seed,
+        reverse_step_kernel<true><<<grid_for(batch, inner / 4), kThreads, 0, (cudaStream_t)stream>>>(
+            x, eps, nullptr, t, betas, alphas, sqrt_om_acp, out, (uint32_t)(inner / 4), seed,
             sample_offset, step_id);
     TDM_CHECK_LAUNCH("tdm_reverse_step");
     return TDM_OK;
@@ -225,9 +219,9 @@ extern "C" int tdm_randn_philox(float* out, int64_t batch, int64_t inner, uint64
     TDM_CHECK_ARG(out, "tdm_randn_philox: null pointer");
     TDM_CHECK_ARG(batch >= 0 && inner > 0 && inner % 4 == 0, "tdm_randn_philox: inner must be a positive multiple of 4");
     TDM_CHECK_ARG(aligned16(out), "tdm_randn_philox: 16-byte alignment required");
-    const int64_t total4 = batch * inner / 4;
-    randn_kernel<<<grid_for(total4), kThreads, 0, (cudaStream_t)stream>>>(
-        out, total4, (uint32_t)(inner / 4), seed, sample_offset, stream_id);
+    TDM_CHECK_EW_SHAPE("tdm_randn_philox");
+    randn_kernel<<<grid_for(batch, inner / 4), kThreads, 0, (cudaStream_t)stream>>>(
+        out, (uint32_t)(inner / 4), seed, sample_offset, stream_id);
     TDM_CHECK_LAUNCH("tdm_randn_philox");
     return TDM_OK;
 }
@@ -238,7 +232,7 @@ extern "C" int tdm_to_unit_range(const float* x, float* out, int64_t n, void* st
     TDM_CHECK_ARG(aligned16(x) && aligned16(out), "tdm_to_unit_range: 16-byte alignment required");
     if (n == 0) return TDM_OK;
     const int64_t nthreads = (n + 3) / 4;
-    unit_range_kernel<<<(unsigned)((nthreads + kThreads - 1) / kThreads), kThreads, 0,
+    unit_range_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0,
                         (cudaStream_t)stream>>>(x, out, n);
     TDM_CHECK_LAUNCH("tdm_to_unit_range");
     return TDM_OK;
