@@ -313,6 +313,18 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups, 1) conv3x3_tc
                 }
             }
 
+            int up_p00[2] = {0, 0};
+            bool up_ok[2] = {false, false};
+            if constexpr (EPI == EPI_RES_UP) {
+                const int my_p00 = b * Geo<28>::S + (2 * y + 1) * Geo<28>::Wp + 2 * c;   // top-left of the 2x2 block
+#pragma unroll
+                for (int hs = 0; hs < 2; ++hs) {
+                    const int src = (lane >> 1) + 16 * hs;
+                    up_p00[hs] = __shfl_sync(0xffffffffu, my_p00, src);
+                    up_ok[hs] = __shfl_sync(0xffffffffu, (int)valid, src) != 0;
+                }
+            }
+
             // ---- phase B: drain the accumulator ----
             mbar_wait(bar_accf + grp, aph);
             tc_fence_after_sync();
@@ -433,16 +445,25 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups, 1) conv3x3_tc
                         o.z = valid ? pack_bf16x2(v[4], v[5]) : 0u;
                         o.w = valid ? pack_bf16x2(v[6], v[7]) : 0u;
                         if constexpr (EPI == EPI_RES_UP) {
-                            // nearest x2 upsample (src/mnist.py:83): one 14x14 pixel -> 2x2 block
-                            // of the 28x28 geometry; pad positions there keep their initial zeros.
-                            if (valid) {
-                                using GU = Geo<28>;
-                                const int64_t p00 = (int64_t)b * GU::S + (2 * y + 1) * GU::Wp + 2 * c;
-                                uint8_t* dst = a.out + plane * a.out_ps + (p00 + GU::GUARD) * 16;
-                                *reinterpret_cast<uint4*>(dst) = o;
-                                *reinterpret_cast<uint4*>(dst + 16) = o;
-                                *reinterpret_cast<uint4*>(dst + GU::Wp * 16) = o;
-                                *reinterpret_cast<uint4*>(dst + GU::Wp * 16 + 16) = o;
+                            // nearest x2 upsample (src/mnist.py:83): one 14x14 pixel -> 2x2 block of the
+                            // 28x28 geometry; pad positions there keep their initial zeros.  Lanes hold
+                            // consecutive source pixels whose destinations are 32 B apart, so lane pairs
+                            // (2k, 2k+1) take pixel k's value and write the two adjacent 16 B halves:
+                            // every store instruction covers contiguous sectors instead of half-sectors.
+                            uint8_t* plane_base = a.out + plane * a.out_ps + (int64_t)Geo<28>::GUARD * 16;
+#pragma unroll
+                            for (int hs = 0; hs < 2; ++hs) {
+                                const int src = (lane >> 1) + 16 * hs;
+                                uint4 v;
+                                v.x = __shfl_sync(0xffffffffu, o.x, src);
+                                v.y = __shfl_sync(0xffffffffu, o.y, src);
+                                v.z = __shfl_sync(0xffffffffu, o.z, src);
+                                v.w = __shfl_sync(0xffffffffu, o.w, src);
+                                if (up_ok[hs]) {
+                                    uint8_t* dst = plane_base + ((int64_t)up_p00[hs] + (lane & 1)) * 16;
+                                    *reinterpret_cast<uint4*>(dst) = v;
+                                    *reinterpret_cast<uint4*>(dst + Geo<28>::Wp * 16) = v;
+                                }
                             }
                         } else {
                             if (owned) *reinterpret_cast<uint4*>(a.out + plane * a.out_ps + (pos + G::GUARD) * 16) = o;
