@@ -8,6 +8,9 @@
 // Epilogues (thread = output row, all N columns of the tile in registers 32 at a time):
 //   GE_BF16    bias (+ReLU) -> bf16 planes                      (QKV, FFN1 of nn.TransformerEncoderLayer)
 //   GE_RES_F32 bias + fp32 residual -> fp32 planes (pre-LN)     (attention out-proj, FFN2)
+//   GE_RES_LN  N == 256 only: bias + fp32 residual, then LayerNorm of the whole row in the epilogue
+//              (row = one thread; the pre-LN values are parked back in the accumulator's TMEM columns
+//              between the statistics pass and the normalise pass) -> fp32 + bf16 planes
 //   GE_ARGMAX  running (max, argmax) over N, optionally mixed with AR logits — the logits are
 //              never written (src/shakespeare.py:389-390, 398-401, 451-467)
 #pragma once
@@ -16,7 +19,7 @@
 
 namespace tdm {
 
-enum : int { GE_BF16 = 0, GE_RES_F32 = 1, GE_ARGMAX = 2 };
+enum : int { GE_BF16 = 0, GE_RES_F32 = 1, GE_ARGMAX = 2, GE_RES_LN = 3 };
 
 constexpr int kBM = 128, kBN = 256, kBK = 64;
 constexpr int kGemmStages = 4;
@@ -44,6 +47,10 @@ struct GemmArgs {
     int64_t res_ps;
     uint8_t* out_f32;      // GE_RES_F32: fp32 planes
     int64_t of_ps;
+    // GE_RES_LN: LayerNorm affine + outputs (fp32 planes -> out_f32, bf16 planes -> out_bf16)
+    const float* gamma;
+    const float* beta;
+    float ln_eps;
     // GE_ARGMAX
     const float* row_scale;  // [M] multiplies the dot product (cosine: 1/||x||), or null
     const float* ar;         // [M][ar_ld] fp32 AR logits, or null
@@ -166,12 +173,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                 const uint32_t aph = (n_mine++) & 1;
                 mbar_wait(bar_accf + grp, aph);
                 tc_fence_after_sync();
+                float ln_sum = 0.f, ln_sq = 0.f;
 #pragma unroll 1
                 for (int c0 = 0; c0 < kBN; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld32(taddr + c0, r);
                     tmem_ld_wait();
-                    if (c0 + 32 == kBN) {
+                    if (EPI != GE_RES_LN && c0 + 32 == kBN) {
                         tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_acce + grp);
@@ -206,6 +214,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                                 *reinterpret_cast<float4*>(a.out_f32 + pl * a.of_ps + (int64_t)row * 16) = o;
                             }
                         }
+                    } else if constexpr (EPI == GE_RES_LN) {
+                        // pass 1 of 2: v = acc + bias + residual; row statistics; park v in TMEM
+                        uint32_t vb[32];
+#pragma unroll
+                        for (int pj = 0; pj < 8; ++pj) {
+                            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (rvalid) rv = *reinterpret_cast<const float4*>(a.res + (int64_t)(nb / 4 + pj) * a.res_ps + (int64_t)row * 16);
+                            const float v0 = __uint_as_float(r[pj * 4 + 0]) + __ldg(a.bias + nb + pj * 4 + 0) + rv.x;
+                            const float v1 = __uint_as_float(r[pj * 4 + 1]) + __ldg(a.bias + nb + pj * 4 + 1) + rv.y;
+                            const float v2 = __uint_as_float(r[pj * 4 + 2]) + __ldg(a.bias + nb + pj * 4 + 2) + rv.z;
+                            const float v3 = __uint_as_float(r[pj * 4 + 3]) + __ldg(a.bias + nb + pj * 4 + 3) + rv.w;
+                            ln_sum += (v0 + v1) + (v2 + v3);
+                            ln_sq = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, ln_sq))));
+                            vb[pj * 4 + 0] = __float_as_uint(v0);
+                            vb[pj * 4 + 1] = __float_as_uint(v1);
+                            vb[pj * 4 + 2] = __float_as_uint(v2);
+                            vb[pj * 4 + 3] = __float_as_uint(v3);
+                        }
+                        tmem_st32(taddr + c0, vb);
                     } else {
                         if (rvalid) {
                             const float* arow = a.ar ? a.ar + (int64_t)row * a.ar_ld : nullptr;
@@ -224,6 +251,38 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                                         best_i = n;
                                     }
                                 }
+                            }
+                        }
+                    }
+                }
+                if constexpr (EPI == GE_RES_LN) {
+                    // pass 2 of 2: normalise (nn.LayerNorm: biased variance, eps inside the sqrt), write both formats
+                    tmem_st_wait();
+                    const float mean = ln_sum * (1.0f / kBN);
+                    const float rstd = rsqrtf(fmaxf(ln_sq * (1.0f / kBN) - mean * mean, 0.f) + a.ln_eps);
+#pragma unroll 1
+                    for (int c0 = 0; c0 < kBN; c0 += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(taddr + c0, r);
+                        tmem_ld_wait();
+                        if (c0 + 32 == kBN) {
+                            tc_fence_before_sync();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar_acce + grp);
+                        }
+                        if (rvalid) {
+#pragma unroll
+                            for (int pj = 0; pj < 4; ++pj) {
+                                float y[8];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    const int n = c0 + pj * 8 + k;
+                                    y[k] = (__uint_as_float(r[pj * 8 + k]) - mean) * rstd * __ldg(a.gamma + n) + __ldg(a.beta + n);
+                                }
+                                *reinterpret_cast<float4*>(a.out_f32 + (int64_t)(c0 / 4 + 2 * pj) * a.of_ps + (int64_t)row * 16) = make_float4(y[0], y[1], y[2], y[3]);
+                                *reinterpret_cast<float4*>(a.out_f32 + (int64_t)(c0 / 4 + 2 * pj + 1) * a.of_ps + (int64_t)row * 16) = make_float4(y[4], y[5], y[6], y[7]);
+                                *reinterpret_cast<uint4*>(a.out_bf16 + (int64_t)(c0 / 8 + pj) * a.ob_ps + (int64_t)row * 16) =
+                                    make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
                             }
                         }
                     }
@@ -251,6 +310,7 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t st, const char* name) {
         TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
         configured = true;
     }
+    TDM_CHECK_ARG(EPI != GE_RES_LN || a.N == kBN, "%s: fused LayerNorm needs N == 256", name);
     TDM_CHECK_ARG(a.Mp % kBM == 0 && a.N % kBN == 0 && a.K % kBK == 0 && a.K > 0 && a.nsplit > 0,
                   "%s: bad GEMM shape M=%d Mp=%d N=%d K=%d", name, a.M, a.Mp, a.N, a.K);
     const int items = (a.Mp / kBM) * a.nsplit;

@@ -529,14 +529,22 @@ static int text_forward_impl(const void* const* ptrs, int depth, uint8_t* ws, in
         g = GemmArgs{};
         g.a = ws + W.att; g.a_ps = W.ps; g.w = (const uint8_t*)p[LW_O]; g.w_ps = (int64_t)D * 16;
         g.bias = (const float*)p[LB_O]; g.M = W.M; g.Mp = W.Mp; g.N = D; g.n_valid = D; g.K = D;
-        g.res = ws + W.h32; g.res_ps = W.ps; g.out_f32 = ws + W.pre; g.of_ps = W.ps; g.nsplit = g.N / kBN;
-        if ((rc = launch_gemm<GE_RES_F32>(g, st, "gemm_out_proj"))) return rc;
-        // LN1 -> h32, h16
+        g.res = ws + W.h32; g.res_ps = W.ps; g.nsplit = g.N / kBN;
         LnArgs ln{};
-        ln.in = ws + W.pre; ln.gamma = (const float*)p[LN1_G]; ln.beta = (const float*)p[LN1_B]; ln.eps = 1e-5f;
-        ln.out32 = ws + W.h32; ln.out16 = ws + W.h16; ln.M = W.M; ln.Mp = W.Mp; ln.D = D; ln.L = L;
-        layernorm_kernel<<<W.Mp / 32, 256, 0, st>>>(ln);
-        TDM_CHECK_LAUNCH("layernorm1");
+        if (D == kBN) {
+            // width 256: the row fits one tile -> LayerNorm fused into the epilogue (in place on h32: each
+            // thread reads its own row's residual before it writes the same row)
+            g.gamma = (const float*)p[LN1_G]; g.beta = (const float*)p[LN1_B]; g.ln_eps = 1e-5f;
+            g.out_f32 = ws + W.h32; g.of_ps = W.ps; g.out_bf16 = ws + W.h16; g.ob_ps = W.ps;
+            if ((rc = launch_gemm<GE_RES_LN>(g, st, "gemm_out_proj_ln"))) return rc;
+        } else {
+            g.out_f32 = ws + W.pre; g.of_ps = W.ps;
+            if ((rc = launch_gemm<GE_RES_F32>(g, st, "gemm_out_proj"))) return rc;
+            ln.in = ws + W.pre; ln.gamma = (const float*)p[LN1_G]; ln.beta = (const float*)p[LN1_B]; ln.eps = 1e-5f;
+            ln.out32 = ws + W.h32; ln.out16 = ws + W.h16; ln.M = W.M; ln.Mp = W.Mp; ln.D = D; ln.L = L;
+            layernorm_kernel<<<W.Mp / 32, 256, 0, st>>>(ln);
+            TDM_CHECK_LAUNCH("layernorm1");
+        }
         // FFN1 + ReLU
         g = GemmArgs{};
         g.a = ws + W.h16; g.a_ps = W.ps; g.w = (const uint8_t*)p[LW_1]; g.w_ps = (int64_t)kFF * 16;
@@ -547,7 +555,15 @@ static int text_forward_impl(const void* const* ptrs, int depth, uint8_t* ws, in
         g = GemmArgs{};
         g.a = ws + W.ffn; g.a_ps = W.ps; g.w = (const uint8_t*)p[LW_2]; g.w_ps = (int64_t)D * 16;
         g.bias = (const float*)p[LB_2]; g.M = W.M; g.Mp = W.Mp; g.N = D; g.n_valid = D; g.K = kFF;
-        g.res = ws + W.h32; g.res_ps = W.ps; g.out_f32 = ws + W.pre; g.of_ps = W.ps; g.nsplit = g.N / kBN;
+        g.res = ws + W.h32; g.res_ps = W.ps; g.nsplit = g.N / kBN;
+        const bool step_here = (li == depth - 1) && sa.fuse_step;
+        if (D == kBN && !step_here) {
+            g.gamma = (const float*)p[LN2_G]; g.beta = (const float*)p[LN2_B]; g.ln_eps = 1e-5f;
+            g.out_f32 = ws + W.h32; g.of_ps = W.ps; g.out_bf16 = ws + W.h16; g.ob_ps = W.ps;
+            if ((rc = launch_gemm<GE_RES_LN>(g, st, "gemm_ffn2_ln"))) return rc;
+            continue;
+        }
+        g.out_f32 = ws + W.pre; g.of_ps = W.ps;
         if ((rc = launch_gemm<GE_RES_F32>(g, st, "gemm_ffn2"))) return rc;
         // LN2 (last layer: + reverse step + next time embedding)
         ln = LnArgs{};
