@@ -11,6 +11,7 @@
 // stream, bf16 [D/8][Mp][8] for GEMM operands.
 #include "common.cuh"
 #include "diffusion_math.cuh"
+#include "ffn_tc.cuh"
 #include "gemm_tc.cuh"
 #include "tc05.cuh"
 
@@ -544,6 +545,22 @@ static int text_forward_impl(const void* const* ptrs, int depth, uint8_t* ws, in
             ln.out32 = ws + W.h32; ln.out16 = ws + W.h16; ln.M = W.M; ln.Mp = W.Mp; ln.D = D; ln.L = L;
             layernorm_kernel<<<W.Mp / 32, 256, 0, st>>>(ln);
             TDM_CHECK_LAUNCH("layernorm1");
+        }
+        if (D == kFfnD) {
+            // width 256: the whole feed-forward half (FFN1, ReLU, FFN2, residual, LayerNorm and, on the last
+            // layer of a sampling step, the reverse-step update) is one kernel; in place on h32 / h16
+            FfnArgs f{};
+            f.a = ws + W.h16; f.w1 = (const uint8_t*)p[LW_1]; f.b1 = (const float*)p[LB_1];
+            f.w2 = (const uint8_t*)p[LW_2]; f.b2 = (const float*)p[LB_2]; f.res = ws + W.h32;
+            f.gamma = (const float*)p[LN2_G]; f.beta = (const float*)p[LN2_B]; f.ln_eps = 1e-5f;
+            f.out_f32 = ws + W.h32; f.out_bf16 = ws + W.h16; f.ps = W.ps; f.M = W.M; f.Mp = W.Mp; f.L = L;
+            if (li == depth - 1 && sa.fuse_step) {
+                f.fuse_step = 1; f.state = ws + W.state; f.t = t; f.z = sa.z; f.betas = sa.betas; f.alphas = sa.alphas;
+                f.sqrt_om = sa.sqrt_om; f.tw = tw; f.tb = tb; f.seed = sa.seed; f.sample_offset = sa.sample_offset;
+                f.step_id = sa.step_id;
+            }
+            if ((rc = launch_ffn(f, st))) return rc;
+            continue;
         }
         // FFN1 + ReLU
         g = GemmArgs{};
