@@ -7,7 +7,11 @@
 //     G1(c)  acc1[c%2] (TMEM, 128 cols)  = A (smem, resident)    x W1[128c:128c+128, :]^T   16 MMAs, N=128
 //     E1(c)  P (smem, bf16 K-major planes) = relu(acc1 + b1)     epilogue group c%2
 //     G2(c)  acc2 (TMEM, 256 cols)      += P                     x W2[:, 128c:128c+128]^T    8 MMAs, N=256
-// W1 / W2 stream through a 3-stage ring of 32 KB (64-wide K blocks, 8 bulk copies each); the MMA thread
+// W1 / W2 stream through a ring of 32 KB stages (64-wide K blocks, 8 bulk copies each).  Every tile needs
+// the same 2 MB of weights, which makes the kernel L2->SMEM bandwidth bound; so CTAs run as clusters of
+// two that walk the weight stream in lock step: each CTA issues half of every K block's copies as a
+// cluster MULTICAST (both CTAs receive all eight planes) and a stage is released only when both CTAs'
+// MMAs have consumed it (commit multicast onto both empty barriers).  The MMA thread
 // issues G1 two chunks ahead of G2 so the tensor pipe stays busy while E1 converts.  After the 16th
 // chunk epilogue group 0 adds bias + residual, LayerNorms the row (two passes over acc2, the pre-LN
 // row parked in TMEM) and — on the last layer of a sampling step — applies the reverse-step update
@@ -29,6 +33,7 @@ constexpr int kFfnA = 128 * kFfnD * 2;          // 64 KB
 constexpr int kFfnP = 128 * kFfnC * 2;          // 32 KB
 constexpr int kFfnSmem = kFfnA + kFfnStages * kFfnStage + kFfnP + 1024;
 constexpr int kFfnThreads = 64 + 256;
+constexpr int kFfnCluster = 2;    // CTAs sharing one multicast weight stream
 
 struct FfnArgs {
     const uint8_t* a;       // bf16 planes [32][Mp][8] (LayerNorm-1 output)
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
     if (threadIdx.x == 0) {
         for (int i = 0; i < kFfnStages; ++i) {
             mbar_init(bar_full + i, 1);
-            mbar_init(bar_empty + i, 1);
+            mbar_init(bar_empty + i, kFfnCluster);   // one commit from every CTA of the cluster
         }
         mbar_init(bar_a_full, 1);
         mbar_init(bar_a_empty, 1);
@@ -98,8 +103,12 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
     if (warp == 2) tmem_alloc<512>(s_tmem);
     tc_fence_before_sync();
     __syncthreads();
+    cluster_sync_all();   // every CTA's mbarriers exist before any peer multicasts into / arrives on them
     tc_fence_after_sync();
     const uint32_t tmem_base = *s_tmem;
+    const uint32_t crank = cluster_ctarank();
+    const int cluster_id = blockIdx.x / kFfnCluster, n_clusters = gridDim.x / kFfnCluster;
+    constexpr uint16_t kAll = (1u << kFfnCluster) - 1;
     const uint32_t t_acc1 = tmem_base;           // two buffers of 128 columns
     const uint32_t t_acc2 = tmem_base + 256;     // 256 columns
     const int m_tiles = a.Mp / 128;
@@ -119,15 +128,16 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
             }
             __syncwarp();
             uint8_t* st = sR + s * kFfnStage;
-            if (lane < 8) {
+            if (lane < 8 && (lane % kFfnCluster) == (int)crank) {   // this CTA's share of the planes, to everyone
                 if (is_w2)   // K index = hidden unit 128c + 64kb + 8*lane .. ; all 256 output rows
-                    bulk_g2s(st + lane * 4096, a.w2 + (int64_t)(16 * c + 8 * kb + lane) * w2_ps, 4096, bar_full + s);
+                    bulk_g2s_multicast(st + lane * 4096, a.w2 + (int64_t)(16 * c + 8 * kb + lane) * w2_ps, 4096,
+                                       bar_full + s, kAll);
                 else         // K index = model channel 64kb + 8*lane .. ; rows 128c .. 128c+127 of W1
-                    bulk_g2s(st + lane * 2048, a.w1 + (int64_t)(8 * kb + lane) * w1_ps + (int64_t)c * (kFfnC * 16), 2048,
-                             bar_full + s);
+                    bulk_g2s_multicast(st + lane * 2048, a.w1 + (int64_t)(8 * kb + lane) * w1_ps + (int64_t)c * (kFfnC * 16),
+                                       2048, bar_full + s, kAll);
             }
         };
-        for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++ti) {
+        for (int mt = cluster_id * kFfnCluster + (int)crank; mt < m_tiles; mt += n_clusters * kFfnCluster, ++ti) {
             if (lane == 0) {
                 mbar_wait(bar_a_empty, (ti & 1) ^ 1);
                 mbar_arrive_expect_tx(bar_a_full, kFfnA);
@@ -164,11 +174,11 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
                         const uint64_t bd = make_smem_desc(b_addr + (2 * ks) * 2048, 2048, 128);
                         umma_bf16(t_acc1 + buf * kFfnC, ad, bd, idesc1, (kb | ks) != 0);
                     }
-                    umma_commit(bar_empty + s);
+                    umma_commit_multicast(bar_empty + s, kAll);
                 }
                 umma_commit(bar_acc1_full + buf);
             };
-            for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++ti) {
+            for (int mt = cluster_id * kFfnCluster + (int)crank; mt < m_tiles; mt += n_clusters * kFfnCluster, ++ti) {
                 mbar_wait(bar_a_full, ti & 1);
                 tc_fence_after_sync();
                 const int cg0 = ti * kFfnChunks;
@@ -190,7 +200,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
                             const uint64_t bd = make_smem_desc(b_addr + (2 * ks) * 4096, 4096, 128);
                             umma_bf16(t_acc2, ad, bd, idesc2, (c | kb | ks) != 0);
                         }
-                        umma_commit(bar_empty + s);
+                        umma_commit_multicast(bar_empty + s, kAll);
                     }
                     umma_commit(bar_p_empty);                 // P may be overwritten once these MMAs retire
                     if (c == kFfnChunks - 1) umma_commit(bar_acc2_full);
@@ -207,7 +217,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
         const int grp = (warp - 2) >> 2;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         int ti = 0;
-        for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++ti) {
+        for (int mt = cluster_id * kFfnCluster + (int)crank; mt < m_tiles; mt += n_clusters * kFfnCluster, ++ti) {
             const int row = mt * 128 + q * 32 + lane;
             const bool rvalid = row < a.M;
             for (int c = grp; c < kFfnChunks; c += 2) {
@@ -343,6 +353,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
     __syncwarp();
     tc_fence_before_sync();
     __syncthreads();
+    cluster_sync_all();   // no CTA leaves while a peer may still multicast into it or arrive on its barriers
     tc_fence_after_sync();
     if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
@@ -354,8 +365,22 @@ static int launch_ffn(const FfnArgs& a, cudaStream_t st) {
         configured = true;
     }
     const int m_tiles = a.Mp / 128;
-    const int grid = m_tiles < num_sms() ? m_tiles : num_sms();
-    ffn_tc_kernel<<<grid, kFfnThreads, kFfnSmem, st>>>(a);
+    TDM_CHECK_ARG(m_tiles % kFfnCluster == 0, "ffn_fused: row tiles (%d) must be a multiple of the cluster size", m_tiles);
+    int grid = m_tiles < num_sms() ? m_tiles : num_sms();
+    grid -= grid % kFfnCluster;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kFfnThreads);
+    cfg.dynamicSmemBytes = kFfnSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kFfnCluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    TDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ffn_tc_kernel, a));
     TDM_CHECK_LAUNCH("ffn_fused");
     return TDM_OK;
 }

@@ -80,6 +80,27 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
         : "memory");
 }
 
+// Same copy, delivered to the same CTA-relative smem offset (and signalling the mbarrier at the same
+// offset) in every CTA of the cluster whose bit is set in cta_mask: one L2 read feeds several SMs.
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                                   uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+
+// ---- thread-block clusters ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // generic-proxy smem writes -> visible to the async proxy (UMMA / bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -158,6 +179,15 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                      smem_u32(bar))
                  : "memory");
+}
+
+// Same, arriving on the mbarrier at this offset in every CTA of the cluster selected by cta_mask
+// (a multicast stage is free only when all receivers have consumed it).
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -449,7 +449,7 @@ constexpr int kFF = 2048;        // nn.TransformerEncoderLayer default dim_feedf
 static TextWs make_text_ws(int64_t B, int L, int D) {
     TextWs w{};
     w.M = (int)(B * L);
-    w.Mp = (w.M + 127) / 128 * 128;
+    w.Mp = (w.M + 255) / 256 * 256;   // row tiles come in pairs (2-CTA clusters share a weight stream)
     w.ps = (int64_t)w.Mp * 16;
     int64_t o = 0;
     auto take = [&](int64_t planes) {
