@@ -184,7 +184,8 @@ static int launch_wgrad(const WgradArgs& a, cudaStream_t st, const char* name) {
 // ---------------------------------------------------------------------------------------------
 // elementwise pieces
 // ---------------------------------------------------------------------------------------------
-constexpr int kChunk = 1024;  // positions per block in the reducing elementwise kernels
+constexpr int kChunk = 512;   // positions per block in the reducing elementwise kernels (few same-address atomics)
+constexpr int kMlp = 4;       // independent 16-byte loads in flight per thread
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -268,34 +269,48 @@ __global__ void mask_reduce_kernel(const uint8_t* __restrict__ g, int64_t ps, in
 #pragma unroll
     for (int k = 0; k < 8; ++k) sp[k] = st[k] = sm[k] = 0.f;
     const int64_t base = (int64_t)blockIdx.x * kChunk;
-    for (int it = 0; it < kChunk / 32; ++it) {
-        const int64_t pos = base + it * 32 + lane;
-        if (pos >= npos) break;
-        const uint4 gv = *reinterpret_cast<const uint4*>(g + j * ps + (pos + halo) * 16);
-        const uint32_t word = mask ? mask[(j >> 2) * mask_stride + pos] : 0xffffffffu;
-        const uint32_t bits = (word >> ((j & 3) * 8)) & 0xffu;
-        float ts = 0.f;
-        if (d_ts) {
-            const int b = (int)(pos / S);
-            ts = b < batch ? (float)__ldg(t + b) / 1000.0f : 0.f;
-        }
-        const uint32_t* gw = &gv.x;
-        uint4 o;
-        uint32_t* ow = &o.x;
+    for (int it = 0; it < kChunk / 32; it += kMlp) {
+        uint4 gvs[kMlp];
+        uint32_t words[kMlp];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 f = unpack_bf16x2(gw[k]);
-            const float m0 = (bits >> (2 * k)) & 1u ? f.x : 0.f;
-            const float m1 = (bits >> (2 * k + 1)) & 1u ? f.y : 0.f;
-            sp[2 * k] += f.x;
-            sp[2 * k + 1] += f.y;
-            st[2 * k] = fmaf(f.x, ts, st[2 * k]);
-            st[2 * k + 1] = fmaf(f.y, ts, st[2 * k + 1]);
-            sm[2 * k] += m0;
-            sm[2 * k + 1] += m1;
-            ow[k] = pack_bf16x2(m0, m1);
+        for (int u = 0; u < kMlp; ++u) {   // issue all loads before using any
+            const int64_t pos = base + (it + u) * 32 + lane;
+            gvs[u] = make_uint4(0, 0, 0, 0);
+            words[u] = 0;
+            if (pos < npos) {
+                gvs[u] = *reinterpret_cast<const uint4*>(g + j * ps + (pos + halo) * 16);
+                words[u] = mask ? mask[(j >> 2) * mask_stride + pos] : 0xffffffffu;
+            }
         }
-        if (out) *reinterpret_cast<uint4*>(out + j * ps + (pos + halo) * 16) = o;
+#pragma unroll
+        for (int u = 0; u < kMlp; ++u) {
+            const int64_t pos = base + (it + u) * 32 + lane;
+            if (pos >= npos) continue;
+            const uint4 gv = gvs[u];
+            const uint32_t bits = (words[u] >> ((j & 3) * 8)) & 0xffu;
+            float ts = 0.f;
+            if (d_ts) {
+                const int b = (int)(pos / S);
+                ts = b < batch ? (float)__ldg(t + b) / 1000.0f : 0.f;
+            }
+            const uint32_t* gw = &gv.x;
+            uint4 o;
+            uint32_t* ow = &o.x;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 f = unpack_bf16x2(gw[k]);
+                const float m0 = (bits >> (2 * k)) & 1u ? f.x : 0.f;
+                const float m1 = (bits >> (2 * k + 1)) & 1u ? f.y : 0.f;
+                sp[2 * k] += f.x;
+                sp[2 * k + 1] += f.y;
+                st[2 * k] = fmaf(f.x, ts, st[2 * k]);
+                st[2 * k + 1] = fmaf(f.y, ts, st[2 * k + 1]);
+                sm[2 * k] += m0;
+                sm[2 * k + 1] += m1;
+                ow[k] = pack_bf16x2(m0, m1);
+            }
+            if (out) *reinterpret_cast<uint4*>(out + j * ps + (pos + halo) * 16) = o;
+        }
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
