@@ -483,7 +483,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
-    ap.add_argument("--batch", type=int, default=4096, help="samples per GPU per step")
+    ap.add_argument("--batch", type=int, default=16384, help="samples per GPU per step")
     ap.add_argument("--train-batch", type=int, default=512, help="training images per GPU per step")
     ap.add_argument("--text-batch", type=int, default=512, help="text sequences per GPU (secondary metric)")
     ap.add_argument("--no-text", action="store_true", help="skip the text secondary metric")
