@@ -305,9 +305,12 @@ def run_ours(args) -> None:
             dist.destroy_process_group()
         return
 
-    # ---- CPU baseline on this box's host cores (bounded sample) ----------------------------
-    sec_per_rstep, cores = cpu_reverse_steps(64, 20, warm=3)
-    cpu_value = 64 / (sec_per_rstep * T_STEPS)
+    # ---- CPU baseline on this box's host cores (bounded sample; rank 0 at N=1 only) ---------
+    cpu_baseline = None
+    if world == 1:
+        sec_per_rstep, cores = cpu_reverse_steps(64, 20, warm=3)
+        cpu_baseline = {"value": 64 / (sec_per_rstep * T_STEPS), "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "20 of 1000 reverse steps at batch 64 (oracle port of src/mnist.py:167-180), extrapolated x50"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -324,8 +327,7 @@ def run_ours(args) -> None:
                 "d2h_bytes_per_step": B * 784 * 4, "steps": e2e_steps},
         "gpu_launches": int(direct_launches + launches_per_replay * T_STEPS * args.steps),
         "roofline": roofline,
-        "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "20 of 1000 reverse steps at batch 64 (oracle port of src/mnist.py:167-180), extrapolated x50"},
+        "cpu_baseline": cpu_baseline,
         "clocks": clocks,
         "train": train,
         "text": text,

@@ -34,7 +34,8 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def u01(bits):
-    return ((bits >> np.uint32(8)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 16777216.0)
+    """23-bit uniform in (0,1), exactly as csrc/common.cuh: never 0, never 1, exactly representable."""
+    return ((bits >> np.uint32(9)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 8388608.0)
 
 
 def normal_block(seed: int, sample, quad, step: int, domain: int):

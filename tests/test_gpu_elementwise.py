@@ -55,6 +55,14 @@ def test_philox_randn_matches_numpy_oracle(cuda):
     assert abs(got.mean()) < 0.02 and abs(got.std() - 1) < 0.02
 
 
+def test_philox_normals_finite_over_2_pow_26_draws(cuda):
+    # 2^26 normals use 2^26 uniforms: every extreme of the 23-bit uniform grid is hit many times
+    z = ops.randn((8192, 8192), cuda, seed=99)
+    assert torch.isfinite(z).all()
+    assert float(z.abs().max()) < 6.0          # sqrt(-2 ln 2^-24) = 5.77
+    assert abs(float(z.mean())) < 1e-3 and abs(float(z.std()) - 1) < 1e-3
+
+
 def test_philox_shard_invariance(cuda):
     # rows depend on (seed, global sample index) only: any split of the batch gives the same rows
     full = ops.randn((64, 784), cuda, seed=9, sample_offset=0, stream_id=3)

@@ -148,6 +148,15 @@ def test_philox_known_answers():
         assert tuple(int(v[0]) for v in got) == want
 
 
+def test_uniform_never_hits_zero_or_one():
+    # the extremes of the 32-bit input must stay strictly inside (0,1): u = 1.0 would zero the
+    # Box-Muller radius (and, with a fast rsqrt-based sqrt, produce NaN)
+    bits = np.array([0, 1, 0x1FF, 0x200, 0x7FFFFFFF, 0xFFFFFE00, 0xFFFFFFFF], dtype=np.uint32)
+    u = PX.u01(bits)
+    assert u.dtype == np.float32 and (u > 0).all() and (u < 1).all()
+    assert np.isfinite(np.log(u)).all()
+
+
 def test_philox_normals_are_standard():
     z = PX.randn(256, 784, 3, 0, 17, PX.DOMAIN_REVERSE)
     assert abs(z.mean()) < 0.01 and abs(z.std() - 1) < 0.01

@@ -66,25 +66,32 @@ __host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t 
     return Philox4{c0, c1, c2, c3};
 }
 
-// 24-bit uniform in (0,1): (bits>>8 + 0.5) * 2^-24  — never 0, never 1.
+// 23-bit uniform in (0,1): (bits>>9 + 0.5) * 2^-23 — every value is exactly representable in fp32,
+// the smallest is 2^-24 and the largest 1 - 2^-24, so it is never 0 and never 1.  (A 24-bit version
+// rounds its top value to exactly 1.0, log gives 0 and the Box-Muller radius degenerates.)
 __host__ __device__ __forceinline__ float u01(uint32_t bits) {
-    return ((float)(bits >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    return ((float)(bits >> 9) + 0.5f) * (1.0f / 8388608.0f);
 }
 
 // Four N(0,1) from one Philox block via two Box–Muller pairs:
 //   (n0, n1) = r(x) * (cos, sin)(2*pi*u(y)),  (n2, n3) = r(z) * (cos, sin)(2*pi*u(w)).
 // Device code uses the MUFU fast paths; the oracle uses libm and the tests carry the tolerance.
 #ifdef __CUDACC__
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t sample, uint32_t quad,
                                                  uint32_t step, uint32_t domain) {
     // counter = (quad, sample_lo, step, domain | sample_hi<<8): sample index may exceed 2^32
     const uint32_t c3 = domain | ((uint32_t)(sample >> 32) << 8);
     Philox4 r = philox4x32_10(quad, (uint32_t)sample, step, c3, (uint32_t)seed,
                               (uint32_t)(seed >> 32));
-    // radius sqrt(-2 ln u): u in (0,1) so the argument is > 0; x*rsqrt(x) is 2 MUFU-path instructions
-    // where the IEEE sqrtf costs ~10 (the oracle uses libm; tests carry the 2e-5 tolerance)
-    const float a0 = -2.0f * __logf(u01(r.x)), a1 = -2.0f * __logf(u01(r.z));
-    const float r0 = a0 * rsqrtf(a0), r1 = a1 * rsqrtf(a1);
+    // radius sqrt(-2 ln u): MUFU square root (sqrt.approx: 0 -> 0, no NaN) instead of the ~10-instruction
+    // IEEE sqrtf; the oracle uses libm and the tests carry the 2e-5 tolerance
+    const float r0 = sqrt_approx(-2.0f * __logf(u01(r.x)));
+    const float r1 = sqrt_approx(-2.0f * __logf(u01(r.z)));
     float s0, c0, s1, c1;
     __sincosf(6.283185307179586f * u01(r.y), &s0, &c0);
     __sincosf(6.283185307179586f * u01(r.w), &s1, &c1);

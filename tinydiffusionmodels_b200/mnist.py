@@ -140,7 +140,7 @@ class SimpleUNet(nn.Module):
             raise _lib.TdmError("SimpleUNet runs on CUDA only (no CPU fallback): call .to('cuda')")
         e = self._engine
         if e is None or e.device != flat.device or e.max_batch < batch:
-            e = UNetEngine(flat.device, batch)
+            e = UNetEngine(flat.device, max(batch, 1))
             self._engine = e
         e.ensure_packed(flat)
         return e

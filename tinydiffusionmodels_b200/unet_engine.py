@@ -102,6 +102,8 @@ class UNetEngine:
     def forward(self, x: torch.Tensor, t: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """eps = SimpleUNet(x, t) (src/mnist.py:76-87). x (B,1,28,28) fp32, t (B,) int64."""
         b = x.shape[0]
+        if b == 0:
+            return torch.empty_like(x) if out is None else out
         self._prep(b)
         x = x.contiguous()
         t = t.to(torch.int64).contiguous()
@@ -116,6 +118,8 @@ class UNetEngine:
                  step_id: int = 0) -> torch.Tensor:
         """One fused reverse step (src/mnist.py:167-180); ``out`` may be ``x`` itself."""
         b = x.shape[0]
+        if b == 0:
+            return torch.empty_like(x) if out is None else out
         self._prep(b)
         x = x.contiguous()
         t = t.to(torch.int64).contiguous()
