@@ -166,6 +166,188 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const WgradArgs a) {
     if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------
+// 3x3 weight gradient with row-shifted duplicates of the gradient tile.
+// With A = G^T only CG (32 or 64) of an MMA's M rows carry data.  Staging copy d of the G tile shifted
+// by d rows (copy d = rows [r0-d, r0-d+128)) makes M-row block d compute
+//     sum_k G[k-d][co] X[k+off][ci]  =  the tap whose offset is off + d
+// so with off = (ky-1)*Wp - 1 one MMA yields the kx = 0,1(,2) taps of a kernel row:
+//   CG = 32: three copies -> M = 128 (96 live rows), 3 MMA groups per k-step instead of 9
+//   CG = 64: two copies   -> M = 128 for (kx0, kx1) plus an M = 64 MMA for kx2 on copy 0
+// Every copy's 128-row windows tile the position axis (offset by d), so each (pos, tap) product is
+// counted exactly once; two extra rows past np are swept so copy 2 reaches the last positions.
+// ---------------------------------------------------------------------------------------------
+template <int W, int CG, int CX>
+struct WgradDupCfg {
+    using G = Geo<W>;
+    static constexpr int NDUP = (CG == 32) ? 3 : 2;
+    static constexpr int GPL = CG / 8, XPL = CX / 8;
+    static constexpr int G_BYTES = 16 * kTile * 16;            // 16 M-groups of 8 channels (M = 128), 32 KB
+    static constexpr int X_BYTES = XPL * G::RT * 16;
+    static constexpr int STAGE_BYTES = G_BYTES + X_BYTES;
+    static constexpr int AVAIL = 227 * 1024 - 1024;
+    static constexpr int NSTAGE = (AVAIL / STAGE_BYTES) > 4 ? 4 : (AVAIL / STAGE_BYTES);
+    static_assert(NSTAGE >= 2, "stages");
+    // TMEM: per kernel row ky one [128 x CX] accumulator; CG = 64 adds one [64 x CX] (kx2) per ky,
+    // two of which share columns through the lane-16 interleave
+    static constexpr int NCOLS = 3 * CX + (CG == 64 ? 2 * CX : 0);
+    static constexpr int TMEM_COLS = NCOLS <= 128 ? 128 : NCOLS <= 256 ? 256 : 512;
+    static_assert(NCOLS <= 512, "TMEM");
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 512;
+    static constexpr int THREADS = 192;
+};
+
+template <int W, int CG, int CX>
+__global__ void __launch_bounds__(192, 1) wgrad_dup_kernel(const WgradArgs a) {
+    using C = WgradDupCfg<W, CG, CX>;
+    using G = Geo<W>;
+    static_assert(CG == 32 || CG == 64, "CG");
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* s_in = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE_BYTES);
+    uint64_t* bar_full = bars;
+    uint64_t* bar_empty = bars + C::NSTAGE;
+    uint64_t* bar_done = bar_empty + C::NSTAGE;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_done + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C::NSTAGE; ++i) {
+            mbar_init(bar_full + i, 1);
+            mbar_init(bar_empty + i, 1);
+        }
+        mbar_init(bar_done, 1);
+        mbar_fence_init();
+    }
+    if (warp == 2) tmem_alloc<C::TMEM_COLS>(s_tmem);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *s_tmem;
+    constexpr int LIVE_PLANES = C::NDUP * C::GPL;     // 12 (CG=32) or 16 (CG=64) of the 16 M-groups hold data
+    constexpr int LIVE_BYTES = LIVE_PLANES * kTile * 16 + C::X_BYTES;
+
+    if (warp == 0) {
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
+            const int s = it % C::NSTAGE;
+            const uint32_t ph = (it / C::NSTAGE) & 1;
+            if (lane == 0) {
+                mbar_wait(bar_empty + s, ph ^ 1);
+                mbar_arrive_expect_tx(bar_full + s, LIVE_BYTES);
+            }
+            __syncwarp();
+            uint8_t* st = s_in + s * C::STAGE_BYTES;
+            if (lane < LIVE_PLANES) {
+                const int d = lane / C::GPL, j = lane - d * C::GPL;   // copy d, channel plane j
+                bulk_g2s(st + lane * (kTile * 16), a.g + j * a.g_ps + ((int64_t)tile * kTile - d + G::GUARD) * 16,
+                         kTile * 16, bar_full + s);
+            } else if (lane >= 16 && lane < 16 + C::XPL) {
+                const int j = lane - 16;
+                bulk_g2s(st + C::G_BYTES + j * (G::RT * 16),
+                         a.x + j * a.x_ps + ((int64_t)tile * kTile - G::HALO + G::GUARD) * 16, G::RT * 16, bar_full + s);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc128 = make_idesc_bf16(128, CX, 1, 1);
+            constexpr uint32_t idesc64 = make_idesc_bf16(64, CX, 1, 1);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
+                const int s = it % C::NSTAGE;
+                const uint32_t ph = (it / C::NSTAGE) & 1;
+                mbar_wait(bar_full + s, ph);
+                tc_fence_after_sync();
+                const uint32_t g_addr = smem_u32(s_in + s * C::STAGE_BYTES);
+                const uint32_t x_addr = g_addr + C::G_BYTES;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int off = (ky - 1) * G::Wp - 1;   // kx = 0; copy d adds d
+#pragma unroll
+                    for (int ks = 0; ks < kTile / 16; ++ks) {
+                        const uint64_t ad = make_smem_desc(g_addr + ks * 256, 128, kTile * 16);
+                        const uint64_t bd = make_smem_desc(x_addr + (G::HALO + off + ks * 16) * 16, 128, G::RT * 16);
+                        umma_bf16(tmem_base + ky * CX, ad, bd, idesc128, (it | ks) != 0);
+                        if constexpr (CG == 64) {
+                            // kx = 2 from copy 0 with the X window moved two rows on; ky = 0,1 share columns
+                            // 3*CX.. through the lane-16 interleave of M = 64 accumulators, ky = 2 sits at 4*CX
+                            const uint64_t bd2 = make_smem_desc(x_addr + (G::HALO + off + 2 + ks * 16) * 16, 128, G::RT * 16);
+                            const uint32_t d2 = tmem_base + (ky < 2 ? 3 * CX + ((uint32_t)(ky * 16) << 16) : 4 * CX);
+                            umma_bf16(d2, ad, bd2, idesc64, (it | ks) != 0);
+                        }
+                    }
+                }
+                umma_commit(bar_empty + s);
+            }
+            if (it > 0) umma_commit(bar_done);
+        }
+    } else if ((int)blockIdx.x < a.nt) {
+        mbar_wait(bar_done, 0);
+        tc_fence_after_sync();
+        const int q = warp & 3;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        // --- M = 128 accumulators: row m = d*CG + co lives in lane m ---
+        const int m = q * 32 + lane;
+        const int d = m / CG, co = m - d * CG;
+        const bool live = d < C::NDUP;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+            for (int c0 = 0; c0 < CX; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + ky * CX + c0, r);
+                tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        atomicAdd(a.dw + ((int64_t)(co * CX + c0 + i) * 9 + ky * 3 + d), __uint_as_float(r[i]));
+                }
+            }
+        }
+        if constexpr (CG == 64) {
+            // --- M = 64 accumulators (kx = 2): row m2 = q*16 + (lane & 15); lanes >= 16 hold ky = 1 ---
+            const int m2 = q * 16 + (lane & 15);
+            const int upper = lane >> 4;
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk) {   // blk 0: columns 3*CX (ky 0 / ky 1 interleaved), blk 1: 4*CX (ky 2)
+                const int ky = blk == 0 ? upper : 2;
+                const bool ok = blk == 0 || upper == 0;
+#pragma unroll
+                for (int c0 = 0; c0 < CX; c0 += 16) {
+                    uint32_t r[16];
+                    tmem_ld16(taddr + (3 + blk) * CX + c0, r);
+                    tmem_ld_wait();
+                    if (ok) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            atomicAdd(a.dw + ((int64_t)(m2 * CX + c0 + i) * 9 + ky * 3 + 2), __uint_as_float(r[i]));
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
+}
+
+template <int W, int CG, int CX>
+static int launch_wgrad_dup(WgradArgs a, int64_t np, cudaStream_t st, const char* name) {
+    using C = WgradDupCfg<W, CG, CX>;
+    auto kern = wgrad_dup_kernel<W, CG, CX>;
+    static bool configured = false;
+    if (!configured) {
+        TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured = true;
+    }
+    a.nt = (int)((np + 2 + kTile - 1) / kTile);   // two rows past np so the shifted copies reach the last positions
+    const int grid = a.nt < num_sms() ? a.nt : num_sms();
+    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(a);
+    TDM_CHECK_LAUNCH(name);
+    return TDM_OK;
+}
+
 template <int W, int CG, int CX, int TAPS>
 static int launch_wgrad(const WgradArgs& a, cudaStream_t st, const char* name) {
     using C = WgradCfg<W, CG, CX, TAPS>;
@@ -513,14 +695,14 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = mask_reduce(ws + L.go28, L.ps28, H28, M(L.m2_4), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
                           dflat + P::rb4_sb, nullptr, dflat + P::rb4_c2b, st))) return rc;
     w = WgradArgs{ws + L.gc28, L.ps28, ws + L.t4, L.ps28, dflat + P::rb4_c2w, nt28};
-    if ((rc = launch_wgrad<28, 32, 32, 9>(w, st, "wgrad_rb4_c2"))) return rc;
+    if ((rc = launch_wgrad_dup<28, 32, 32>(w, L.np28, st, "wgrad_rb4_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
     c.in = ws + L.gc28; c.in_ps = L.ps28; c.w = wp + WP::d_rb4_c2; c.out = ws + L.gh28; c.out_ps = L.ps28;
     if ((rc = launch_conv<28, 32, 32, EPI_PLAIN, false, 9, KX::rb4c2>(c, st, "dgrad_rb4_c2"))) return rc;
     if ((rc = mask_reduce(ws + L.gh28, L.ps28, H28, M(L.m1_4), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
                           dflat + P::rb4_tb, dflat + P::rb4_tw, dflat + P::rb4_c1b, st))) return rc;
     w = WgradArgs{ws + L.gc28, L.ps28, ws + L.cat, L.ps28, dflat + P::rb4_c1w, nt28};
-    if ((rc = launch_wgrad<28, 32, 96, 9>(w, st, "wgrad_rb4_c1"))) return rc;
+    if ((rc = launch_wgrad_dup<28, 32, 96>(w, L.np28, st, "wgrad_rb4_c1"))) return rc;
     w = WgradArgs{ws + L.go28, L.ps28, ws + L.cat, L.ps28, dflat + P::rb4_sw, nt28};
     if ((rc = launch_wgrad<28, 32, 96, 1>(w, st, "wgrad_rb4_skip"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
@@ -537,14 +719,14 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = mask_reduce(ws + L.go14a, L.ps14, H14, M(L.m2_3), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
                           nullptr, nullptr, dflat + P::rb3_c2b, st))) return rc;
     w = WgradArgs{ws + L.gc14, L.ps14, ws + L.t3, L.ps14, dflat + P::rb3_c2w, nt14};
-    if ((rc = launch_wgrad<14, 64, 64, 9>(w, st, "wgrad_rb3_c2"))) return rc;
+    if ((rc = launch_wgrad_dup<14, 64, 64>(w, L.np14, st, "wgrad_rb3_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
     c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb3_c2; c.out = ws + L.gh14; c.out_ps = L.ps14;
     if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false, 9, KX::rb3c2>(c, st, "dgrad_rb3_c2"))) return rc;
     if ((rc = mask_reduce(ws + L.gh14, L.ps14, H14, M(L.m1_3), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
                           dflat + P::rb3_tb, dflat + P::rb3_tw, dflat + P::rb3_c1b, st))) return rc;
     w = WgradArgs{ws + L.gc14, L.ps14, ws + L.h2, L.ps14, dflat + P::rb3_c1w, nt14};
-    if ((rc = launch_wgrad<14, 64, 64, 9>(w, st, "wgrad_rb3_c1"))) return rc;
+    if ((rc = launch_wgrad_dup<14, 64, 64>(w, L.np14, st, "wgrad_rb3_c1"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
     c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb3_c1; c.res = ws + L.go14a; c.res_ps = L.ps14;
     c.out = ws + L.go14b; c.out_ps = L.ps14;   // g_out of rb2
@@ -554,14 +736,14 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = mask_reduce(ws + L.go14b, L.ps14, H14, M(L.m2_2), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
                           dflat + P::rb2_sb, nullptr, dflat + P::rb2_c2b, st))) return rc;
     w = WgradArgs{ws + L.gc14, L.ps14, ws + L.t2, L.ps14, dflat + P::rb2_c2w, nt14};
-    if ((rc = launch_wgrad<14, 64, 64, 9>(w, st, "wgrad_rb2_c2"))) return rc;
+    if ((rc = launch_wgrad_dup<14, 64, 64>(w, L.np14, st, "wgrad_rb2_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
     c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb2_c2; c.out = ws + L.gh14; c.out_ps = L.ps14;
     if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false, 9, KX::rb2c2>(c, st, "dgrad_rb2_c2"))) return rc;
     if ((rc = mask_reduce(ws + L.gh14, L.ps14, H14, M(L.m1_2), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
                           dflat + P::rb2_tb, dflat + P::rb2_tw, dflat + P::rb2_c1b, st))) return rc;
     w = WgradArgs{ws + L.gc14, L.ps14, ws + L.p1, L.ps14, dflat + P::rb2_c1w, nt14};
-    if ((rc = launch_wgrad<14, 64, 32, 9>(w, st, "wgrad_rb2_c1"))) return rc;
+    if ((rc = launch_wgrad_dup<14, 64, 32>(w, L.np14, st, "wgrad_rb2_c1"))) return rc;
     w = WgradArgs{ws + L.go14b, L.ps14, ws + L.p1, L.ps14, dflat + P::rb2_sw, nt14};
     if ((rc = launch_wgrad<14, 64, 32, 1>(w, st, "wgrad_rb2_skip"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
@@ -579,7 +761,7 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = mask_reduce(ws + L.go28, L.ps28, H28, M(L.m2_1), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
                           dflat + P::rb1_sb, nullptr, dflat + P::rb1_c2b, st))) return rc;
     w = WgradArgs{ws + L.gc28, L.ps28, ws + L.t1, L.ps28, dflat + P::rb1_c2w, nt28};
-    if ((rc = launch_wgrad<28, 32, 32, 9>(w, st, "wgrad_rb1_c2"))) return rc;
+    if ((rc = launch_wgrad_dup<28, 32, 32>(w, L.np28, st, "wgrad_rb1_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
     c.in = ws + L.gc28; c.in_ps = L.ps28; c.w = wp + WP::d_rb1_c2; c.out = ws + L.gh28; c.out_ps = L.ps28;
     if ((rc = launch_conv<28, 32, 32, EPI_PLAIN, false, 9, KX::rb1c2>(c, st, "dgrad_rb1_c2"))) return rc;
