@@ -196,62 +196,53 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups, 1) conv3x3_tc
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, C::NMAIN);
-            constexpr uint32_t idesc_skip = make_idesc_bf16(128, COUT);
-            mbar_wait(bar_w, 0);
-            const uint32_t w_addr = smem_u32(s_w);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < nt; tile += gridDim.x, ++it) {
-                const int s = it % C::NSTAGE;
-                const uint32_t ph = (it / C::NSTAGE) & 1;
-                const int acc = it % C::NACC;
-                const uint32_t aph = (it / C::NACC) & 1;
-                mbar_wait(bar_acce + acc, aph ^ 1);
-                mbar_wait(bar_full + s, ph);
-                tc_fence_after_sync();
-                const uint32_t in_addr = smem_u32(s_in + s * C::STAGE_BYTES);
-                const uint32_t d = tmem_base + acc * C::ACC_COLS;
-                if constexpr (KXC) {
+        // ===== MMA issuer: the whole warp runs this loop convergently, one elected lane issues =====
+        constexpr uint32_t idesc = make_idesc_bf16(128, C::NMAIN);
+        constexpr uint32_t idesc_skip = make_idesc_bf16(128, COUT);
+        mbar_wait(bar_w, 0);
+        constexpr uint32_t B_LBO = (KXC ? 3 * COUT : COUT) * 16;
+        const uint64_t w_base = make_smem_desc(smem_u32(s_w), B_LBO, 128);
+        const uint64_t ws_base = make_smem_desc(smem_u32(s_w) + C::WCONV_BYTES, COUT * 16, 128);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < nt; tile += gridDim.x, ++it) {
+            const int s = it % C::NSTAGE;
+            const uint32_t ph = (it / C::NSTAGE) & 1;
+            const int acc = it % C::NACC;
+            const uint32_t aph = (it / C::NACC) & 1;
+            mbar_wait(bar_acce + acc, aph ^ 1);
+            mbar_wait(bar_full + s, ph);
+            tc_fence_after_sync();
+            const uint64_t in_base = make_smem_desc(smem_u32(s_in + s * C::STAGE_BYTES), G::RT * 16, 128);
+            const uint32_t d = tmem_base + acc * C::ACC_COLS;
+            if constexpr (KXC) {
 #pragma unroll
-                    for (int ky = 0; ky < 3; ++ky) {
-#pragma unroll
-                        for (int ks = 0; ks < CIN / 16; ++ks) {
-                            const uint64_t ad = make_smem_desc(
-                                in_addr + (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp) * 16, G::RT * 16, 128);
-                            const uint64_t bd = make_smem_desc(
-                                w_addr + ((ky * C::NPL + 2 * ks) * 3 * COUT) * 16, 3 * COUT * 16, 128);
-                            umma_bf16(d, ad, bd, idesc, (ky | ks) != 0);
-                        }
-                    }
-                } else {
-#pragma unroll
-                    for (int tap = 0; tap < TAPS; ++tap) {
-                        const int off = (TAPS == 1) ? 0 : (tap / 3 - 1) * G::Wp + (tap % 3 - 1);
-#pragma unroll
-                        for (int ks = 0; ks < CIN / 16; ++ks) {
-                            const uint64_t ad = make_smem_desc(
-                                in_addr + (2 * ks) * (G::RT * 16) + (G::HALO + off) * 16, G::RT * 16, 128);
-                            const uint64_t bd = make_smem_desc(
-                                w_addr + ((tap * C::NPL + 2 * ks) * COUT) * 16, COUT * 16, 128);
-                            umma_bf16(d, ad, bd, idesc, (tap | ks) != 0);
-                        }
-                    }
-                }
-                if constexpr (SKIPG) {
+                for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
                     for (int ks = 0; ks < CIN / 16; ++ks) {
-                        const uint64_t ad = make_smem_desc(
-                            in_addr + (2 * ks) * (G::RT * 16) + G::HALO * 16, G::RT * 16, 128);
-                        const uint64_t bd = make_smem_desc(
-                            w_addr + C::WCONV_BYTES + ((2 * ks) * COUT) * 16, COUT * 16, 128);
-                        umma_bf16(d + C::NMAIN, ad, bd, idesc_skip, ks != 0);
+                        umma_bf16_elect(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp) * 16),
+                                        desc_add(w_base, ((ky * C::NPL + 2 * ks) * 3 * COUT) * 16), idesc, (ky | ks) != 0);
                     }
                 }
-                umma_commit(bar_empty + s);   // smem stage reusable once these MMAs retire
-                umma_commit(bar_accf + acc);  // accumulator complete
+            } else {
+#pragma unroll
+                for (int tap = 0; tap < TAPS; ++tap) {
+                    const int off = (TAPS == 1) ? 0 : (tap / 3 - 1) * G::Wp + (tap % 3 - 1);
+#pragma unroll
+                    for (int ks = 0; ks < CIN / 16; ++ks) {
+                        umma_bf16_elect(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + off) * 16),
+                                        desc_add(w_base, ((tap * C::NPL + 2 * ks) * COUT) * 16), idesc, (tap | ks) != 0);
+                    }
+                }
             }
+            if constexpr (SKIPG) {
+#pragma unroll
+                for (int ks = 0; ks < CIN / 16; ++ks) {
+                    umma_bf16_elect(d + C::NMAIN, desc_add(in_base, (2 * ks) * (G::RT * 16) + G::HALO * 16),
+                                    desc_add(ws_base, ((2 * ks) * COUT) * 16), idesc_skip, ks != 0);
+                }
+            }
+            umma_commit_elect(bar_empty + s);   // smem stage reusable once these MMAs retire
+            umma_commit_elect(bar_accf + acc);  // accumulator complete
         }
     } else {
         // ===== epilogue: group g = (warp-2)/4 owns accumulator stage g (tiles it = g, g+NACC, ..),

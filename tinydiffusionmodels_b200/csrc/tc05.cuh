@@ -174,6 +174,35 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- warp-convergent issue: the WHOLE warp executes these with identical (warp-uniform) operands
+// and one elected lane issues.  Keeping the issue loop out of a divergent `if (lane == 0)` lets the
+// compiler hold descriptors in uniform registers and drops the per-instruction ELECT/BRA.U.ANY loop
+// it otherwise wraps around every UTCHMMA (12 -> ~4 SASS instructions per MMA; the single issuing
+// thread was the bottleneck of the small-N convolutions).
+__device__ __forceinline__ void umma_bf16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar))
+        : "memory");
+}
+// descriptor = per-tile base + compile-time byte offset (the 14-bit address field cannot carry out:
+// shared memory is < 256 KB)
+__device__ __forceinline__ uint64_t desc_add(uint64_t base, uint32_t byte_off) {
+    return base + (uint64_t)(byte_off >> 4);
+}
+
 // Arrive on an mbarrier once every tcgen05 op issued so far by this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
