@@ -122,35 +122,33 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(kBM, kBN);
-            int kit = 0, it = 0;
-            for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int mt = item / a.nsplit, sp = item - mt * a.nsplit;
-                const int n0 = (int)((int64_t)sp * n_tiles / a.nsplit), n1 = (int)((int64_t)(sp + 1) * n_tiles / a.nsplit);
-                for (int nt = n0; nt < n1; ++nt, ++it) {
-                    const int acc = it & 1;
-                    const uint32_t aph = (it >> 1) & 1;
-                    mbar_wait(bar_acce + acc, aph ^ 1);
-                    const uint32_t d = tmem_base + acc * kBN;
-                    for (int kb = 0; kb < kblocks; ++kb, ++kit) {
-                        const int s = kit % kGemmStages;
-                        const uint32_t ph = (kit / kGemmStages) & 1;
-                        mbar_wait(bar_full + s, ph);
-                        tc_fence_after_sync();
-                        const uint32_t a_addr = smem_u32(smem + s * kGemmStage);
-                        const uint32_t b_addr = a_addr + kGemmStageA;
+        // ===== MMA issuer: whole warp, one elected lane issues (tc05.cuh: warp-convergent issue) =====
+        constexpr uint32_t idesc = make_idesc_bf16(kBM, kBN);
+        int kit = 0, it = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int mt = item / a.nsplit, sp = item - mt * a.nsplit;
+            const int n0 = (int)((int64_t)sp * n_tiles / a.nsplit), n1 = (int)((int64_t)(sp + 1) * n_tiles / a.nsplit);
+            for (int nt = n0; nt < n1; ++nt, ++it) {
+                const int acc = it & 1;
+                const uint32_t aph = (it >> 1) & 1;
+                mbar_wait(bar_acce + acc, aph ^ 1);
+                const uint32_t d = tmem_base + acc * kBN;
+                for (int kb = 0; kb < kblocks; ++kb, ++kit) {
+                    const int s = kit % kGemmStages;
+                    const uint32_t ph = (kit / kGemmStages) & 1;
+                    mbar_wait(bar_full + s, ph);
+                    tc_fence_after_sync();
+                    const uint32_t a_addr = smem_u32(smem + s * kGemmStage);
+                    const uint64_t a_base = make_smem_desc(a_addr, kBM * 16, 128);
+                    const uint64_t b_base = make_smem_desc(a_addr + kGemmStageA, kBN * 16, 128);
+                    const uint32_t acc_flag = kb != 0;
 #pragma unroll
-                        for (int ks = 0; ks < kBK / 16; ++ks) {
-                            const uint64_t ad = make_smem_desc(a_addr + (2 * ks) * (kBM * 16), kBM * 16, 128);
-                            const uint64_t bd = make_smem_desc(b_addr + (2 * ks) * (kBN * 16), kBN * 16, 128);
-                            umma_bf16(d, ad, bd, idesc, (kb | ks) != 0);
-                        }
-                        umma_commit(bar_empty + s);
-                    }
-                    umma_commit(bar_accf + acc);
+                    for (int ks = 0; ks < kBK / 16; ++ks)
+                        umma_bf16_elect(d, desc_add(a_base, (2 * ks) * (kBM * 16)), desc_add(b_base, (2 * ks) * (kBN * 16)), idesc,
+                                        ks != 0 ? 1u : acc_flag);
+                    umma_commit_elect(bar_empty + s);
                 }
+                umma_commit_elect(bar_accf + acc);
             }
         }
     } else {

@@ -108,31 +108,30 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const WgradArgs a) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(64, CX, 1, 1);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
-                const int s = it % C::NSTAGE;
-                const uint32_t ph = (it / C::NSTAGE) & 1;
-                mbar_wait(bar_full + s, ph);
-                tc_fence_after_sync();
-                const uint32_t g_addr = smem_u32(s_in + s * C::STAGE_BYTES);
-                const uint32_t x_addr = g_addr + C::G_BYTES;
+        // whole warp, one elected lane issues (tc05.cuh: warp-convergent issue)
+        constexpr uint32_t idesc = make_idesc_bf16(64, CX, 1, 1);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
+            const int s = it % C::NSTAGE;
+            const uint32_t ph = (it / C::NSTAGE) & 1;
+            mbar_wait(bar_full + s, ph);
+            tc_fence_after_sync();
+            const uint32_t g_addr = smem_u32(s_in + s * C::STAGE_BYTES);
+            const uint64_t g_base = make_smem_desc(g_addr, 128, kTile * 16);
+            const uint64_t x_base = make_smem_desc(g_addr + C::G_BYTES, 128, G::RT * 16);
+            const uint32_t acc_flag = it != 0;
 #pragma unroll
-                for (int tap = 0; tap < TAPS; ++tap) {
-                    const int off = (TAPS == 1) ? 0 : (tap / 3 - 1) * G::Wp + (tap % 3 - 1);
-                    const uint32_t d = tmem_base + (tap < 5 ? tap * CX : ((16u << 16) + (tap - 5) * CX));
+            for (int tap = 0; tap < TAPS; ++tap) {
+                const int off = (TAPS == 1) ? 0 : (tap / 3 - 1) * G::Wp + (tap % 3 - 1);
+                const uint32_t d = tmem_base + (tap < 5 ? tap * CX : ((16u << 16) + (tap - 5) * CX));
 #pragma unroll
-                    for (int ks = 0; ks < kTile / 16; ++ks) {
-                        const uint64_t ad = make_smem_desc(g_addr + ks * 256, 128, kTile * 16);
-                        const uint64_t bd = make_smem_desc(x_addr + (G::HALO + off + ks * 16) * 16, 128, G::RT * 16);
-                        umma_bf16(d, ad, bd, idesc, (it | ks) != 0);
-                    }
-                }
-                umma_commit(bar_empty + s);
+                for (int ks = 0; ks < kTile / 16; ++ks)
+                    umma_bf16_elect(d, desc_add(g_base, ks * 256), desc_add(x_base, (G::HALO + off + ks * 16) * 16), idesc,
+                                    ks != 0 ? 1u : acc_flag);
             }
-            if (it > 0) umma_commit(bar_done);
+            umma_commit_elect(bar_empty + s);
         }
+        if (it > 0) umma_commit_elect(bar_done);
     } else if ((int)blockIdx.x < a.nt) {
         // ===== one final flush: TMEM -> atomics into the flat gradient =====
         mbar_wait(bar_done, 0);
@@ -248,38 +247,39 @@ __global__ void __launch_bounds__(192, 1) wgrad_dup_kernel(const WgradArgs a) {
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc128 = make_idesc_bf16(128, CX, 1, 1);
-            constexpr uint32_t idesc64 = make_idesc_bf16(64, CX, 1, 1);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
-                const int s = it % C::NSTAGE;
-                const uint32_t ph = (it / C::NSTAGE) & 1;
-                mbar_wait(bar_full + s, ph);
-                tc_fence_after_sync();
-                const uint32_t g_addr = smem_u32(s_in + s * C::STAGE_BYTES);
-                const uint32_t x_addr = g_addr + C::G_BYTES;
+        // whole warp, one elected lane issues (tc05.cuh: warp-convergent issue)
+        constexpr uint32_t idesc128 = make_idesc_bf16(128, CX, 1, 1);
+        constexpr uint32_t idesc64 = make_idesc_bf16(64, CX, 1, 1);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
+            const int s = it % C::NSTAGE;
+            const uint32_t ph = (it / C::NSTAGE) & 1;
+            mbar_wait(bar_full + s, ph);
+            tc_fence_after_sync();
+            const uint32_t g_addr = smem_u32(s_in + s * C::STAGE_BYTES);
+            const uint64_t g_base = make_smem_desc(g_addr, 128, kTile * 16);
+            const uint64_t x_base = make_smem_desc(g_addr + C::G_BYTES, 128, G::RT * 16);
+            const uint32_t acc_flag = it != 0;
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
-                    const int off = (ky - 1) * G::Wp - 1;   // kx = 0; copy d adds d
+            for (int ky = 0; ky < 3; ++ky) {
+                const int off = (ky - 1) * G::Wp - 1;   // kx = 0; copy d adds d
 #pragma unroll
-                    for (int ks = 0; ks < kTile / 16; ++ks) {
-                        const uint64_t ad = make_smem_desc(g_addr + ks * 256, 128, kTile * 16);
-                        const uint64_t bd = make_smem_desc(x_addr + (G::HALO + off + ks * 16) * 16, 128, G::RT * 16);
-                        umma_bf16(tmem_base + ky * CX, ad, bd, idesc128, (it | ks) != 0);
-                        if constexpr (CG == 64) {
-                            // kx = 2 from copy 0 with the X window moved two rows on; ky = 0,1 share columns
-                            // 3*CX.. through the lane-16 interleave of M = 64 accumulators, ky = 2 sits at 4*CX
-                            const uint64_t bd2 = make_smem_desc(x_addr + (G::HALO + off + 2 + ks * 16) * 16, 128, G::RT * 16);
-                            const uint32_t d2 = tmem_base + (ky < 2 ? 3 * CX + ((uint32_t)(ky * 16) << 16) : 4 * CX);
-                            umma_bf16(d2, ad, bd2, idesc64, (it | ks) != 0);
-                        }
+                for (int ks = 0; ks < kTile / 16; ++ks) {
+                    const uint64_t ad = desc_add(g_base, ks * 256);
+                    umma_bf16_elect(tmem_base + ky * CX, ad, desc_add(x_base, (G::HALO + off + ks * 16) * 16), idesc128,
+                                    ks != 0 ? 1u : acc_flag);
+                    if constexpr (CG == 64) {
+                        // kx = 2 from copy 0 with the X window moved two rows on; ky = 0,1 share columns
+                        // 3*CX.. through the lane-16 interleave of M = 64 accumulators, ky = 2 sits at 4*CX
+                        const uint32_t d2 = tmem_base + (ky < 2 ? 3 * CX + ((uint32_t)(ky * 16) << 16) : 4 * CX);
+                        umma_bf16_elect(d2, ad, desc_add(x_base, (G::HALO + off + 2 + ks * 16) * 16), idesc64,
+                                        ks != 0 ? 1u : acc_flag);
                     }
                 }
-                umma_commit(bar_empty + s);
             }
-            if (it > 0) umma_commit(bar_done);
+            umma_commit_elect(bar_empty + s);
         }
+        if (it > 0) umma_commit_elect(bar_done);
     } else if ((int)blockIdx.x < a.nt) {
         mbar_wait(bar_done, 0);
         tc_fence_after_sync();
