@@ -162,8 +162,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
             const int n0 = (int)((int64_t)sp * n_tiles / a.nsplit), n1 = (int)((int64_t)(sp + 1) * n_tiles / a.nsplit);
             const int row = mt * kBM + q * 32 + lane;
             const bool rvalid = row < a.M;
-            float best = -INFINITY;
-            int64_t best_i = INT64_MAX;
+            // four independent running maxima (columns k % 4): one serial compare/select chain over all
+            // 256 columns of a tile is a ~2000-cycle dependency chain per thread
+            float best4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            int best4_i[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
             float rs = 1.f;
             if (EPI == GE_ARGMAX && a.row_scale && rvalid) rs = __ldg(a.row_scale + row);
             for (int nt = n0; nt < n1; ++nt, ++it) {
@@ -176,6 +178,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                 for (int c0 = 0; c0 < kBN; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld32(taddr + c0, r);
+                    // lane l fetches the bias of column c0 + l (one coalesced 128 B load); columns get it by shuffle
+                    const float bias_l = a.bias ? __ldg(a.bias + nt * kBN + c0 + lane) : 0.f;
                     tmem_ld_wait();
                     if (EPI != GE_RES_LN && c0 + 32 == kBN) {
                         tc_fence_before_sync();
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                             float v[8];
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
-                                v[k] = __uint_as_float(r[pj * 8 + k]) + (a.bias ? __ldg(a.bias + nb + pj * 8 + k) : 0.f);
+                                v[k] = __uint_as_float(r[pj * 8 + k]) + __shfl_sync(0xffffffffu, bias_l, pj * 8 + k);
                                 if (a.relu) v[k] = fmaxf(v[k], 0.f);
                             }
                             if (rvalid) {
@@ -201,14 +205,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                     } else if constexpr (EPI == GE_RES_F32) {
 #pragma unroll
                         for (int pj = 0; pj < 8; ++pj) {
+                            float bq[4];   // shuffles stay outside the row-validity branch (all lanes take part)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) bq[k] = __shfl_sync(0xffffffffu, bias_l, pj * 4 + k);
                             if (rvalid) {
                                 const int64_t pl = nb / 4 + pj;
                                 const float4 rv = *reinterpret_cast<const float4*>(a.res + pl * a.res_ps + (int64_t)row * 16);
                                 float4 o;
-                                o.x = __uint_as_float(r[pj * 4 + 0]) + __ldg(a.bias + nb + pj * 4 + 0) + rv.x;
-                                o.y = __uint_as_float(r[pj * 4 + 1]) + __ldg(a.bias + nb + pj * 4 + 1) + rv.y;
-                                o.z = __uint_as_float(r[pj * 4 + 2]) + __ldg(a.bias + nb + pj * 4 + 2) + rv.z;
-                                o.w = __uint_as_float(r[pj * 4 + 3]) + __ldg(a.bias + nb + pj * 4 + 3) + rv.w;
+                                o.x = __uint_as_float(r[pj * 4 + 0]) + bq[0] + rv.x;
+                                o.y = __uint_as_float(r[pj * 4 + 1]) + bq[1] + rv.y;
+                                o.z = __uint_as_float(r[pj * 4 + 2]) + bq[2] + rv.z;
+                                o.w = __uint_as_float(r[pj * 4 + 3]) + bq[3] + rv.w;
                                 *reinterpret_cast<float4*>(a.out_f32 + pl * a.of_ps + (int64_t)row * 16) = o;
                             }
                         }
@@ -219,10 +226,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                         for (int pj = 0; pj < 8; ++pj) {
                             float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (rvalid) rv = *reinterpret_cast<const float4*>(a.res + (int64_t)(nb / 4 + pj) * a.res_ps + (int64_t)row * 16);
-                            const float v0 = __uint_as_float(r[pj * 4 + 0]) + __ldg(a.bias + nb + pj * 4 + 0) + rv.x;
-                            const float v1 = __uint_as_float(r[pj * 4 + 1]) + __ldg(a.bias + nb + pj * 4 + 1) + rv.y;
-                            const float v2 = __uint_as_float(r[pj * 4 + 2]) + __ldg(a.bias + nb + pj * 4 + 2) + rv.z;
-                            const float v3 = __uint_as_float(r[pj * 4 + 3]) + __ldg(a.bias + nb + pj * 4 + 3) + rv.w;
+                            const float v0 = __uint_as_float(r[pj * 4 + 0]) + __shfl_sync(0xffffffffu, bias_l, pj * 4 + 0) + rv.x;
+                            const float v1 = __uint_as_float(r[pj * 4 + 1]) + __shfl_sync(0xffffffffu, bias_l, pj * 4 + 1) + rv.y;
+                            const float v2 = __uint_as_float(r[pj * 4 + 2]) + __shfl_sync(0xffffffffu, bias_l, pj * 4 + 2) + rv.z;
+                            const float v3 = __uint_as_float(r[pj * 4 + 3]) + __shfl_sync(0xffffffffu, bias_l, pj * 4 + 3) + rv.w;
                             ln_sum += (v0 + v1) + (v2 + v3);
                             ln_sq = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, ln_sq))));
                             vb[pj * 4 + 0] = __float_as_uint(v0);
@@ -232,23 +239,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                         }
                         tmem_st32(taddr + c0, vb);
                     } else {
-                        if (rvalid) {
-                            const float* arow = a.ar ? a.ar + (int64_t)row * a.ar_ld : nullptr;
+                        const float* arow = (a.ar && rvalid) ? a.ar + (int64_t)row * a.ar_ld : nullptr;
+                        const bool full = nb + 32 <= a.n_valid;   // tile-uniform: only the last tile of a padded vocabulary is partial
 #pragma unroll
-                            for (int k = 0; k < 32; ++k) {
-                                const int n = nb + k;
-                                if (n < a.n_valid) {
-                                    float v = __uint_as_float(r[k]) * rs + (a.bias ? __ldg(a.bias + n) : 0.f);
-                                    if (arow) {
-                                        // src/shakespeare.py:449-466: both logit sets divided by the
-                                        // temperature, then mixed (1-alpha)*ar + alpha*diff
-                                        v = (1.0f - a.alpha) * (__ldg(arow + n) * a.inv_temp) + a.alpha * (v * a.inv_temp);
-                                    }
-                                    if (v > best) {   // strict: first (lowest) index wins ties, as torch.argmax
-                                        best = v;
-                                        best_i = n;
-                                    }
-                                }
+                        for (int k = 0; k < 32; ++k) {
+                            const int n = nb + k;
+                            float v = __uint_as_float(r[k]) * rs + __shfl_sync(0xffffffffu, bias_l, k);
+                            if (arow) {
+                                // src/shakespeare.py:449-466: both logit sets divided by the temperature,
+                                // then mixed (1-alpha)*ar + alpha*diff
+                                v = (1.0f - a.alpha) * (__ldg(arow + (full || n < a.n_valid ? n : 0)) * a.inv_temp) + a.alpha * (v * a.inv_temp);
+                            }
+                            if (!full && n >= a.n_valid) v = -INFINITY;
+                            if (v > best4[k & 3]) {   // strict: first (lowest) index wins ties, as torch.argmax
+                                best4[k & 3] = v;
+                                best4_i[k & 3] = n;
                             }
                         }
                     }
@@ -287,9 +292,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                 }
             }
             if constexpr (EPI == GE_ARGMAX) {
+                float best = best4[0];
+                int bi = best4_i[0];
+#pragma unroll
+                for (int j = 1; j < 4; ++j) {
+                    if (best4[j] > best || (best4[j] == best && best4_i[j] < bi)) {
+                        best = best4[j];
+                        bi = best4_i[j];
+                    }
+                }
                 const int64_t slot = (int64_t)(sp * 2 + grp) * a.Mp + row;
                 a.part_val[slot] = best;
-                a.part_idx[slot] = best_i;
+                a.part_idx[slot] = bi == 0x7fffffff ? INT64_MAX : (int64_t)bi;
             }
         }
     }
