@@ -153,61 +153,58 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc1 = make_idesc_bf16(128, kFfnC);
-            constexpr uint32_t idesc2 = make_idesc_bf16(128, kFfnD);
-            const uint32_t a_addr = smem_u32(sA), p_addr = smem_u32(sP);
-            int kit = 0, ti = 0;
-            auto g1 = [&](int cg) {   // cg: chunk counter across tiles (buffer cg&1, use index cg>>1)
-                const int buf = cg & 1;
-                mbar_wait(bar_acc1_empty + buf, ((cg >> 1) & 1) ^ 1);
+        // ===== MMA issuer: whole warp, one elected lane issues (tc05.cuh: warp-convergent issue) =====
+        constexpr uint32_t idesc1 = make_idesc_bf16(128, kFfnC);
+        constexpr uint32_t idesc2 = make_idesc_bf16(128, kFfnD);
+        const uint64_t a_base = make_smem_desc(smem_u32(sA), 2048, 128);
+        const uint64_t p_base = make_smem_desc(smem_u32(sP), 2048, 128);
+        int kit = 0, ti = 0;
+        auto g1 = [&](int cg) {   // cg: chunk counter across tiles (buffer cg&1, use index cg>>1)
+            const int buf = cg & 1;
+            mbar_wait(bar_acc1_empty + buf, ((cg >> 1) & 1) ^ 1);
+            tc_fence_after_sync();
+            for (int kb = 0; kb < 4; ++kb, ++kit) {
+                const int s = kit % kFfnStages;
+                mbar_wait(bar_full + s, (kit / kFfnStages) & 1);
                 tc_fence_after_sync();
-                for (int kb = 0; kb < 4; ++kb, ++kit) {
+                const uint64_t b_base = make_smem_desc(smem_u32(sR + s * kFfnStage), 2048, 128);
+                const uint32_t acc_flag = kb != 0;
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    umma_bf16_elect(t_acc1 + buf * kFfnC, desc_add(a_base, (kb * 8 + 2 * ks) * 2048), desc_add(b_base, (2 * ks) * 2048),
+                                    idesc1, ks != 0 ? 1u : acc_flag);
+                umma_commit_multicast_elect(bar_empty + s, kAll);
+            }
+            umma_commit_elect(bar_acc1_full + buf);
+        };
+        for (int mt = cluster_id * kFfnCluster + (int)crank; mt < m_tiles; mt += n_clusters * kFfnCluster, ++ti) {
+            mbar_wait(bar_a_full, ti & 1);
+            tc_fence_after_sync();
+            const int cg0 = ti * kFfnChunks;
+            g1(cg0);
+            g1(cg0 + 1);
+            for (int c = 0; c < kFfnChunks; ++c) {
+                const int cg = cg0 + c;
+                if (c == 0) mbar_wait(bar_acc2_empty, (ti & 1) ^ 1);
+                mbar_wait(bar_p_full, cg & 1);
+                tc_fence_after_sync();
+                for (int kb = 0; kb < 2; ++kb, ++kit) {
                     const int s = kit % kFfnStages;
                     mbar_wait(bar_full + s, (kit / kFfnStages) & 1);
                     tc_fence_after_sync();
-                    const uint32_t b_addr = smem_u32(sR + s * kFfnStage);
+                    const uint64_t b_base = make_smem_desc(smem_u32(sR + s * kFfnStage), 4096, 128);
+                    const uint32_t acc_flag = (c | kb) != 0;
 #pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t ad = make_smem_desc(a_addr + (kb * 8 + 2 * ks) * 2048, 2048, 128);
-                        const uint64_t bd = make_smem_desc(b_addr + (2 * ks) * 2048, 2048, 128);
-                        umma_bf16(t_acc1 + buf * kFfnC, ad, bd, idesc1, (kb | ks) != 0);
-                    }
-                    umma_commit_multicast(bar_empty + s, kAll);
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_bf16_elect(t_acc2, desc_add(p_base, (kb * 8 + 2 * ks) * 2048), desc_add(b_base, (2 * ks) * 4096), idesc2,
+                                        ks != 0 ? 1u : acc_flag);
+                    umma_commit_multicast_elect(bar_empty + s, kAll);
                 }
-                umma_commit(bar_acc1_full + buf);
-            };
-            for (int mt = cluster_id * kFfnCluster + (int)crank; mt < m_tiles; mt += n_clusters * kFfnCluster, ++ti) {
-                mbar_wait(bar_a_full, ti & 1);
-                tc_fence_after_sync();
-                const int cg0 = ti * kFfnChunks;
-                g1(cg0);
-                g1(cg0 + 1);
-                for (int c = 0; c < kFfnChunks; ++c) {
-                    const int cg = cg0 + c;
-                    if (c == 0) mbar_wait(bar_acc2_empty, (ti & 1) ^ 1);
-                    mbar_wait(bar_p_full, cg & 1);
-                    tc_fence_after_sync();
-                    for (int kb = 0; kb < 2; ++kb, ++kit) {
-                        const int s = kit % kFfnStages;
-                        mbar_wait(bar_full + s, (kit / kFfnStages) & 1);
-                        tc_fence_after_sync();
-                        const uint32_t b_addr = smem_u32(sR + s * kFfnStage);
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            const uint64_t ad = make_smem_desc(p_addr + (kb * 8 + 2 * ks) * 2048, 2048, 128);
-                            const uint64_t bd = make_smem_desc(b_addr + (2 * ks) * 4096, 4096, 128);
-                            umma_bf16(t_acc2, ad, bd, idesc2, (c | kb | ks) != 0);
-                        }
-                        umma_commit_multicast(bar_empty + s, kAll);
-                    }
-                    umma_commit(bar_p_empty);                 // P may be overwritten once these MMAs retire
-                    if (c == kFfnChunks - 1) umma_commit(bar_acc2_full);
-                    if (c + 2 < kFfnChunks) {
-                        g1(cg + 2);
-                        if (c + 2 == kFfnChunks - 1) umma_commit(bar_a_empty);   // last G1 of the tile: A may be reloaded
-                    }
+                umma_commit_elect(bar_p_empty);                 // P may be overwritten once these MMAs retire
+                if (c == kFfnChunks - 1) umma_commit_elect(bar_acc2_full);
+                if (c + 2 < kFfnChunks) {
+                    g1(cg + 2);
+                    if (c + 2 == kFfnChunks - 1) umma_commit_elect(bar_a_empty);   // last G1 of the tile: A may be reloaded
                 }
             }
         }
@@ -229,6 +226,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
                 for (int c0 = 0; c0 < kFfnC; c0 += 32) {
                     uint32_t r[32];
                     tmem_ld32(t_acc1 + lane_base + grp * kFfnC + c0, r);
+                    const float bias_l = __ldg(a.b1 + c * kFfnC + c0 + lane);   // coalesced; broadcast by shuffle below
                     tmem_ld_wait();
                     if (c0 + 32 == kFfnC) {
                         tc_fence_before_sync();
@@ -240,7 +238,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
                         float v[8];
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
-                            v[k] = fmaxf(__uint_as_float(r[pj * 8 + k]) + __ldg(a.b1 + c * kFfnC + c0 + pj * 8 + k), 0.f);
+                            v[k] = fmaxf(__uint_as_float(r[pj * 8 + k]) + __shfl_sync(0xffffffffu, bias_l, pj * 8 + k), 0.f);
                         pk[c0 / 8 + pj] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                                                      pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
                     }
@@ -263,15 +261,16 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
             for (int c0 = 0; c0 < kFfnD; c0 += 32) {
                 uint32_t r[32], vb[32];
                 tmem_ld32(taddr + c0, r);
+                const float bias_l = __ldg(a.b2 + c0 + lane);
                 tmem_ld_wait();
 #pragma unroll
                 for (int pj = 0; pj < 8; ++pj) {
                     float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (rvalid) rv = *reinterpret_cast<const float4*>(a.res + (int64_t)(c0 / 4 + pj) * a.ps + (int64_t)row * 16);
-                    const float v0 = __uint_as_float(r[pj * 4 + 0]) + __ldg(a.b2 + c0 + pj * 4 + 0) + rv.x;
-                    const float v1 = __uint_as_float(r[pj * 4 + 1]) + __ldg(a.b2 + c0 + pj * 4 + 1) + rv.y;
-                    const float v2 = __uint_as_float(r[pj * 4 + 2]) + __ldg(a.b2 + c0 + pj * 4 + 2) + rv.z;
-                    const float v3 = __uint_as_float(r[pj * 4 + 3]) + __ldg(a.b2 + c0 + pj * 4 + 3) + rv.w;
+                    const float v0 = __uint_as_float(r[pj * 4 + 0]) + __shfl_sync(0xffffffffu, bias_l, pj * 4 + 0) + rv.x;
+                    const float v1 = __uint_as_float(r[pj * 4 + 1]) + __shfl_sync(0xffffffffu, bias_l, pj * 4 + 1) + rv.y;
+                    const float v2 = __uint_as_float(r[pj * 4 + 2]) + __shfl_sync(0xffffffffu, bias_l, pj * 4 + 2) + rv.z;
+                    const float v3 = __uint_as_float(r[pj * 4 + 3]) + __shfl_sync(0xffffffffu, bias_l, pj * 4 + 3) + rv.w;
                     ln_sum += (v0 + v1) + (v2 + v3);
                     ln_sq = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, ln_sq))));
                     vb[pj * 4 + 0] = __float_as_uint(v0);

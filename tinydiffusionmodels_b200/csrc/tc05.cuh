@@ -197,6 +197,14 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
         ::"r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void umma_commit_multicast_elect(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+        ::"r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
 // descriptor = per-tile base + compile-time byte offset (the 14-bit address field cannot carry out:
 // shared memory is < 256 KB)
 __device__ __forceinline__ uint64_t desc_add(uint64_t base, uint32_t byte_off) {
