@@ -103,12 +103,13 @@ int tdm_unet_pack_weights(const float* flat_params, void* wpack, void* stream);
 /* The workspace must be zero-filled once after allocation (guard rows), then may be reused
  * for the same batch size; zero it again before using it with a different batch size. */
 
-/* Test/debug aid: workspace layout for `batch` as 14 int64 written to HOST memory:
+/* Test/debug aid: workspace layout for `batch` as 16 int64 written to HOST memory:
  * {tiles28, tiles14, plane_stride28, plane_stride14, off_t1, off_cat, off_p1, off_t2, off_s2,
- *  off_h2, off_t3, off_t4, off_s4, total_bytes}.  Activation tensor [C][pos] lives at
+ *  off_h2, off_t3, off_t4, off_s4, total_bytes, off_h3, 0}.  Activation tensor [C][pos] lives at
  * off + (c/8)*plane_stride + (GUARD + pos)*16 + (c%8)*2 with pos(b,y,x) = b*S + (y+1)*(W+1) + x,
- * S = (W+1)^2, GUARD = 40 (W=28) or 24 (W=14). */
-int tdm_unet_debug_layout(int64_t batch, int64_t* host_out14);
+ * S = (W+1)^2, GUARD = 40 (W=28) or 24 (W=14).  In the sampling path rb3's output stays at 14x14
+ * (off_h3) and channels 0..63 of the concat buffer are not materialised. */
+int tdm_unet_debug_layout(int64_t batch, int64_t* host_out16);
 
 /* SimpleUNet.forward(x, t) (src/mnist.py:76-87).  x: [batch,1,28,28] fp32, t: [batch] int64,
  * eps_out: [batch,1,28,28] fp32. */

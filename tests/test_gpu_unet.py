@@ -55,12 +55,16 @@ def test_unet_forward_matches_oracle(cuda, batch):
     torch.cuda.synchronize()
     # layer-by-layer report first: a failure names the first layer that diverges
     inter = _oracle_intermediates(sd, x, t)
-    checks = [("t1", "rb1.t", None), ("cat", "cat", None), ("p1", "p1", None), ("t2", "rb2.t", None),
-              ("s2", "rb2.s", None), ("h2", "h2", None), ("t3", "rb3.t", None), ("t4", "rb4.t", None),
-              ("s4", "rb4.s", None)]
+    # (workspace buffer, oracle tensor, channel slice of the buffer): in the sampling path the concat
+    # buffer only holds h1 (channels 64..95); h3 stays at 14x14 and is upsampled inside rb4.conv1
+    checks = [("t1", "rb1.t", None), ("cat", "h1", slice(64, 96)), ("p1", "p1", None), ("t2", "rb2.t", None),
+              ("s2", "rb2.s", None), ("h2", "h2", None), ("t3", "rb3.t", None), ("h3", "h3", None),
+              ("t4", "rb4.t", None), ("s4", "rb4.s", None)]
     report = []
-    for ws_name, key, _ in checks:
+    for ws_name, key, sl in checks:
         a = read_activation(eng, ws_name, batch).cpu()
+        if sl is not None:
+            a = a[:, sl]
         report.append((ws_name, rel_rms(a, inter[key])))
     msg = ", ".join(f"{n}={e:.2e}" for n, e in report)
     print("layer rel-rms:", msg)

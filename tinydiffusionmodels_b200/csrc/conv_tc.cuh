@@ -5,6 +5,9 @@
 //               per iteration via 1-D bulk async copies into a ring of smem stages
 //   warp 1      one thread issues the tcgen05.mma of a tile (M = 128 positions, K = 16 channels);
 //               the A operand of every tap is the same smem tile at a shifted row offset
+//   last PROD   (PROD > 0 only) gather producers: build the first 8 channel planes of the tile from a
+//               HALF-resolution tensor (nearest x2 upsample, src/mnist.py:83) so the upsampled
+//               activation is never written to HBM; the remaining planes still arrive by bulk copy
 //   warps 2..   kEpiGroups groups of 8 epilogue warps; group g owns TMEM accumulator stage g; inside a
 //               group two warps share each TMEM lane quarter and take alternate 16-channel chunks
 //
@@ -61,12 +64,24 @@ struct ConvArgs {
     // training forward: ReLU masks, one uint32 per 32 channels per position: mask[chunk*mask_stride+pos]
     uint32_t* mask;
     int64_t mask_stride;
+    // PROD = 1: half-resolution source of input planes 0..7 (14x14 geometry, row -GUARD of plane 0)
+    const uint8_t* in2;
+    int64_t in2_ps;
 };
 
 constexpr int kEpiGroups = 4;  // epilogue warp groups == TMEM accumulator stages (tiles in flight)
 constexpr int kHalves = 1;     // warps per TMEM lane quarter inside a group (2: alternate 16-channel chunks)
 
-template <int W, int CIN, int COUT, bool SKIPG, int TAPS, bool KXC>
+constexpr int kGatherPlanes = 8;   // planes built by the gather producers when PROD > 0 (the 64 h3 channels)
+#ifndef TDM_GATHER_WARPS
+#define TDM_GATHER_WARPS 2
+#endif
+#ifndef TDM_GATHER_MODE
+#define TDM_GATHER_MODE 2   // 0 = LDG.128 -> registers -> STS.128; 1 = cp.async.cg; 2 = cp.async.ca
+#endif
+constexpr int kGatherWarps = TDM_GATHER_WARPS;   // PROD used by rb4.conv1 on the sampling path
+
+template <int W, int CIN, int COUT, bool SKIPG, int TAPS, bool KXC, int PROD = 0>
 struct ConvCfg {
     using G = Geo<W>;
     static constexpr int NPL = CIN / 8;
@@ -88,7 +103,8 @@ struct ConvCfg {
     static_assert(NMAIN <= 256 && NMAIN % 16 == 0, "UMMA N");
     static constexpr int SMEM_BYTES = W_BYTES + NSTAGE * STAGE_BYTES + PARAM_BYTES + XCH_BYTES + 256;
     // warp 0 producer, warp 1 MMA issuer, then NACC groups of 8 epilogue warps
-    static constexpr int THREADS = 64 + 128 * kHalves * NACC;
+    static constexpr int THREADS = 64 + 128 * kHalves * NACC + 32 * PROD;
+    static constexpr int BULK_PLANES = PROD ? NPL - kGatherPlanes : NPL;
     // tile t: accumulator rows [t*TSTRIDE - ROW0, +128), output rows are tile rows [ROW0, 128-ROW0)
     static constexpr int TSTRIDE = KXC ? 126 : 128;
     static constexpr int ROW0 = KXC ? 1 : 0;
@@ -105,9 +121,10 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, bool KXC = false>
-__global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups, 1) conv3x3_tc_kernel(const ConvArgs a) {
-    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC>;
+template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, bool KXC = false, int PROD = 0>
+__global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1) conv3x3_tc_kernel(const ConvArgs a) {
+    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC, PROD>;
+    static_assert(PROD == 0 || (W == 28 && CIN == 96), "gather producers serve rb4.conv1's concat input");
     using G = Geo<W>;
     static_assert(COUT == 32 || COUT == 64 || COUT == 96, "COUT");
     static_assert(TAPS == 9 || TAPS == 1, "3x3 or 1x1");
@@ -153,7 +170,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups, 1) conv3x3_tc
     if (threadIdx.x == 0) {
         mbar_init(bar_w, 1);
         for (int i = 0; i < C::NSTAGE; ++i) {
-            mbar_init(bar_full + i, 1);
+            mbar_init(bar_full + i, 1 + (PROD ? (TDM_GATHER_MODE != 0 ? 32 : 1) : 0));   // bulk issuer + the gather warp owning the tile (per lane for cp.async)
             mbar_init(bar_empty + i, 1);
         }
         for (int i = 0; i < C::NACC; ++i) {
@@ -185,14 +202,15 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups, 1) conv3x3_tc
             const uint32_t ph = (it / C::NSTAGE) & 1;
             if (lane == 0) {
                 mbar_wait(bar_empty + s, ph ^ 1);
-                mbar_arrive_expect_tx(bar_full + s, C::STAGE_BYTES);
+                mbar_arrive_expect_tx(bar_full + s, C::BULK_PLANES * G::RT * 16);
             }
             __syncwarp();
-            if (lane < C::NPL) {
-                // smem row 0 = global row tile*TSTRIDE - ROW0 - HALO; the buffer starts at row -GUARD
+            if (lane < C::BULK_PLANES) {
+                // smem row 0 = global row tile*TSTRIDE - ROW0 - HALO; the buffer starts at row -GUARD.
+                // With gather producers the bulk planes (a.in = their first plane) sit after the gathered ones.
                 const int64_t row = (int64_t)tile * C::TSTRIDE - C::ROW0 - G::HALO + G::GUARD;
-                bulk_g2s(s_in + s * C::STAGE_BYTES + lane * (G::RT * 16), a.in + lane * a.in_ps + row * 16,
-                         G::RT * 16, bar_full + s);
+                bulk_g2s(s_in + s * C::STAGE_BYTES + (lane + (C::NPL - C::BULK_PLANES)) * (G::RT * 16),
+                         a.in + lane * a.in_ps + row * 16, G::RT * 16, bar_full + s);
             }
         }
     } else if (warp == 1) {
@@ -211,6 +229,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups, 1) conv3x3_tc
             const uint32_t aph = (it / C::NACC) & 1;
             mbar_wait(bar_acce + acc, aph ^ 1);
             mbar_wait(bar_full + s, ph);
+            if constexpr (PROD != 0 && TDM_GATHER_MODE != 0) fence_proxy_async_smem();   // cp.async (generic proxy) data -> async-proxy MMA reads
             tc_fence_after_sync();
             const uint64_t in_base = make_smem_desc(smem_u32(s_in + s * C::STAGE_BYTES), G::RT * 16, 128);
             const uint32_t d = tmem_base + acc * C::ACC_COLS;
@@ -244,6 +263,89 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups, 1) conv3x3_tc
             umma_commit_elect(bar_empty + s);   // smem stage reusable once these MMAs retire
             umma_commit_elect(bar_accf + acc);  // accumulator complete
         }
+    } else if (PROD != 0 && warp >= 2 + 4 * kHalves * kEpiGroups) {
+        // ===== gather producers (PROD warps): planes 0..7 of the tile = nearest-x2 upsample of the 14x14 source.
+        //       Warp w owns tiles it = w (mod PROD) entirely; lane = smem row.  Measured on B200 @16384 (kernel us):
+        //         TDM_GATHER_MODE 2  cp.async.ca (through L1), 2 warps   936   <- default
+        //                         1  cp.async.cg (L1 bypass),  2 warps  1036   (ncu: 34 smem wavefronts per LDGSTS,
+        //                                                                       one per lane; the x2/y2 duplicates
+        //                                                                       also go back to L2)
+        //                         0  LDG.128 -> regs -> STS.128, 2 warps 1263   (latency-bound: 16 loads in flight)
+        //         gather skipped (upper bound of what is left to win)    761
+        //       Warp count: registers are per SM sub-partition, so <= 20 warps (5 per SMSP) keep the 96-register
+        //       cap the epilogue warps need; 21+ warps drop it to 80 and cost ~90 us.  cp.async needs no staging
+        //       registers and no waiting: completion reaches the full barrier through
+        //       cp.async.mbarrier.arrive.noinc (one arrival per lane), so a warp runs ahead as far as the ring
+        //       has free stages. =====
+        const int pw = warp - (2 + 4 * kHalves * kEpiGroups);
+        using GS = Geo<14>;
+        static_assert(PROD == 0 || G::RT % 64 == 0, "two rows per lane per iteration");
+        for (int it = pw, tile = blockIdx.x + pw * gridDim.x; tile < nt; tile += PROD * gridDim.x, it += PROD) {
+            const int s = it % C::NSTAGE;
+            const uint32_t ph = (it / C::NSTAGE) & 1;
+            mbar_wait(bar_empty + s, ph ^ 1);
+            uint8_t* st = s_in + s * C::STAGE_BYTES;
+            const int pos0 = tile * C::TSTRIDE - C::ROW0 - G::HALO;   // may be negative for tile 0
+#if TDM_GATHER_MODE != 0
+#pragma unroll 1
+            for (int r = lane; r < G::RT; r += 32) {   // smem row
+                const int pos = pos0 + r;
+                const uint8_t* src = a.in2;            // any valid address when the row is zero-filled
+                uint32_t nbytes = 0;
+                if (pos >= 0) {
+                    const int b = (int)((uint32_t)pos / (uint32_t)G::S);
+                    const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)G::S);
+                    const int rw = rem / G::Wp, c = rem - rw * G::Wp;
+                    if (b < a.batch && rw >= 1 && c < G::W) {
+                        const int64_t p14 = (int64_t)b * GS::S + ((rw - 1) / 2 + 1) * GS::Wp + c / 2;
+                        src = a.in2 + (p14 + GS::GUARD) * 16;
+                        nbytes = 16;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kGatherPlanes; ++j)
+                    cp_async16<TDM_GATHER_MODE == 2>(st + j * (G::RT * 16) + r * 16, nbytes ? src + j * a.in2_ps : src, nbytes);
+            }
+            cp_async_arrive_noinc(bar_full + s);
+#else
+#pragma unroll 1
+            for (int r = lane; r < G::RT; r += 64) {   // smem rows r and r + 32
+                const uint8_t* src[2];
+                bool ok[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int pos = pos0 + r + 32 * h;
+                    src[h] = a.in2;
+                    ok[h] = false;
+                    if (pos >= 0) {
+                        const int b = (int)((uint32_t)pos / (uint32_t)G::S);   // positions fit 32 bits: multiply-shift
+                        const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)G::S);
+                        const int rw = rem / G::Wp, c = rem - rw * G::Wp;
+                        if (b < a.batch && rw >= 1 && c < G::W) {
+                            const int64_t p14 = (int64_t)b * GS::S + ((rw - 1) / 2 + 1) * GS::Wp + c / 2;
+                            src[h] = a.in2 + (p14 + GS::GUARD) * 16;
+                            ok[h] = true;
+                        }
+                    }
+                }
+                uint4 v[2][kGatherPlanes];
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < kGatherPlanes; ++j)
+                        v[h][j] = ok[h] ? __ldg(reinterpret_cast<const uint4*>(src[h] + j * a.in2_ps))
+                                        : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < kGatherPlanes; ++j)
+                        *reinterpret_cast<uint4*>(st + j * (G::RT * 16) + (r + 32 * h) * 16) = v[h][j];
+            }
+            fence_proxy_async_smem();   // this lane's generic-proxy stores -> visible to the MMA's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_full + s);
+#endif
+        }
     } else {
         // ===== epilogue: group g = (warp-2)/4 owns accumulator stage g (tiles it = g, g+NACC, ..),
         //       so the epilogues of consecutive tiles overlap; TMEM lane quarter = warp % 4 =====
@@ -258,8 +360,8 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups, 1) conv3x3_tc
             const int trow = q * 32 + lane;                                   // row inside the tile
             const int64_t pos = (int64_t)tile * C::TSTRIDE - C::ROW0 + trow;  // global position
             const bool owned = trow >= C::ROW0 && trow < 128 - C::ROW0 && pos < a.np;  // this tile outputs pos
-            const int b = (int)(pos / G::S);
-            const int rem = (int)(pos - (int64_t)b * G::S);
+            const int b = (int)((uint32_t)pos / (uint32_t)G::S);   // positions fit 32 bits: division by a constant is a multiply-shift
+            const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)G::S);
             const int r = rem / G::Wp, c = rem - r * G::Wp;
             const bool valid = owned && pos >= 0 && b < a.batch && r >= 1 && c < G::W;
             const int y = r - 1;
@@ -505,10 +607,10 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups, 1) conv3x3_tc
     if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
-template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, bool KXC = false>
+template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, bool KXC = false, int PROD = 0>
 static int launch_conv(const ConvArgs& a, cudaStream_t st, const char* name) {
-    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC>;
-    auto kern = conv3x3_tc_kernel<W, CIN, COUT, EPI, SKIPG, TAPS, KXC>;
+    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC, PROD>;
+    auto kern = conv3x3_tc_kernel<W, CIN, COUT, EPI, SKIPG, TAPS, KXC, PROD>;
     static bool configured = false;
     if (!configured) {
         TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));

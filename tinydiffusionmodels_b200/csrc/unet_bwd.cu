@@ -395,8 +395,8 @@ loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
     for (int it = 0; it < kChunk / 32; ++it) {
         const int64_t pos = base + it * 32 + lane;
         if (pos >= npos) break;
-        const int b = (int)(pos / G::S);
-        const int rem = (int)(pos - (int64_t)b * G::S);
+        const int b = (int)((uint32_t)pos / (uint32_t)G::S);   // positions fit 32 bits: division by a constant is a multiply-shift
+        const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)G::S);
         const int r = rem / G::Wp, c = rem - r * G::Wp;
         const bool valid = b < batch && r >= 1 && c < G::W;
         uint4 o = make_uint4(0, 0, 0, 0);
@@ -472,7 +472,7 @@ __global__ void mask_reduce_kernel(const uint8_t* __restrict__ g, int64_t ps, in
             const uint32_t bits = (words[u] >> ((j & 3) * 8)) & 0xffu;
             float ts = 0.f;
             if (d_ts) {
-                const int b = (int)(pos / S);
+                const int b = (int)((uint32_t)pos / (uint32_t)S);
                 ts = b < batch ? (float)__ldg(t + b) / 1000.0f : 0.f;
             }
             const uint32_t* gw = &gv.x;
@@ -513,8 +513,8 @@ upsample_bwd_kernel(const uint8_t* __restrict__ in, int64_t in_ps, uint8_t* __re
     using GO = Geo<14>;
     const int64_t pos = (int64_t)blockIdx.x * 128 + threadIdx.x;
     const int plane = blockIdx.y;
-    const int b = (int)(pos / GO::S);
-    const int rem = (int)(pos - (int64_t)b * GO::S);
+    const int b = (int)((uint32_t)pos / (uint32_t)GO::S);   // positions fit 32 bits: division by a constant is a multiply-shift
+    const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)GO::S);
     const int r = rem / GO::Wp, c = rem - r * GO::Wp;
     uint4 o = make_uint4(0, 0, 0, 0);
     if (b < batch && r >= 1 && c < GO::W) {
@@ -545,8 +545,8 @@ pool_bwd_add_kernel(const uint8_t* __restrict__ a, int64_t a_ps, const uint8_t* 
     using G14 = Geo<14>;
     const int64_t pos = (int64_t)blockIdx.x * 128 + threadIdx.x;
     const int plane = blockIdx.y;
-    const int b = (int)(pos / G28::S);
-    const int rem = (int)(pos - (int64_t)b * G28::S);
+    const int b = (int)((uint32_t)pos / (uint32_t)G28::S);   // positions fit 32 bits: division by a constant is a multiply-shift
+    const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)G28::S);
     const int r = rem / G28::Wp, c = rem - r * G28::Wp;
     uint4 o = make_uint4(0, 0, 0, 0);
     if (b < batch && r >= 1 && c < G28::W) {
@@ -596,8 +596,8 @@ rb1_wgrad_kernel(const uint8_t* __restrict__ gc, const uint8_t* __restrict__ go,
         for (int i = tid; i < 128 * 9; i += 320) {
             const int p = i / 9, tap = i - p * 9;
             const int64_t pos = (int64_t)tile * 128 + p;
-            const int b = (int)(pos / G::S);
-            const int rem = (int)(pos - (int64_t)b * G::S);
+            const int b = (int)((uint32_t)pos / (uint32_t)G::S);   // positions fit 32 bits: division by a constant is a multiply-shift
+            const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)G::S);
             const int r = rem / G::Wp, c = rem - r * G::Wp;
             float v = 0.f;
             if (b < batch && r >= 1 && c < G::W) {

@@ -123,8 +123,8 @@ rb1_conv1_kernel(const float* __restrict__ x, const int64_t* __restrict__ t,
         float v = 0.f, tsv = 0.f;
         bool ok = false;
         if (pos >= 0) {
-            const int b = (int)(pos / G::S);
-            const int rem = (int)(pos - (int64_t)b * G::S);
+            const int b = (int)((uint32_t)pos / (uint32_t)G::S);   // positions fit 32 bits: division by a constant is a multiply-shift
+            const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)G::S);
             const int r = rem / G::Wp, c = rem - r * G::Wp;
             ok = b < batch && r >= 1 && c < G::W;
             if (ok) {
@@ -202,8 +202,8 @@ avgpool_kernel(const uint8_t* __restrict__ in, int64_t in_ps, uint8_t* __restric
     using GO = Geo<14>;
     const int64_t pos = (int64_t)blockIdx.x * 128 + threadIdx.x;
     const int plane = blockIdx.y;
-    const int b = (int)(pos / GO::S);
-    const int rem = (int)(pos - (int64_t)b * GO::S);
+    const int b = (int)((uint32_t)pos / (uint32_t)GO::S);   // positions fit 32 bits: division by a constant is a multiply-shift
+    const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)GO::S);
     const int r = rem / GO::Wp, c = rem - r * GO::Wp;
     const bool valid = b < batch && r >= 1 && c < GO::W;
     uint4 o = make_uint4(0, 0, 0, 0);
@@ -307,18 +307,33 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     TDM_PROF(6);
     a = ConvArgs{}; a.t = t; a.batch = B; a.np = (int)L.np14;
     a.in = ws + L.t3; a.in_ps = L.ps14; a.w = wp + WP::rb3_c2; a.bias = fp + P::rb3_c2b;
-    a.res = ws + L.h2; a.res_ps = L.ps14; a.out = ws + L.cat; a.out_ps = L.ps28;
+    a.res = ws + L.h2; a.res_ps = L.ps14;
     a.mask = mk(L.m2_3); a.mask_stride = L.np14;
-    if ((rc = launch_conv<14, 64, 64, EPI_RES_UP, false, 9, KX::rb3c2>(a, st, "rb3_conv2"))) return rc;
+    if (sa.train) {
+        // training: the weight gradient of rb4.conv1 needs the concatenated input as a tensor
+        a.out = ws + L.cat; a.out_ps = L.ps28;
+        if ((rc = launch_conv<14, 64, 64, EPI_RES_UP, false, 9, KX::rb3c2>(a, st, "rb3_conv2"))) return rc;
+    } else {
+        // sampling: h3 stays at 14x14; rb4.conv1's gather producers upsample it into the smem tile
+        a.out = ws + L.h3; a.out_ps = L.ps14;
+        if ((rc = launch_conv<14, 64, 64, EPI_RES, false, 9, KX::rb3c2>(a, st, "rb3_conv2"))) return rc;
+    }
 
     // k8: rb4.conv1 (+skip) -> t4, s4
     TDM_PROF(7);
     a = ConvArgs{}; a.t = t; a.batch = B; a.np = (int)L.np28;
-    a.in = ws + L.cat; a.in_ps = L.ps28; a.w = wp + WP::rb4_c1; a.bias = fp + P::rb4_c1b;
+    a.w = wp + WP::rb4_c1; a.bias = fp + P::rb4_c1b;
     a.tw = fp + P::rb4_tw; a.tb = fp + P::rb4_tb; a.sbias = fp + P::rb4_sb;
     a.out = ws + L.t4; a.out_ps = L.ps28; a.out2 = ws + L.s4; a.out2_ps = L.ps28;
     a.mask = mk(L.m1_4); a.mask_stride = L.np28;
-    if ((rc = launch_conv<28, 96, 32, EPI_CONV1, true, 9, KX::rb4c1>(a, st, "rb4_conv1"))) return rc;
+    if (sa.train) {
+        a.in = ws + L.cat; a.in_ps = L.ps28;
+        if ((rc = launch_conv<28, 96, 32, EPI_CONV1, true, 9, KX::rb4c1>(a, st, "rb4_conv1"))) return rc;
+    } else {
+        a.in = ws + L.cat + 8 * L.ps28; a.in_ps = L.ps28;   // h1 planes (bulk); planes 0..7 gathered from h3
+        a.in2 = ws + L.h3; a.in2_ps = L.ps14;
+        if ((rc = launch_conv<28, 96, 32, EPI_CONV1, true, 9, KX::rb4c1, kGatherWarps>(a, st, "rb4_conv1"))) return rc;
+    }
 
     // k9: rb4.conv2 + s4, out conv, optional reverse step
     TDM_PROF(8);
@@ -346,12 +361,12 @@ extern "C" int64_t tdm_unet_workspace_bytes(int64_t batch, int for_backward) {
     return make_ws(batch, for_backward != 0).total;
 }
 
-extern "C" int tdm_unet_debug_layout(int64_t batch, int64_t* host_out14) {
-    TDM_CHECK_ARG(batch > 0 && host_out14, "tdm_unet_debug_layout: bad arguments");
+extern "C" int tdm_unet_debug_layout(int64_t batch, int64_t* host_out16) {
+    TDM_CHECK_ARG(batch > 0 && host_out16, "tdm_unet_debug_layout: bad arguments");
     const UNetWs w = make_ws(batch, false);
-    const int64_t v[14] = {w.nt28, w.nt14, w.ps28, w.ps14, w.t1, w.cat, w.p1,
-                           w.t2,   w.s2,   w.h2,   w.t3,   w.t4, w.s4,  w.total};
-    for (int i = 0; i < 14; ++i) host_out14[i] = v[i];
+    const int64_t v[16] = {w.nt28, w.nt14, w.ps28, w.ps14, w.t1, w.cat, w.p1, w.t2,
+                           w.s2,   w.h2,   w.t3,   w.t4,   w.s4, w.total, w.h3, 0};
+    for (int i = 0; i < 16; ++i) host_out16[i] = v[i];
     return TDM_OK;
 }
 

@@ -10,7 +10,7 @@ struct UNetWs {
     int64_t nt28, nt14, ps28, ps14;  // tiles, plane stride in bytes
     int64_t np28, np14;              // positions covered by tiles (nt*128): mask stride
     // forward activations (bf16 planes)
-    int64_t t1, cat, p1, t2, s2, h2, t3, t4, s4;
+    int64_t t1, cat, p1, t2, s2, h2, t3, t4, s4, h3;
     int64_t fwd_total;
     // training extras: h4, ReLU masks (uint32 per 32 channels per position), gradient scratch
     int64_t h4;
@@ -43,6 +43,7 @@ static inline UNetWs make_ws(int64_t batch, bool for_backward) {
     w.t3 = take(8 * w.ps14);
     w.t4 = take(4 * w.ps28);
     w.s4 = take(4 * w.ps28);
+    w.h3 = take(8 * w.ps14);   // rb3 output at 14x14 (sampling path: upsampled on the fly by rb4.conv1)
     w.fwd_total = o;
     if (for_backward) {
         w.h4 = take(4 * w.ps28);

@@ -159,18 +159,18 @@ class UNetEngine:
 # ---------------------------------------------------------------------------------------------
 _WS_NAMES = ("t1", "cat", "p1", "t2", "s2", "h2", "t3", "t4", "s4")
 _WS_GEOM = {"t1": (28, 32), "cat": (28, 96), "p1": (14, 32), "t2": (14, 64), "s2": (14, 64),
-            "h2": (14, 64), "t3": (14, 64), "t4": (28, 32), "s4": (28, 32)}
+            "h2": (14, 64), "t3": (14, 64), "t4": (28, 32), "s4": (28, 32), "h3": (14, 64)}
 
 
 def read_activation(engine: UNetEngine, name: str, batch: int) -> torch.Tensor:
     """Decode workspace buffer ``name`` into a (B, C, H, W) fp32 tensor (pads dropped)."""
     import ctypes
 
-    arr = (ctypes.c_int64 * 14)()
+    arr = (ctypes.c_int64 * 16)()
     _lib.check(engine.lib.tdm_unet_debug_layout(batch, arr), "tdm_unet_debug_layout")
     v = list(arr)
     ps = {28: v[2], 14: v[3]}
-    off = dict(zip(_WS_NAMES, v[4:13]))[name]
+    off = {**dict(zip(_WS_NAMES, v[4:13])), "h3": v[14]}[name]
     w, c = _WS_GEOM[name]
     halo = (32 if w == 28 else 16) + 8   # GUARD rows in front of position 0
     wp, s = w + 1, (w + 1) * (w + 1)
