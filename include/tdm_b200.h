@@ -99,6 +99,18 @@ int64_t tdm_unet_workspace_bytes(int64_t batch, int for_backward);
  * rb1.conv1.bias, rb1.conv2.weight, ..., out.weight, out.bias; conv weights OIHW) into the
  * kernel-side packed image (bf16 [tap][Cin/8][Cout][8] planes + fp32 biases). */
 int tdm_unet_pack_weights(const float* flat_params, void* wpack, void* stream);
+/* Same, and additionally registers a HOST copy of the flat parameters (181,473 floats, copied into
+ * library-owned memory) for this `wpack` buffer.  While a mirror is registered, tdm_unet_forward /
+ * tdm_unet_p_sample pass the per-channel epilogue vectors (conv / skip biases, time-embedding weight
+ * and bias, the 1x1 out conv) to the kernels BY VALUE as launch arguments - they are then read through
+ * the constant bank instead of shared memory, which the tensor-core operand reads already saturate.
+ * The caller guarantees host and device copies hold the same values.  Repacking the buffer with
+ * tdm_unet_pack_weights drops the mirror (training updates parameters on the device only);
+ * tdm_unet_forget_host_params drops it explicitly (call before freeing `wpack`).  Launch arguments
+ * captured into a CUDA graph are frozen: re-capture after loading new weights. */
+int tdm_unet_pack_weights_host(const float* flat_params, const float* flat_params_host, void* wpack,
+                               void* stream);
+int tdm_unet_forget_host_params(const void* wpack);
 
 /* The workspace must be zero-filled once after allocation (guard rows), then may be reused
  * for the same batch size; zero it again before using it with a different batch size. */

@@ -33,6 +33,8 @@ SIGNATURES: dict[str, tuple] = {
     "tdm_unet_workspace_bytes": (c_int64, [c_int64, c_int]),
     "tdm_unet_debug_layout": (c_int, [c_int64, ctypes.POINTER(c_int64)]),
     "tdm_unet_pack_weights": (c_int, [_P, _P, _P]),
+    "tdm_unet_pack_weights_host": (c_int, [_P, _P, _P, _P]),
+    "tdm_unet_forget_host_params": (c_int, [_P]),
     "tdm_unet_forward": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P]),
     "tdm_unet_p_sample": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_uint64, c_uint64, c_uint32, _P]),
     "tdm_unet_forward_train": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P]),

@@ -22,6 +22,7 @@
 //                tripling N cuts the operand traffic per FLOP by ~2x.  Tiles overlap by
 //                two rows: tile t computes Y for rows [126t-1, 126t+127) and outputs [126t, 126t+126).
 #pragma once
+#include <cstring>
 #include "common.cuh"
 #include "diffusion_math.cuh"
 #include "tc05.cuh"
@@ -31,6 +32,21 @@ namespace tdm {
 
 // EPI_PLAIN: out = acc (+ residual if given) — no bias, no ReLU: the data-gradient convolutions.
 enum : int { EPI_CONV1 = 0, EPI_RES = 1, EPI_RES_X = 2, EPI_RES_UP = 3, EPI_FINAL = 4, EPI_PLAIN = 5 };
+
+// Per-channel epilogue parameters BY VALUE (CPAR = true).  Kernel arguments live in the constant bank, so a
+// compile-time-indexed a.cp.bias[ch] is a c[0x0][..] operand of the FADD itself: no load instruction and,
+// what matters, no shared-memory wavefront.  ncu (profiles/r01_ncu_full_unet_convs_B16384_f.csv): the
+// broadcast LDS.128 of these vectors cost ~8 wavefronts each (4 "ideal" + bank conflicts with the MMA's own
+// operand reads) and kept l1tex__data_pipe_lsu_wavefronts at 80-90 % in rb1.conv2 / rb2.conv1 / rb4.conv1.
+// The values must be known on the host at launch: the sampling engines register a host mirror of the flat
+// parameters (tdm_unet_pack_weights_host); training updates parameters on the device and keeps CPAR = false.
+struct ChanPar {
+    float bias[64];
+    float tw[64];
+    float tb[64];
+    float sbias[64];
+    float aux[72];   // as s_aux: [0,32) aux_w, [32,64) aux_b (EPI_RES_X) / [32] out bias (EPI_FINAL)
+};
 
 struct ConvArgs {
     const uint8_t* in;     // input planes: row -GUARD of plane 0
@@ -67,6 +83,7 @@ struct ConvArgs {
     // PROD = 1: half-resolution source of input planes 0..7 (14x14 geometry, row -GUARD of plane 0)
     const uint8_t* in2;
     int64_t in2_ps;
+    ChanPar cp;            // CPAR = true only
 };
 
 constexpr int kEpiGroups = 4;  // epilogue warp groups == TMEM accumulator stages (tiles in flight)
@@ -121,8 +138,9 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, bool KXC = false, int PROD = 0>
-__global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1) conv3x3_tc_kernel(const ConvArgs a) {
+template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, bool KXC = false, int PROD = 0, bool CPAR = false>
+__global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1) conv3x3_tc_kernel(const __grid_constant__ ConvArgs a) {
+    static_assert(!CPAR || (COUT <= 64 && EPI != EPI_PLAIN), "by-value channel parameters: forward epilogues, <= 64 channels");
     using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC, PROD>;
     static_assert(PROD == 0 || (W == 28 && CIN == 96), "gather producers serve rb4.conv1's concat input");
     using G = Geo<W>;
@@ -157,7 +175,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
     const int nt = (a.np + C::TSTRIDE - 1) / C::TSTRIDE;
 
     // ---- setup -----------------------------------------------------------------------------
-    if (threadIdx.x < COUT) {
+    if (!CPAR && threadIdx.x < COUT) {
         const int c = threadIdx.x;
         s_bias[c] = (EPI == EPI_PLAIN) ? 0.f : a.bias[c];
         s_tw[c] = (EPI == EPI_CONV1) ? a.tw[c] : 0.f;
@@ -499,7 +517,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
                         if constexpr (EPI == EPI_PLAIN) {
                             v[k] = acc[pj * 8 + k];
                         } else {
-                            v[k] = fmaxf(acc[pj * 8 + k] + s_bias[ch], 0.f);
+                            v[k] = fmaxf(acc[pj * 8 + k] + (CPAR ? a.cp.bias[ch] : s_bias[ch]), 0.f);
                         }
                     }
                     if (EPI != EPI_PLAIN && a.mask) {   // training only (uniform branch)
@@ -510,13 +528,13 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const int ch = c0 + pj * 8 + k;
-                            v[k] += fmaf(s_tw[ch], ts, s_tb[ch]);
+                            v[k] += CPAR ? fmaf(a.cp.tw[ch], ts, a.cp.tb[ch]) : fmaf(s_tw[ch], ts, s_tb[ch]);
                         }
                     } else if constexpr (EPI == EPI_RES_X) {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const int ch = c0 + pj * 8 + k;
-                            v[k] += fmaf(s_aux[ch], xin, s_aux[32 + ch]);
+                            v[k] += CPAR ? fmaf(a.cp.aux[ch], xin, a.cp.aux[32 + ch]) : fmaf(s_aux[ch], xin, s_aux[32 + ch]);
                         }
                     } else {
                         const uint32_t* rw = &rv[ci * 2 + pj].x;
@@ -529,7 +547,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
                     }
                     if constexpr (EPI == EPI_FINAL) {
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) dot = fmaf(s_aux[c0 + pj * 8 + k], v[k], dot);
+                        for (int k = 0; k < 8; ++k) dot = fmaf(CPAR ? a.cp.aux[c0 + pj * 8 + k] : s_aux[c0 + pj * 8 + k], v[k], dot);
                     }
                     if (EPI != EPI_FINAL || a.out) {
                         uint4 o;
@@ -568,8 +586,8 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
                             const int ch = c0 + pj * 8 + 2 * k;
-                            const float s0 = __uint_as_float(r2[pj * 8 + 2 * k]) + s_sbias[ch];
-                            const float s1 = __uint_as_float(r2[pj * 8 + 2 * k + 1]) + s_sbias[ch + 1];
+                            const float s0 = __uint_as_float(r2[pj * 8 + 2 * k]) + (CPAR ? a.cp.sbias[ch] : s_sbias[ch]);
+                            const float s1 = __uint_as_float(r2[pj * 8 + 2 * k + 1]) + (CPAR ? a.cp.sbias[ch + 1] : s_sbias[ch + 1]);
                             ow[k] = valid ? pack_bf16x2(s0, s1) : 0u;
                         }
                         if (owned) *reinterpret_cast<uint4*>(a.out2 + plane * a.out2_ps + (pos + G::GUARD) * 16) = o2;
@@ -591,7 +609,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
                     if (half == 0) dot += *sd;
                 }
                 if (half == 0 && valid) {
-                    const float eps = dot + s_aux[32];  // out conv bias (src/mnist.py:87)
+                    const float eps = dot + (CPAR ? a.cp.aux[32] : s_aux[32]);  // out conv bias (src/mnist.py:87)
                     const int64_t oi = (int64_t)b * 784 + y * 28 + c;
                     a.fout[oi] = a.fuse_step ? rstep1(sc, xin, eps, zz, add_noise) : eps;
                 }
@@ -607,10 +625,10 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
     if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
-template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, bool KXC = false, int PROD = 0>
+template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, bool KXC = false, int PROD = 0, bool CPAR = false>
 static int launch_conv(const ConvArgs& a, cudaStream_t st, const char* name) {
     using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC, PROD>;
-    auto kern = conv3x3_tc_kernel<W, CIN, COUT, EPI, SKIPG, TAPS, KXC, PROD>;
+    auto kern = conv3x3_tc_kernel<W, CIN, COUT, EPI, SKIPG, TAPS, KXC, PROD, CPAR>;
     static bool configured = false;
     if (!configured) {
         TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -621,6 +639,22 @@ static int launch_conv(const ConvArgs& a, cudaStream_t st, const char* name) {
     kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(a);
     TDM_CHECK_LAUNCH(name);
     return TDM_OK;
+}
+
+// Forward-pass launch: with a host mirror `hfp` of the flat fp32 parameters (the device copy is `fp`), the
+// per-channel vectors travel by value (CPAR); their host addresses follow from the device pointers in `a`.
+template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, bool KXC = false, int PROD = 0>
+static int launch_conv_fwd(ConvArgs& a, const float* fp, const float* hfp, cudaStream_t st, const char* name) {
+    if (!hfp) return launch_conv<W, CIN, COUT, EPI, SKIPG, TAPS, KXC, PROD, false>(a, st, name);
+    auto mirror = [&](float* dst, const float* dev, int n) {
+        if (dev) std::memcpy(dst, hfp + (dev - fp), (size_t)n * sizeof(float));
+    };
+    mirror(a.cp.bias, a.bias, COUT);
+    if (EPI == EPI_CONV1) { mirror(a.cp.tw, a.tw, COUT); mirror(a.cp.tb, a.tb, COUT); }
+    if (SKIPG) mirror(a.cp.sbias, a.sbias, COUT);
+    if (EPI == EPI_RES_X) { mirror(a.cp.aux, a.aux_w, 32); mirror(a.cp.aux + 32, a.aux_b, 32); }
+    if (EPI == EPI_FINAL) { mirror(a.cp.aux, a.aux_w, 32); mirror(a.cp.aux + 32, a.aux_b, 1); }
+    return launch_conv<W, CIN, COUT, EPI, SKIPG, TAPS, KXC, PROD, true>(a, st, name);
 }
 
 }  // namespace tdm

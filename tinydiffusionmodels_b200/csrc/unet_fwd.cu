@@ -17,6 +17,9 @@
 // warp 1 issues 9*Cin/16 tcgen05.mma (M=128 positions, N=Cout, K=16) per tile whose A operand is
 // the *same* smem tile addressed at nine different row offsets, warps 2-5 drain the TMEM
 // accumulator (double buffered) through the fused epilogue.  Weights stay resident in smem.
+#include <memory>
+#include <mutex>
+#include <vector>
 #include "common.cuh"
 #include "diffusion_math.cuh"
 #include "tc05.cuh"
@@ -229,6 +232,29 @@ avgpool_kernel(const uint8_t* __restrict__ in, int64_t in_ps, uint8_t* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// host mirrors of the flat parameters, keyed by the packed-weight buffer they describe
+// (tdm_unet_pack_weights_host registers, tdm_unet_pack_weights / tdm_unet_forget_host_params drop)
+// ---------------------------------------------------------------------------------------------
+struct HostMirror {
+    const void* wpack;
+    std::unique_ptr<float[]> v;   // heap block: its address survives vector growth
+};
+static std::mutex g_hm_mu;
+static std::vector<HostMirror> g_hm;
+
+static const float* find_host_params(const void* wpack) {
+    std::lock_guard<std::mutex> lk(g_hm_mu);
+    for (const auto& m : g_hm)
+        if (m.wpack == wpack) return m.v.get();
+    return nullptr;
+}
+static void drop_host_params(const void* wpack) {
+    std::lock_guard<std::mutex> lk(g_hm_mu);
+    for (size_t i = 0; i < g_hm.size(); ++i)
+        if (g_hm[i].wpack == wpack) { g_hm.erase(g_hm.begin() + (long)i); return; }
+}
+
+// ---------------------------------------------------------------------------------------------
 // the nine-launch forward
 // ---------------------------------------------------------------------------------------------
 // optional per-kernel timing (bench.py's roofline): events recorded between the nine launches
@@ -249,6 +275,8 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     TDM_CHECK_ARG(ws_bytes >= L.total, "unet_forward: workspace too small (%lld < %lld)",
                   (long long)ws_bytes, (long long)L.total);
     const float* fp = reinterpret_cast<const float*>(wp + WP::flat);
+    // sampling with a registered host mirror: per-channel epilogue parameters go by value (conv_tc.cuh: ChanPar)
+    const float* hfp = sa.train ? nullptr : find_host_params(wp);
     const int B = (int)batch;
     const int nt28 = (int)L.nt28, nt14 = (int)L.nt14;
     int rc;
@@ -271,7 +299,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     a.out = ws + L.cat + 8 * L.ps28; a.out_ps = L.ps28;
     a.x = x; a.aux_w = fp + P::rb1_sw; a.aux_b = fp + P::rb1_sb; a.np = (int)L.np28;
     a.mask = mk(L.m2_1); a.mask_stride = L.np28;
-    if ((rc = launch_conv<28, 32, 32, EPI_RES_X, false, 9, KX::rb1c2>(a, st, "rb1_conv2"))) return rc;
+    if ((rc = launch_conv_fwd<28, 32, 32, EPI_RES_X, false, 9, KX::rb1c2>(a, fp, hfp, st, "rb1_conv2"))) return rc;
 
     // k3: pool h1 -> p1
     TDM_PROF(2);
@@ -285,7 +313,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     a.tw = fp + P::rb2_tw; a.tb = fp + P::rb2_tb; a.sbias = fp + P::rb2_sb;
     a.out = ws + L.t2; a.out_ps = L.ps14; a.out2 = ws + L.s2; a.out2_ps = L.ps14;
     a.mask = mk(L.m1_2); a.mask_stride = L.np14;
-    if ((rc = launch_conv<14, 32, 64, EPI_CONV1, true, 9, KX::rb2c1>(a, st, "rb2_conv1"))) return rc;
+    if ((rc = launch_conv_fwd<14, 32, 64, EPI_CONV1, true, 9, KX::rb2c1>(a, fp, hfp, st, "rb2_conv1"))) return rc;
 
     // k5: rb2.conv2 + s2 -> h2
     TDM_PROF(4);
@@ -293,7 +321,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     a.in = ws + L.t2; a.in_ps = L.ps14; a.w = wp + WP::rb2_c2; a.bias = fp + P::rb2_c2b;
     a.res = ws + L.s2; a.res_ps = L.ps14; a.out = ws + L.h2; a.out_ps = L.ps14;
     a.mask = mk(L.m2_2); a.mask_stride = L.np14;
-    if ((rc = launch_conv<14, 64, 64, EPI_RES, false, 9, KX::rb2c2>(a, st, "rb2_conv2"))) return rc;
+    if ((rc = launch_conv_fwd<14, 64, 64, EPI_RES, false, 9, KX::rb2c2>(a, fp, hfp, st, "rb2_conv2"))) return rc;
 
     // k6: rb3.conv1 -> t3
     TDM_PROF(5);
@@ -301,7 +329,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     a.in = ws + L.h2; a.in_ps = L.ps14; a.w = wp + WP::rb3_c1; a.bias = fp + P::rb3_c1b;
     a.tw = fp + P::rb3_tw; a.tb = fp + P::rb3_tb; a.out = ws + L.t3; a.out_ps = L.ps14;
     a.mask = mk(L.m1_3); a.mask_stride = L.np14;
-    if ((rc = launch_conv<14, 64, 64, EPI_CONV1, false, 9, KX::rb3c1>(a, st, "rb3_conv1"))) return rc;
+    if ((rc = launch_conv_fwd<14, 64, 64, EPI_CONV1, false, 9, KX::rb3c1>(a, fp, hfp, st, "rb3_conv1"))) return rc;
 
     // k7: rb3.conv2 + h2 -> upsampled into cat planes 0..7
     TDM_PROF(6);
@@ -316,7 +344,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     } else {
         // sampling: h3 stays at 14x14; rb4.conv1's gather producers upsample it into the smem tile
         a.out = ws + L.h3; a.out_ps = L.ps14;
-        if ((rc = launch_conv<14, 64, 64, EPI_RES, false, 9, KX::rb3c2>(a, st, "rb3_conv2"))) return rc;
+        if ((rc = launch_conv_fwd<14, 64, 64, EPI_RES, false, 9, KX::rb3c2>(a, fp, hfp, st, "rb3_conv2"))) return rc;
     }
 
     // k8: rb4.conv1 (+skip) -> t4, s4
@@ -332,7 +360,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     } else {
         a.in = ws + L.cat + 8 * L.ps28; a.in_ps = L.ps28;   // h1 planes (bulk); planes 0..7 gathered from h3
         a.in2 = ws + L.h3; a.in2_ps = L.ps14;
-        if ((rc = launch_conv<28, 96, 32, EPI_CONV1, true, 9, KX::rb4c1, kGatherWarps>(a, st, "rb4_conv1"))) return rc;
+        if ((rc = launch_conv_fwd<28, 96, 32, EPI_CONV1, true, 9, KX::rb4c1, kGatherWarps>(a, fp, hfp, st, "rb4_conv1"))) return rc;
     }
 
     // k9: rb4.conv2 + s4, out conv, optional reverse step
@@ -345,7 +373,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     if (sa.train) { a.out = ws + L.h4; a.out_ps = L.ps28; }
     a.fuse_step = sa.fuse_step; a.z = sa.z; a.betas = sa.betas; a.alphas = sa.alphas;
     a.sqrt_om = sa.sqrt_om; a.seed = sa.seed; a.sample_offset = sa.sample_offset; a.step_id = sa.step_id;
-    if ((rc = launch_conv<28, 32, 32, EPI_FINAL, false, 9, KX::rb4c2>(a, st, "rb4_conv2"))) return rc;
+    if ((rc = launch_conv_fwd<28, 32, 32, EPI_FINAL, false, 9, KX::rb4c2>(a, fp, hfp, st, "rb4_conv2"))) return rc;
     TDM_PROF(9);
     return TDM_OK;
 }
@@ -372,11 +400,32 @@ extern "C" int tdm_unet_debug_layout(int64_t batch, int64_t* host_out16) {
 
 extern "C" int tdm_unet_pack_weights(const float* flat_params, void* wpack, void* stream) {
     TDM_CHECK_ARG(flat_params && wpack, "tdm_unet_pack_weights: null pointer");
+    drop_host_params(wpack);   // the device copy is about to change: a host mirror of the old values is stale
     pack_weights_kernel<<<dim3(32, kPackJobs), 256, 0, (cudaStream_t)stream>>>(
         flat_params, reinterpret_cast<uint8_t*>(wpack));
     TDM_CHECK_LAUNCH("tdm_unet_pack_weights");
     return TDM_OK;
 }
+
+extern "C" int tdm_unet_forget_host_params(const void* wpack) {
+    drop_host_params(wpack);
+    return TDM_OK;
+}
+
+extern "C" int tdm_unet_pack_weights_host(const float* flat_params, const float* flat_params_host, void* wpack,
+                                          void* stream) {
+    TDM_CHECK_ARG(flat_params_host, "tdm_unet_pack_weights_host: null host mirror");
+    const int rc = tdm_unet_pack_weights(flat_params, wpack, stream);   // also drops a previous mirror
+    if (rc != TDM_OK) return rc;
+    HostMirror m;
+    m.wpack = wpack;
+    m.v.reset(new float[P::count]);
+    std::memcpy(m.v.get(), flat_params_host, sizeof(float) * P::count);
+    std::lock_guard<std::mutex> lk(g_hm_mu);
+    g_hm.push_back(std::move(m));
+    return TDM_OK;
+}
+
 
 extern "C" int tdm_unet_forward(const void* wpack, const float* x, const int64_t* t, float* eps_out,
                                 void* workspace, int64_t workspace_bytes, int64_t batch, void* stream) {

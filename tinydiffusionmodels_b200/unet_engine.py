@@ -78,9 +78,19 @@ class UNetEngine:
         if flat.numel() != PARAM_COUNT or flat.dtype != torch.float32 or not flat.is_cuda:
             raise ValueError("flat params must be a CUDA fp32 vector of 181,473 elements")
         flat = flat.contiguous()
-        _lib.check(self.lib.tdm_unet_pack_weights(flat.data_ptr(), self.wpack.data_ptr(),
-                                                  _lib.stream_ptr(self.device)), "tdm_unet_pack_weights")
+        # The host mirror lets the kernels take their per-channel epilogue vectors as launch arguments
+        # (constant bank) instead of shared-memory loads; weights are static while sampling.
+        host = flat.detach().to("cpu", copy=True).contiguous()   # synchronises: not graph-capturable
+        _lib.check(self.lib.tdm_unet_pack_weights_host(flat.data_ptr(), host.data_ptr(), self.wpack.data_ptr(),
+                                                       _lib.stream_ptr(self.device)),
+                   "tdm_unet_pack_weights_host")
         self._packed_from = (flat.data_ptr(), flat._version)
+
+    def __del__(self):
+        try:
+            self.lib.tdm_unet_forget_host_params(self.wpack.data_ptr())
+        except Exception:   # interpreter teardown
+            pass
 
     def load_state_dict(self, sd: dict) -> None:
         self.load_flat(flatten_state_dict(sd, self.device))
