@@ -98,7 +98,7 @@ constexpr int kGatherPlanes = 8;   // planes built by the gather producers when 
 #endif
 constexpr int kGatherWarps = TDM_GATHER_WARPS;   // PROD used by rb4.conv1 on the sampling path
 
-template <int W, int CIN, int COUT, bool SKIPG, int TAPS, bool KXC, int PROD = 0>
+template <int W, int CIN, int COUT, bool SKIPG, int TAPS, int KXC, int PROD = 0>
 struct ConvCfg {
     using G = Geo<W>;
     static constexpr int NPL = CIN / 8;
@@ -106,13 +106,13 @@ struct ConvCfg {
     static constexpr int WCONV_BYTES = TAPS * CIN * COUT * 2;
     static constexpr int W_BYTES = WCONV_BYTES + (SKIPG ? CIN * COUT * 2 : 0);
     static constexpr int PARAM_BYTES = 5 * 96 * 4;
-    static constexpr int XCH_BYTES = (KXC ? kEpiGroups * kHalves * 4 * 2 * COUT * 4 : 0) + kEpiGroups * 2 * 128 * 4;
+    static constexpr int XCH_BYTES = (KXC == 1 ? kEpiGroups * kHalves * 4 * 2 * COUT * 4 : KXC == 2 ? kEpiGroups * kHalves * 4 * COUT * 4 : 0) + kEpiGroups * 2 * 128 * 4;
     static constexpr int MAX_SMEM = 227 * 1024;
     static constexpr int AVAIL = MAX_SMEM - W_BYTES - PARAM_BYTES - XCH_BYTES - 256;
     static constexpr int NSTAGE = (AVAIL / STAGE_BYTES) > 4 ? 4 : (AVAIL / STAGE_BYTES);
     static_assert(NSTAGE >= 2, "need at least two input stages");
     static constexpr int NACC = kEpiGroups;
-    static constexpr int NMAIN = KXC ? 3 * COUT : COUT;            // columns of the conv accumulator
+    static constexpr int NMAIN = KXC == 1 ? 3 * COUT : KXC == 2 ? 2 * COUT : COUT;   // columns of the conv accumulator
     static constexpr int ACC_COLS = NMAIN + (SKIPG ? COUT : 0);
     static constexpr int TMEM_COLS = (NACC * ACC_COLS <= 32) ? 32 : (NACC * ACC_COLS <= 64) ? 64
                                    : (NACC * ACC_COLS <= 128) ? 128 : (NACC * ACC_COLS <= 256) ? 256 : 512;
@@ -122,9 +122,10 @@ struct ConvCfg {
     // warp 0 producer, warp 1 MMA issuer, then NACC groups of 8 epilogue warps
     static constexpr int THREADS = 64 + 128 * kHalves * NACC + 32 * PROD;
     static constexpr int BULK_PLANES = PROD ? NPL - kGatherPlanes : NPL;
-    // tile t: accumulator rows [t*TSTRIDE - ROW0, +128), output rows are tile rows [ROW0, 128-ROW0)
-    static constexpr int TSTRIDE = KXC ? 126 : 128;
+    // tile t: accumulator rows [t*TSTRIDE - ROW0, +128)
+    static constexpr int TSTRIDE = KXC == 1 ? 126 : KXC == 2 ? 127 : 128;
     static constexpr int ROW0 = KXC ? 1 : 0;
+    static constexpr int ROW1 = KXC == 1 ? 127 : 128;   // output rows are tile rows [ROW0, ROW1)
     static constexpr int CW = 16;              // channels per epilogue chunk
 };
 
@@ -138,7 +139,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, bool KXC = false, int PROD = 0, bool CPAR = false>
+template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, int KXC = 0, int PROD = 0, bool CPAR = false>
 __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1) conv3x3_tc_kernel(const __grid_constant__ ConvArgs a) {
     static_assert(!CPAR || (COUT <= 64 && EPI != EPI_PLAIN), "by-value channel parameters: forward epilogues, <= 64 channels");
     using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC, PROD>;
@@ -146,7 +147,8 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
     using G = Geo<W>;
     static_assert(COUT == 32 || COUT == 64 || COUT == 96, "COUT");
     static_assert(TAPS == 9 || TAPS == 1, "3x3 or 1x1");
-    static_assert(!KXC || TAPS == 9, "kx-combining is a 3x3 schedule");
+    static_assert(KXC == 0 || TAPS == 9, "kx-combining is a 3x3 schedule");
+    static_assert(KXC >= 0 && KXC <= 2, "KXC: 0 nine taps, 1 kx-triple, 2 kx-pair");
     static_assert(!SKIPG || COUT <= 64, "skip GEMM variant is forward-only");
     static_assert(EPI != EPI_FINAL || COUT == 32, "final epilogue expects 32 channels");
     constexpr int CW = C::CW;
@@ -251,13 +253,26 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
             tc_fence_after_sync();
             const uint64_t in_base = make_smem_desc(smem_u32(s_in + s * C::STAGE_BYTES), G::RT * 16, 128);
             const uint32_t d = tmem_base + acc * C::ACC_COLS;
-            if constexpr (KXC) {
+            if constexpr (KXC == 1) {
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
                     for (int ks = 0; ks < CIN / 16; ++ks) {
                         umma_bf16_elect(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp) * 16),
                                         desc_add(w_base, ((ky * C::NPL + 2 * ks) * 3 * COUT) * 16), idesc, (ky | ks) != 0);
+                    }
+                }
+            } else if constexpr (KXC == 2) {
+                // kx = 0,1 share one N = 2*COUT MMA (columns [Z0 | Z1], A at the centre column); kx = 2 is a plain
+                // tap accumulated into Z1 with A one row further.  Same weight image as the triple schedule.
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky) {
+#pragma unroll
+                    for (int ks = 0; ks < CIN / 16; ++ks) {
+                        umma_bf16_elect(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp) * 16),
+                                        desc_add(w_base, ((ky * C::NPL + 2 * ks) * 3 * COUT) * 16), idesc, (ky | ks) != 0);
+                        umma_bf16_elect(d + COUT, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp + 1) * 16),
+                                        desc_add(w_base, ((ky * C::NPL + 2 * ks) * 3 * COUT + 2 * COUT) * 16), idesc_skip, 1u);
                     }
                 }
             } else {
@@ -377,7 +392,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
             // ---- phase A: everything that does not need the accumulator (overlaps the MMAs) ----
             const int trow = q * 32 + lane;                                   // row inside the tile
             const int64_t pos = (int64_t)tile * C::TSTRIDE - C::ROW0 + trow;  // global position
-            const bool owned = trow >= C::ROW0 && trow < 128 - C::ROW0 && pos < a.np;  // this tile outputs pos
+            const bool owned = trow >= C::ROW0 && trow < C::ROW1 && pos < a.np;  // this tile outputs pos
             const int b = (int)((uint32_t)pos / (uint32_t)G::S);   // positions fit 32 bits: division by a constant is a multiply-shift
             const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)G::S);
             const int r = rem / G::Wp, c = rem - r * G::Wp;
@@ -448,7 +463,41 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
                 const bool last_chunk = ci == COUT / (kHalves * CW) - 1;
                 float acc[CW];
                 uint32_t r2[CW];
-                if constexpr (KXC) {
+                if constexpr (KXC == 2) {
+                    // out[p] = Z0[p-1] + Z1[p]: one shuffle per channel; the row above lane 0 comes through smem
+                    uint32_t d0[CW], d1[CW];
+                    tmem_ld_n<CW>(taddr + c0, d0);
+                    tmem_ld_n<CW>(taddr + COUT + c0, d1);
+                    if constexpr (SKIPG) tmem_ld_n<CW>(taddr + C::NMAIN + c0, r2);
+                    tmem_ld_wait();
+                    if (last_chunk) {
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_acce + grp);
+                    }
+                    float4* xs = reinterpret_cast<float4*>(s_xch + (grp * 4 + q) * COUT + c0);   // per (group, quarter)
+                    if (lane == 31) {
+#pragma unroll
+                        for (int k = 0; k < CW / 4; ++k)
+                            xs[k] = make_float4(__uint_as_float(d0[4 * k]), __uint_as_float(d0[4 * k + 1]),
+                                                __uint_as_float(d0[4 * k + 2]), __uint_as_float(d0[4 * k + 3]));
+                    }
+                    named_bar_sync(1 + grp * kHalves + half, 128);
+                    // q == 0: tile row 0 is never an output row, any finite value will do
+                    const float4* xprev = reinterpret_cast<const float4*>(s_xch + (grp * 4 + (q > 0 ? q - 1 : 0)) * COUT + c0);
+                    const bool first = lane == 0;
+#pragma unroll
+                    for (int k4 = 0; k4 < CW / 4; ++k4) {
+                        const float4 pu = xprev[k4];   // same address for all lanes: broadcast
+                        const float pus[4] = {pu.x, pu.y, pu.z, pu.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int k = 4 * k4 + j;
+                            const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(d0[k]), 1);
+                            acc[k] = (first ? pus[j] : up) + __uint_as_float(d1[k]);
+                        }
+                    }
+                } else if constexpr (KXC == 1) {
                     uint32_t d0[CW], d1[CW], d2[CW];
                     tmem_ld_n<CW>(taddr + c0, d0);
                     tmem_ld_n<CW>(taddr + COUT + c0, d1);
@@ -625,7 +674,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
     if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
-template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, bool KXC = false, int PROD = 0, bool CPAR = false>
+template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, int KXC = 0, int PROD = 0, bool CPAR = false>
 static int launch_conv(const ConvArgs& a, cudaStream_t st, const char* name) {
     using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC, PROD>;
     auto kern = conv3x3_tc_kernel<W, CIN, COUT, EPI, SKIPG, TAPS, KXC, PROD, CPAR>;
@@ -643,7 +692,7 @@ static int launch_conv(const ConvArgs& a, cudaStream_t st, const char* name) {
 
 // Forward-pass launch: with a host mirror `hfp` of the flat fp32 parameters (the device copy is `fp`), the
 // per-channel vectors travel by value (CPAR); their host addresses follow from the device pointers in `a`.
-template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, bool KXC = false, int PROD = 0>
+template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, int KXC = 0, int PROD = 0>
 static int launch_conv_fwd(ConvArgs& a, const float* fp, const float* hfp, cudaStream_t st, const char* name) {
     if (!hfp) return launch_conv<W, CIN, COUT, EPI, SKIPG, TAPS, KXC, PROD, false>(a, st, name);
     auto mirror = [&](float* dst, const float* dev, int n) {

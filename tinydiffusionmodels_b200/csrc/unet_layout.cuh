@@ -106,20 +106,30 @@ constexpr int64_t flat = (bf16_end + 255) / 256 * 256;     // fp32 copy of the f
 constexpr int64_t total = (flat + 4LL * P::count + 255) / 256 * 256;
 }  // namespace WP
 
-// ---- MMA schedule per 3x3 convolution (conv_tc.cuh): bit set = kx-combined (N = 3*Cout) ------------
-// Chosen from measurements on B200 (profiles/r01_kxc_sweep.txt): combining pays where the MMA count
-// dominates (rb4.conv1, K = 9*96); elsewhere the leaner nine-tap epilogue wins.
+// ---- MMA schedule per 3x3 convolution (conv_tc.cuh) -------------------------------------------------
+// bit i of TDM_KXC_MASK: kx-triple (one N = 3*Cout MMA per ky); of TDM_KX2_MASK: kx-pair (N = 2*Cout + N = Cout).
+// A tcgen05.mma with both operands in shared memory costs max(N/2, (4096 + 32 N)/128) cycles
+// (tools/micro/mma_rate.cu), so small-N taps are bound by re-reading the A tile; sharing it between taps
+// helps until the shift-add epilogue / TMEM footprint eats the gain.  Chosen from B200 sweeps
+// (profiles/r01_kxc_sweep_B4096.txt, profiles/r01_kx2_sweep_B16384.txt): triple where the MMA count
+// dominates (rb4.conv1, K = 9*96), pair on the three 64->64 convolutions (4 x 128 TMEM columns still fit),
+// nine taps on the 32->32 ones.
 #ifndef TDM_KXC_MASK
 #define TDM_KXC_MASK 0x20
 #endif
+#ifndef TDM_KX2_MASK
+#define TDM_KX2_MASK 0x1C
+#endif
 namespace KX {
-constexpr bool rb1c2 = (TDM_KXC_MASK >> 0) & 1;
-constexpr bool rb2c1 = (TDM_KXC_MASK >> 1) & 1;
-constexpr bool rb2c2 = (TDM_KXC_MASK >> 2) & 1;
-constexpr bool rb3c1 = (TDM_KXC_MASK >> 3) & 1;
-constexpr bool rb3c2 = (TDM_KXC_MASK >> 4) & 1;
-constexpr bool rb4c1 = (TDM_KXC_MASK >> 5) & 1;
-constexpr bool rb4c2 = (TDM_KXC_MASK >> 6) & 1;
+// 0 = nine taps, 1 = kx-triple (N = 3*Cout), 2 = kx-pair (N = 2*Cout + N = Cout); conv_tc.cuh
+constexpr int sel(int bit) { return ((TDM_KXC_MASK >> bit) & 1) ? 1 : ((TDM_KX2_MASK >> bit) & 1) ? 2 : 0; }
+constexpr int rb1c2 = sel(0);
+constexpr int rb2c1 = sel(1);
+constexpr int rb2c2 = sel(2);
+constexpr int rb3c1 = sel(3);
+constexpr int rb3c2 = sel(4);
+constexpr int rb4c1 = sel(5);
+constexpr int rb4c2 = sel(6);
 }  // namespace KX
 
 }  // namespace tdm
