@@ -89,10 +89,23 @@ struct ConvArgs {
 constexpr int kEpiGroups = 4;  // epilogue warp groups == TMEM accumulator stages (tiles in flight)
 constexpr int kHalves = 1;     // warps per TMEM lane quarter inside a group (2: alternate 16-channel chunks)
 
+#ifndef TDM_MAX_STAGES
+#define TDM_MAX_STAGES 4
+#endif
+constexpr int kBarBytes = 512;               // smem reserved for the mbarriers + the TMEM base slot
+constexpr int kMaxStages = TDM_MAX_STAGES;   // input ring depth cap (bytes in flight per SM = stages x tile bytes)
 constexpr int kGatherPlanes = 8;   // planes built by the gather producers when PROD > 0 (the 64 h3 channels)
 #ifndef TDM_GATHER_WARPS
 #define TDM_GATHER_WARPS 2
 #endif
+#ifndef TDM_IM2COL_UNROLL
+#define TDM_IM2COL_UNROLL 4
+#endif
+#ifndef TDM_IM2COL_WARPS
+#define TDM_IM2COL_WARPS 8
+#endif
+constexpr int kIm2colWarps = TDM_IM2COL_WARPS;   // PROD used by rb1.conv1
+constexpr int kIm2colUnroll = TDM_IM2COL_UNROLL; // tile rows per lane whose 9 loads are in flight together
 #ifndef TDM_GATHER_MODE
 #define TDM_GATHER_MODE 2   // 0 = LDG.128 -> registers -> STS.128; 1 = cp.async.cg; 2 = cp.async.ca
 #endif
@@ -108,8 +121,12 @@ struct ConvCfg {
     static constexpr int PARAM_BYTES = 5 * 96 * 4;
     static constexpr int XCH_BYTES = (KXC == 1 ? kEpiGroups * kHalves * 4 * 2 * COUT * 4 : KXC == 2 ? kEpiGroups * kHalves * 4 * COUT * 4 : 0) + kEpiGroups * 2 * 128 * 4;
     static constexpr int MAX_SMEM = 227 * 1024;
-    static constexpr int AVAIL = MAX_SMEM - W_BYTES - PARAM_BYTES - XCH_BYTES - 256;
-    static constexpr int NSTAGE = (AVAIL / STAGE_BYTES) > 4 ? 4 : (AVAIL / STAGE_BYTES);
+    static constexpr int AVAIL = MAX_SMEM - W_BYTES - PARAM_BYTES - XCH_BYTES - kBarBytes;
+    // a gather warp may run at most one ring phase ahead of the MMA warp (mbarrier parity), so the ring is
+    // at least as deep as there are gather warps
+    static constexpr int STAGE_CAP = PROD > kMaxStages ? PROD : kMaxStages;
+    static constexpr int NSTAGE = (AVAIL / STAGE_BYTES) > STAGE_CAP ? STAGE_CAP : (AVAIL / STAGE_BYTES);
+    static_assert(PROD <= NSTAGE, "more gather warps than input stages");
     static_assert(NSTAGE >= 2, "need at least two input stages");
     static constexpr int NACC = kEpiGroups;
     static constexpr int NMAIN = KXC == 1 ? 3 * COUT : KXC == 2 ? 2 * COUT : COUT;   // columns of the conv accumulator
@@ -118,10 +135,17 @@ struct ConvCfg {
                                    : (NACC * ACC_COLS <= 128) ? 128 : (NACC * ACC_COLS <= 256) ? 256 : 512;
     static_assert(NACC * ACC_COLS <= 512, "accumulators exceed TMEM");
     static_assert(NMAIN <= 256 && NMAIN % 16 == 0, "UMMA N");
-    static constexpr int SMEM_BYTES = W_BYTES + NSTAGE * STAGE_BYTES + PARAM_BYTES + XCH_BYTES + 256;
+    static constexpr int SMEM_BYTES = W_BYTES + NSTAGE * STAGE_BYTES + PARAM_BYTES + XCH_BYTES + kBarBytes;
+    static_assert((1 + 2 * NSTAGE + 2 * kEpiGroups) * 8 + 8 <= kBarBytes, "mbarrier block overflows its smem slot");
     // warp 0 producer, warp 1 MMA issuer, then NACC groups of 8 epilogue warps
     static constexpr int THREADS = 64 + 128 * kHalves * NACC + 32 * PROD;
-    static constexpr int BULK_PLANES = PROD ? NPL - kGatherPlanes : NPL;
+    // gather kind: 0 none, 1 nearest-x2 upsample of the 64 h3 channels (rb4.conv1), 2 im2col of the
+    // single-channel image (rb1.conv1 as a 1x1 convolution over 32 "channels" = 27 hi/lo tap terms)
+    static constexpr int GK = PROD == 0 ? 0 : (CIN == 96 ? 1 : 2);
+    static constexpr int BULK_PLANES = GK == 0 ? NPL : GK == 1 ? NPL - kGatherPlanes : 0;
+    // arrivals on a stage's full barrier: the bulk issuer, plus the gather warp owning the tile
+    // (one per lane when it copies with cp.async)
+    static constexpr int FULL_ARRIVALS = (BULK_PLANES > 0 ? 1 : 0) + (GK == 0 ? 0 : (GK == 1 && TDM_GATHER_MODE != 0) ? 32 : 1);
     // tile t: accumulator rows [t*TSTRIDE - ROW0, +128)
     static constexpr int TSTRIDE = KXC == 1 ? 126 : KXC == 2 ? 127 : 128;
     static constexpr int ROW0 = KXC ? 1 : 0;
@@ -143,7 +167,8 @@ template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, int KXC =
 __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1) conv3x3_tc_kernel(const __grid_constant__ ConvArgs a) {
     static_assert(!CPAR || (COUT <= 64 && EPI != EPI_PLAIN), "by-value channel parameters: forward epilogues, <= 64 channels");
     using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC, PROD>;
-    static_assert(PROD == 0 || (W == 28 && CIN == 96), "gather producers serve rb4.conv1's concat input");
+    static_assert(C::GK != 1 || (W == 28 && CIN == 96), "upsample gather serves rb4.conv1's concat input");
+    static_assert(C::GK != 2 || (W == 28 && CIN == 32 && COUT == 32 && TAPS == 1 && KXC == 0), "im2col gather serves rb1.conv1");
     using G = Geo<W>;
     static_assert(COUT == 32 || COUT == 64 || COUT == 96, "COUT");
     static_assert(TAPS == 9 || TAPS == 1, "3x3 or 1x1");
@@ -190,7 +215,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
     if (threadIdx.x == 0) {
         mbar_init(bar_w, 1);
         for (int i = 0; i < C::NSTAGE; ++i) {
-            mbar_init(bar_full + i, 1 + (PROD ? (TDM_GATHER_MODE != 0 ? 32 : 1) : 0));   // bulk issuer + the gather warp owning the tile (per lane for cp.async)
+            mbar_init(bar_full + i, C::FULL_ARRIVALS);
             mbar_init(bar_empty + i, 1);
         }
         for (int i = 0; i < C::NACC; ++i) {
@@ -217,7 +242,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
             }
         }
         int it = 0;
-        for (int tile = blockIdx.x; tile < nt; tile += gridDim.x, ++it) {
+        for (int tile = blockIdx.x; C::BULK_PLANES > 0 && tile < nt; tile += gridDim.x, ++it) {
             const int s = it % C::NSTAGE;
             const uint32_t ph = (it / C::NSTAGE) & 1;
             if (lane == 0) {
@@ -249,7 +274,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
             const uint32_t aph = (it / C::NACC) & 1;
             mbar_wait(bar_acce + acc, aph ^ 1);
             mbar_wait(bar_full + s, ph);
-            if constexpr (PROD != 0 && TDM_GATHER_MODE != 0) fence_proxy_async_smem();   // cp.async (generic proxy) data -> async-proxy MMA reads
+            if constexpr (C::GK == 1 && TDM_GATHER_MODE != 0) fence_proxy_async_smem();   // cp.async (generic proxy) data -> async-proxy MMA reads
             tc_fence_after_sync();
             const uint64_t in_base = make_smem_desc(smem_u32(s_in + s * C::STAGE_BYTES), G::RT * 16, 128);
             const uint32_t d = tmem_base + acc * C::ACC_COLS;
@@ -311,6 +336,59 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
         //       cp.async.mbarrier.arrive.noinc (one arrival per lane), so a warp runs ahead as far as the ring
         //       has free stages. =====
         const int pw = warp - (2 + 4 * kHalves * kEpiGroups);
+        if constexpr (C::GK == 2) {
+            // ===== im2col of the single-channel image (src/mnist.py:74 conv1 of rb1): tile row p gets the 3x3
+            //       window of x around p as 32 "channels", so the 1 -> 32 convolution is one K = 32 GEMM:
+            //         k  0.. 8  hi(x_tap)   x  hi(w_tap)        hi(v) = bf16(v), lo(v) = bf16(v - hi(v))
+            //         k  9..17  lo(x_tap)   x  hi(w_tap)
+            //         k 18..26  hi(x_tap)   x  lo(w_tap)        (k 27..31 zero)
+            //       i.e. the product keeps ~16 mantissa bits of both factors with fp32 accumulation - the
+            //       CUDA-core fp32 version of this layer was issue-bound at 0.41 ms (B = 16384).
+            //       Only tile rows [0,128) are built: a 1x1 convolution reads no halo. =====
+            for (int it = pw, tile = blockIdx.x + pw * gridDim.x; tile < nt; tile += PROD * gridDim.x, it += PROD) {
+                const int s = it % C::NSTAGE;
+                const uint32_t ph = (it / C::NSTAGE) & 1;
+                mbar_wait(bar_empty + s, ph ^ 1);
+                uint8_t* st = s_in + s * C::STAGE_BYTES + G::HALO * 16;   // tile row 0 of plane 0
+#pragma unroll kIm2colUnroll
+                for (int r = lane; r < 128; r += 32) {
+                    const int pos = tile * 128 + r;
+                    const int b = (int)((uint32_t)pos / (uint32_t)G::S);
+                    const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)G::S);
+                    const int rw = rem / G::Wp, c = rem - rw * G::Wp;
+                    const bool ok = b < a.batch && rw >= 1 && c < G::W;
+                    const float* xb = a.x + (int64_t)b * 784 + (rw - 1) * 28 + c;   // centre pixel
+                    float hi[9], lo[9];
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const bool in = ok && (unsigned)(rw - 1 + ky - 1) < 28u && (unsigned)(c + kx - 1) < 28u;
+                            const float v = in ? __ldg(xb + (ky - 1) * 28 + (kx - 1)) : 0.f;
+                            const float h = __bfloat162float(__float2bfloat16_rn(v));
+                            hi[ky * 3 + kx] = h;
+                            lo[ky * 3 + kx] = v - h;
+                        }
+                    float e[32];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) { e[k] = hi[k]; e[9 + k] = lo[k]; e[18 + k] = hi[k]; }
+#pragma unroll
+                    for (int k = 27; k < 32; ++k) e[k] = 0.f;
+#pragma unroll
+                    for (int pl = 0; pl < 4; ++pl) {
+                        uint4 o;
+                        o.x = pack_bf16x2(e[8 * pl + 0], e[8 * pl + 1]);
+                        o.y = pack_bf16x2(e[8 * pl + 2], e[8 * pl + 3]);
+                        o.z = pack_bf16x2(e[8 * pl + 4], e[8 * pl + 5]);
+                        o.w = pack_bf16x2(e[8 * pl + 6], e[8 * pl + 7]);
+                        *reinterpret_cast<uint4*>(st + pl * (G::RT * 16) + r * 16) = o;
+                    }
+                }
+                fence_proxy_async_smem();   // this lane's generic-proxy stores -> visible to the MMA's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_full + s);
+            }
+        } else {
         using GS = Geo<14>;
         static_assert(PROD == 0 || G::RT % 64 == 0, "two rows per lane per iteration");
         for (int it = pw, tile = blockIdx.x + pw * gridDim.x; tile < nt; tile += PROD * gridDim.x, it += PROD) {
@@ -378,6 +456,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_full + s);
 #endif
+        }
         }
     } else {
         // ===== epilogue: group g = (warp-2)/4 owns accumulator stage g (tiles it = g, g+NACC, ..),

@@ -84,114 +84,25 @@ __global__ void pack_weights_kernel(const float* __restrict__ flat, uint8_t* __r
         const int src_tap = j.transpose ? (j.taps - 1 - tap) : tap;   // 180-degree flip
         dst[i] = __float2bfloat16_rn(flat[j.src + (co * j.cin + ci) * j.taps + src_tap]);
     }
+    if (blockIdx.y == 1) {
+        // rb1.conv1 [32,1,3,3] as the B operand of the im2col GEMM: [K/8 = 4][32][8], k = tap terms
+        // hi(w) (k 0..8, pairs with hi(x)), hi(w) again (k 9..17, pairs with lo(x)), lo(w) (k 18..26, pairs with hi(x))
+        __nv_bfloat16* d1 = reinterpret_cast<__nv_bfloat16*>(wpack + WP::rb1_c1);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 32 * 32; i += gridDim.x * blockDim.x) {
+            const int k = (i >> 8) * 8 + (i & 7), co = (i >> 3) & 31;
+            float v = 0.f;
+            if (k < 27) {
+                const float w = flat[P::rb1_c1w + co * 9 + k % 9];
+                const float h = __bfloat162float(__float2bfloat16_rn(w));
+                v = k < 18 ? h : w - h;
+            }
+            d1[i] = __float2bfloat16_rn(v);
+        }
+    }
     if (blockIdx.y == 0) {
         float* f = reinterpret_cast<float*>(wpack + WP::flat);
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P::count; i += gridDim.x * blockDim.x)
             f[i] = flat[i];
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// k1: rb1.conv1 (1 -> 32), relu, + time bias.  fp32 math on CUDA cores (K = 9 is too thin for the
-// tensor pipe).  The block stages its 128 positions of x (+ halo) in the padded position geometry in
-// smem, so taps are constant shifts; a thread owns 4 consecutive positions x 8 channels (one plane):
-// 72 weights arrive as 18 LDS.128 and feed 288 FMAs.  block = 128 threads = 32 quads x 4 planes.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-rb1_conv1_kernel(const float* __restrict__ x, const int64_t* __restrict__ t,
-                 const float* __restrict__ fp, uint8_t* __restrict__ out, int64_t out_ps, int batch,
-                 uint32_t* __restrict__ mask, int nt) {
-    using G = Geo<28>;
-    constexpr int HL = G::Wp + 1;                     // halo rows on each side
-    __shared__ __align__(16) float s_w[4][9][8];      // [plane][tap][channel in plane]
-    __shared__ float s_b[32], s_tw[32], s_tb[32];
-    __shared__ float s_x[128 + 2 * HL];               // x at positions p0-HL .. p0+128+HL (0 at pads)
-    __shared__ float s_ts[128];
-    __shared__ uint8_t s_valid[128];
-    for (int i = threadIdx.x; i < 288; i += 128) {
-        const int co = i / 9, tap = i - co * 9;
-        s_w[co >> 3][tap][co & 7] = fp[P::rb1_c1w + i];
-    }
-    if (threadIdx.x < 32) {
-        s_b[threadIdx.x] = fp[P::rb1_c1b + threadIdx.x];
-        s_tw[threadIdx.x] = fp[P::rb1_tw + threadIdx.x];
-        s_tb[threadIdx.x] = fp[P::rb1_tb + threadIdx.x];
-    }
-    // grid-stride over tiles so the weight staging above is paid once per block, not per tile
-    for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
-    __syncthreads();
-    const int64_t p0 = (int64_t)tile * 128;
-    for (int i = threadIdx.x; i < 128 + 2 * HL; i += 128) {
-        const int64_t pos = p0 - HL + i;
-        float v = 0.f, tsv = 0.f;
-        bool ok = false;
-        if (pos >= 0) {
-            const int b = (int)((uint32_t)pos / (uint32_t)G::S);   // positions fit 32 bits: division by a constant is a multiply-shift
-            const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)G::S);
-            const int r = rem / G::Wp, c = rem - r * G::Wp;
-            ok = b < batch && r >= 1 && c < G::W;
-            if (ok) {
-                v = __ldg(x + (int64_t)b * 784 + (r - 1) * 28 + c);
-                tsv = (float)__ldg(t + b) / 1000.0f;  // src/mnist.py:77
-            }
-        }
-        s_x[i] = v;
-        if (i >= HL && i < HL + 128) {
-            s_ts[i - HL] = tsv;
-            s_valid[i - HL] = ok;
-        }
-    }
-    __syncthreads();
-    const int plane = threadIdx.x & 3;
-    const int quad = threadIdx.x >> 2;
-    // 3 x 6 window of x around the 4 positions (rows -Wp, 0, +Wp; columns -1 .. +4)
-    float win[3][6];
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int j = 0; j < 6; ++j) win[ky][j] = s_x[HL + quad * 4 + (ky - 1) * G::Wp + j - 1];
-    float acc[4][8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) acc[i][k] = s_b[plane * 8 + k];
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            const float4 w0 = *reinterpret_cast<const float4*>(&s_w[plane][ky * 3 + kx][0]);
-            const float4 w1 = *reinterpret_cast<const float4*>(&s_w[plane][ky * 3 + kx][4]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float v = win[ky][i + kx];
-                acc[i][0] = fmaf(w0.x, v, acc[i][0]);
-                acc[i][1] = fmaf(w0.y, v, acc[i][1]);
-                acc[i][2] = fmaf(w0.z, v, acc[i][2]);
-                acc[i][3] = fmaf(w0.w, v, acc[i][3]);
-                acc[i][4] = fmaf(w1.x, v, acc[i][4]);
-                acc[i][5] = fmaf(w1.y, v, acc[i][5]);
-                acc[i][6] = fmaf(w1.z, v, acc[i][6]);
-                acc[i][7] = fmaf(w1.w, v, acc[i][7]);
-            }
-        }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int pl = quad * 4 + i;
-        const bool ok = s_valid[pl];
-        const float tsv = s_ts[pl];
-        uint32_t bits = 0;
-        float h[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int co = plane * 8 + k;
-            bits |= (acc[i][k] > 0.f ? 1u : 0u) << k;
-            h[k] = fmaxf(acc[i][k], 0.f) + fmaf(s_tw[co], tsv, s_tb[co]);
-        }
-        uint4 o = make_uint4(0, 0, 0, 0);
-        if (ok) o = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-        *reinterpret_cast<uint4*>(out + plane * out_ps + (p0 + pl + G::GUARD) * 16) = o;
-        if (mask) reinterpret_cast<uint8_t*>(mask + p0 + pl)[plane] = ok ? (uint8_t)bits : (uint8_t)0;
-    }
     }
 }
 
@@ -278,20 +189,21 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     // sampling with a registered host mirror: per-channel epilogue parameters go by value (conv_tc.cuh: ChanPar)
     const float* hfp = sa.train ? nullptr : find_host_params(wp);
     const int B = (int)batch;
-    const int nt28 = (int)L.nt28, nt14 = (int)L.nt14;
+    const int nt14 = (int)L.nt14;
     int rc;
 
-    // k1
+    // k1: rb1.conv1 (1 -> 32) + ReLU + time bias -> t1, on the tensor pipe: gather warps build the im2col of x
     TDM_PROF(0);
     auto mk = [&](int64_t off) { return sa.train ? reinterpret_cast<uint32_t*>(ws + off) : nullptr; };
-    {
-        const int grid = nt28 < 12 * num_sms() ? nt28 : 12 * num_sms();
-        rb1_conv1_kernel<<<grid, 128, 0, st>>>(x, t, fp, ws + L.t1, L.ps28, B, mk(L.m1_1), nt28);
-    }
-    TDM_CHECK_LAUNCH("rb1_conv1");
+    ConvArgs a{};
+    a.t = t; a.batch = B; a.np = (int)L.np28;
+    a.x = x; a.w = wp + WP::rb1_c1; a.bias = fp + P::rb1_c1b; a.tw = fp + P::rb1_tw; a.tb = fp + P::rb1_tb;
+    a.out = ws + L.t1; a.out_ps = L.ps28;
+    a.mask = mk(L.m1_1); a.mask_stride = L.np28;
+    if ((rc = launch_conv_fwd<28, 32, 32, EPI_CONV1, false, 1, 0, kIm2colWarps>(a, fp, hfp, st, "rb1_conv1"))) return rc;
 
     TDM_PROF(1);
-    ConvArgs a{};
+    a = ConvArgs{};
     a.t = t;
     a.batch = B;
     // k2: rb1.conv2 -> h1 = cat planes 8..11

@@ -101,7 +101,9 @@ constexpr int64_t d_rb3_c1 = d_rb3_c2 + conv_bytes(64, 64);         // 64 -> 64
 constexpr int64_t d_rb4_c2 = d_rb3_c1 + conv_bytes(64, 64);         // 32 -> 32
 constexpr int64_t d_rb4_c1 = d_rb4_c2 + conv_bytes(32, 32);         // 32 -> 96
 constexpr int64_t d_rb4_sk = d_rb4_c1 + conv_bytes(32, 96);         // 32 -> 96 (1x1)
-constexpr int64_t bf16_end = d_rb4_sk + skip_bytes(32, 96);
+// rb1.conv1 as a K = 32 GEMM over the im2col of x: [4][32][8] bf16, k = hi/hi/lo tap terms (conv_tc.cuh)
+constexpr int64_t rb1_c1 = d_rb4_sk + skip_bytes(32, 96);
+constexpr int64_t bf16_end = rb1_c1 + 32 * 32 * 2;
 constexpr int64_t flat = (bf16_end + 255) / 256 * 256;     // fp32 copy of the flat parameters
 constexpr int64_t total = (flat + 4LL * P::count + 255) / 256 * 256;
 }  // namespace WP

@@ -9,7 +9,7 @@
 #include "tc05.cuh"
 using namespace tdm;
 
-template <int N, bool A_TMEM>
+template <int N, bool A_TMEM, int A_OFF = 0, int NCHAIN = 2>
 __global__ void __launch_bounds__(128) rate_kernel(long long* out, int iters) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint32_t slot;
@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(128) rate_kernel(long long* out, int iters) {
     const int warp = threadIdx.x >> 5;
     if (warp == 0) tmem_alloc<512>(&slot);
     if (threadIdx.x == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
-    for (int i = threadIdx.x; i < (128 * 32 + 256 * 32) / 4; i += 128) ((uint32_t*)smem)[i] = 0;
+    for (int i = threadIdx.x; i < (8192 + 256 * 32) / 4; i += 128) ((uint32_t*)smem)[i] = 0;
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
@@ -25,8 +25,8 @@ __global__ void __launch_bounds__(128) rate_kernel(long long* out, int iters) {
     const uint32_t tm = slot;
     if (warp == 1) {
         // A: 128 rows x 16 k: two planes of [128][8] -> LBO = 2048, SBO = 128.  B: N rows, planes after A.
-        const uint64_t adesc = make_smem_desc(smem_u32(smem), 2048, 128);
-        const uint64_t bdesc = make_smem_desc(smem_u32(smem) + 4096, 256 * 16, 128);
+        const uint64_t adesc = make_smem_desc(smem_u32(smem) + A_OFF * 16, 2048 + 512, 128);   // A_OFF rows off the 128-byte core-matrix grid
+        const uint64_t bdesc = make_smem_desc(smem_u32(smem) + 8192, 256 * 16, 128);
         constexpr uint32_t idesc = make_idesc_bf16(128, N);
         long long t0 = clock64();
         for (int i = 0; i < iters; ++i) {
@@ -34,10 +34,10 @@ __global__ void __launch_bounds__(128) rate_kernel(long long* out, int iters) {
                 asm volatile(
                     "{\n\t.reg .pred p, e;\n\tsetp.ne.b32 p, %4, 0;\n\telect.sync _|e, 0xffffffff;\n\t"
                     "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-                    ::"r"(tm + (uint32_t)((i & 1) * 256)), "r"(tm + 256u + 128u), "l"(bdesc), "r"(idesc), "r"(1u)
+                    ::"r"(tm + (uint32_t)((i % NCHAIN) * (512 / (NCHAIN < 2 ? 2 : NCHAIN)))), "r"(tm + 256u + 128u), "l"(bdesc), "r"(idesc), "r"(1u)
                     : "memory");
             } else {
-                umma_bf16_elect(tm + (uint32_t)((i & 1) * 256), adesc, bdesc, idesc, 1u);
+                umma_bf16_elect(tm + (uint32_t)((i % NCHAIN) * (512 / (NCHAIN < 2 ? 2 : NCHAIN))), adesc, bdesc, idesc, 1u);
             }
         }
         umma_commit_elect(&bar);
@@ -50,14 +50,14 @@ __global__ void __launch_bounds__(128) rate_kernel(long long* out, int iters) {
     if (warp == 0) tmem_dealloc<512>(tm);
 }
 
-template <int N, bool A_TMEM>
+template <int N, bool A_TMEM, int A_OFF = 0, int NCHAIN = 2>
 void run(const char* name) {
     long long* d; cudaMalloc(&d, 148 * sizeof(long long));
     const int iters = 4096;
-    cudaFuncSetAttribute(rate_kernel<N, A_TMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    cudaFuncSetAttribute(rate_kernel<N, A_TMEM, A_OFF, NCHAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     for (int grid : {1, 148}) {
-        rate_kernel<N, A_TMEM><<<grid, 128, 65536>>>(d, iters);
-        rate_kernel<N, A_TMEM><<<grid, 128, 65536>>>(d, iters);
+        rate_kernel<N, A_TMEM, A_OFF, NCHAIN><<<grid, 128, 65536>>>(d, iters);
+        rate_kernel<N, A_TMEM, A_OFF, NCHAIN><<<grid, 128, 65536>>>(d, iters);
         cudaError_t e = cudaDeviceSynchronize();
         long long h[148]; cudaMemcpy(h, d, grid * sizeof(long long), cudaMemcpyDeviceToHost);
         long long mx = 0; for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
@@ -73,5 +73,13 @@ int main() {
     run<16, false>("A=smem"); run<32, false>("A=smem"); run<64, false>("A=smem"); run<96, false>("A=smem");
     run<128, false>("A=smem"); run<192, false>("A=smem"); run<256, false>("A=smem");
     run<32, true>("A=tmem"); run<64, true>("A=tmem"); run<96, true>("A=tmem"); run<128, true>("A=tmem"); run<256, true>("A=tmem");
+    // A tile starting 1..7 rows off the 8-row core-matrix grid (what a conv tap at row offset +-1, +-29 does)
+    run<32, false, 1>("A+1row"); run<32, false, 4>("A+4rows"); run<32, false, 7>("A+7rows");
+    run<64, false, 1>("A+1row"); run<96, false, 1>("A+1row"); run<128, false, 1>("A+1row");
+    // dependent accumulation: every MMA adds into the SAME accumulator (a conv tile's 18 taps) vs 2 / 4 chains
+    run<32, false, 0, 1>("1 chain"); run<32, false, 0, 2>("2 chains"); run<32, false, 0, 4>("4 chains");
+    run<64, false, 0, 1>("1 chain"); run<64, false, 0, 2>("2 chains");
+    run<96, false, 0, 1>("1 chain"); run<96, false, 0, 2>("2 chains");
+    run<128, false, 0, 1>("1 chain"); run<128, false, 0, 2>("2 chains");
     return 0;
 }
