@@ -303,6 +303,9 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
             } else {
 #pragma unroll
                 for (int tap = 0; tap < TAPS; ++tap) {
+#ifdef TDM_DBG_TAPS
+                    if (tap >= TDM_DBG_TAPS) break;   // timing experiment only (wrong results)
+#endif
                     const int off = (TAPS == 1) ? 0 : (tap / 3 - 1) * G::Wp + (tap % 3 - 1);
 #pragma unroll
                     for (int ks = 0; ks < CIN / 16; ++ks) {

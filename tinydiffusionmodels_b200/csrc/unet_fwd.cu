@@ -1,22 +1,24 @@
 // unet_fwd.cu — SimpleUNet.forward (src/mnist.py:76-87) and the fused p_sample
 // (src/mnist.py:167-180) as nine launches:
 //
-//   k1  rb1.conv1   1->32  @28   CUDA cores (K = 9 is too thin for the tensor pipe), fp32 in
+//   k1  rb1.conv1   1->32  @28   tcgen05: 8 gather warps build the im2col of x (hi/lo bf16 terms, K = 32) -> t1
 //   k2  rb1.conv2   32->32 @28   tcgen05, epilogue relu + 1x1 skip of x           -> h1 (cat[8:12])
 //   k3  avg_pool2                                                                  -> p1
 //   k4  rb2.conv1   32->64 @14   tcgen05 (+ 1x1 skip GEMM into a 2nd accumulator)  -> t2, s2
-//   k5  rb2.conv2   64->64 @14   tcgen05, epilogue relu + s2                       -> h2
-//   k6  rb3.conv1   64->64 @14   tcgen05                                           -> t3
-//   k7  rb3.conv2   64->64 @14   tcgen05, epilogue relu + h2, nearest x2 scatter   -> cat[0:8]
-//   k8  rb4.conv1   96->32 @28   tcgen05 (+ 1x1 skip GEMM)                         -> t4, s4
+//   k5  rb2.conv2   64->64 @14   tcgen05 (kx-pair), epilogue relu + s2             -> h2
+//   k6  rb3.conv1   64->64 @14   tcgen05 (kx-pair)                                 -> t3
+//   k7  rb3.conv2   64->64 @14   tcgen05 (kx-pair), epilogue relu + h2             -> h3 @14 (sampling)
+//                                training: nearest x2 scatter                      -> cat[0:8]
+//   k8  rb4.conv1   96->32 @28   tcgen05 (kx-triple, + 1x1 skip GEMM); sampling: 2 gather warps upsample
+//                                h3 into the smem tile, h1 arrives by bulk copy    -> t4, s4
 //   k9  rb4.conv2   32->32 @28   tcgen05, epilogue relu + s4, 1x1 out conv, and (p_sample) the
 //                                reverse-step update with in-kernel Philox noise   -> eps | x_{t-1}
 //
-// Every tensor-core conv is the same persistent warp-specialised kernel: warp 0 streams input
+// Every convolution is the same persistent warp-specialised kernel (conv_tc.cuh): warp 0 streams input
 // tiles (one bulk async copy per 8-channel plane, halo included) into a ring of smem stages,
-// warp 1 issues 9*Cin/16 tcgen05.mma (M=128 positions, N=Cout, K=16) per tile whose A operand is
-// the *same* smem tile addressed at nine different row offsets, warps 2-5 drain the TMEM
-// accumulator (double buffered) through the fused epilogue.  Weights stay resident in smem.
+// warp 1 issues the tcgen05.mma of a tile (M=128 positions, K=16) whose A operand is the *same* smem tile
+// addressed at different row offsets per tap, four groups of four warps drain the four TMEM accumulator
+// stages through the fused epilogue.  Weights stay resident in smem.
 #include <memory>
 #include <mutex>
 #include <vector>
