@@ -28,12 +28,23 @@ namespace tdm {
 // M = 64: TMEM row m lives in lane (m%16) + 32*(m/16); a second accumulator set is interleaved at
 // lane offset 16, so nine taps need only 5*CX columns.
 // ---------------------------------------------------------------------------------------------
+// 16 consecutive fp32 accumulated with four 16-byte vector reductions (RED.E.ADD.F32x4 on sm_90+): the
+// per-CTA flush of a weight gradient was the cost of the small-batch wgrad kernels when it went out as
+// 4-byte atomics 36 bytes apart (OIHW order: the 9 taps of one (co, ci) are adjacent, consecutive ci are not).
+__device__ __forceinline__ void red_add_f32x16(float* dst, const uint32_t (&r)[16]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        atomicAdd(reinterpret_cast<float4*>(dst) + i,
+                  make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                              __uint_as_float(r[4 * i + 3])));
+}
+
 struct WgradArgs {
     const uint8_t* g;   // gradient planes (row -HALO of plane 0), CG channels
     int64_t g_ps;
     const uint8_t* x;   // activation planes, CX channels
     int64_t x_ps;
-    float* dw;          // [CG][CX][TAPS] fp32, accumulated with atomics
+    float* dw;          // fp32, accumulated with 16-byte vector atomics: [CG][CX] (1x1) or TAP-MAJOR [9][CG][CX] (3x3 scratch)
     int nt;
 };
 
@@ -151,9 +162,13 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const WgradArgs a) {
                 tmem_ld16(taddr + ts * CX + c0, r);
                 tmem_ld_wait();
                 if (live) {
+                    if constexpr (TAPS == 1) {
+                        red_add_f32x16(a.dw + (int64_t)m * CX + c0, r);
+                    } else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        atomicAdd(a.dw + ((int64_t)(m * CX + c0 + i) * TAPS + tap), __uint_as_float(r[i]));
+                        for (int i = 0; i < 16; ++i)
+                            atomicAdd(a.dw + ((int64_t)(m * CX + c0 + i) * TAPS + tap), __uint_as_float(r[i]));
+                    }
                 }
             }
         }
@@ -296,11 +311,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_dup_kernel(const WgradArgs a) {
                 uint32_t r[16];
                 tmem_ld16(taddr + ky * CX + c0, r);
                 tmem_ld_wait();
-                if (live) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        atomicAdd(a.dw + ((int64_t)(co * CX + c0 + i) * 9 + ky * 3 + d), __uint_as_float(r[i]));
-                }
+                if (live) red_add_f32x16(a.dw + ((int64_t)((ky * 3 + d) * CG + co) * CX + c0), r);
             }
         }
         if constexpr (CG == 64) {
@@ -316,11 +327,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_dup_kernel(const WgradArgs a) {
                     uint32_t r[16];
                     tmem_ld16(taddr + (3 + blk) * CX + c0, r);
                     tmem_ld_wait();
-                    if (ok) {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            atomicAdd(a.dw + ((int64_t)(m2 * CX + c0 + i) * 9 + ky * 3 + 2), __uint_as_float(r[i]));
-                    }
+                    if (ok) red_add_f32x16(a.dw + ((int64_t)((ky * 3 + 2) * CG + m2) * CX + c0), r);
                 }
             }
         }
@@ -665,6 +672,28 @@ static int mask_reduce(const uint8_t* g, int64_t ps, int halo, const uint32_t* m
     return TDM_OK;
 }
 
+// 3x3 weight gradients leave the wgrad kernels tap-major ([tap][Cout][Cin], contiguous along Cin so the flush is
+// vector atomics); this puts them into the flat gradient in the parameter order (OIHW) and re-zeroes the scratch.
+struct UnpermJob { int off, cout, cin; };
+constexpr int kUnpermJobs = 7;
+__constant__ UnpermJob c_unperm[kUnpermJobs] = {
+    {P::rb1_c2w, 32, 32}, {P::rb2_c1w, 64, 32}, {P::rb2_c2w, 64, 64}, {P::rb3_c1w, 64, 64},
+    {P::rb3_c2w, 64, 64}, {P::rb4_c1w, 32, 96}, {P::rb4_c2w, 32, 32}};
+static_assert(P::rb1_c2w % 4 == 0 && P::rb2_c1w % 4 == 0 && P::rb2_c2w % 4 == 0 && P::rb3_c1w % 4 == 0 &&
+              P::rb3_c2w % 4 == 0 && P::rb4_c1w % 4 == 0 && P::rb4_c2w % 4 == 0 && P::rb2_sw % 4 == 0 &&
+              P::rb4_sw % 4 == 0, "16-byte vector atomics need 4-float aligned tensors");
+
+__global__ void wgrad_unpermute_kernel(float* __restrict__ scr, float* __restrict__ dflat) {
+    const UnpermJob j = c_unperm[blockIdx.y];
+    const int n = j.cout * j.cin * 9;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int tap = i % 9, rest = i / 9;           // rest = co * cin + ci
+        float* s = scr + j.off + tap * (j.cout * j.cin) + rest;
+        dflat[j.off + i] = *s;
+        *s = 0.f;
+    }
+}
+
 static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* t, const float* noise,
                               const float* eps, float* dflat, float* loss, uint8_t* ws,
                               int64_t ws_bytes, int64_t batch, cudaStream_t st) {
@@ -681,6 +710,7 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     int rc;
     ConvArgs c{};
     WgradArgs w{};
+    float* gscr = reinterpret_cast<float*>(ws + L.gscr);
 
     TDM_CHECK_CUDA(cudaMemsetAsync(dflat, 0, sizeof(float) * P::count, st));
     TDM_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
@@ -694,14 +724,14 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     // ---- rb4: x_in = cat (96), h = t4, g_out = go28 ----------------------------------------
     if ((rc = mask_reduce(ws + L.go28, L.ps28, H28, M(L.m2_4), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
                           dflat + P::rb4_sb, nullptr, dflat + P::rb4_c2b, st))) return rc;
-    w = WgradArgs{ws + L.gc28, L.ps28, ws + L.t4, L.ps28, dflat + P::rb4_c2w, nt28};
+    w = WgradArgs{ws + L.gc28, L.ps28, ws + L.t4, L.ps28, gscr + P::rb4_c2w, nt28};
     if ((rc = launch_wgrad_dup<28, 32, 32>(w, L.np28, st, "wgrad_rb4_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
     c.in = ws + L.gc28; c.in_ps = L.ps28; c.w = wp + WP::d_rb4_c2; c.out = ws + L.gh28; c.out_ps = L.ps28;
     if ((rc = launch_conv<28, 32, 32, EPI_PLAIN, false, 9, KX::rb4c2>(c, st, "dgrad_rb4_c2"))) return rc;
     if ((rc = mask_reduce(ws + L.gh28, L.ps28, H28, M(L.m1_4), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
                           dflat + P::rb4_tb, dflat + P::rb4_tw, dflat + P::rb4_c1b, st))) return rc;
-    w = WgradArgs{ws + L.gc28, L.ps28, ws + L.cat, L.ps28, dflat + P::rb4_c1w, nt28};
+    w = WgradArgs{ws + L.gc28, L.ps28, ws + L.cat, L.ps28, gscr + P::rb4_c1w, nt28};
     if ((rc = launch_wgrad_dup<28, 32, 96>(w, L.np28, st, "wgrad_rb4_c1"))) return rc;
     w = WgradArgs{ws + L.go28, L.ps28, ws + L.cat, L.ps28, dflat + P::rb4_sw, nt28};
     if ((rc = launch_wgrad<28, 32, 96, 1>(w, st, "wgrad_rb4_skip"))) return rc;
@@ -718,14 +748,14 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     // ---- rb3: x_in = h2, h = t3, identity skip, g_out = go14a -------------------------------
     if ((rc = mask_reduce(ws + L.go14a, L.ps14, H14, M(L.m2_3), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
                           nullptr, nullptr, dflat + P::rb3_c2b, st))) return rc;
-    w = WgradArgs{ws + L.gc14, L.ps14, ws + L.t3, L.ps14, dflat + P::rb3_c2w, nt14};
+    w = WgradArgs{ws + L.gc14, L.ps14, ws + L.t3, L.ps14, gscr + P::rb3_c2w, nt14};
     if ((rc = launch_wgrad_dup<14, 64, 64>(w, L.np14, st, "wgrad_rb3_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
     c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb3_c2; c.out = ws + L.gh14; c.out_ps = L.ps14;
     if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false, 9, KX::rb3c2>(c, st, "dgrad_rb3_c2"))) return rc;
     if ((rc = mask_reduce(ws + L.gh14, L.ps14, H14, M(L.m1_3), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
                           dflat + P::rb3_tb, dflat + P::rb3_tw, dflat + P::rb3_c1b, st))) return rc;
-    w = WgradArgs{ws + L.gc14, L.ps14, ws + L.h2, L.ps14, dflat + P::rb3_c1w, nt14};
+    w = WgradArgs{ws + L.gc14, L.ps14, ws + L.h2, L.ps14, gscr + P::rb3_c1w, nt14};
     if ((rc = launch_wgrad_dup<14, 64, 64>(w, L.np14, st, "wgrad_rb3_c1"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
     c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb3_c1; c.res = ws + L.go14a; c.res_ps = L.ps14;
@@ -735,14 +765,14 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     // ---- rb2: x_in = p1 (32), h = t2, skip 32->64, g_out = go14b ----------------------------
     if ((rc = mask_reduce(ws + L.go14b, L.ps14, H14, M(L.m2_2), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
                           dflat + P::rb2_sb, nullptr, dflat + P::rb2_c2b, st))) return rc;
-    w = WgradArgs{ws + L.gc14, L.ps14, ws + L.t2, L.ps14, dflat + P::rb2_c2w, nt14};
+    w = WgradArgs{ws + L.gc14, L.ps14, ws + L.t2, L.ps14, gscr + P::rb2_c2w, nt14};
     if ((rc = launch_wgrad_dup<14, 64, 64>(w, L.np14, st, "wgrad_rb2_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
     c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb2_c2; c.out = ws + L.gh14; c.out_ps = L.ps14;
     if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false, 9, KX::rb2c2>(c, st, "dgrad_rb2_c2"))) return rc;
     if ((rc = mask_reduce(ws + L.gh14, L.ps14, H14, M(L.m1_2), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
                           dflat + P::rb2_tb, dflat + P::rb2_tw, dflat + P::rb2_c1b, st))) return rc;
-    w = WgradArgs{ws + L.gc14, L.ps14, ws + L.p1, L.ps14, dflat + P::rb2_c1w, nt14};
+    w = WgradArgs{ws + L.gc14, L.ps14, ws + L.p1, L.ps14, gscr + P::rb2_c1w, nt14};
     if ((rc = launch_wgrad_dup<14, 64, 32>(w, L.np14, st, "wgrad_rb2_c1"))) return rc;
     w = WgradArgs{ws + L.go14b, L.ps14, ws + L.p1, L.ps14, dflat + P::rb2_sw, nt14};
     if ((rc = launch_wgrad<14, 64, 32, 1>(w, st, "wgrad_rb2_skip"))) return rc;
@@ -760,7 +790,7 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     // ---- rb1: x_in = x (1 channel), h = t1, skip 1->32, g_out = go28 ------------------------
     if ((rc = mask_reduce(ws + L.go28, L.ps28, H28, M(L.m2_1), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
                           dflat + P::rb1_sb, nullptr, dflat + P::rb1_c2b, st))) return rc;
-    w = WgradArgs{ws + L.gc28, L.ps28, ws + L.t1, L.ps28, dflat + P::rb1_c2w, nt28};
+    w = WgradArgs{ws + L.gc28, L.ps28, ws + L.t1, L.ps28, gscr + P::rb1_c2w, nt28};
     if ((rc = launch_wgrad_dup<28, 32, 32>(w, L.np28, st, "wgrad_rb1_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
     c.in = ws + L.gc28; c.in_ps = L.ps28; c.w = wp + WP::d_rb1_c2; c.out = ws + L.gh28; c.out_ps = L.ps28;
@@ -773,6 +803,8 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
                                                dflat + P::rb1_sw, B, nt28);
         TDM_CHECK_LAUNCH("rb1_wgrad");
     }
+    wgrad_unpermute_kernel<<<dim3(16, kUnpermJobs), 256, 0, st>>>(gscr, dflat);
+    TDM_CHECK_LAUNCH("wgrad_unpermute");
     return TDM_OK;
 }
 

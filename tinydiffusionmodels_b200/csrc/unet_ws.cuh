@@ -17,6 +17,7 @@ struct UNetWs {
     int64_t m1_1, m2_1, m1_2, m2_2, m1_3, m2_3, m1_4, m2_4;
     int64_t go28, gc28, gh28, gcat;       // 28-level gradients: 32, 32, 32, 96 channels
     int64_t go14a, go14b, gc14, gh14, gp1;  // 14-level gradients: 64, 64, 64, 64, 32 channels
+    int64_t gscr;                           // fp32 [P::count]: 3x3 weight gradients as [tap][Cout][Cin] at the tensor's flat offset
     int64_t total;
 };
 
@@ -64,6 +65,7 @@ static inline UNetWs make_ws(int64_t batch, bool for_backward) {
         w.gc14 = take(8 * w.ps14);
         w.gh14 = take(8 * w.ps14);
         w.gp1 = take(4 * w.ps14);
+        w.gscr = take(4LL * P::count);   // tap-major weight-gradient scratch, kept all-zero between steps (unet_bwd.cu)
     }
     w.total = o;
     return w;
