@@ -31,7 +31,8 @@ constexpr int kFfnStage = 32768;
 constexpr int kFfnStages = 4;
 constexpr int kFfnA = 128 * kFfnD * 2;          // 64 KB
 constexpr int kFfnP = 128 * kFfnC * 2;          // 32 KB
-constexpr int kFfnSmem = kFfnA + kFfnStages * kFfnStage + kFfnP + 1024;
+constexpr int kFfnLn = 2 * 128 * 8;             // LayerNorm partial sums exchanged between the two epilogue groups
+constexpr int kFfnSmem = kFfnA + kFfnStages * kFfnStage + kFfnP + kFfnLn + 1024;   // = 227 KB exactly
 constexpr int kFfnThreads = 64 + 256;
 constexpr int kFfnCluster = 2;    // CTAs sharing one multicast weight stream
 
@@ -69,7 +70,8 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
     uint8_t* sA = smem;
     uint8_t* sR = smem + kFfnA;
     uint8_t* sP = sR + kFfnStages * kFfnStage;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kFfnP);
+    float2* s_ln = reinterpret_cast<float2*>(sP + kFfnP);   // [group][row of the tile]: (sum, sum of squares) over the group's columns
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kFfnP + kFfnLn);
     uint64_t* bar_full = bars;                       // [stages]
     uint64_t* bar_empty = bars + kFfnStages;         // [stages]
     uint64_t* bar_a_full = bar_empty + kFfnStages;
@@ -97,7 +99,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
         mbar_init(bar_p_full, 4);
         mbar_init(bar_p_empty, 1);
         mbar_init(bar_acc2_full, 1);
-        mbar_init(bar_acc2_empty, 4);
+        mbar_init(bar_acc2_empty, 8);   // both epilogue groups read the tile accumulator
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc<512>(s_tmem);
@@ -209,7 +211,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
             }
         }
     } else {
-        // ===== epilogue groups: group g converts chunks c = g (mod 2); group 0 also finishes the tile =====
+        // ===== epilogue groups: group g converts chunks c = g (mod 2) and finishes columns [128g, 128g+128) of the tile =====
         const int q = warp & 3;
         const int grp = (warp - 2) >> 2;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -251,14 +253,17 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_p_full);
             }
-            if (grp != 0) continue;
-            // ---- tile epilogue: bias + residual, LayerNorm, optional reverse step ----
+            // ---- tile epilogue: bias + residual, LayerNorm, optional reverse step.  The two groups split the
+            //      256 columns (same TMEM lanes, i.e. rows; disjoint columns) and exchange the row statistics
+            //      through smem: with one group the last layer's Philox + reverse-step epilogue was 67 us
+            //      of a 184 us kernel (profiles/r01_ncu_launches_text_B512.csv). ----
             mbar_wait(bar_acc2_full, ti & 1);
             tc_fence_after_sync();
             const uint32_t taddr = t_acc2 + lane_base;
+            const int col_lo = grp * (kFfnD / 2), col_hi = col_lo + kFfnD / 2;
             float ln_sum = 0.f, ln_sq = 0.f;
 #pragma unroll 1
-            for (int c0 = 0; c0 < kFfnD; c0 += 32) {
+            for (int c0 = col_lo; c0 < col_hi; c0 += 32) {
                 uint32_t r[32], vb[32];
                 tmem_ld32(taddr + c0, r);
                 const float bias_l = __ldg(a.b2 + c0 + lane);
@@ -281,6 +286,13 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
                 tmem_st32(taddr + c0, vb);
             }
             tmem_st_wait();
+            s_ln[grp * 128 + q * 32 + lane] = make_float2(ln_sum, ln_sq);
+            asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps
+            {
+                const float2 o = s_ln[(grp ^ 1) * 128 + q * 32 + lane];
+                ln_sum += o.x;
+                ln_sq += o.y;
+            }
             const float mean = ln_sum * (1.0f / kFfnD);
             const float rstd = rsqrtf(fmaxf(ln_sq * (1.0f / kFfnD) - mean * mean, 0.f) + a.ln_eps);
             StepCoef sc{};
@@ -295,11 +307,11 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
                 tsn = (float)(tb_ - 1) / 1000.0f;
             }
 #pragma unroll 1
-            for (int c0 = 0; c0 < kFfnD; c0 += 32) {
+            for (int c0 = col_lo; c0 < col_hi; c0 += 32) {
                 uint32_t r[32];
                 tmem_ld32(taddr + c0, r);
                 tmem_ld_wait();
-                if (c0 + 32 == kFfnD) {
+                if (c0 + 32 == col_hi) {
                     tc_fence_before_sync();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_acc2_empty);
