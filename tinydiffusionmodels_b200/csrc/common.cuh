@@ -1,5 +1,6 @@
 // common.cuh — error plumbing, launch accounting and the counter-based RNG shared by all kernels.
 #pragma once
+#include <cstdlib>
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
@@ -19,6 +20,44 @@ void count_launch(int n = 1);
             return TDM_ERR_ARG;           \
         }                                 \
     } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A kernel launched through launch_pdl may become resident while its
+// predecessor in the stream is still draining; everything before pdl_wait() (barrier init, TMEM allocation)
+// then overlaps the predecessor's tail and the launch latency.  Rules kept by every kernel that uses it:
+//   * no global-memory access before pdl_wait();
+//   * pdl_launch_dependents() only AFTER pdl_wait(), so a kernel never overlaps anything but its direct
+//     predecessor (which therefore has itself waited for everything older).
+// Kernels launched the ordinary way see both instructions as no-ops.  Set TDM_NO_PDL=1 to launch everything
+// the ordinary way (debugging aid).
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = std::getenv("TDM_NO_PDL");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 #define TDM_CHECK_LAUNCH(name)                                                          \
     do {                                                                                \

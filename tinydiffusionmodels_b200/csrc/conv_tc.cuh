@@ -201,17 +201,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
     const int lane = threadIdx.x & 31;
     const int nt = (a.np + C::TSTRIDE - 1) / C::TSTRIDE;
 
-    // ---- setup -----------------------------------------------------------------------------
-    if (!CPAR && threadIdx.x < COUT) {
-        const int c = threadIdx.x;
-        s_bias[c] = (EPI == EPI_PLAIN) ? 0.f : a.bias[c];
-        s_tw[c] = (EPI == EPI_CONV1) ? a.tw[c] : 0.f;
-        s_tb[c] = (EPI == EPI_CONV1) ? a.tb[c] : 0.f;
-        s_sbias[c] = SKIPG ? a.sbias[c] : 0.f;
-        s_aux[c] = (EPI == EPI_RES_X || EPI == EPI_FINAL) ? a.aux_w[c] : 0.f;
-        if (EPI == EPI_RES_X) s_aux[32 + c] = a.aux_b[c];
-        if (EPI == EPI_FINAL && c == 0) s_aux[32] = a.aux_b[0];
-    }
+    // ---- setup (everything before pdl_wait touches no global memory: it may overlap the previous kernel) ----
     if (threadIdx.x == 0) {
         mbar_init(bar_w, 1);
         for (int i = 0; i < C::NSTAGE; ++i) {
@@ -225,6 +215,18 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc<C::TMEM_COLS>(s_tmem);
+    pdl_wait();                 // the previous kernel's results are visible from here on
+    pdl_launch_dependents();    // the next kernel may start its own setup as our CTAs retire
+    if (!CPAR && threadIdx.x < COUT) {
+        const int c = threadIdx.x;
+        s_bias[c] = (EPI == EPI_PLAIN) ? 0.f : a.bias[c];
+        s_tw[c] = (EPI == EPI_CONV1) ? a.tw[c] : 0.f;
+        s_tb[c] = (EPI == EPI_CONV1) ? a.tb[c] : 0.f;
+        s_sbias[c] = SKIPG ? a.sbias[c] : 0.f;
+        s_aux[c] = (EPI == EPI_RES_X || EPI == EPI_FINAL) ? a.aux_w[c] : 0.f;
+        if (EPI == EPI_RES_X) s_aux[32 + c] = a.aux_b[c];
+        if (EPI == EPI_FINAL && c == 0) s_aux[32] = a.aux_b[0];
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -767,7 +769,7 @@ static int launch_conv(const ConvArgs& a, cudaStream_t st, const char* name) {
     }
     const int nt = (a.np + C::TSTRIDE - 1) / C::TSTRIDE;
     const int grid = nt < num_sms() ? nt : num_sms();
-    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(a);
+    launch_pdl(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, a);
     TDM_CHECK_LAUNCH(name);
     return TDM_OK;
 }

@@ -143,6 +143,8 @@ unit_range_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t 
 }
 
 __global__ void add_i64_kernel(int64_t* __restrict__ t, int64_t n, int64_t delta) {
+    pdl_wait();   // the kernel before us still reads t
+    pdl_launch_dependents();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) t[i] += delta;
 }
@@ -241,7 +243,7 @@ extern "C" int tdm_to_unit_range(const float* x, float* out, int64_t n, void* st
 extern "C" int tdm_timestep_advance(int64_t* t, int64_t batch, int64_t delta, void* stream) {
     if (batch == 0) return TDM_OK;
     TDM_CHECK_ARG(t && batch > 0, "tdm_timestep_advance: bad arguments");
-    add_i64_kernel<<<(unsigned)((batch + 255) / 256), 256, 0, (cudaStream_t)stream>>>(t, batch, delta);
+    launch_pdl(add_i64_kernel, dim3((unsigned)((batch + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, t, batch, delta);
     TDM_CHECK_LAUNCH("tdm_timestep_advance");
     return TDM_OK;
 }

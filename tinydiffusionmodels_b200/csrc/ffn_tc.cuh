@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
     __syncthreads();
     cluster_sync_all();   // every CTA's mbarriers exist before any peer multicasts into / arrives on them
     tc_fence_after_sync();
+    pdl_wait();                 // PDL (common.cuh): nothing above touches global memory
+    pdl_launch_dependents();
     const uint32_t tmem_base = *s_tmem;
     const uint32_t crank = cluster_ctarank();
     const int cluster_id = blockIdx.x / kFfnCluster, n_clusters = gridDim.x / kFfnCluster;
@@ -384,13 +386,15 @@ static int launch_ffn(const FfnArgs& a, cudaStream_t st) {
     cfg.blockDim = dim3(kFfnThreads);
     cfg.dynamicSmemBytes = kFfnSmem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = kFfnCluster;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     TDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ffn_tc_kernel, a));
     TDM_CHECK_LAUNCH("ffn_fused");
     return TDM_OK;

@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+    pdl_wait();                 // PDL (common.cuh): nothing above touches global memory
+    pdl_launch_dependents();
     const uint32_t tmem_base = *s_tmem;
 
     const int m_tiles = a.Mp / kBM;
@@ -327,7 +329,7 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t st, const char* name) {
                   "%s: bad GEMM shape M=%d Mp=%d N=%d K=%d", name, a.M, a.Mp, a.N, a.K);
     const int items = (a.Mp / kBM) * a.nsplit;
     const int grid = items < num_sms() ? items : num_sms();
-    kern<<<grid, kGemmThreads, kGemmSmem, st>>>(a);
+    launch_pdl(kern, dim3(grid), dim3(kGemmThreads), kGemmSmem, st, a);
     TDM_CHECK_LAUNCH(name);
     return TDM_OK;
 }

@@ -183,6 +183,8 @@ __global__ void __launch_bounds__(128) attn_tc_kernel(const uint8_t* __restrict_
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+    pdl_wait();                 // PDL (common.cuh): nothing above touches global memory
+    pdl_launch_dependents();
     const uint32_t tmem_base = *s_tmem;
 
     if (warp == 0) {
@@ -321,6 +323,8 @@ struct LnArgs {
 };
 
 __global__ void __launch_bounds__(256) layernorm_kernel(const LnArgs a) {
+    pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
+    pdl_launch_dependents();
     __shared__ float s_sum[8][32], s_sq[8][32];
     const int slice = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 32 + lane;
@@ -485,7 +489,7 @@ static int launch_attn(const uint8_t* qkv, int64_t ps, int D, int heads, int64_t
         TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         configured = true;
     }
-    kern<<<(unsigned)(B * heads), 128, C::SMEM, st>>>(qkv, ps, D, heads, out, ps);
+    launch_pdl(kern, dim3((unsigned)(B * heads)), dim3(128), C::SMEM, st, qkv, ps, D, heads, out, ps);
     TDM_CHECK_LAUNCH("attention");
     return TDM_OK;
 }
@@ -543,7 +547,7 @@ static int text_forward_impl(const void* const* ptrs, int depth, uint8_t* ws, in
             if ((rc = launch_gemm<GE_RES_F32>(g, st, "gemm_out_proj"))) return rc;
             ln.in = ws + W.pre; ln.gamma = (const float*)p[LN1_G]; ln.beta = (const float*)p[LN1_B]; ln.eps = 1e-5f;
             ln.out32 = ws + W.h32; ln.out16 = ws + W.h16; ln.M = W.M; ln.Mp = W.Mp; ln.D = D; ln.L = L;
-            layernorm_kernel<<<W.Mp / 32, 256, 0, st>>>(ln);
+            launch_pdl(layernorm_kernel, dim3(W.Mp / 32), dim3(256), 0, st, ln);
             TDM_CHECK_LAUNCH("layernorm1");
         }
         if (D == kFfnD) {
@@ -591,7 +595,7 @@ static int text_forward_impl(const void* const* ptrs, int depth, uint8_t* ws, in
             ln.alphas = sa.alphas; ln.sqrt_om = sa.sqrt_om; ln.tw = tw; ln.tb = tb; ln.seed = sa.seed;
             ln.sample_offset = sa.sample_offset; ln.step_id = sa.step_id;
         }
-        layernorm_kernel<<<W.Mp / 32, 256, 0, st>>>(ln);
+        launch_pdl(layernorm_kernel, dim3(W.Mp / 32), dim3(256), 0, st, ln);
         TDM_CHECK_LAUNCH("layernorm2");
     }
     return TDM_OK;

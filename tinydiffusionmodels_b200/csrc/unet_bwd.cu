@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const WgradArgs a) {
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+    pdl_wait();                 // PDL (common.cuh): nothing above touches global memory
+    pdl_launch_dependents();
     const uint32_t tmem_base = *s_tmem;
 
     if (warp == 0) {
@@ -236,6 +238,8 @@ __global__ void __launch_bounds__(192, 1) wgrad_dup_kernel(const WgradArgs a) {
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+    pdl_wait();                 // PDL (common.cuh): nothing above touches global memory
+    pdl_launch_dependents();
     const uint32_t tmem_base = *s_tmem;
     constexpr int LIVE_PLANES = C::NDUP * C::GPL;     // 12 (CG=32) or 16 (CG=64) of the 16 M-groups hold data
     constexpr int LIVE_BYTES = LIVE_PLANES * kTile * 16 + C::X_BYTES;
@@ -350,7 +354,7 @@ static int launch_wgrad_dup(WgradArgs a, int64_t np, cudaStream_t st, const char
     }
     a.nt = (int)((np + 2 + kTile - 1) / kTile);   // two rows past np so the shifted copies reach the last positions
     const int grid = a.nt < num_sms() ? a.nt : num_sms();
-    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(a);
+    launch_pdl(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, a);
     TDM_CHECK_LAUNCH(name);
     return TDM_OK;
 }
@@ -365,7 +369,7 @@ static int launch_wgrad(const WgradArgs& a, cudaStream_t st, const char* name) {
         configured = true;
     }
     const int grid = a.nt < num_sms() ? a.nt : num_sms();
-    kern<<<grid, C::THREADS, C::SMEM_BYTES, st>>>(a);
+    launch_pdl(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, a);
     TDM_CHECK_LAUNCH(name);
     return TDM_OK;
 }
@@ -389,6 +393,8 @@ loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
                  const uint8_t* __restrict__ h4, int64_t ps, const float* __restrict__ wo,
                  uint8_t* __restrict__ go, float* __restrict__ d_wo, float* __restrict__ d_bo,
                  float* __restrict__ loss, int batch, int64_t npos, float inv_n) {
+    pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
+    pdl_launch_dependents();
     using G = Geo<28>;
     const int lane = threadIdx.x, j = threadIdx.y;
     float w[8], acc[8];
@@ -453,6 +459,8 @@ __global__ void mask_reduce_kernel(const uint8_t* __restrict__ g, int64_t ps, in
                                    uint8_t* __restrict__ out, const int64_t* __restrict__ t, int S,
                                    int batch, int64_t npos, float* __restrict__ d_plain,
                                    float* __restrict__ d_ts, float* __restrict__ d_masked) {
+    pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
+    pdl_launch_dependents();
     const int lane = threadIdx.x, j = threadIdx.y;
     float sp[8], st[8], sm[8];
 #pragma unroll
@@ -516,6 +524,8 @@ __global__ void mask_reduce_kernel(const uint8_t* __restrict__ g, int64_t ps, in
 __global__ void __launch_bounds__(128)
 upsample_bwd_kernel(const uint8_t* __restrict__ in, int64_t in_ps, uint8_t* __restrict__ out,
                     int64_t out_ps, int batch) {
+    pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
+    pdl_launch_dependents();
     using GI = Geo<28>;
     using GO = Geo<14>;
     const int64_t pos = (int64_t)blockIdx.x * 128 + threadIdx.x;
@@ -548,6 +558,8 @@ upsample_bwd_kernel(const uint8_t* __restrict__ in, int64_t in_ps, uint8_t* __re
 __global__ void __launch_bounds__(128)
 pool_bwd_add_kernel(const uint8_t* __restrict__ a, int64_t a_ps, const uint8_t* __restrict__ gp,
                     int64_t gp_ps, uint8_t* __restrict__ out, int64_t out_ps, int batch) {
+    pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
+    pdl_launch_dependents();
     using G28 = Geo<28>;
     using G14 = Geo<14>;
     const int64_t pos = (int64_t)blockIdx.x * 128 + threadIdx.x;
@@ -579,6 +591,8 @@ __global__ void __launch_bounds__(320)
 rb1_wgrad_kernel(const uint8_t* __restrict__ gc, const uint8_t* __restrict__ go, int64_t ps,
                  const float* __restrict__ x, float* __restrict__ d_w1, float* __restrict__ d_ws,
                  int batch, int nt) {
+    pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
+    pdl_launch_dependents();
     using G = Geo<28>;
     __shared__ float s_gc[128][33], s_go[128][33], s_x[128][9];
     const int tid = threadIdx.x;
@@ -638,6 +652,8 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
              float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
              float grad_scale, const int64_t* __restrict__ step) {
+    pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
+    pdl_launch_dependents();
     __shared__ float s_c[2];
     if (threadIdx.x == 0) {
         const double k = (double)*step;
@@ -666,7 +682,7 @@ static int mask_reduce(const uint8_t* g, int64_t ps, int halo, const uint32_t* m
                        uint8_t* out, int ch, const int64_t* t, int S, int batch, int64_t npos,
                        float* d_plain, float* d_ts, float* d_masked, cudaStream_t st) {
     const unsigned grid = (unsigned)((npos + kChunk - 1) / kChunk);
-    mask_reduce_kernel<<<grid, dim3(32, ch / 8), 0, st>>>(g, ps, halo, mask, mstride, out, t, S, batch,
+    launch_pdl(mask_reduce_kernel, dim3(grid), dim3(32, ch / 8), 0, st, g, ps, halo, mask, mstride, out, t, S, batch,
                                                           npos, d_plain, d_ts, d_masked);
     TDM_CHECK_LAUNCH("mask_reduce");
     return TDM_OK;
@@ -684,6 +700,8 @@ static_assert(P::rb1_c2w % 4 == 0 && P::rb2_c1w % 4 == 0 && P::rb2_c2w % 4 == 0 
               P::rb4_sw % 4 == 0, "16-byte vector atomics need 4-float aligned tensors");
 
 __global__ void wgrad_unpermute_kernel(float* __restrict__ scr, float* __restrict__ dflat) {
+    pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
+    pdl_launch_dependents();
     const UnpermJob j = c_unperm[blockIdx.y];
     const int n = j.cout * j.cin * 9;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -716,7 +734,7 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     TDM_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
 
     // ---- loss and out conv ---------------------------------------------------------------
-    loss_grad_kernel<<<(unsigned)((L.np28 + kChunk - 1) / kChunk), dim3(32, 4), 0, st>>>(
+    launch_pdl(loss_grad_kernel, dim3((unsigned)((L.np28 + kChunk - 1) / kChunk)), dim3(32, 4), 0, st, 
         eps, noise, ws + L.h4, L.ps28, fp + P::out_w, ws + L.go28, dflat + P::out_w, dflat + P::out_b,
         loss, B, L.np28, 1.0f / (float)(batch * 784));
     TDM_CHECK_LAUNCH("loss_grad");
@@ -742,7 +760,7 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = launch_conv<28, 32, 96, EPI_PLAIN, false, 1>(c, st, "dgrad_rb4_skip"))) return rc;
 
     // ---- through the concat: channels 0..63 -> up(h3)^T -> g_out of rb3 ---------------------
-    upsample_bwd_kernel<<<dim3(nt14, 8), 128, 0, st>>>(ws + L.gcat, L.ps28, ws + L.go14a, L.ps14, B);
+    launch_pdl(upsample_bwd_kernel, dim3(nt14, 8), dim3(128), 0, st, ws + L.gcat, L.ps28, ws + L.go14a, L.ps14, B);
     TDM_CHECK_LAUNCH("upsample_bwd");
 
     // ---- rb3: x_in = h2, h = t3, identity skip, g_out = go14a -------------------------------
@@ -783,7 +801,7 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = launch_conv<14, 64, 32, EPI_PLAIN, false, 1>(c, st, "dgrad_rb2_skip"))) return rc;
 
     // ---- h1 receives: concat channels 64..95 + avg-pool transpose of g_p1 -------------------
-    pool_bwd_add_kernel<<<dim3(nt28, 4), 128, 0, st>>>(ws + L.gcat + 8 * L.ps28, L.ps28, ws + L.gp1, L.ps14,
+    launch_pdl(pool_bwd_add_kernel, dim3(nt28, 4), dim3(128), 0, st, ws + L.gcat + 8 * L.ps28, L.ps28, ws + L.gp1, L.ps14,
                                                       ws + L.go28, L.ps28, B);
     TDM_CHECK_LAUNCH("pool_bwd_add");
 
@@ -799,11 +817,11 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
                           dflat + P::rb1_tb, dflat + P::rb1_tw, dflat + P::rb1_c1b, st))) return rc;
     {
         const int grid = nt28 < 4 * num_sms() ? nt28 : 4 * num_sms();
-        rb1_wgrad_kernel<<<grid, 320, 0, st>>>(ws + L.gc28, ws + L.go28, L.ps28, x, dflat + P::rb1_c1w,
+        launch_pdl(rb1_wgrad_kernel, dim3(grid), dim3(320), 0, st, ws + L.gc28, ws + L.go28, L.ps28, x, dflat + P::rb1_c1w,
                                                dflat + P::rb1_sw, B, nt28);
         TDM_CHECK_LAUNCH("rb1_wgrad");
     }
-    wgrad_unpermute_kernel<<<dim3(16, kUnpermJobs), 256, 0, st>>>(gscr, dflat);
+    launch_pdl(wgrad_unpermute_kernel, dim3(16, kUnpermJobs), dim3(256), 0, st, gscr, dflat);
     TDM_CHECK_LAUNCH("wgrad_unpermute");
     return TDM_OK;
 }
@@ -836,7 +854,7 @@ extern "C" int tdm_adamw_flat(float* params, const float* grads, float* exp_avg,
                               void* stream) {
     TDM_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && step_dev && n >= 0, "tdm_adamw_flat: bad arguments");
     if (n == 0) return TDM_OK;
-    adamw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(adamw_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
         params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step_dev);
     TDM_CHECK_LAUNCH("tdm_adamw_flat");
     return TDM_OK;

@@ -56,6 +56,8 @@ __constant__ PackJob c_jobs[kPackJobs] = {
     {P::rb4_sw, WP::d_rb4_sk, 96, 32, 1, 1, 0}};
 
 __global__ void pack_weights_kernel(const float* __restrict__ flat, uint8_t* __restrict__ wpack) {
+    pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
+    pdl_launch_dependents();
     const PackJob j = c_jobs[blockIdx.y];
     const int n = j.taps * j.cin * j.cout;
     __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(wpack + j.dst);
@@ -116,6 +118,8 @@ avgpool_kernel(const uint8_t* __restrict__ in, int64_t in_ps, uint8_t* __restric
                int64_t out_ps, int batch) {
     using GI = Geo<28>;
     using GO = Geo<14>;
+    pdl_wait();
+    pdl_launch_dependents();
     const int64_t pos = (int64_t)blockIdx.x * 128 + threadIdx.x;
     const int plane = blockIdx.y;
     const int b = (int)((uint32_t)pos / (uint32_t)GO::S);   // positions fit 32 bits: division by a constant is a multiply-shift
@@ -217,7 +221,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
 
     // k3: pool h1 -> p1
     TDM_PROF(2);
-    avgpool_kernel<<<dim3(nt14, 4), 128, 0, st>>>(ws + L.cat + 8 * L.ps28, L.ps28, ws + L.p1, L.ps14, B);
+    launch_pdl(avgpool_kernel, dim3(nt14, 4), dim3(128), 0, st, ws + L.cat + 8 * L.ps28, L.ps28, ws + L.p1, L.ps14, B);
     TDM_CHECK_LAUNCH("avgpool");
 
     // k4: rb2.conv1 (+skip) -> t2, s2
@@ -315,7 +319,7 @@ extern "C" int tdm_unet_debug_layout(int64_t batch, int64_t* host_out16) {
 extern "C" int tdm_unet_pack_weights(const float* flat_params, void* wpack, void* stream) {
     TDM_CHECK_ARG(flat_params && wpack, "tdm_unet_pack_weights: null pointer");
     drop_host_params(wpack);   // the device copy is about to change: a host mirror of the old values is stale
-    pack_weights_kernel<<<dim3(32, kPackJobs), 256, 0, (cudaStream_t)stream>>>(
+    launch_pdl(pack_weights_kernel, dim3(32, kPackJobs), dim3(256), 0, (cudaStream_t)stream, 
         flat_params, reinterpret_cast<uint8_t*>(wpack));
     TDM_CHECK_LAUNCH("tdm_unet_pack_weights");
     return TDM_OK;
