@@ -115,3 +115,69 @@ def test_fused_p_sample_matches_oracle(cuda, tval):
     xin = x.to(cuda).clone()
     eng.p_sample(xin, t.to(cuda), z.to(cuda), out=xin)
     assert torch.equal(xin.cpu(), got)
+
+
+def _forward_without_mirror(eng, sd, x, t, cuda):
+    """Re-pack through tdm_unet_pack_weights (drops the host mirror) and run the forward again."""
+    from tinydiffusionmodels_b200 import _lib
+    from tinydiffusionmodels_b200.unet_engine import flatten_state_dict
+    flat = flatten_state_dict(sd, cuda)
+    _lib.check(eng.lib.tdm_unet_pack_weights(flat.data_ptr(), eng.wpack.data_ptr(), _lib.stream_ptr(cuda)),
+               "tdm_unet_pack_weights")
+    out = eng.forward(x, t)
+    torch.cuda.synchronize()
+    return out
+
+
+def test_host_mirror_path_is_bit_identical_to_smem_path(cuda):
+    """Per-channel vectors by value (constant bank, tdm_unet_pack_weights_host) vs staged in shared
+    memory (tdm_unet_pack_weights): same arithmetic, so the outputs must be equal bit for bit."""
+    sd = random_unet_state_dict(3)
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(37, 1, 28, 28, generator=g).to(cuda)
+    t = torch.randint(0, 1000, (37,), generator=g).to(cuda)
+    eng = UNetEngine(cuda, 37)
+    eng.load_state_dict(sd)                      # registers the host mirror
+    with_mirror = eng.forward(x, t).clone()
+    torch.cuda.synchronize()
+    without = _forward_without_mirror(eng, sd, x, t, cuda)
+    assert torch.equal(with_mirror, without)
+
+
+def test_repack_drops_a_stale_host_mirror(cuda):
+    """Loading new weights through the plain pack entry point must not leave the old biases in the
+    launch arguments: the result has to follow the NEW parameters."""
+    sd_a, sd_b = random_unet_state_dict(4), random_unet_state_dict(5)
+    g = torch.Generator().manual_seed(78)
+    x = torch.randn(5, 1, 28, 28, generator=g)
+    t = torch.randint(0, 1000, (5,), generator=g)
+    eng = UNetEngine(cuda, 5)
+    eng.load_state_dict(sd_a)                    # mirror of A
+    eng.forward(x.to(cuda), t.to(cuda))
+    got_b = _forward_without_mirror(eng, sd_b, x.to(cuda), t.to(cuda), cuda)   # device weights B, mirror dropped
+    ref_b = O.unet_forward(sd_b, x, t)
+    assert rel_rms(got_b.cpu(), ref_b) < RMS_TOL
+    eng.load_state_dict(sd_a)                    # and back, with a fresh mirror
+    got_a = eng.forward(x.to(cuda), t.to(cuda))
+    torch.cuda.synchronize()
+    assert rel_rms(got_a.cpu(), O.unet_forward(sd_a, x, t)) < RMS_TOL
+
+
+def test_first_conv_keeps_fp32_like_precision(cuda):
+    """rb1.conv1 runs on the tensor pipe as hi/lo bf16 products (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo):
+    its output is then rounded to bf16 once, so it must sit at the bf16 rounding floor (2^-9 relative),
+    well below the 2e-2 per-layer bar - also for inputs far outside the unit range."""
+    import torch.nn.functional as F
+    sd = random_unet_state_dict(6)
+    g = torch.Generator().manual_seed(79)
+    x = torch.randn(9, 1, 28, 28, generator=g) * 50.0
+    t = torch.randint(0, 1000, (9,), generator=g)
+    eng = UNetEngine(cuda, 9)
+    eng.load_state_dict(sd)
+    eng.forward(x.to(cuda), t.to(cuda))
+    torch.cuda.synchronize()
+    got = read_activation(eng, "t1", 9).cpu()
+    tt = (t.float() / 1000).view(-1, 1)
+    ref = F.relu(F.conv2d(x, sd["rb1.conv1.weight"], sd["rb1.conv1.bias"], padding=1))
+    ref = ref + F.linear(tt, sd["rb1.time_emb.weight"], sd["rb1.time_emb.bias"]).view(9, -1, 1, 1)
+    assert rel_rms(got, ref) < 3e-3
