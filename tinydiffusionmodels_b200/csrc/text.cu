@@ -153,8 +153,11 @@ struct AttnCfg {
     static constexpr int P_BYTES = L * L * 2;
     static constexpr int SMEM = 3 * QKV_BYTES + P_BYTES + 256;
     static constexpr int NO = HD > 256 ? 256 : HD;       // columns of one PV MMA
-    static constexpr int TCOLS_RAW = L + NO;
-    static constexpr int TCOLS = TCOLS_RAW <= 128 ? 128 : TCOLS_RAW <= 256 ? 256 : 512;
+    // O reuses the columns of S: the softmax has read all of S into registers (and the block has synchronised)
+    // before the first PV MMA is issued.  Halving the TMEM footprint doubles the CTAs resident per SM, which is
+    // what this latency-bound kernel (one short dependent chain per CTA) is limited by.
+    static constexpr int TCOLS_RAW = L > NO ? L : NO;
+    static constexpr int TCOLS = TCOLS_RAW <= 32 ? 32 : TCOLS_RAW <= 64 ? 64 : TCOLS_RAW <= 128 ? 128 : TCOLS_RAW <= 256 ? 256 : 512;
     static_assert(SMEM <= 227 * 1024, "attention tile does not fit in shared memory");
 };
 
@@ -264,13 +267,13 @@ __global__ void __launch_bounds__(128) attn_tc_kernel(const uint8_t* __restrict_
             for (int ks = 0; ks < L / 16; ++ks) {
                 const uint64_t ad = make_smem_desc(p_addr + (2 * ks) * (L * 16), L * 16, 128);
                 const uint64_t bd = make_smem_desc(v_addr + (ch * C::NO / 8) * (L * 16) + ks * 256, 128, L * 16);
-                umma_bf16(tmem_base + L, ad, bd, idesc, ks != 0);
+                umma_bf16(tmem_base, ad, bd, idesc, ks != 0);
             }
             umma_commit(bars + 2);
         }
         mbar_wait(bars + 2, ch & 1);
         tc_fence_after_sync();
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + L;
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
         for (int c0 = 0; c0 < C::NO; c0 += 32) {
             uint32_t r[32];
