@@ -386,9 +386,12 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// MSE gradient + 1x1 output convolution backward.  blockDim = (32, 4): lane -> position, y -> plane.
+// MSE gradient + 1x1 output convolution backward.  blockDim = (32, 4, kLgGroups): x -> position, y -> plane,
+// z -> quarter of the block's kChunk positions (same shape as mask_reduce_kernel below: one round trip of loads
+// per thread, shared-memory combine, one set of atomics per block).
 //   g = 2*(eps - noise)/n ; go4[c] = out.weight[c]*g ; d out.weight[c] += g*h4[c] ; d out.bias += g
-__global__ void __launch_bounds__(128)
+constexpr int kLgGroups = 4;
+__global__ void __launch_bounds__(32 * 4 * kLgGroups)
 loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
                  const uint8_t* __restrict__ h4, int64_t ps, const float* __restrict__ wo,
                  uint8_t* __restrict__ go, float* __restrict__ d_wo, float* __restrict__ d_bo,
@@ -396,7 +399,9 @@ loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
     pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
     pdl_launch_dependents();
     using G = Geo<28>;
-    const int lane = threadIdx.x, j = threadIdx.y;
+    constexpr int kIter = kChunk / (32 * kLgGroups);
+    __shared__ float s_red[kLgGroups][4][10];   // [group][plane][d_wo 0..7 | loss 8 | d_bo 9]
+    const int lane = threadIdx.x, j = threadIdx.y, zg = threadIdx.z;
     float w[8], acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -404,21 +409,34 @@ loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
         acc[k] = 0.f;
     }
     float lsum = 0.f, gsum = 0.f;
-    const int64_t base = (int64_t)blockIdx.x * kChunk;
-    for (int it = 0; it < kChunk / 32; ++it) {
-        const int64_t pos = base + it * 32 + lane;
-        if (pos >= npos) break;
+    const int64_t base = (int64_t)blockIdx.x * kChunk + zg * (kIter * 32);
+    float dv[kIter];
+    uint4 hvs[kIter];
+    bool ok[kIter];
+#pragma unroll
+    for (int u = 0; u < kIter; ++u) {   // issue all loads before using any
+        const int64_t pos = base + u * 32 + lane;
         const int b = (int)((uint32_t)pos / (uint32_t)G::S);   // positions fit 32 bits: division by a constant is a multiply-shift
         const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)G::S);
         const int r = rem / G::Wp, c = rem - r * G::Wp;
-        const bool valid = b < batch && r >= 1 && c < G::W;
-        uint4 o = make_uint4(0, 0, 0, 0);
-        if (valid) {
+        ok[u] = pos < npos && b < batch && r >= 1 && c < G::W;
+        dv[u] = 0.f;
+        hvs[u] = make_uint4(0, 0, 0, 0);
+        if (ok[u]) {
             const int64_t i = (int64_t)b * 784 + (r - 1) * 28 + c;
-            const float d = __ldg(eps + i) - __ldg(noise + i);
+            dv[u] = __ldg(eps + i) - __ldg(noise + i);
+            hvs[u] = *reinterpret_cast<const uint4*>(h4 + j * ps + (pos + G::GUARD) * 16);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < kIter; ++u) {
+        const int64_t pos = base + u * 32 + lane;
+        if (pos >= npos) continue;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (ok[u]) {
+            const float d = dv[u];
             const float g = 2.0f * d * inv_n;
-            const uint4 hv = *reinterpret_cast<const uint4*>(h4 + j * ps + (pos + G::GUARD) * 16);
-            const uint32_t* hw = &hv.x;
+            const uint32_t* hw = &hvs[u].x;
             uint32_t* ow = &o.x;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -436,16 +454,22 @@ loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float s = warp_sum(acc[k]);
-        if (lane == 0) atomicAdd(d_wo + j * 8 + k, s);
+        const float v = warp_sum(acc[k]);
+        if (lane == 0) s_red[zg][j][k] = v;
     }
-    if (j == 0) {
-        lsum = warp_sum(lsum);
-        gsum = warp_sum(gsum);
-        if (lane == 0) {
-            atomicAdd(loss, lsum);
-            atomicAdd(d_bo, gsum);
-        }
+    lsum = warp_sum(lsum);
+    gsum = warp_sum(gsum);
+    if (lane == 0) {
+        s_red[zg][j][8] = lsum;   // zero except on plane 0
+        s_red[zg][j][9] = gsum;
+    }
+    __syncthreads();
+    if (zg == 0 && lane < 10) {
+        float v = 0.f;
+#pragma unroll
+        for (int z = 0; z < kLgGroups; ++z) v += s_red[z][j][lane];
+        if (lane < 8) atomicAdd(d_wo + j * 8 + lane, v);
+        else if (j == 0) atomicAdd(lane == 8 ? loss : d_bo, v);
     }
 }
 
@@ -748,7 +772,7 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     TDM_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), st));
 
     // ---- loss and out conv ---------------------------------------------------------------
-    launch_pdl(loss_grad_kernel, dim3((unsigned)((L.np28 + kChunk - 1) / kChunk)), dim3(32, 4), 0, st, 
+    launch_pdl(loss_grad_kernel, dim3((unsigned)((L.np28 + kChunk - 1) / kChunk)), dim3(32, 4, kLgGroups), 0, st, 
         eps, noise, ws + L.h4, L.ps28, fp + P::out_w, ws + L.go28, dflat + P::out_w, dflat + P::out_b,
         loss, B, L.np28, 1.0f / (float)(batch * 784));
     TDM_CHECK_LAUNCH("loss_grad");
