@@ -624,35 +624,52 @@ pool_bwd_add_kernel(const uint8_t* __restrict__ a, int64_t a_ps, const uint8_t* 
 
 // rb1.conv1 (Cin = 1) and rb1.skip (1x1, Cin = 1) weight gradients:
 //   dW1[co][tap] += sum gc[pos][co] * x[pos + off(tap)]      dWs[co] += sum go[pos][co] * x[pos]
-// block = 320 threads: 288 (co, tap) pairs + 32 skip channels, over chunks of 128 positions.
-__global__ void __launch_bounds__(320)
+// block = 256 threads = 8 channel groups (4 channels) x 32 position slices (4 positions) of a 128-position
+// tile; a thread keeps its 4 x 9 + 4 partial sums in registers over all the block's tiles (11 shared-memory
+// loads per 40 FMAs; one (co, tap) pair per thread was 2 loads per FMA and shared-memory bound at 50 us for
+// B = 512), then the slices are combined once: shuffles inside a warp, shared memory across the 8 warps.
+constexpr int kR1Stride = 36;   // floats per staged position (32 channels, padded so rows stay 16-byte aligned)
+__global__ void __launch_bounds__(256)
 rb1_wgrad_kernel(const uint8_t* __restrict__ gc, const uint8_t* __restrict__ go, int64_t ps,
                  const float* __restrict__ x, float* __restrict__ d_w1, float* __restrict__ d_ws,
                  int batch, int nt) {
     pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
     pdl_launch_dependents();
     using G = Geo<28>;
-    __shared__ float s_gc[128][33], s_go[128][33], s_x[128][9];
+    __shared__ __align__(16) float s_gc[128 * kR1Stride], s_go[128 * kR1Stride];
+    __shared__ float s_x[128][9];
     const int tid = threadIdx.x;
-    float acc = 0.f;
+    const int cg = tid & 7, sl = tid >> 3;
+    float acc[4][9], accs[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        accs[c] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[c][k] = 0.f;
+    }
     for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
         __syncthreads();
-        for (int i = tid; i < 128 * 4; i += 320) {
+        for (int i = tid; i < 128 * 4; i += 256) {
             const int p = i & 127, j = i >> 7;
             const int64_t pos = (int64_t)tile * 128 + p;
             const uint4 v = *reinterpret_cast<const uint4*>(gc + j * ps + (pos + G::GUARD) * 16);
             const uint4 u = *reinterpret_cast<const uint4*>(go + j * ps + (pos + G::GUARD) * 16);
             const uint32_t *vw = &v.x, *uw = &u.x;
+            float fv[8], fu[8];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float2 f = unpack_bf16x2(vw[k]), h = unpack_bf16x2(uw[k]);
-                s_gc[p][j * 8 + 2 * k] = f.x;
-                s_gc[p][j * 8 + 2 * k + 1] = f.y;
-                s_go[p][j * 8 + 2 * k] = h.x;
-                s_go[p][j * 8 + 2 * k + 1] = h.y;
+                fv[2 * k] = f.x; fv[2 * k + 1] = f.y;
+                fu[2 * k] = h.x; fu[2 * k + 1] = h.y;
             }
+            float4* dg = reinterpret_cast<float4*>(s_gc + p * kR1Stride + j * 8);
+            float4* du = reinterpret_cast<float4*>(s_go + p * kR1Stride + j * 8);
+            dg[0] = make_float4(fv[0], fv[1], fv[2], fv[3]);
+            dg[1] = make_float4(fv[4], fv[5], fv[6], fv[7]);
+            du[0] = make_float4(fu[0], fu[1], fu[2], fu[3]);
+            du[1] = make_float4(fu[4], fu[5], fu[6], fu[7]);
         }
-        for (int i = tid; i < 128 * 9; i += 320) {
+        for (int i = tid; i < 128 * 9; i += 256) {
             const int p = i / 9, tap = i - p * 9;
             const int64_t pos = (int64_t)tile * 128 + p;
             const int b = (int)((uint32_t)pos / (uint32_t)G::S);   // positions fit 32 bits: division by a constant is a multiply-shift
@@ -666,18 +683,47 @@ rb1_wgrad_kernel(const uint8_t* __restrict__ gc, const uint8_t* __restrict__ go,
             s_x[p][tap] = v;
         }
         __syncthreads();
-        if (tid < 288) {
-            const int co = tid / 9, tap = tid - co * 9;
-#pragma unroll 8
-            for (int p = 0; p < 128; ++p) acc = fmaf(s_gc[p][co], s_x[p][tap], acc);
-        } else {
-            const int co = tid - 288;
-#pragma unroll 8
-            for (int p = 0; p < 128; ++p) acc = fmaf(s_go[p][co], s_x[p][4], acc);
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) {
+            const int p = sl * 4 + pp;
+            const float4 g4 = *reinterpret_cast<const float4*>(s_gc + p * kR1Stride + cg * 4);
+            const float4 o4 = *reinterpret_cast<const float4*>(s_go + p * kR1Stride + cg * 4);
+            const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, ov[4] = {o4.x, o4.y, o4.z, o4.w};
+            float xv[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) xv[k] = s_x[p][k];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) acc[c][k] = fmaf(gv[c], xv[k], acc[c][k]);
+                accs[c] = fmaf(ov[c], xv[4], accs[c]);
+            }
         }
     }
-    if (tid < 288) atomicAdd(d_w1 + tid, acc);
-    else atomicAdd(d_ws + (tid - 288), acc);
+    // combine the 32 position slices: lanes differing in bits 3,4 share cg; then the 8 warps through smem
+    __syncthreads();
+    float* s_red = s_gc;   // reuse: [8 warps][8 cg][40]
+    const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            float v = k < 9 ? acc[c][k] : accs[c];
+            v += __shfl_xor_sync(0xffffffffu, v, 8);
+            v += __shfl_xor_sync(0xffffffffu, v, 16);
+            if (lane < 8) s_red[(warp * 8 + lane) * 40 + c * 10 + k] = v;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 320; i += 256) {   // i = cg*40 + c*10 + k
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += s_red[w * 320 + i];
+        const int g = i / 40, c = (i % 40) / 10, k = i % 10;
+        const int co = g * 4 + c;
+        if (k < 9) atomicAdd(d_w1 + co * 9 + k, v);
+        else atomicAdd(d_ws + co, v);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -855,7 +901,7 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
                           dflat + P::rb1_tb, dflat + P::rb1_tw, dflat + P::rb1_c1b, st))) return rc;
     {
         const int grid = nt28 < 4 * num_sms() ? nt28 : 4 * num_sms();
-        launch_pdl(rb1_wgrad_kernel, dim3(grid), dim3(320), 0, st, ws + L.gc28, ws + L.go28, L.ps28, x, dflat + P::rb1_c1w,
+        launch_pdl(rb1_wgrad_kernel, dim3(grid), dim3(256), 0, st, ws + L.gc28, ws + L.go28, L.ps28, x, dflat + P::rb1_c1w,
                                                dflat + P::rb1_sw, B, nt28);
         TDM_CHECK_LAUNCH("rb1_wgrad");
     }
