@@ -31,7 +31,11 @@
 namespace tdm {
 
 // EPI_PLAIN: out = acc (+ residual if given) — no bias, no ReLU: the data-gradient convolutions.
-enum : int { EPI_CONV1 = 0, EPI_RES = 1, EPI_RES_X = 2, EPI_RES_UP = 3, EPI_FINAL = 4, EPI_PLAIN = 5 };
+// EPI_PLAIN_MASK: the data gradient of a block's conv2, finished for conv1 in the same pass:
+//     out = acc (.) relu_mask1      red_plain[c] += sum acc[c]   (time_emb.bias gradient)
+//     red_ts[c] += sum acc[c]*t/1000 (time_emb.weight gradient)  red_masked[c] += sum out[c] (conv1.bias gradient)
+// (src/mnist.py:74-76 backward).  The unmasked gradient never reaches HBM.
+enum : int { EPI_CONV1 = 0, EPI_RES = 1, EPI_RES_X = 2, EPI_RES_UP = 3, EPI_FINAL = 4, EPI_PLAIN = 5, EPI_PLAIN_MASK = 6 };
 
 // Per-channel epilogue parameters BY VALUE (CPAR = true).  Kernel arguments live in the constant bank, so a
 // compile-time-indexed a.cp.bias[ch] is a c[0x0][..] operand of the FADD itself: no load instruction and,
@@ -78,8 +82,12 @@ struct ConvArgs {
     int np;                // positions covered by the buffers (multiple of 128)
     int batch;
     // training forward: ReLU masks, one uint32 per 32 channels per position: mask[chunk*mask_stride+pos]
+    // (written by the forward epilogues, read by EPI_PLAIN_MASK)
     uint32_t* mask;
     int64_t mask_stride;
+    float* red_plain;      // EPI_PLAIN_MASK: per-channel reductions accumulated with atomics
+    float* red_ts;
+    float* red_masked;
     // PROD = 1: half-resolution source of input planes 0..7 (14x14 geometry, row -GUARD of plane 0)
     const uint8_t* in2;
     int64_t in2_ps;
@@ -159,13 +167,41 @@ __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]) {
     else tmem_ld32(taddr, r);
 }
 
+// Sum x[0..15] over the 32 lanes of a warp so that lane l (and l ^ 16) ends up with the total of x[l & 15]:
+// recursive halving (8 + 4 + 2 + 1 exchanges) plus one exchange across the half-warps - 16 shuffles where sixteen
+// independent butterfly reductions would take 80.
+__device__ __forceinline__ float lane_transpose_sum16(const float (&x)[16], int lane) {
+    float a8[8], a4[4], a2[2];
+    const bool b3 = lane & 8, b2 = lane & 4, b1 = lane & 2, b0 = lane & 1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float keep = b3 ? x[8 + i] : x[i], send = b3 ? x[i] : x[8 + i];
+        a8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float keep = b2 ? a8[4 + i] : a8[i], send = b2 ? a8[i] : a8[4 + i];
+        a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float keep = b1 ? a4[2 + i] : a4[i], send = b1 ? a4[i] : a4[2 + i];
+        a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const float keep = b0 ? a2[1] : a2[0], send = b0 ? a2[0] : a2[1];
+    float v = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    return v;   // channel index = 8*b3 + 4*b2 + 2*b1 + b0 = lane & 15
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
 template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, int KXC = 0, int PROD = 0, bool CPAR = false>
 __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1) conv3x3_tc_kernel(const __grid_constant__ ConvArgs a) {
-    static_assert(!CPAR || (COUT <= 64 && EPI != EPI_PLAIN), "by-value channel parameters: forward epilogues, <= 64 channels");
+    constexpr bool kPlain = (EPI == EPI_PLAIN || EPI == EPI_PLAIN_MASK);
+    static_assert(!CPAR || (COUT <= 64 && !kPlain), "by-value channel parameters: forward epilogues, <= 64 channels");
     using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC, PROD>;
     static_assert(C::GK != 1 || (W == 28 && CIN == 96), "upsample gather serves rb4.conv1's concat input");
     static_assert(C::GK != 2 || (W == 28 && CIN == 32 && COUT == 32 && TAPS == 1 && KXC == 0), "im2col gather serves rb1.conv1");
@@ -219,7 +255,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
     pdl_launch_dependents();    // the next kernel may start its own setup as our CTAs retire
     if (!CPAR && threadIdx.x < COUT) {
         const int c = threadIdx.x;
-        s_bias[c] = (EPI == EPI_PLAIN) ? 0.f : a.bias[c];
+        s_bias[c] = kPlain ? 0.f : a.bias[c];
         s_tw[c] = (EPI == EPI_CONV1) ? a.tw[c] : 0.f;
         s_tb[c] = (EPI == EPI_CONV1) ? a.tb[c] : 0.f;
         s_sbias[c] = SKIPG ? a.sbias[c] : 0.f;
@@ -470,6 +506,11 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
         const int grp = (warp - 2) / (4 * kHalves);
         const int half = ((warp - 2) >> 2) % kHalves;   // which alternate 16-channel chunks this warp owns
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * C::ACC_COLS;
+        // EPI_PLAIN_MASK: lane l (and l ^ 16) carries the running sums of channel 16*chunk + (l & 15)
+        constexpr int kRed = (EPI == EPI_PLAIN_MASK) ? COUT / (kHalves * CW) : 1;
+        float red_p[kRed], red_t[kRed], red_m[kRed];
+#pragma unroll
+        for (int i = 0; i < kRed; ++i) red_p[i] = red_t[i] = red_m[i] = 0.f;
         int n = 0;
         for (int tile = blockIdx.x + grp * gridDim.x; tile < nt; tile += C::NACC * gridDim.x, ++n) {
             const uint32_t aph = n & 1;
@@ -484,11 +525,16 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
             const int y = r - 1;
 
             float ts = 0.f;
-            if (EPI == EPI_CONV1 && valid) ts = (float)__ldg(a.t + b) / 1000.0f;
+            if ((EPI == EPI_CONV1 || EPI == EPI_PLAIN_MASK) && valid) ts = (float)__ldg(a.t + b) / 1000.0f;
+            uint32_t mw[EPI == EPI_PLAIN_MASK ? (COUT + 31) / 32 : 1];
+            if constexpr (EPI == EPI_PLAIN_MASK) {
+#pragma unroll
+                for (int i = 0; i < (COUT + 31) / 32; ++i) mw[i] = (valid && owned) ? __ldg(a.mask + i * a.mask_stride + pos) : 0u;
+            }
             float xin = 0.f;
             if ((EPI == EPI_RES_X || (EPI == EPI_FINAL && half == 0)) && valid && a.x)
                 xin = __ldg(a.x + (int64_t)b * 784 + y * 28 + c);
-            constexpr bool kHasRes = (EPI == EPI_RES || EPI == EPI_RES_UP || EPI == EPI_FINAL || EPI == EPI_PLAIN);
+            constexpr bool kHasRes = (EPI == EPI_RES || EPI == EPI_RES_UP || EPI == EPI_FINAL || EPI == EPI_PLAIN);   // EPI_PLAIN_MASK: none
             // residual planes of this warp's chunks only: local index i -> plane (i/2)*4 + half*2 + i%2
             uint4 rv[kHasRes ? COUT / (8 * kHalves) : 1];
             if constexpr (kHasRes) {
@@ -640,6 +686,22 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
 #pragma unroll
                     for (int k = 0; k < CW; ++k) acc[k] = __uint_as_float(r1[k]);
                 }
+                if constexpr (EPI == EPI_PLAIN_MASK) {
+                    // rows this tile does not own (overlapping kx-combined tiles) and pad rows contribute nothing
+                    const bool mine = valid && owned;
+                    const uint32_t bits = mw[c0 / 32] >> (c0 & 31);
+                    float gp[CW], gt[CW];
+#pragma unroll
+                    for (int k = 0; k < CW; ++k) {
+                        const float g = mine ? acc[k] : 0.f;
+                        gp[k] = g;
+                        gt[k] = g * ts;
+                        acc[k] = (bits >> k) & 1u ? g : 0.f;   // what is stored: the gradient w.r.t. conv1's pre-activation
+                    }
+                    red_p[ci] += lane_transpose_sum16(gp, lane);
+                    red_t[ci] += lane_transpose_sum16(gt, lane);
+                    red_m[ci] += lane_transpose_sum16(acc, lane);
+                }
 #pragma unroll
                 for (int pj = 0; pj < CW / 8; ++pj) {
                     const int plane = c0 / 8 + pj;
@@ -647,13 +709,13 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
                         const int ch = c0 + pj * 8 + k;
-                        if constexpr (EPI == EPI_PLAIN) {
+                        if constexpr (kPlain) {
                             v[k] = acc[pj * 8 + k];
                         } else {
                             v[k] = fmaxf(acc[pj * 8 + k] + (CPAR ? a.cp.bias[ch] : s_bias[ch]), 0.f);
                         }
                     }
-                    if (EPI != EPI_PLAIN && a.mask) {   // training only (uniform branch)
+                    if (!kPlain && a.mask) {   // training only (uniform branch)
 #pragma unroll
                         for (int k = 0; k < 8; ++k) mbits |= (v[k] > 0.f ? 1u : 0u) << ((c0 + pj * 8 + k) & 31);
                     }
@@ -669,7 +731,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
                             const int ch = c0 + pj * 8 + k;
                             v[k] += CPAR ? fmaf(a.cp.aux[ch], xin, a.cp.aux[32 + ch]) : fmaf(s_aux[ch], xin, s_aux[32 + ch]);
                         }
-                    } else {
+                    } else if constexpr (kHasRes) {
                         const uint32_t* rw = &rv[ci * 2 + pj].x;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
@@ -726,7 +788,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
                         if (owned) *reinterpret_cast<uint4*>(a.out2 + plane * a.out2_ps + (pos + G::GUARD) * 16) = o2;
                     }
                 }
-                if (EPI != EPI_PLAIN && a.mask && owned) {
+                if (!kPlain && a.mask && owned) {
                     // one uint32 per 32 channels per position; this warp owns 16 of its bits
                     uint16_t* m16 = reinterpret_cast<uint16_t*>(a.mask + (c0 / 32) * a.mask_stride + pos);
                     m16[(c0 >> 4) & 1] = valid ? (uint16_t)(mbits >> (c0 & 16)) : (uint16_t)0;
@@ -745,6 +807,17 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
                     const float eps = dot + (CPAR ? a.cp.aux[32] : s_aux[32]);  // out conv bias (src/mnist.py:87)
                     const int64_t oi = (int64_t)b * 784 + y * 28 + c;
                     a.fout[oi] = a.fuse_step ? rstep1(sc, xin, eps, zz, add_noise) : eps;
+                }
+            }
+        }
+        if constexpr (EPI == EPI_PLAIN_MASK) {
+            if (lane < 16) {
+#pragma unroll
+                for (int ci = 0; ci < kRed; ++ci) {
+                    const int ch = (kHalves * ci + half) * CW + lane;
+                    if (a.red_plain) atomicAdd(a.red_plain + ch, red_p[ci]);
+                    if (a.red_ts) atomicAdd(a.red_ts + ch, red_t[ci]);
+                    if (a.red_masked) atomicAdd(a.red_masked + ch, red_m[ci]);
                 }
             }
         }

@@ -830,15 +830,17 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = launch_wgrad_dup<28, 32, 32>(w, L.np28, st, "wgrad_rb4_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
     c.in = ws + L.gc28; c.in_ps = L.ps28; c.w = wp + WP::d_rb4_c2; c.out = ws + L.gh28; c.out_ps = L.ps28;
-    if ((rc = launch_conv<28, 32, 32, EPI_PLAIN, false, 9, KX::rb4c2>(c, st, "dgrad_rb4_c2"))) return rc;
-    if ((rc = mask_reduce(ws + L.gh28, L.ps28, H28, M(L.m1_4), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
-                          dflat + P::rb4_tb, dflat + P::rb4_tw, dflat + P::rb4_c1b, st))) return rc;
-    w = WgradArgs{ws + L.gc28, L.ps28, ws + L.cat, L.ps28, gscr + P::rb4_c1w, nt28};
+    // conv2's data gradient leaves the kernel already multiplied by conv1's ReLU mask, with the time-embedding and
+    // conv1-bias gradients reduced in the same epilogue (EPI_PLAIN_MASK): the buffer holds d loss / d conv1 pre-activation
+    c.mask = const_cast<uint32_t*>(M(L.m1_4)); c.mask_stride = L.np28;
+    c.red_plain = dflat + P::rb4_tb; c.red_ts = dflat + P::rb4_tw; c.red_masked = dflat + P::rb4_c1b;
+    if ((rc = launch_conv<28, 32, 32, EPI_PLAIN_MASK, false, 9, KX::rb4c2>(c, st, "dgrad_rb4_c2"))) return rc;
+    w = WgradArgs{ws + L.gh28, L.ps28, ws + L.cat, L.ps28, gscr + P::rb4_c1w, nt28};
     if ((rc = launch_wgrad_dup<28, 32, 96>(w, L.np28, st, "wgrad_rb4_c1"))) return rc;
     w = WgradArgs{ws + L.go28, L.ps28, ws + L.cat, L.ps28, dflat + P::rb4_sw, nt28};
     if ((rc = launch_wgrad<28, 32, 96, 1>(w, st, "wgrad_rb4_skip"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
-    c.in = ws + L.gc28; c.in_ps = L.ps28; c.w = wp + WP::d_rb4_c1; c.out = ws + L.gcat; c.out_ps = L.ps28;
+    c.in = ws + L.gh28; c.in_ps = L.ps28; c.w = wp + WP::d_rb4_c1; c.out = ws + L.gcat; c.out_ps = L.ps28;
     if ((rc = launch_conv<28, 32, 96, EPI_PLAIN, false>(c, st, "dgrad_rb4_c1"))) return rc;
     c.in = ws + L.go28; c.w = wp + WP::d_rb4_sk; c.res = ws + L.gcat; c.res_ps = L.ps28;
     if ((rc = launch_conv<28, 32, 96, EPI_PLAIN, false, 1>(c, st, "dgrad_rb4_skip"))) return rc;
@@ -854,13 +856,15 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = launch_wgrad_dup<14, 64, 64>(w, L.np14, st, "wgrad_rb3_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
     c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb3_c2; c.out = ws + L.gh14; c.out_ps = L.ps14;
-    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false, 9, KX::rb3c2>(c, st, "dgrad_rb3_c2"))) return rc;
-    if ((rc = mask_reduce(ws + L.gh14, L.ps14, H14, M(L.m1_3), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
-                          dflat + P::rb3_tb, dflat + P::rb3_tw, dflat + P::rb3_c1b, st))) return rc;
-    w = WgradArgs{ws + L.gc14, L.ps14, ws + L.h2, L.ps14, gscr + P::rb3_c1w, nt14};
+    // conv2's data gradient leaves the kernel already multiplied by conv1's ReLU mask, with the time-embedding and
+    // conv1-bias gradients reduced in the same epilogue (EPI_PLAIN_MASK): the buffer holds d loss / d conv1 pre-activation
+    c.mask = const_cast<uint32_t*>(M(L.m1_3)); c.mask_stride = L.np14;
+    c.red_plain = dflat + P::rb3_tb; c.red_ts = dflat + P::rb3_tw; c.red_masked = dflat + P::rb3_c1b;
+    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN_MASK, false, 9, KX::rb3c2>(c, st, "dgrad_rb3_c2"))) return rc;
+    w = WgradArgs{ws + L.gh14, L.ps14, ws + L.h2, L.ps14, gscr + P::rb3_c1w, nt14};
     if ((rc = launch_wgrad_dup<14, 64, 64>(w, L.np14, st, "wgrad_rb3_c1"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
-    c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb3_c1; c.res = ws + L.go14a; c.res_ps = L.ps14;
+    c.in = ws + L.gh14; c.in_ps = L.ps14; c.w = wp + WP::d_rb3_c1; c.res = ws + L.go14a; c.res_ps = L.ps14;
     c.out = ws + L.go14b; c.out_ps = L.ps14;   // g_out of rb2
     if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false, 9, KX::rb3c1>(c, st, "dgrad_rb3_c1"))) return rc;
 
@@ -871,15 +875,17 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = launch_wgrad_dup<14, 64, 64>(w, L.np14, st, "wgrad_rb2_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
     c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb2_c2; c.out = ws + L.gh14; c.out_ps = L.ps14;
-    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false, 9, KX::rb2c2>(c, st, "dgrad_rb2_c2"))) return rc;
-    if ((rc = mask_reduce(ws + L.gh14, L.ps14, H14, M(L.m1_2), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
-                          dflat + P::rb2_tb, dflat + P::rb2_tw, dflat + P::rb2_c1b, st))) return rc;
-    w = WgradArgs{ws + L.gc14, L.ps14, ws + L.p1, L.ps14, gscr + P::rb2_c1w, nt14};
+    // conv2's data gradient leaves the kernel already multiplied by conv1's ReLU mask, with the time-embedding and
+    // conv1-bias gradients reduced in the same epilogue (EPI_PLAIN_MASK): the buffer holds d loss / d conv1 pre-activation
+    c.mask = const_cast<uint32_t*>(M(L.m1_2)); c.mask_stride = L.np14;
+    c.red_plain = dflat + P::rb2_tb; c.red_ts = dflat + P::rb2_tw; c.red_masked = dflat + P::rb2_c1b;
+    if ((rc = launch_conv<14, 64, 64, EPI_PLAIN_MASK, false, 9, KX::rb2c2>(c, st, "dgrad_rb2_c2"))) return rc;
+    w = WgradArgs{ws + L.gh14, L.ps14, ws + L.p1, L.ps14, gscr + P::rb2_c1w, nt14};
     if ((rc = launch_wgrad_dup<14, 64, 32>(w, L.np14, st, "wgrad_rb2_c1"))) return rc;
     w = WgradArgs{ws + L.go14b, L.ps14, ws + L.p1, L.ps14, dflat + P::rb2_sw, nt14};
     if ((rc = launch_wgrad<14, 64, 32, 1>(w, st, "wgrad_rb2_skip"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
-    c.in = ws + L.gc14; c.in_ps = L.ps14; c.w = wp + WP::d_rb2_c1; c.out = ws + L.gp1; c.out_ps = L.ps14;
+    c.in = ws + L.gh14; c.in_ps = L.ps14; c.w = wp + WP::d_rb2_c1; c.out = ws + L.gp1; c.out_ps = L.ps14;
     if ((rc = launch_conv<14, 64, 32, EPI_PLAIN, false, 9, KX::rb2c1>(c, st, "dgrad_rb2_c1"))) return rc;
     c.in = ws + L.go14b; c.w = wp + WP::d_rb2_sk; c.res = ws + L.gp1; c.res_ps = L.ps14;
     if ((rc = launch_conv<14, 64, 32, EPI_PLAIN, false, 1>(c, st, "dgrad_rb2_skip"))) return rc;
@@ -896,12 +902,14 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = launch_wgrad_dup<28, 32, 32>(w, L.np28, st, "wgrad_rb1_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
     c.in = ws + L.gc28; c.in_ps = L.ps28; c.w = wp + WP::d_rb1_c2; c.out = ws + L.gh28; c.out_ps = L.ps28;
-    if ((rc = launch_conv<28, 32, 32, EPI_PLAIN, false, 9, KX::rb1c2>(c, st, "dgrad_rb1_c2"))) return rc;
-    if ((rc = mask_reduce(ws + L.gh28, L.ps28, H28, M(L.m1_1), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
-                          dflat + P::rb1_tb, dflat + P::rb1_tw, dflat + P::rb1_c1b, st))) return rc;
+    // conv2's data gradient leaves the kernel already multiplied by conv1's ReLU mask, with the time-embedding and
+    // conv1-bias gradients reduced in the same epilogue (EPI_PLAIN_MASK): the buffer holds d loss / d conv1 pre-activation
+    c.mask = const_cast<uint32_t*>(M(L.m1_1)); c.mask_stride = L.np28;
+    c.red_plain = dflat + P::rb1_tb; c.red_ts = dflat + P::rb1_tw; c.red_masked = dflat + P::rb1_c1b;
+    if ((rc = launch_conv<28, 32, 32, EPI_PLAIN_MASK, false, 9, KX::rb1c2>(c, st, "dgrad_rb1_c2"))) return rc;
     {
         const int grid = nt28 < 4 * num_sms() ? nt28 : 4 * num_sms();
-        launch_pdl(rb1_wgrad_kernel, dim3(grid), dim3(256), 0, st, ws + L.gc28, ws + L.go28, L.ps28, x, dflat + P::rb1_c1w,
+        launch_pdl(rb1_wgrad_kernel, dim3(grid), dim3(256), 0, st, ws + L.gh28, ws + L.go28, L.ps28, x, dflat + P::rb1_c1w,
                                                dflat + P::rb1_sw, B, nt28);
         TDM_CHECK_LAUNCH("rb1_wgrad");
     }
