@@ -477,21 +477,41 @@ loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
 //   d_plain[c] += sum g[c]            (time_emb.bias or skip.bias gradient; nullable)
 //   d_ts[c]    += sum g[c]*t/1000     (time_emb.weight gradient; nullable)
 //   d_masked[c]+= sum g[c]*mask       (conv bias gradient; nullable)
+// where g is a block's output gradient, produced on the fly from its sources (SRC) and also stored unmasked
+// (`gout`, for the block's skip path) unless it already exists as a tensor:
+//   MR_PLANES      g = in[pos]                                               (gout unused)
+//   MR_UPSAMPLE_T  g = 2x2 sum of the 28x28 planes `in` (transpose of the nearest x2 upsample, src/mnist.py:83)
+//   MR_POOL_T      g = in[pos] + 0.25 * in2[pos14(y/2, x/2)]   (concat slice + transpose of avg_pool2d, :80)
 // blockDim = (32, CH/8, kMrGroups): x -> position, y -> channel plane, z -> quarter of the block's kChunk
-// positions.  Every thread has its kMlp loads in flight at once (one round trip per block), the four position
+// positions.  Every thread has its loads in flight at once (one round trip per block), the four position
 // groups are combined in shared memory, and 24 lanes per plane issue the block's atomics in parallel
 // (ncu, B=512: the one-warp-per-plane version ran at 27 % occupancy and 42 % issue, 27 us per launch).
-// `out` may alias `g`.
+// `out` may alias `in` for MR_PLANES.
+enum : int { MR_PLANES = 0, MR_UPSAMPLE_T = 1, MR_POOL_T = 2 };
+struct MaskReduceArgs {
+    const uint8_t* in;      // source planes (MR_UPSAMPLE_T / MR_POOL_T: 28x28 geometry)
+    int64_t in_ps;
+    const uint8_t* in2;     // MR_POOL_T: 14x14 planes
+    int64_t in2_ps;
+    const uint32_t* mask;   // one uint32 per 32 channels per position, null = all ones
+    int64_t mask_stride;
+    uint8_t* out;           // g (.) mask, geometry W
+    uint8_t* gout;          // g unmasked (nullable)
+    int64_t out_ps;
+    const int64_t* t;
+    int batch;
+    int64_t npos;
+    float* d_plain;
+    float* d_ts;
+    float* d_masked;
+};
 constexpr int kMrGroups = 4;
 static_assert(kChunk == kMrGroups * kMlp * 32, "one batch of loads per thread");
-__global__ void __launch_bounds__(32 * 8 * kMrGroups)
-mask_reduce_kernel(const uint8_t* __restrict__ g, int64_t ps, int halo,
-                                   const uint32_t* __restrict__ mask, int64_t mask_stride,
-                                   uint8_t* __restrict__ out, const int64_t* __restrict__ t, int S,
-                                   int batch, int64_t npos, float* __restrict__ d_plain,
-                                   float* __restrict__ d_ts, float* __restrict__ d_masked) {
+template <int SRC, int W>
+__global__ void __launch_bounds__(32 * 8 * kMrGroups) mask_reduce_kernel(const MaskReduceArgs a) {
     pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
     pdl_launch_dependents();
+    using G = Geo<W>;
     __shared__ float s_red[kMrGroups][8][24];   // [position group][plane][plain 0..7 | ts 8..15 | masked 16..23]
     const int lane = threadIdx.x, j = threadIdx.y, zg = threadIdx.z;
     float sp[8], st[8], sm[8];
@@ -505,21 +525,59 @@ mask_reduce_kernel(const uint8_t* __restrict__ g, int64_t ps, int halo,
         const int64_t pos = base + u * 32 + lane;
         gvs[u] = make_uint4(0, 0, 0, 0);
         words[u] = 0;
-        if (pos < npos) {
-            gvs[u] = *reinterpret_cast<const uint4*>(g + j * ps + (pos + halo) * 16);
-            words[u] = mask ? mask[(j >> 2) * mask_stride + pos] : 0xffffffffu;
+        if (pos >= a.npos) continue;
+        words[u] = a.mask ? a.mask[(j >> 2) * a.mask_stride + pos] : 0xffffffffu;
+        if constexpr (SRC == MR_PLANES) {
+            gvs[u] = *reinterpret_cast<const uint4*>(a.in + j * a.in_ps + (pos + G::GUARD) * 16);
+        } else {
+            const int b = (int)((uint32_t)pos / (uint32_t)G::S);   // positions fit 32 bits: multiply-shift
+            const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)G::S);
+            const int r = rem / G::Wp, c = rem - r * G::Wp;
+            if (b < a.batch && r >= 1 && c < G::W) {
+                uint32_t* ow = &gvs[u].x;
+                if constexpr (SRC == MR_UPSAMPLE_T) {
+                    static_assert(SRC != MR_UPSAMPLE_T || W == 14, "2x2 sum: 28x28 -> 14x14");
+                    using GI = Geo<28>;
+                    const int64_t p00 = (int64_t)b * GI::S + (2 * (r - 1) + 1) * GI::Wp + 2 * c;
+                    const uint8_t* src = a.in + j * a.in_ps + (p00 + GI::GUARD) * 16;
+                    const uint4 q0 = *reinterpret_cast<const uint4*>(src);
+                    const uint4 q1 = *reinterpret_cast<const uint4*>(src + 16);
+                    const uint4 q2 = *reinterpret_cast<const uint4*>(src + GI::Wp * 16);
+                    const uint4 q3 = *reinterpret_cast<const uint4*>(src + GI::Wp * 16 + 16);
+                    const uint32_t *a0 = &q0.x, *a1 = &q1.x, *a2 = &q2.x, *a3 = &q3.x;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 f0 = unpack_bf16x2(a0[k]), f1 = unpack_bf16x2(a1[k]);
+                        const float2 f2 = unpack_bf16x2(a2[k]), f3 = unpack_bf16x2(a3[k]);
+                        ow[k] = pack_bf16x2(f0.x + f1.x + f2.x + f3.x, f0.y + f1.y + f2.y + f3.y);
+                    }
+                } else {
+                    static_assert(SRC != MR_POOL_T || W == 28, "pool transpose: 14x14 -> 28x28");
+                    using G14 = Geo<14>;
+                    const int64_t p14 = (int64_t)b * G14::S + ((r - 1) / 2 + 1) * G14::Wp + c / 2;
+                    const uint4 av = *reinterpret_cast<const uint4*>(a.in + j * a.in_ps + (pos + G::GUARD) * 16);
+                    const uint4 pv = *reinterpret_cast<const uint4*>(a.in2 + j * a.in2_ps + (p14 + G14::GUARD) * 16);
+                    const uint32_t *aw = &av.x, *pw = &pv.x;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 f = unpack_bf16x2(aw[k]), h = unpack_bf16x2(pw[k]);
+                        ow[k] = pack_bf16x2(fmaf(0.25f, h.x, f.x), fmaf(0.25f, h.y, f.y));
+                    }
+                }
+            }
         }
     }
 #pragma unroll
     for (int u = 0; u < kMlp; ++u) {
         const int64_t pos = base + u * 32 + lane;
-        if (pos >= npos) continue;
+        if (pos >= a.npos) continue;
         const uint4 gv = gvs[u];
+        if (SRC != MR_PLANES && a.gout) *reinterpret_cast<uint4*>(a.gout + j * a.out_ps + (pos + G::GUARD) * 16) = gv;
         const uint32_t bits = (words[u] >> ((j & 3) * 8)) & 0xffu;
         float ts = 0.f;
-        if (d_ts) {
-            const int b = (int)((uint32_t)pos / (uint32_t)S);
-            ts = b < batch ? (float)__ldg(t + b) / 1000.0f : 0.f;
+        if (a.d_ts) {
+            const int b = (int)((uint32_t)pos / (uint32_t)G::S);
+            ts = b < a.batch ? (float)__ldg(a.t + b) / 1000.0f : 0.f;
         }
         const uint32_t* gw = &gv.x;
         uint4 o;
@@ -537,15 +595,15 @@ mask_reduce_kernel(const uint8_t* __restrict__ g, int64_t ps, int halo,
             sm[2 * k + 1] += m1;
             ow[k] = pack_bf16x2(m0, m1);
         }
-        if (out) *reinterpret_cast<uint4*>(out + j * ps + (pos + halo) * 16) = o;
+        if (a.out) *reinterpret_cast<uint4*>(a.out + j * a.out_ps + (pos + G::GUARD) * 16) = o;
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float a = warp_sum(sp[k]), b = warp_sum(st[k]), c = warp_sum(sm[k]);
+        const float x = warp_sum(sp[k]), y = warp_sum(st[k]), z = warp_sum(sm[k]);
         if (lane == 0) {
-            s_red[zg][j][k] = a;
-            s_red[zg][j][8 + k] = b;
-            s_red[zg][j][16 + k] = c;
+            s_red[zg][j][k] = x;
+            s_red[zg][j][8 + k] = y;
+            s_red[zg][j][16 + k] = z;
         }
     }
     __syncthreads();
@@ -553,73 +611,9 @@ mask_reduce_kernel(const uint8_t* __restrict__ g, int64_t ps, int halo,
         float v = 0.f;
 #pragma unroll
         for (int z = 0; z < kMrGroups; ++z) v += s_red[z][j][lane];
-        float* dst = lane < 8 ? d_plain : lane < 16 ? d_ts : d_masked;
+        float* dst = lane < 8 ? a.d_plain : lane < 16 ? a.d_ts : a.d_masked;
         if (dst) atomicAdd(dst + j * 8 + (lane & 7), v);
     }
-}
-
-// transpose of the nearest x2 upsample (src/mnist.py:83): 2x2 sum, 28-geometry -> 14-geometry
-__global__ void __launch_bounds__(128)
-upsample_bwd_kernel(const uint8_t* __restrict__ in, int64_t in_ps, uint8_t* __restrict__ out,
-                    int64_t out_ps, int batch) {
-    pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
-    pdl_launch_dependents();
-    using GI = Geo<28>;
-    using GO = Geo<14>;
-    const int64_t pos = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    const int plane = blockIdx.y;
-    const int b = (int)((uint32_t)pos / (uint32_t)GO::S);   // positions fit 32 bits: division by a constant is a multiply-shift
-    const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)GO::S);
-    const int r = rem / GO::Wp, c = rem - r * GO::Wp;
-    uint4 o = make_uint4(0, 0, 0, 0);
-    if (b < batch && r >= 1 && c < GO::W) {
-        const int64_t p00 = (int64_t)b * GI::S + (2 * (r - 1) + 1) * GI::Wp + 2 * c;
-        const uint8_t* src = in + plane * in_ps + (p00 + GI::GUARD) * 16;
-        const uint4 q0 = *reinterpret_cast<const uint4*>(src);
-        const uint4 q1 = *reinterpret_cast<const uint4*>(src + 16);
-        const uint4 q2 = *reinterpret_cast<const uint4*>(src + GI::Wp * 16);
-        const uint4 q3 = *reinterpret_cast<const uint4*>(src + GI::Wp * 16 + 16);
-        const uint32_t *a0 = &q0.x, *a1 = &q1.x, *a2 = &q2.x, *a3 = &q3.x;
-        uint32_t* ow = &o.x;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 f0 = unpack_bf16x2(a0[k]), f1 = unpack_bf16x2(a1[k]);
-            const float2 f2 = unpack_bf16x2(a2[k]), f3 = unpack_bf16x2(a3[k]);
-            ow[k] = pack_bf16x2(f0.x + f1.x + f2.x + f3.x, f0.y + f1.y + f2.y + f3.y);
-        }
-    }
-    *reinterpret_cast<uint4*>(out + plane * out_ps + (pos + GO::GUARD) * 16) = o;
-}
-
-// transpose of avg_pool2d(2) (src/mnist.py:80) added to the gradient h1 receives through the
-// concat: out[pos28] = a[pos28] + 0.25 * gp[pos14(y/2, x/2)]
-__global__ void __launch_bounds__(128)
-pool_bwd_add_kernel(const uint8_t* __restrict__ a, int64_t a_ps, const uint8_t* __restrict__ gp,
-                    int64_t gp_ps, uint8_t* __restrict__ out, int64_t out_ps, int batch) {
-    pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
-    pdl_launch_dependents();
-    using G28 = Geo<28>;
-    using G14 = Geo<14>;
-    const int64_t pos = (int64_t)blockIdx.x * 128 + threadIdx.x;
-    const int plane = blockIdx.y;
-    const int b = (int)((uint32_t)pos / (uint32_t)G28::S);   // positions fit 32 bits: division by a constant is a multiply-shift
-    const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)G28::S);
-    const int r = rem / G28::Wp, c = rem - r * G28::Wp;
-    uint4 o = make_uint4(0, 0, 0, 0);
-    if (b < batch && r >= 1 && c < G28::W) {
-        const int y = r - 1;
-        const int64_t p14 = (int64_t)b * G14::S + (y / 2 + 1) * G14::Wp + c / 2;
-        const uint4 av = *reinterpret_cast<const uint4*>(a + plane * a_ps + (pos + G28::GUARD) * 16);
-        const uint4 gv = *reinterpret_cast<const uint4*>(gp + plane * gp_ps + (p14 + G14::GUARD) * 16);
-        const uint32_t *aw = &av.x, *gw = &gv.x;
-        uint32_t* ow = &o.x;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float2 f = unpack_bf16x2(aw[k]), h = unpack_bf16x2(gw[k]);
-            ow[k] = pack_bf16x2(fmaf(0.25f, h.x, f.x), fmaf(0.25f, h.y, f.y));
-        }
-    }
-    *reinterpret_cast<uint4*>(out + plane * out_ps + (pos + G28::GUARD) * 16) = o;
 }
 
 // rb1.conv1 (Cin = 1) and rb1.skip (1x1, Cin = 1) weight gradients:
@@ -762,12 +756,10 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
 // ---------------------------------------------------------------------------------------------
 // orchestration
 // ---------------------------------------------------------------------------------------------
-static int mask_reduce(const uint8_t* g, int64_t ps, int halo, const uint32_t* mask, int64_t mstride,
-                       uint8_t* out, int ch, const int64_t* t, int S, int batch, int64_t npos,
-                       float* d_plain, float* d_ts, float* d_masked, cudaStream_t st) {
-    const unsigned grid = (unsigned)((npos + kChunk - 1) / kChunk);
-    launch_pdl(mask_reduce_kernel, dim3(grid), dim3(32, ch / 8, kMrGroups), 0, st, g, ps, halo, mask, mstride, out, t, S, batch,
-                                                          npos, d_plain, d_ts, d_masked);
+template <int SRC, int W>
+static int mask_reduce(const MaskReduceArgs& a, int ch, cudaStream_t st) {
+    const unsigned grid = (unsigned)((a.npos + kChunk - 1) / kChunk);
+    launch_pdl(mask_reduce_kernel<SRC, W>, dim3(grid), dim3(32, ch / 8, kMrGroups), 0, st, a);
     TDM_CHECK_LAUNCH("mask_reduce");
     return TDM_OK;
 }
@@ -824,8 +816,11 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     TDM_CHECK_LAUNCH("loss_grad");
 
     // ---- rb4: x_in = cat (96), h = t4, g_out = go28 ----------------------------------------
-    if ((rc = mask_reduce(ws + L.go28, L.ps28, H28, M(L.m2_4), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
-                          dflat + P::rb4_sb, nullptr, dflat + P::rb4_c2b, st))) return rc;
+    MaskReduceArgs mr{};
+    mr.in = ws + L.go28; mr.in_ps = L.ps28; mr.mask = M(L.m2_4); mr.mask_stride = L.np28;
+    mr.out = ws + L.gc28; mr.out_ps = L.ps28; mr.t = t; mr.batch = B; mr.npos = L.np28;
+    mr.d_plain = dflat + P::rb4_sb; mr.d_masked = dflat + P::rb4_c2b;
+    if ((rc = mask_reduce<MR_PLANES, 28>(mr, 32, st))) return rc;
     w = WgradArgs{ws + L.gc28, L.ps28, ws + L.t4, L.ps28, gscr + P::rb4_c2w, nt28};
     if ((rc = launch_wgrad_dup<28, 32, 32>(w, L.np28, st, "wgrad_rb4_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
@@ -846,12 +841,13 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = launch_conv<28, 32, 96, EPI_PLAIN, false, 1>(c, st, "dgrad_rb4_skip"))) return rc;
 
     // ---- through the concat: channels 0..63 -> up(h3)^T -> g_out of rb3 ---------------------
-    launch_pdl(upsample_bwd_kernel, dim3(nt14, 8), dim3(128), 0, st, ws + L.gcat, L.ps28, ws + L.go14a, L.ps14, B);
-    TDM_CHECK_LAUNCH("upsample_bwd");
-
     // ---- rb3: x_in = h2, h = t3, identity skip, g_out = go14a -------------------------------
-    if ((rc = mask_reduce(ws + L.go14a, L.ps14, H14, M(L.m2_3), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
-                          nullptr, nullptr, dflat + P::rb3_c2b, st))) return rc;
+    // one pass: go14a = up^T(gcat[0:64]) (kept for the identity skip), gc14 = go14a (.) mask, conv2-bias gradient
+    mr = MaskReduceArgs{};
+    mr.in = ws + L.gcat; mr.in_ps = L.ps28; mr.mask = M(L.m2_3); mr.mask_stride = L.np14;
+    mr.out = ws + L.gc14; mr.gout = ws + L.go14a; mr.out_ps = L.ps14; mr.t = t; mr.batch = B; mr.npos = L.np14;
+    mr.d_masked = dflat + P::rb3_c2b;
+    if ((rc = mask_reduce<MR_UPSAMPLE_T, 14>(mr, 64, st))) return rc;
     w = WgradArgs{ws + L.gc14, L.ps14, ws + L.t3, L.ps14, gscr + P::rb3_c2w, nt14};
     if ((rc = launch_wgrad_dup<14, 64, 64>(w, L.np14, st, "wgrad_rb3_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
@@ -869,8 +865,11 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = launch_conv<14, 64, 64, EPI_PLAIN, false, 9, KX::rb3c1>(c, st, "dgrad_rb3_c1"))) return rc;
 
     // ---- rb2: x_in = p1 (32), h = t2, skip 32->64, g_out = go14b ----------------------------
-    if ((rc = mask_reduce(ws + L.go14b, L.ps14, H14, M(L.m2_2), L.np14, ws + L.gc14, 64, t, S14, B, L.np14,
-                          dflat + P::rb2_sb, nullptr, dflat + P::rb2_c2b, st))) return rc;
+    mr = MaskReduceArgs{};
+    mr.in = ws + L.go14b; mr.in_ps = L.ps14; mr.mask = M(L.m2_2); mr.mask_stride = L.np14;
+    mr.out = ws + L.gc14; mr.out_ps = L.ps14; mr.t = t; mr.batch = B; mr.npos = L.np14;
+    mr.d_plain = dflat + P::rb2_sb; mr.d_masked = dflat + P::rb2_c2b;
+    if ((rc = mask_reduce<MR_PLANES, 14>(mr, 64, st))) return rc;
     w = WgradArgs{ws + L.gc14, L.ps14, ws + L.t2, L.ps14, gscr + P::rb2_c2w, nt14};
     if ((rc = launch_wgrad_dup<14, 64, 64>(w, L.np14, st, "wgrad_rb2_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
@@ -891,13 +890,15 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     if ((rc = launch_conv<14, 64, 32, EPI_PLAIN, false, 1>(c, st, "dgrad_rb2_skip"))) return rc;
 
     // ---- h1 receives: concat channels 64..95 + avg-pool transpose of g_p1 -------------------
-    launch_pdl(pool_bwd_add_kernel, dim3(nt28, 4), dim3(128), 0, st, ws + L.gcat + 8 * L.ps28, L.ps28, ws + L.gp1, L.ps14,
-                                                      ws + L.go28, L.ps28, B);
-    TDM_CHECK_LAUNCH("pool_bwd_add");
+    // (fused below: go28 = gcat[64:96] + pool^T(gp1) is produced by the pass that also masks it)
 
     // ---- rb1: x_in = x (1 channel), h = t1, skip 1->32, g_out = go28 ------------------------
-    if ((rc = mask_reduce(ws + L.go28, L.ps28, H28, M(L.m2_1), L.np28, ws + L.gc28, 32, t, S28, B, L.np28,
-                          dflat + P::rb1_sb, nullptr, dflat + P::rb1_c2b, st))) return rc;
+    mr = MaskReduceArgs{};
+    mr.in = ws + L.gcat + 8 * L.ps28; mr.in_ps = L.ps28; mr.in2 = ws + L.gp1; mr.in2_ps = L.ps14;
+    mr.mask = M(L.m2_1); mr.mask_stride = L.np28;
+    mr.out = ws + L.gc28; mr.gout = ws + L.go28; mr.out_ps = L.ps28; mr.t = t; mr.batch = B; mr.npos = L.np28;
+    mr.d_plain = dflat + P::rb1_sb; mr.d_masked = dflat + P::rb1_c2b;
+    if ((rc = mask_reduce<MR_POOL_T, 28>(mr, 32, st))) return rc;
     w = WgradArgs{ws + L.gc28, L.ps28, ws + L.t1, L.ps28, gscr + P::rb1_c2w, nt28};
     if ((rc = launch_wgrad_dup<28, 32, 32>(w, L.np28, st, "wgrad_rb1_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
