@@ -390,17 +390,21 @@ __device__ __forceinline__ float warp_sum(float v) {
 // z -> quarter of the block's kChunk positions (same shape as mask_reduce_kernel below: one round trip of loads
 // per thread, shared-memory combine, one set of atomics per block).
 //   g = 2*(eps - noise)/n ; go4[c] = out.weight[c]*g ; d out.weight[c] += g*h4[c] ; d out.bias += g
+// and, in the same pass, what rb4 needs from its output gradient (src/mnist.py:65-66 backward):
+//   gc4 = go4 (.) relu_mask2 ; d rb4.skip.bias[c] += sum go4[c] ; d rb4.conv2.bias[c] += sum gc4[c]
 constexpr int kLgGroups = 4;
 __global__ void __launch_bounds__(32 * 4 * kLgGroups)
 loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
                  const uint8_t* __restrict__ h4, int64_t ps, const float* __restrict__ wo,
                  uint8_t* __restrict__ go, float* __restrict__ d_wo, float* __restrict__ d_bo,
-                 float* __restrict__ loss, int batch, int64_t npos, float inv_n) {
+                 float* __restrict__ loss, int batch, int64_t npos, float inv_n,
+                 const uint32_t* __restrict__ mask, uint8_t* __restrict__ gc, float* __restrict__ d_plain,
+                 float* __restrict__ d_masked) {
     pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
     pdl_launch_dependents();
     using G = Geo<28>;
     constexpr int kIter = kChunk / (32 * kLgGroups);
-    __shared__ float s_red[kLgGroups][4][10];   // [group][plane][d_wo 0..7 | loss 8 | d_bo 9]
+    __shared__ float s_red[kLgGroups][4][26];   // [group][plane][d_wo 0..7 | loss 8 | d_bo 9 | plain 10..17 | masked 18..25]
     const int lane = threadIdx.x, j = threadIdx.y, zg = threadIdx.z;
     float w[8], acc[8];
 #pragma unroll
@@ -409,9 +413,13 @@ loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
         acc[k] = 0.f;
     }
     float lsum = 0.f, gsum = 0.f;
+    float sp[8], sm[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sp[k] = sm[k] = 0.f;
     const int64_t base = (int64_t)blockIdx.x * kChunk + zg * (kIter * 32);
     float dv[kIter];
     uint4 hvs[kIter];
+    uint32_t words[kIter];
     bool ok[kIter];
 #pragma unroll
     for (int u = 0; u < kIter; ++u) {   // issue all loads before using any
@@ -422,7 +430,9 @@ loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
         ok[u] = pos < npos && b < batch && r >= 1 && c < G::W;
         dv[u] = 0.f;
         hvs[u] = make_uint4(0, 0, 0, 0);
+        words[u] = 0;
         if (ok[u]) {
+            words[u] = mask[pos];   // 32 channels: one word per position
             const int64_t i = (int64_t)b * 784 + (r - 1) * 28 + c;
             dv[u] = __ldg(eps + i) - __ldg(noise + i);
             hvs[u] = *reinterpret_cast<const uint4*>(h4 + j * ps + (pos + G::GUARD) * 16);
@@ -451,11 +461,32 @@ loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
             }
         }
         *reinterpret_cast<uint4*>(go + j * ps + (pos + G::GUARD) * 16) = o;
+        // the masked copy and the two bias reductions, on the bf16 values just stored
+        const uint32_t bits = (words[u] >> (j * 8)) & 0xffu;
+        const uint32_t* ow2 = &o.x;
+        uint4 om;
+        uint32_t* mwp = &om.x;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float2 f = unpack_bf16x2(ow2[k]);
+            const float m0 = (bits >> (2 * k)) & 1u ? f.x : 0.f;
+            const float m1 = (bits >> (2 * k + 1)) & 1u ? f.y : 0.f;
+            sp[2 * k] += f.x;
+            sp[2 * k + 1] += f.y;
+            sm[2 * k] += m0;
+            sm[2 * k + 1] += m1;
+            mwp[k] = pack_bf16x2(m0, m1);
+        }
+        *reinterpret_cast<uint4*>(gc + j * ps + (pos + G::GUARD) * 16) = om;
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const float v = warp_sum(acc[k]);
-        if (lane == 0) s_red[zg][j][k] = v;
+        const float v = warp_sum(acc[k]), x = warp_sum(sp[k]), y = warp_sum(sm[k]);
+        if (lane == 0) {
+            s_red[zg][j][k] = v;
+            s_red[zg][j][10 + k] = x;
+            s_red[zg][j][18 + k] = y;
+        }
     }
     lsum = warp_sum(lsum);
     gsum = warp_sum(gsum);
@@ -464,12 +495,14 @@ loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
         s_red[zg][j][9] = gsum;
     }
     __syncthreads();
-    if (zg == 0 && lane < 10) {
+    if (zg == 0 && lane < 26) {
         float v = 0.f;
 #pragma unroll
         for (int z = 0; z < kLgGroups; ++z) v += s_red[z][j][lane];
         if (lane < 8) atomicAdd(d_wo + j * 8 + lane, v);
-        else if (j == 0) atomicAdd(lane == 8 ? loss : d_bo, v);
+        else if (lane < 10) { if (j == 0) atomicAdd(lane == 8 ? loss : d_bo, v); }
+        else if (lane < 18) atomicAdd(d_plain + j * 8 + (lane - 10), v);
+        else atomicAdd(d_masked + j * 8 + (lane - 18), v);
     }
 }
 
@@ -812,15 +845,12 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     // ---- loss and out conv ---------------------------------------------------------------
     launch_pdl(loss_grad_kernel, dim3((unsigned)((L.np28 + kChunk - 1) / kChunk)), dim3(32, 4, kLgGroups), 0, st, 
         eps, noise, ws + L.h4, L.ps28, fp + P::out_w, ws + L.go28, dflat + P::out_w, dflat + P::out_b,
-        loss, B, L.np28, 1.0f / (float)(batch * 784));
+        loss, B, L.np28, 1.0f / (float)(batch * 784), M(L.m2_4), ws + L.gc28, dflat + P::rb4_sb, dflat + P::rb4_c2b);
     TDM_CHECK_LAUNCH("loss_grad");
 
     // ---- rb4: x_in = cat (96), h = t4, g_out = go28 ----------------------------------------
+    // (rb4's output gradient was masked and reduced by loss_grad_kernel above: gc28, skip.bias, conv2.bias)
     MaskReduceArgs mr{};
-    mr.in = ws + L.go28; mr.in_ps = L.ps28; mr.mask = M(L.m2_4); mr.mask_stride = L.np28;
-    mr.out = ws + L.gc28; mr.out_ps = L.ps28; mr.t = t; mr.batch = B; mr.npos = L.np28;
-    mr.d_plain = dflat + P::rb4_sb; mr.d_masked = dflat + P::rb4_c2b;
-    if ((rc = mask_reduce<MR_PLANES, 28>(mr, 32, st))) return rc;
     w = WgradArgs{ws + L.gc28, L.ps28, ws + L.t4, L.ps28, gscr + P::rb4_c2w, nt28};
     if ((rc = launch_wgrad_dup<28, 32, 32>(w, L.np28, st, "wgrad_rb4_c2"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
