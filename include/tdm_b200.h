@@ -164,6 +164,26 @@ int tdm_adamw_flat(float* params, const float* grads, float* exp_avg, float* exp
                    float lr, float beta1, float beta2, float eps, float weight_decay,
                    float grad_scale, const int64_t* step_dev, void* stream);
 
+/* ---- data-parallel training: gradient exchange fused into the optimizer (csrc/peer.cu, csrc/unet_bwd.cu) ----
+ * No counterpart in the reference (src/mnist.py:129-164 trains on one device).  Each rank allocates one buffer
+ * of tdm_peer_buffer_bytes(n) with tdm_peer_alloc, exports its 64-byte CUDA-IPC handle (host memory), exchanges
+ * handles with the other ranks (e.g. torch.distributed.all_gather) and maps theirs with tdm_peer_import.  The
+ * backward of step k (1-based, the value of *step_dev) writes its flat gradient at
+ * base + tdm_peer_grad_offset(n, k & 1); tdm_adamw_flat_peer then waits - on the device - until every rank has
+ * announced gradient k, sums the `world` gradients over NVLink in rank order and applies AdamW (grad_scale
+ * = 1/world gives the mean).  host_peer_bases[r] is rank r's buffer as mapped in THIS process ([rank] = own).
+ * All ranks must call it once per step, in step order; at most 8 ranks. */
+int64_t tdm_peer_buffer_bytes(int64_t n);
+int64_t tdm_peer_grad_offset(int64_t n, int parity);
+int tdm_peer_alloc(int64_t bytes, void** out_ptr);
+int tdm_peer_free(void* ptr);
+int tdm_peer_export(const void* ptr, void* host_handle64);
+int tdm_peer_import(const void* host_handle64, void** out_ptr);
+int tdm_peer_close(void* ptr);
+int tdm_adamw_flat_peer(float* params, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, float grad_scale, const int64_t* step_dev,
+                        const void* const* host_peer_bases, int world, int rank, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Shakespeare embedding-space sampler (src/shakespeare.py): TinyTransformer denoiser, reverse step,
  * rounding.  Supported shapes: seq_len 64 or 128, width 256 or 2048 (4 heads, FFN 2048, post-LN,

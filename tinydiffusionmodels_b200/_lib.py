@@ -40,6 +40,15 @@ SIGNATURES: dict[str, tuple] = {
     "tdm_unet_forward_train": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P]),
     "tdm_unet_backward": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P]),
     "tdm_adamw_flat": (c_int, [_P, _P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, _P, _P]),
+    "tdm_peer_buffer_bytes": (c_int64, [c_int64]),
+    "tdm_peer_grad_offset": (c_int64, [c_int64, c_int]),
+    "tdm_peer_alloc": (c_int, [c_int64, ctypes.POINTER(_P)]),
+    "tdm_peer_free": (c_int, [_P]),
+    "tdm_peer_export": (c_int, [_P, _P]),
+    "tdm_peer_import": (c_int, [_P, ctypes.POINTER(_P)]),
+    "tdm_peer_close": (c_int, [_P]),
+    "tdm_adamw_flat_peer": (c_int, [_P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, _P,
+                                    ctypes.POINTER(_P), c_int, c_int, _P]),
     "tdm_pack_linear": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "tdm_text_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "tdm_text_load_state": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, _P]),

@@ -759,23 +759,78 @@ rb1_wgrad_kernel(const uint8_t* __restrict__ gc, const uint8_t* __restrict__ go,
 //   p -= (lr / (1-b1^k)) * m / (sqrt(v)/sqrt(1-b2^k) + eps)
 // `step` lives on the device (1-based k of THIS update) so a captured graph can be replayed.
 // ---------------------------------------------------------------------------------------------
+//
+// PEER = true is the data-parallel form, "gradient all-reduce + AdamW" in one kernel (peer.cu has the buffer
+// layout): every rank's gradient of step k sits in slot k & 1 of a buffer all ranks have mapped; the kernel
+//   1. announces "my gradient k is complete" by storing k into flags[rank] on every peer (release, system scope),
+//   2. waits until flags[r] >= k for every r in its OWN buffer (acquire, system scope; bounded spin, then trap),
+//   3. sums the world gradients with loads over NVLink in rank order - the same order on every rank, so the
+//      replicas stay bit-identical - and applies the update.
+// No rank can be more than one step ahead of a peer that is still reading (it would need that peer's flag for
+// the next step first), which is why two slots are enough.
+constexpr int kMaxPeers = 8;
+struct PeerBases { const uint8_t* base[kMaxPeers]; };
+
+__device__ __forceinline__ void st_release_sys(uint64_t* p, uint64_t v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <bool PEER>
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
              float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
-             float grad_scale, const int64_t* __restrict__ step) {
+             float grad_scale, const int64_t* __restrict__ step, PeerBases peers, int world, int rank,
+             int64_t grad_off0, int64_t grad_slot_floats) {
     pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
     pdl_launch_dependents();
     __shared__ float s_c[2];
+    const int64_t kstep = *step;
     if (threadIdx.x == 0) {
-        const double k = (double)*step;
+        const double k = (double)kstep;
         s_c[0] = (float)((double)lr / (1.0 - pow((double)b1, k)));   // step size
         s_c[1] = (float)sqrt(1.0 - pow((double)b2, k));               // sqrt(bias_correction2)
+    }
+    if constexpr (PEER) {
+        if ((int)threadIdx.x < world) {
+            const int r = threadIdx.x;
+            if (blockIdx.x == 0) {
+                __threadfence_system();   // this rank's gradient (earlier kernels of the stream) before the flag
+                st_release_sys(reinterpret_cast<uint64_t*>(const_cast<uint8_t*>(peers.base[r])) + rank, (uint64_t)kstep);
+            }
+            const uint64_t* mine = reinterpret_cast<const uint64_t*>(peers.base[rank]) + r;
+            const long long t0 = clock64();
+            while (ld_acquire_sys(mine) < (uint64_t)kstep) {
+                if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer died; fail loudly instead of hanging
+                    printf("tdm adamw_peer: rank %d timed out waiting for rank %d at step %lld\n", rank, r, (long long)kstep);
+                    __trap();
+                }
+                __nanosleep(200);
+            }
+        }
     }
     __syncthreads();
     const float step_size = s_c[0], sbc2 = s_c[1];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float gi = g[i] * grad_scale;
+    float gsum;
+    if constexpr (PEER) {
+        const int64_t off = grad_off0 + (kstep & 1) * grad_slot_floats * 4;
+        gsum = 0.f;
+        for (int r = 0; r < world; ++r) gsum += ld_relaxed_sys(reinterpret_cast<const float*>(peers.base[r] + off) + i);
+    } else {
+        gsum = g[i];
+    }
+    const float gi = gsum * grad_scale;
     float pi = p[i] * (1.0f - lr * wd);
     const float mi = m[i] + (gi - m[i]) * (1.0f - b1);
     const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
@@ -977,8 +1032,33 @@ extern "C" int tdm_adamw_flat(float* params, const float* grads, float* exp_avg,
                               void* stream) {
     TDM_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && step_dev && n >= 0, "tdm_adamw_flat: bad arguments");
     if (n == 0) return TDM_OK;
-    launch_pdl(adamw_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
-        params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step_dev);
+    launch_pdl(adamw_kernel<false>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
+               params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step_dev,
+               PeerBases{}, 1, 0, (int64_t)0, (int64_t)0);
     TDM_CHECK_LAUNCH("tdm_adamw_flat");
+    return TDM_OK;
+}
+
+extern "C" int64_t tdm_peer_grad_offset(int64_t n, int parity);
+
+extern "C" int tdm_adamw_flat_peer(float* params, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                                   float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                                   const int64_t* step_dev, const void* const* host_peer_bases, int world,
+                                   int rank, void* stream) {
+    TDM_CHECK_ARG(params && exp_avg && exp_avg_sq && step_dev && host_peer_bases && n > 0,
+                  "tdm_adamw_flat_peer: bad arguments");
+    TDM_CHECK_ARG(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world,
+                  "tdm_adamw_flat_peer: world %d / rank %d out of range (max %d ranks)", world, rank, kMaxPeers);
+    PeerBases pb{};
+    for (int r = 0; r < world; ++r) {
+        TDM_CHECK_ARG(host_peer_bases[r], "tdm_adamw_flat_peer: null peer buffer %d", r);
+        pb.base[r] = reinterpret_cast<const uint8_t*>(host_peer_bases[r]);
+    }
+    const int64_t off0 = tdm_peer_grad_offset(n, 0);
+    const int64_t slot = (tdm_peer_grad_offset(n, 1) - off0) / 4;
+    launch_pdl(adamw_kernel<true>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
+               params, (const float*)nullptr, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, grad_scale,
+               step_dev, pb, world, rank, off0, slot);
+    TDM_CHECK_LAUNCH("tdm_adamw_flat_peer");
     return TDM_OK;
 }

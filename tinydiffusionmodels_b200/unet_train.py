@@ -2,11 +2,16 @@
 
 ``UNetTrainer.step(x0)`` is the whole inner loop body of the reference's ``train`` as device work:
 t ~ U{0..T-1}, noise ~ N(0,I) (Philox, in-kernel), q_sample, UNet forward (keeping ReLU masks),
-MSE, backward into ONE flat gradient buffer, optional NCCL all-reduce of that buffer (data
-parallel), fused AdamW on the flat master parameters, weight re-pack.  Nothing synchronises the
-host; the loss comes back as a device scalar.
+MSE, backward into ONE flat gradient buffer, fused AdamW on the flat master parameters, weight
+re-pack.  Data parallel (one process per GPU): every rank's gradient buffer is mapped by all ranks
+(CUDA IPC over NVLink) and the optimizer kernel itself sums them - "all-reduce + AdamW" is one
+kernel (``PeerGrads``, csrc/peer.cu); ``TDM_ALLREDUCE=nccl`` selects a plain NCCL all-reduce of the
+buffer instead.  Nothing synchronises the host; the loss comes back as a device scalar.
 """
 from __future__ import annotations
+
+import ctypes
+import os
 
 import torch
 
@@ -50,11 +55,68 @@ class TrainEngine:
         return eps_out
 
     def backward(self, x, t, noise, eps, flat_grad, loss_out) -> None:
+        """``flat_grad``: a CUDA fp32 tensor or a raw device address (a slot of a peer buffer)."""
         b = x.shape[0]
+        grad_ptr = flat_grad if isinstance(flat_grad, int) else flat_grad.data_ptr()
         _lib.check(self.lib.tdm_unet_backward(self.wpack.data_ptr(), x.data_ptr(), t.data_ptr(),
-                                              noise.data_ptr(), eps.data_ptr(), flat_grad.data_ptr(),
+                                              noise.data_ptr(), eps.data_ptr(), grad_ptr,
                                               loss_out.data_ptr(), self.ws.data_ptr(), self.ws_bytes, b,
                                               _lib.stream_ptr(self.device)), "tdm_unet_backward")
+
+
+class PeerGrads:
+    """This rank's gradient buffer, mapped by every rank of the group, and theirs mapped here.
+
+    Layout and protocol: csrc/peer.cu.  Handles travel through ``torch.distributed.all_gather`` once, at
+    construction; afterwards the ranks only meet inside ``tdm_adamw_flat_peer`` (device-side flags).
+    """
+
+    def __init__(self, lib, device, n: int, group=None):
+        import torch.distributed as dist
+
+        self.lib, self.device, self.n = lib, torch.device(device), int(n)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise _lib.TdmError("peer gradient exchange supports at most 8 ranks (one NVSwitch domain)")
+        with torch.cuda.device(self.device):
+            own = ctypes.c_void_p()
+            _lib.check(lib.tdm_peer_alloc(lib.tdm_peer_buffer_bytes(self.n), ctypes.byref(own)), "tdm_peer_alloc")
+            self.own = own.value
+            handle = (ctypes.c_uint8 * 64)()
+            _lib.check(lib.tdm_peer_export(self.own, handle), "tdm_peer_export")
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+            gathered = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(gathered, mine, group=group)
+            self.bases = (ctypes.c_void_p * self.world)()
+            self._imported = []
+            for r, h in enumerate(gathered):
+                if r == self.rank:
+                    self.bases[r] = self.own
+                    continue
+                raw = (ctypes.c_uint8 * 64)(*h.cpu().tolist())
+                peer = ctypes.c_void_p()
+                _lib.check(lib.tdm_peer_import(raw, ctypes.byref(peer)), "tdm_peer_import")
+                self.bases[r] = peer.value
+                self._imported.append(peer.value)
+        dist.barrier(group=group)   # every rank has mapped every buffer before anyone signals into one
+
+    def grad_ptr(self, step_k: int) -> int:
+        """Device address of this rank's gradient slot for (1-based) step ``step_k``."""
+        return self.own + int(self.lib.tdm_peer_grad_offset(self.n, step_k & 1))
+
+    def close(self) -> None:
+        for p in getattr(self, "_imported", []):
+            self.lib.tdm_peer_close(p)
+        self._imported = []
+        if getattr(self, "own", None):
+            self.lib.tdm_peer_free(self.own)
+            self.own = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # interpreter teardown
+            pass
 
 
 def loss_and_flat_grad(model, x_noisy: torch.Tensor, t: torch.Tensor, noise: torch.Tensor):
@@ -105,6 +167,12 @@ class UNetTrainer:
         self._bufs = {}
         self._graph_cache = {}
         self.use_graph = use_graph
+        # data parallel: gradients are exchanged inside the optimizer kernel over peer-mapped buffers
+        # (TDM_ALLREDUCE=nccl: torch.distributed.all_reduce of the flat buffer between the two halves of the step)
+        self.peer = None
+        if self.world > 1 and os.environ.get("TDM_ALLREDUCE", "peer") != "nccl":
+            self.peer = PeerGrads(self.engine.lib, dev, PARAM_COUNT, process_group)
+        self._k = 1   # host copy of the 1-based step index in step_dev (selects the peer gradient slot)
 
     def _buffers(self, b: int):
         if b not in self._bufs:
@@ -114,7 +182,7 @@ class UNetTrainer:
         return self._bufs[b]
 
     # -- device work of one step, split at the (optional) gradient exchange --------------------
-    def _fwd_bwd(self, x0, t, noise, b):
+    def _fwd_bwd(self, x0, t, noise, b, k: int | None = None):
         lib = self.engine.lib
         st = _lib.stream_ptr(self.device)
         x_noisy, noise_buf, eps = self._buffers(b)
@@ -134,25 +202,35 @@ class UNetTrainer:
                                         s.sqrt_one_minus_alphas_cumprod.data_ptr(), x_noisy.data_ptr(), b, 784,
                                         s.timesteps, st), "tdm_q_sample")
         self.engine.forward(x_noisy, t, eps)
-        self.engine.backward(x_noisy, t, noise, eps, self.grad, self.loss)
+        grad = self.grad if self.peer is None else self.peer.grad_ptr(self._k if k is None else k)
+        self.engine.backward(x_noisy, t, noise, eps, grad, self.loss)
 
-    def _update(self):
+    def _update(self, local_only: bool = False):
         lib = self.engine.lib
         st = _lib.stream_ptr(self.device)
-        _lib.check(lib.tdm_adamw_flat(self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(),
-                                      self.v.data_ptr(), PARAM_COUNT, self.lr, self.betas[0], self.betas[1],
-                                      self.eps, self.wd, 1.0 / self.world, self.step_dev.data_ptr(), st),
-                   "tdm_adamw_flat")
+        if self.peer is not None and not local_only:
+            p = self.peer
+            _lib.check(lib.tdm_adamw_flat_peer(self.flat.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), PARAM_COUNT,
+                                               self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                                               1.0 / self.world, self.step_dev.data_ptr(), p.bases, p.world, p.rank,
+                                               st), "tdm_adamw_flat_peer")
+        else:
+            grad_ptr = self.grad.data_ptr() if self.peer is None else self.peer.grad_ptr(self._k)
+            _lib.check(lib.tdm_adamw_flat(self.flat.data_ptr(), grad_ptr, self.m.data_ptr(),
+                                          self.v.data_ptr(), PARAM_COUNT, self.lr, self.betas[0], self.betas[1],
+                                          self.eps, self.wd, 1.0 / self.world, self.step_dev.data_ptr(), st),
+                       "tdm_adamw_flat")
         _lib.check(lib.tdm_timestep_advance(self.step_dev.data_ptr(), 1, 1, st), "tdm_timestep_advance")
         self.engine.pack(self.flat)
 
     def _exchange(self):
-        if self.world > 1:
+        if self.world > 1 and self.peer is None:
             torch.distributed.all_reduce(self.grad, group=self.pg)   # NCCL sum of the 726 KB flat buffer
 
     def _graphs(self, b: int):
-        """Two captured graphs per batch size: [q_sample, forward, backward] and [AdamW, re-pack];
-        the gradient all-reduce (if any) runs between them on the same stream."""
+        """Captured graphs per batch size: [q_sample, forward, backward] - one per gradient slot in peer mode,
+        because the slot address is a launch argument - and [AdamW, re-pack]; an NCCL all-reduce (if selected)
+        runs between them on the same stream."""
         if b not in self._graph_cache:
             dev = self.device
             x_s = torch.zeros(b, 1, 28, 28, device=dev)
@@ -162,13 +240,17 @@ class UNetTrainer:
             side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(side):       # warm-up outside capture (lazy attribute setup)
                 self._fwd_bwd(x_s, t_s, None, b)
-                self._update()
+                self._update(local_only=True)   # no cross-rank handshake for a step that is rolled back
             torch.cuda.current_stream(dev).wait_stream(side)
             self.flat.copy_(keep[0]); self.m.copy_(keep[1]); self.v.copy_(keep[2]); self.step_dev.copy_(keep[3])
             self.engine.pack(self.flat)
-            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1):
-                self._fwd_bwd(x_s, t_s, None, b)
+            g1 = []
+            for parity in ((0, 1) if self.peer is not None else (0,)):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._fwd_bwd(x_s, t_s, None, b, k=parity)
+                g1.append(g)
+            g2 = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g2):
                 self._update()
             self._graph_cache[b] = (g1, g2, x_s, t_s)
@@ -183,7 +265,7 @@ class UNetTrainer:
             g1, g2, x_s, t_s = self._graphs(b)
             x_s.copy_(x0, non_blocking=True)
             t_s.copy_(t, non_blocking=True)
-            g1.replay()
+            g1[(self._k & 1) if self.peer is not None else 0].replay()
             self._exchange()
             g2.replay()
         else:
@@ -194,6 +276,7 @@ class UNetTrainer:
             self._exchange()
             self._update()
         self.iteration += 1
+        self._k += 1
         return self.loss[0].clone()   # the buffer is overwritten by the next step
 
 
