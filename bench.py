@@ -339,7 +339,8 @@ def run_ours(args) -> None:
 
 def bench_train(dev, rank, world, batch, barrier, steps: int = 30, warmup: int = 5) -> dict:
     """UNet DDPM training step (src/mnist.py:153-159) on synthetic U(-1,1) images, `batch` per GPU,
-    gradients all-reduced over NCCL when world > 1.  Device-resident and host-fed variants."""
+    gradients summed inside the optimizer kernel over peer-mapped buffers when world > 1 (NCCL all-reduce if the
+    ranks cannot map each other).  Device-resident and host-fed variants."""
     import torch
     import torch.distributed as dist
 
@@ -397,6 +398,8 @@ def bench_train(dev, rank, world, batch, barrier, steps: int = 30, warmup: int =
         "tflops_per_gpu": flops / (ms / steps * 1e-3) / 1e12,
         "gpu_launches_per_step": int(launches),
         "allreduce_bytes_per_step": 181_473 * 4 if world > 1 else 0,
+        "gradient_exchange": ("none" if world == 1 else "fused into AdamW over peer-mapped buffers"
+                              if trainer.peer is not None else "NCCL all-reduce"),
         "final_loss": float(trainer.loss.item()),
     }
 

@@ -72,33 +72,48 @@ class PeerGrads:
     """
 
     def __init__(self, lib, device, n: int, group=None):
+        """Never raises between collectives: every rank runs the same all_gather whatever happens locally and
+        reports the outcome in ``self.ok`` / ``self.error`` (the caller votes on it)."""
         import torch.distributed as dist
 
         self.lib, self.device, self.n = lib, torch.device(device), int(n)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
-        if self.world > 8:
-            raise _lib.TdmError("peer gradient exchange supports at most 8 ranks (one NVSwitch domain)")
+        self.own, self._imported, self.error = None, [], ""
+        self.bases = (ctypes.c_void_p * self.world)()
+        msg = torch.zeros(65, dtype=torch.uint8)   # [ok, 64-byte CUDA-IPC handle]
         with torch.cuda.device(self.device):
-            own = ctypes.c_void_p()
-            _lib.check(lib.tdm_peer_alloc(lib.tdm_peer_buffer_bytes(self.n), ctypes.byref(own)), "tdm_peer_alloc")
-            self.own = own.value
-            handle = (ctypes.c_uint8 * 64)()
-            _lib.check(lib.tdm_peer_export(self.own, handle), "tdm_peer_export")
-            mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+            try:
+                if self.world > 8:
+                    raise _lib.TdmError("peer gradient exchange supports at most 8 ranks (one NVSwitch domain)")
+                own = ctypes.c_void_p()
+                _lib.check(lib.tdm_peer_alloc(lib.tdm_peer_buffer_bytes(self.n), ctypes.byref(own)), "tdm_peer_alloc")
+                self.own = own.value
+                handle = (ctypes.c_uint8 * 64)()
+                _lib.check(lib.tdm_peer_export(self.own, handle), "tdm_peer_export")
+                msg[0] = 1
+                msg[1:] = torch.tensor(list(handle), dtype=torch.uint8)
+            except Exception as e:   # noqa: BLE001
+                self.error = str(e)
+            mine = msg.to(self.device)
             gathered = [torch.empty_like(mine) for _ in range(self.world)]
             dist.all_gather(gathered, mine, group=group)
-            self.bases = (ctypes.c_void_p * self.world)()
-            self._imported = []
-            for r, h in enumerate(gathered):
-                if r == self.rank:
-                    self.bases[r] = self.own
-                    continue
-                raw = (ctypes.c_uint8 * 64)(*h.cpu().tolist())
-                peer = ctypes.c_void_p()
-                _lib.check(lib.tdm_peer_import(raw, ctypes.byref(peer)), "tdm_peer_import")
-                self.bases[r] = peer.value
-                self._imported.append(peer.value)
-        dist.barrier(group=group)   # every rank has mapped every buffer before anyone signals into one
+            gathered = [g.cpu() for g in gathered]
+            self.ok = all(int(g[0]) == 1 for g in gathered)
+            if self.ok:
+                try:
+                    for r, h in enumerate(gathered):
+                        if r == self.rank:
+                            self.bases[r] = self.own
+                            continue
+                        raw = (ctypes.c_uint8 * 64)(*h[1:].tolist())
+                        peer = ctypes.c_void_p()
+                        _lib.check(lib.tdm_peer_import(raw, ctypes.byref(peer)), "tdm_peer_import")
+                        self.bases[r] = peer.value
+                        self._imported.append(peer.value)
+                except Exception as e:   # noqa: BLE001
+                    self.ok, self.error = False, str(e)
+            elif not self.error:
+                self.error = "another rank could not export its buffer"
 
     def grad_ptr(self, step_k: int) -> int:
         """Device address of this rank's gradient slot for (1-based) step ``step_k``."""
@@ -171,8 +186,24 @@ class UNetTrainer:
         # (TDM_ALLREDUCE=nccl: torch.distributed.all_reduce of the flat buffer between the two halves of the step)
         self.peer = None
         if self.world > 1 and os.environ.get("TDM_ALLREDUCE", "peer") != "nccl":
-            self.peer = PeerGrads(self.engine.lib, dev, PARAM_COUNT, process_group)
+            self.peer = self._open_peer_grads(process_group)
         self._k = 1   # host copy of the 1-based step index in step_dev (selects the peer gradient slot)
+
+    def _open_peer_grads(self, group):
+        """Map every rank's gradient buffer, or - if ANY rank cannot (no peer access between the GPUs, IPC
+        disabled in the container, more than 8 ranks) - agree collectively on the NCCL all-reduce instead."""
+        import warnings
+        peer = PeerGrads(self.engine.lib, self.device, PARAM_COUNT, group)
+        err = peer.error
+        ok = torch.tensor([1 if peer.ok else 0], device=self.device, dtype=torch.int32)
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN, group=group)   # also the barrier before step 1
+        if int(ok) == 1:
+            return peer
+        peer.close()
+        if self.rank == 0:
+            warnings.warn(f"peer-mapped gradient exchange unavailable ({err or 'failed on another rank'}); "
+                          "using the NCCL all-reduce", stacklevel=2)
+        return None
 
     def _buffers(self, b: int):
         if b not in self._bufs:
