@@ -206,9 +206,11 @@ class _SyntheticTokenizer:
 
 
 class _SyntheticLM(nn.Module):
-    """Random-init bigram LM standing in for google/gemma-2b-it when --synthetic is given."""
+    """Random-init bigram LM standing in for google/gemma-2b-it when --synthetic is given; like Gemma-2b its
+    embedding width is 2048, so the default flags build the same TinyTransformer(2048) the reference CLI does
+    (``--use_learned_embeddings --embed_dim 256`` selects the deployed width)."""
 
-    def __init__(self, vocab, dim=64):
+    def __init__(self, vocab, dim=2048):
         super().__init__()
         self.emb = nn.Embedding(vocab, dim)
         self.out = nn.Linear(dim, vocab)
