@@ -663,8 +663,10 @@ rb1_wgrad_kernel(const uint8_t* __restrict__ gc, const uint8_t* __restrict__ go,
     pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
     pdl_launch_dependents();
     using G = Geo<28>;
+    constexpr int HL = G::Wp + 1;   // largest tap offset
     __shared__ __align__(16) float s_gc[128 * kR1Stride], s_go[128 * kR1Stride];
-    __shared__ float s_x[128][9];
+    __shared__ float s_x[128 + 2 * HL];   // x at positions p0-HL .. p0+127+HL in the padded geometry (0 at pads): every tap
+                                          // is then a fixed offset into this window, no per-tap bounds checks
     const int tid = threadIdx.x;
     const int cg = tid & 7, sl = tid >> 3;
     float acc[4][9], accs[4];
@@ -696,18 +698,16 @@ rb1_wgrad_kernel(const uint8_t* __restrict__ gc, const uint8_t* __restrict__ go,
             du[0] = make_float4(fu[0], fu[1], fu[2], fu[3]);
             du[1] = make_float4(fu[4], fu[5], fu[6], fu[7]);
         }
-        for (int i = tid; i < 128 * 9; i += 256) {
-            const int p = i / 9, tap = i - p * 9;
-            const int64_t pos = (int64_t)tile * 128 + p;
-            const int b = (int)((uint32_t)pos / (uint32_t)G::S);   // positions fit 32 bits: division by a constant is a multiply-shift
-            const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)G::S);
-            const int r = rem / G::Wp, c = rem - r * G::Wp;
+        if (tid < 128 + 2 * HL) {
+            const int pos = tile * 128 - HL + tid;
             float v = 0.f;
-            if (b < batch && r >= 1 && c < G::W) {
-                const int yy = r - 1 + tap / 3 - 1, xx = c + tap % 3 - 1;
-                if (yy >= 0 && yy < 28 && xx >= 0 && xx < 28) v = __ldg(x + (int64_t)b * 784 + yy * 28 + xx);
+            if (pos >= 0) {
+                const int b = (int)((uint32_t)pos / (uint32_t)G::S);   // positions fit 32 bits: division by a constant is a multiply-shift
+                const int rem = (int)((uint32_t)pos - (uint32_t)b * (uint32_t)G::S);
+                const int r = rem / G::Wp, c = rem - r * G::Wp;
+                if (b < batch && r >= 1 && c < G::W) v = __ldg(x + (int64_t)b * 784 + (r - 1) * 28 + c);
             }
-            s_x[p][tap] = v;
+            s_x[tid] = v;
         }
         __syncthreads();
 #pragma unroll
@@ -716,9 +716,10 @@ rb1_wgrad_kernel(const uint8_t* __restrict__ gc, const uint8_t* __restrict__ go,
             const float4 g4 = *reinterpret_cast<const float4*>(s_gc + p * kR1Stride + cg * 4);
             const float4 o4 = *reinterpret_cast<const float4*>(s_go + p * kR1Stride + cg * 4);
             const float gv[4] = {g4.x, g4.y, g4.z, g4.w}, ov[4] = {o4.x, o4.y, o4.z, o4.w};
+            // gradients at pad positions are stored as zeros, so whatever the window holds around them is harmless
             float xv[9];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) xv[k] = s_x[p][k];
+            for (int k = 0; k < 9; ++k) xv[k] = s_x[HL + p + (k / 3 - 1) * G::Wp + (k % 3 - 1)];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
 #pragma unroll
