@@ -1,26 +1,33 @@
 // conv_tc.cuh — the persistent warp-specialised tcgen05 implicit-GEMM convolution shared by the
 // UNet forward (unet_fwd.cu) and the data-gradient pass of the backward (unet_bwd.cu).
 //
-//   warp 0      producer: weights once, then one input tile (all channel planes, halo included)
-//               per iteration via 1-D bulk async copies into a ring of smem stages
-//   warp 1      one thread issues the tcgen05.mma of a tile (M = 128 positions, K = 16 channels);
-//               the A operand of every tap is the same smem tile at a shifted row offset
-//   last PROD   (PROD > 0 only) gather producers: build the first 8 channel planes of the tile from a
-//               HALF-resolution tensor (nearest x2 upsample, src/mnist.py:83) so the upsampled
-//               activation is never written to HBM; the remaining planes still arrive by bulk copy
-//   warps 2..   kEpiGroups groups of 8 epilogue warps; group g owns TMEM accumulator stage g; inside a
-//               group two warps share each TMEM lane quarter and take alternate 16-channel chunks
+//   warp 0        producer: weights once, then one input tile (all channel planes, halo included)
+//                 per iteration via 1-D bulk async copies into a ring of smem stages
+//   warp 1        MMA issuer: the whole warp runs the issue loop convergently, one elected lane issues the
+//                 tcgen05.mma of a tile (M = 128 positions, K = 16 channels); the A operand of every tap is
+//                 the same smem tile at a shifted row offset
+//   warps 2..17   kEpiGroups = 4 groups of 4 epilogue warps; group g owns TMEM accumulator stage g, so four
+//                 tiles are in flight; TMEM lane quarter = warp % 4, one thread per output position
+//   warps 18..    (PROD > 0 only) gather warps that BUILD input planes in the smem stage instead of copying them:
+//                 the nearest-x2 upsample of the 14x14 rb3 output for rb4.conv1 (cp.async; the upsampled tensor
+//                 never reaches HBM), or the im2col of the single-channel image for rb1.conv1
 //
-// Two MMA schedules:
-//   KXC = false  nine taps, N = COUT each:            D[p]            = sum_tap W_tap X[p + off(tap)]
-//   KXC = true   the three kx taps of a row share one MMA with N = 3*COUT (weights of kx = 0,1,2
-//                side by side), A shifted by (ky-1)*Wp only:
-//                                                      Y[q][kx]        = sum_ky W[ky][kx] X[q + (ky-1)Wp]
-//                and the epilogue finishes                out[p]      = Y[p-1][0] + Y[p][1] + Y[p+1][2]
-//                with two warp shuffles per channel (neighbour rows are neighbour lanes).  An MMA costs
-//                about 32 (A) + N/4 (B) + 15 cycles of shared-memory operand fetch whatever N is, so
-//                tripling N cuts the operand traffic per FLOP by ~2x.  Tiles overlap by
-//                two rows: tile t computes Y for rows [126t-1, 126t+127) and outputs [126t, 126t+126).
+// Three MMA schedules (template KXC), chosen per layer from measured sweeps (unet_layout.cuh).  With both
+// operands in shared memory one MMA costs max(N/2, (4096 + 32 N)/128) cycles (tools/micro/mma_rate.cu), i.e. a
+// small-N tap is bound by re-reading the A tile, and sharing that read between taps pays until the epilogue
+// that undoes the sharing costs more:
+//   0  nine taps, N = COUT each:              D[p]     = sum_tap W_tap X[p + off(tap)]
+//   1  kx-triple: the three kx taps of a kernel row share one MMA with N = 3*COUT (weights of kx = 0,1,2 side
+//      by side), A shifted by (ky-1)*Wp only:  Y[q][kx] = sum_ky W[ky][kx] X[q + (ky-1)Wp]
+//      and the epilogue finishes               out[p]   = Y[p-1][0] + Y[p][1] + Y[p+1][2]
+//      with two warp shuffles per channel (neighbour rows are neighbour lanes; the rows across a warp boundary
+//      travel through smem).  Tiles overlap by two rows: tile t outputs rows [126t, 126t+126).
+//   2  kx-pair: kx = 0,1 share an N = 2*COUT MMA, kx = 2 is accumulated into the kx = 1 columns with A one row
+//      further:                                out[p]   = Z0[p-1] + Z1[p]       (one shuffle; tiles of 127 rows)
+//
+// Epilogues (template EPI): bias/ReLU/time-embedding, residual or 1x1-skip variants, the 2x2 upsample scatter
+// (training), the final 1x1 out conv fused with the DDPM reverse step and in-kernel Philox noise, and for the
+// backward the plain data gradient or the data gradient already masked and reduced for the ReLU it enters.
 #pragma once
 #include <cstring>
 #include "common.cuh"
