@@ -95,7 +95,7 @@ struct ConvArgs {
     float* red_plain;      // EPI_PLAIN_MASK: per-channel reductions accumulated with atomics
     float* red_ts;
     float* red_masked;
-    // PROD = 1: half-resolution source of input planes 0..7 (14x14 geometry, row -GUARD of plane 0)
+    // upsample gather (rb4.conv1, sampling): half-resolution source of input planes 0..7 (14x14 geometry, row -GUARD of plane 0)
     const uint8_t* in2;
     int64_t in2_ps;
     ChanPar cp;            // CPAR = true only
@@ -152,7 +152,7 @@ struct ConvCfg {
     static_assert(NMAIN <= 256 && NMAIN % 16 == 0, "UMMA N");
     static constexpr int SMEM_BYTES = W_BYTES + NSTAGE * STAGE_BYTES + PARAM_BYTES + XCH_BYTES + kBarBytes;
     static_assert((1 + 2 * NSTAGE + 2 * kEpiGroups) * 8 + 8 <= kBarBytes, "mbarrier block overflows its smem slot");
-    // warp 0 producer, warp 1 MMA issuer, then NACC groups of 8 epilogue warps
+    // warp 0 producer, warp 1 MMA issuer, NACC groups of 4 epilogue warps, then the gather warps
     static constexpr int THREADS = 64 + 128 * kHalves * NACC + 32 * PROD;
     // gather kind: 0 none, 1 nearest-x2 upsample of the 64 h3 channels (rb4.conv1), 2 im2col of the
     // single-channel image (rb1.conv1 as a 1x1 convolution over 32 "channels" = 27 hi/lo tap terms)

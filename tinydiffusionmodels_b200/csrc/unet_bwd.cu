@@ -2,14 +2,21 @@
 //   loss = mse(model(q_sample(x0, t, noise), t), noise); loss.backward(); AdamW.step()
 //
 // Gradients flow through the same plane layout as the activations (bf16, fp32 accumulation):
-//   * data gradients   : conv3x3_tc_kernel (conv_tc.cuh) with transposed, tap-flipped weights
-//   * weight gradients : wgrad_tc_kernel below — per tile of 128 positions, TAPS*8 tcgen05.mma
-//                        with BOTH operands MN-major straight from the plane tiles (K = positions),
-//                        all taps accumulated in TMEM across the CTA's tiles, one atomic flush
-//   * ReLU masks / bias / time-embedding gradients: mask_reduce_kernel (elementwise, HBM-bound)
-//   * rb1.conv1 (Cin = 1), pooling / upsampling transposes, MSE gradient: small SIMT kernels
-// All parameter gradients land in ONE flat fp32 buffer in the reference's state_dict order — the
-// buffer the NCCL all-reduce and the fused AdamW operate on.
+//   * data gradients   : conv3x3_tc_kernel (conv_tc.cuh) with transposed, tap-flipped weights; conv2's data
+//                        gradient is multiplied by conv1's ReLU mask and reduced into the time-embedding / conv1-bias
+//                        gradients in the same epilogue (EPI_PLAIN_MASK)
+//   * weight gradients : wgrad_dup_kernel (3x3) / wgrad_tc_kernel (1x1 skips) below — tcgen05.mma with BOTH operands
+//                        MN-major straight from the plane tiles (K = positions), all taps accumulated in TMEM across
+//                        the CTA's tiles, flushed once with 16-byte vector reductions into a tap-major scratch that
+//                        wgrad_unpermute_kernel turns into the flat gradient
+//   * a block's output gradient, its ReLU mask and the skip/conv2-bias gradients: one pass each —
+//     loss_grad_kernel (rb4, with the MSE gradient and the out conv), mask_reduce_kernel<MR_UPSAMPLE_T> (rb3, with
+//     the transpose of the upsample), <MR_POOL_T> (rb1, with the concat slice and the transpose of the pool),
+//     <MR_PLANES> (rb2)
+//   * rb1.conv1 / rb1.skip (Cin = 1): rb1_wgrad_kernel (SIMT)
+// All parameter gradients land in ONE flat fp32 buffer in the reference's state_dict order — the buffer the fused
+// AdamW operates on; data parallel, that buffer is a slot of a peer-mapped allocation and adamw_kernel<true> sums
+// the ranks' gradients while it applies the update (peer.cu).
 #include "common.cuh"
 #include "conv_tc.cuh"
 #include "tc05.cuh"
