@@ -286,6 +286,15 @@ def run_ours(args) -> None:
         tj = json.loads(tfile.read_text())
         if tj.get("kernel") == names[top] and tj.get("batch") == B:
             traffic = tj["dram_bytes_per_launch"]   # dram read+write of one launch, ncu --set full
+    # whole reverse step against the HBM roofline of the per-layer design: DRAM bytes ncu counted for every kernel of
+    # one step (profiles/r01_traffic_step.json) / the live per-kernel times / the measured copy bandwidth
+    step_traffic = step_hbm_frac = None
+    sfile = ROOT / "profiles" / "r01_traffic_step.json"
+    if sfile.exists():
+        sj = json.loads(sfile.read_text())
+        if sj.get("batch") == B:
+            step_traffic = sj["dram_bytes_per_step"]
+            step_hbm_frac = step_traffic / (step_ms_sum * 1e-3) / (float(peaks["hbm_gbs"]) * 1e9)
     roofline = {
         "bound": "tensor", "kernel": names[top], "achieved": achieved_tf, "peak": peak_tf,
         "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
@@ -293,6 +302,7 @@ def run_ours(args) -> None:
         "kernel_ms": {n: round(v, 4) for n, v in zip(names, kms)},
         "kernel_share_of_step": round(kms[top] / step_ms_sum, 4),
         "whole_unet_tflops": FLOPS_PER_IMAGE_STEP * B / (step_ms_sum * 1e-3) / 1e12,
+        "step_dram_bytes": step_traffic, "step_hbm_frac": step_hbm_frac,
     }
 
     # ---- secondary metric: UNet train images/s (BASELINE.json configs[1]), data-parallel ------
