@@ -98,6 +98,10 @@ struct ConvArgs {
     // upsample gather (rb4.conv1, sampling): half-resolution source of input planes 0..7 (14x14 geometry, row -GUARD of plane 0)
     const uint8_t* in2;
     int64_t in2_ps;
+    // CIN2 > 0: a second input (same geometry, CIN2 channels) whose 1x1 convolution accumulates into the same output:
+    // the skip path's data gradient rides in the kernel of conv1's (weights: right after the 3x3 image)
+    const uint8_t* in3;
+    int64_t in3_ps;
     ChanPar cp;            // CPAR = true only
 };
 
@@ -126,13 +130,14 @@ constexpr int kIm2colUnroll = TDM_IM2COL_UNROLL; // tile rows per lane whose 9 l
 #endif
 constexpr int kGatherWarps = TDM_GATHER_WARPS;   // PROD used by rb4.conv1 on the sampling path
 
-template <int W, int CIN, int COUT, bool SKIPG, int TAPS, int KXC, int PROD = 0>
+template <int W, int CIN, int COUT, bool SKIPG, int TAPS, int KXC, int PROD = 0, int CIN2 = 0>
 struct ConvCfg {
     using G = Geo<W>;
     static constexpr int NPL = CIN / 8;
-    static constexpr int STAGE_BYTES = NPL * G::RT * 16;
+    static constexpr int NPL_ALL = (CIN + CIN2) / 8;   // planes of a stage: the 3x3 input, then the extra 1x1 input
+    static constexpr int STAGE_BYTES = NPL_ALL * G::RT * 16;
     static constexpr int WCONV_BYTES = TAPS * CIN * COUT * 2;
-    static constexpr int W_BYTES = WCONV_BYTES + (SKIPG ? CIN * COUT * 2 : 0);
+    static constexpr int W_BYTES = WCONV_BYTES + (SKIPG ? CIN * COUT * 2 : 0) + CIN2 * COUT * 2;
     static constexpr int PARAM_BYTES = 5 * 96 * 4;
     static constexpr int XCH_BYTES = (KXC == 1 ? kEpiGroups * kHalves * 4 * 2 * COUT * 4 : KXC == 2 ? kEpiGroups * kHalves * 4 * COUT * 4 : 0) + kEpiGroups * 2 * 128 * 4;
     static constexpr int MAX_SMEM = 227 * 1024;
@@ -157,7 +162,8 @@ struct ConvCfg {
     // gather kind: 0 none, 1 nearest-x2 upsample of the 64 h3 channels (rb4.conv1), 2 im2col of the
     // single-channel image (rb1.conv1 as a 1x1 convolution over 32 "channels" = 27 hi/lo tap terms)
     static constexpr int GK = PROD == 0 ? 0 : (CIN == 96 ? 1 : 2);
-    static constexpr int BULK_PLANES = GK == 0 ? NPL : GK == 1 ? NPL - kGatherPlanes : 0;
+    static constexpr int BULK_PLANES = GK == 0 ? NPL_ALL : GK == 1 ? NPL - kGatherPlanes : 0;
+    static_assert(CIN2 == 0 || (GK == 0 && KXC == 0 && !SKIPG && CIN2 % 16 == 0 && NPL_ALL <= 32), "extra 1x1 input: plain nine-tap kernels only");
     // arrivals on a stage's full barrier: the bulk issuer, plus the gather warp owning the tile
     // (one per lane when it copies with cp.async)
     static constexpr int FULL_ARRIVALS = (BULK_PLANES > 0 ? 1 : 0) + (GK == 0 ? 0 : (GK == 1 && TDM_GATHER_MODE != 0) ? 32 : 1);
@@ -205,11 +211,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, int KXC = 0, int PROD = 0, bool CPAR = false>
+template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, int KXC = 0, int PROD = 0, bool CPAR = false, int CIN2 = 0>
 __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1) conv3x3_tc_kernel(const __grid_constant__ ConvArgs a) {
     constexpr bool kPlain = (EPI == EPI_PLAIN || EPI == EPI_PLAIN_MASK);
     static_assert(!CPAR || (COUT <= 64 && !kPlain), "by-value channel parameters: forward epilogues, <= 64 channels");
-    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC, PROD>;
+    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC, PROD, CIN2>;
     static_assert(C::GK != 1 || (W == 28 && CIN == 96), "upsample gather serves rb4.conv1's concat input");
     static_assert(C::GK != 2 || (W == 28 && CIN == 32 && COUT == 32 && TAPS == 1 && KXC == 0), "im2col gather serves rb1.conv1");
     using G = Geo<W>;
@@ -296,11 +302,13 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
             }
             __syncwarp();
             if (lane < C::BULK_PLANES) {
-                // smem row 0 = global row tile*TSTRIDE - ROW0 - HALO; the buffer starts at row -GUARD.
-                // With gather producers the bulk planes (a.in = their first plane) sit after the gathered ones.
+                // smem row 0 = global row tile*TSTRIDE - ROW0 - HALO; the buffers start at row -GUARD.
+                // With gather producers the bulk planes (a.in = their first plane) sit after the gathered ones;
+                // with an extra 1x1 input its planes (a.in3) follow the 3x3 input's.
                 const int64_t row = (int64_t)tile * C::TSTRIDE - C::ROW0 - G::HALO + G::GUARD;
-                bulk_g2s(s_in + s * C::STAGE_BYTES + (lane + (C::NPL - C::BULK_PLANES)) * (G::RT * 16),
-                         a.in + lane * a.in_ps + row * 16, G::RT * 16, bar_full + s);
+                const uint8_t* src = (CIN2 > 0 && lane >= C::NPL) ? a.in3 + (lane - C::NPL) * a.in3_ps : a.in + lane * a.in_ps;
+                bulk_g2s(s_in + s * C::STAGE_BYTES + (lane + (C::NPL_ALL - C::BULK_PLANES)) * (G::RT * 16), src + row * 16,
+                         G::RT * 16, bar_full + s);
             }
         }
     } else if (warp == 1) {
@@ -356,6 +364,14 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
                     for (int ks = 0; ks < CIN / 16; ++ks) {
                         umma_bf16_elect(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + off) * 16),
                                         desc_add(w_base, ((tap * C::NPL + 2 * ks) * COUT) * 16), idesc, (tap | ks) != 0);
+                    }
+                }
+                if constexpr (CIN2 > 0) {
+                    // the extra input's 1x1 convolution lands in the same accumulator (centre tap, its own weights)
+#pragma unroll
+                    for (int ks = 0; ks < CIN2 / 16; ++ks) {
+                        umma_bf16_elect(d, desc_add(in_base, (C::NPL + 2 * ks) * (G::RT * 16) + G::HALO * 16),
+                                        desc_add(ws_base, ((2 * ks) * COUT) * 16), idesc, 1u);
                     }
                 }
             }
@@ -838,10 +854,10 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
     if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
-template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, int KXC = 0, int PROD = 0, bool CPAR = false>
+template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, int KXC = 0, int PROD = 0, bool CPAR = false, int CIN2 = 0>
 static int launch_conv(const ConvArgs& a, cudaStream_t st, const char* name) {
-    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC, PROD>;
-    auto kern = conv3x3_tc_kernel<W, CIN, COUT, EPI, SKIPG, TAPS, KXC, PROD, CPAR>;
+    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC, PROD, CIN2>;
+    auto kern = conv3x3_tc_kernel<W, CIN, COUT, EPI, SKIPG, TAPS, KXC, PROD, CPAR, CIN2>;
     static bool configured = false;
     if (!configured) {
         TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));

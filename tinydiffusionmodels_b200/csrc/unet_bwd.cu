@@ -928,10 +928,12 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     w = WgradArgs{ws + L.go28, L.ps28, ws + L.cat, L.ps28, dflat + P::rb4_sw, nt28};
     if ((rc = launch_wgrad<28, 32, 96, 1>(w, st, "wgrad_rb4_skip"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
-    c.in = ws + L.gh28; c.in_ps = L.ps28; c.w = wp + WP::d_rb4_c1; c.out = ws + L.gcat; c.out_ps = L.ps28;
-    if ((rc = launch_conv<28, 32, 96, EPI_PLAIN, false>(c, st, "dgrad_rb4_c1"))) return rc;
-    c.in = ws + L.go28; c.w = wp + WP::d_rb4_sk; c.res = ws + L.gcat; c.res_ps = L.ps28;
-    if ((rc = launch_conv<28, 32, 96, EPI_PLAIN, false, 1>(c, st, "dgrad_rb4_skip"))) return rc;
+    // gradient w.r.t. the concat input = conv1^T(gc1) + skip^T(g_out): one kernel, the 1x1 skip transpose accumulates
+    // into the same tile from a second input (its packed weights sit right behind conv1's)
+    static_assert(WP::d_rb4_sk == WP::d_rb4_c1 + WP::conv_bytes(32, 96), "skip image must follow the 3x3 image");
+    c.in = ws + L.gh28; c.in_ps = L.ps28; c.in3 = ws + L.go28; c.in3_ps = L.ps28;
+    c.w = wp + WP::d_rb4_c1; c.out = ws + L.gcat; c.out_ps = L.ps28;
+    if ((rc = launch_conv<28, 32, 96, EPI_PLAIN, false, 9, 0, 0, false, 32>(c, st, "dgrad_rb4_c1_skip"))) return rc;
 
     // ---- through the concat: channels 0..63 -> up(h3)^T -> g_out of rb3 ---------------------
     // ---- rb3: x_in = h2, h = t3, identity skip, g_out = go14a -------------------------------
@@ -977,10 +979,10 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     w = WgradArgs{ws + L.go14b, L.ps14, ws + L.p1, L.ps14, dflat + P::rb2_sw, nt14};
     if ((rc = launch_wgrad<14, 64, 32, 1>(w, st, "wgrad_rb2_skip"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np14;
-    c.in = ws + L.gh14; c.in_ps = L.ps14; c.w = wp + WP::d_rb2_c1; c.out = ws + L.gp1; c.out_ps = L.ps14;
-    if ((rc = launch_conv<14, 64, 32, EPI_PLAIN, false, 9, KX::rb2c1>(c, st, "dgrad_rb2_c1"))) return rc;
-    c.in = ws + L.go14b; c.w = wp + WP::d_rb2_sk; c.res = ws + L.gp1; c.res_ps = L.ps14;
-    if ((rc = launch_conv<14, 64, 32, EPI_PLAIN, false, 1>(c, st, "dgrad_rb2_skip"))) return rc;
+    static_assert(WP::d_rb2_sk == WP::d_rb2_c1 + WP::conv_bytes(64, 32) && KX::rb2c1 == 0, "skip image must follow the 3x3 image");
+    c.in = ws + L.gh14; c.in_ps = L.ps14; c.in3 = ws + L.go14b; c.in3_ps = L.ps14;
+    c.w = wp + WP::d_rb2_c1; c.out = ws + L.gp1; c.out_ps = L.ps14;
+    if ((rc = launch_conv<14, 64, 32, EPI_PLAIN, false, 9, 0, 0, false, 64>(c, st, "dgrad_rb2_c1_skip"))) return rc;
 
     // ---- h1 receives: concat channels 64..95 + avg-pool transpose of g_p1 -------------------
     // (fused below: go28 = gcat[64:96] + pool^T(gp1) is produced by the pass that also masks it)
