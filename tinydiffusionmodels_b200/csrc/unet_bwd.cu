@@ -53,6 +53,10 @@ struct WgradArgs {
     int64_t x_ps;
     float* dw;          // fp32, accumulated with 16-byte vector atomics: [CG][CX] (1x1) or TAP-MAJOR [9][CG][CX] (3x3 scratch)
     int nt;
+    // wgrad_dup_kernel<.., SKIPW = true> (CG = 32): a second gradient (the block's unmasked output gradient) rides in
+    // the spare quarter of the M = 128 tile and yields the 1x1 skip's weight gradient dws[CG][CX] from the same X tile
+    const uint8_t* g2;
+    float* dws;
 };
 
 template <int W, int CG, int CX, int TAPS>
@@ -220,11 +224,12 @@ struct WgradDupCfg {
     static constexpr int THREADS = 192;
 };
 
-template <int W, int CG, int CX>
+template <int W, int CG, int CX, bool SKIPW = false>
 __global__ void __launch_bounds__(192, 1) wgrad_dup_kernel(const WgradArgs a) {
     using C = WgradDupCfg<W, CG, CX>;
     using G = Geo<W>;
     static_assert(CG == 32 || CG == 64, "CG");
+    static_assert(!SKIPW || CG == 32, "the skip gradient uses the fourth quarter of the M = 128 tile (three copies at CG = 32)");
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* s_in = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::NSTAGE * C::STAGE_BYTES);
@@ -248,7 +253,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_dup_kernel(const WgradArgs a) {
     pdl_wait();                 // PDL (common.cuh): nothing above touches global memory
     pdl_launch_dependents();
     const uint32_t tmem_base = *s_tmem;
-    constexpr int LIVE_PLANES = C::NDUP * C::GPL;     // 12 (CG=32) or 16 (CG=64) of the 16 M-groups hold data
+    // 12 (CG=32) or 16 (CG=64) of the 16 M-groups hold data; SKIPW fills the last four with the second gradient,
+    // staged like copy 1 (shifted one row) so that the ky = 1 MMA, whose X window starts one row early, pairs
+    // g2[pos] with X[pos]: the centre tap, i.e. the 1x1 convolution
+    constexpr int LIVE_PLANES = C::NDUP * C::GPL + (SKIPW ? C::GPL : 0);
     constexpr int LIVE_BYTES = LIVE_PLANES * kTile * 16 + C::X_BYTES;
 
     if (warp == 0) {
@@ -264,7 +272,9 @@ __global__ void __launch_bounds__(192, 1) wgrad_dup_kernel(const WgradArgs a) {
             uint8_t* st = s_in + s * C::STAGE_BYTES;
             if (lane < LIVE_PLANES) {
                 const int d = lane / C::GPL, j = lane - d * C::GPL;   // copy d, channel plane j
-                bulk_g2s(st + lane * (kTile * 16), a.g + j * a.g_ps + ((int64_t)tile * kTile - d + G::GUARD) * 16,
+                const uint8_t* gsrc = (SKIPW && d == C::NDUP) ? a.g2 : a.g;
+                const int shift = (SKIPW && d == C::NDUP) ? 1 : d;
+                bulk_g2s(st + lane * (kTile * 16), gsrc + j * a.g_ps + ((int64_t)tile * kTile - shift + G::GUARD) * 16,
                          kTile * 16, bar_full + s);
             } else if (lane >= 16 && lane < 16 + C::XPL) {
                 const int j = lane - 16;
@@ -323,6 +333,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_dup_kernel(const WgradArgs a) {
                 tmem_ld16(taddr + ky * CX + c0, r);
                 tmem_ld_wait();
                 if (live) red_add_f32x16(a.dw + ((int64_t)((ky * 3 + d) * CG + co) * CX + c0), r);
+                if (SKIPW && d == C::NDUP && ky == 1) red_add_f32x16(a.dws + (int64_t)co * CX + c0, r);
             }
         }
         if constexpr (CG == 64) {
@@ -350,10 +361,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_dup_kernel(const WgradArgs a) {
     if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
-template <int W, int CG, int CX>
+template <int W, int CG, int CX, bool SKIPW = false>
 static int launch_wgrad_dup(WgradArgs a, int64_t np, cudaStream_t st, const char* name) {
     using C = WgradDupCfg<W, CG, CX>;
-    auto kern = wgrad_dup_kernel<W, CG, CX>;
+    auto kern = wgrad_dup_kernel<W, CG, CX, SKIPW>;
     static bool configured = false;
     if (!configured) {
         TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -923,10 +934,10 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     c.mask = const_cast<uint32_t*>(M(L.m1_4)); c.mask_stride = L.np28;
     c.red_plain = dflat + P::rb4_tb; c.red_ts = dflat + P::rb4_tw; c.red_masked = dflat + P::rb4_c1b;
     if ((rc = launch_conv<28, 32, 32, EPI_PLAIN_MASK, false, 9, KX::rb4c2>(c, st, "dgrad_rb4_c2"))) return rc;
+    // conv1's and the 1x1 skip's weight gradients share the concat tile: the skip's comes out of the spare quarter
     w = WgradArgs{ws + L.gh28, L.ps28, ws + L.cat, L.ps28, gscr + P::rb4_c1w, nt28};
-    if ((rc = launch_wgrad_dup<28, 32, 96>(w, L.np28, st, "wgrad_rb4_c1"))) return rc;
-    w = WgradArgs{ws + L.go28, L.ps28, ws + L.cat, L.ps28, dflat + P::rb4_sw, nt28};
-    if ((rc = launch_wgrad<28, 32, 96, 1>(w, st, "wgrad_rb4_skip"))) return rc;
+    w.g2 = ws + L.go28; w.dws = dflat + P::rb4_sw;
+    if ((rc = launch_wgrad_dup<28, 32, 96, true>(w, L.np28, st, "wgrad_rb4_c1_skip"))) return rc;
     c = ConvArgs{}; c.t = t; c.batch = B; c.np = (int)L.np28;
     // gradient w.r.t. the concat input = conv1^T(gc1) + skip^T(g_out): one kernel, the 1x1 skip transpose accumulates
     // into the same tile from a second input (its packed weights sit right behind conv1's)
