@@ -411,7 +411,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // and, in the same pass, what rb4 needs from its output gradient (src/mnist.py:65-66 backward):
 //   gc4 = go4 (.) relu_mask2 ; d rb4.skip.bias[c] += sum go4[c] ; d rb4.conv2.bias[c] += sum gc4[c]
 constexpr int kLgGroups = 4;
-__global__ void __launch_bounds__(32 * 4 * kLgGroups)
+__global__ void __launch_bounds__(32 * 4 * kLgGroups, 2)   // <= 64 registers: two blocks per SM (86 registers left one, 24 % occupancy)
 loss_grad_kernel(const float* __restrict__ eps, const float* __restrict__ noise,
                  const uint8_t* __restrict__ h4, int64_t ps, const float* __restrict__ wo,
                  uint8_t* __restrict__ go, float* __restrict__ d_wo, float* __restrict__ d_bo,
