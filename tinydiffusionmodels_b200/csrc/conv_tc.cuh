@@ -130,7 +130,7 @@ constexpr int kIm2colUnroll = TDM_IM2COL_UNROLL; // tile rows per lane whose 9 l
 #endif
 constexpr int kGatherWarps = TDM_GATHER_WARPS;   // PROD used by rb4.conv1 on the sampling path
 
-template <int W, int CIN, int COUT, bool SKIPG, int TAPS, int KXC, int PROD = 0, int CIN2 = 0>
+template <int W, int CIN, int COUT, bool SKIPG, int TAPS, int KXC, int PROD = 0, int CIN2 = 0, int NGRP = kEpiGroups>
 struct ConvCfg {
     using G = Geo<W>;
     static constexpr int NPL = CIN / 8;
@@ -139,7 +139,7 @@ struct ConvCfg {
     static constexpr int WCONV_BYTES = TAPS * CIN * COUT * 2;
     static constexpr int W_BYTES = WCONV_BYTES + (SKIPG ? CIN * COUT * 2 : 0) + CIN2 * COUT * 2;
     static constexpr int PARAM_BYTES = 5 * 96 * 4;
-    static constexpr int XCH_BYTES = (KXC == 1 ? kEpiGroups * kHalves * 4 * 2 * COUT * 4 : KXC == 2 ? kEpiGroups * kHalves * 4 * COUT * 4 : 0) + kEpiGroups * 2 * 128 * 4;
+    static constexpr int XCH_BYTES = (KXC == 1 ? NGRP * kHalves * 4 * 2 * COUT * 4 : KXC == 2 ? NGRP * kHalves * 4 * COUT * 4 : 0) + NGRP * 2 * 128 * 4;
     static constexpr int MAX_SMEM = 227 * 1024;
     static constexpr int AVAIL = MAX_SMEM - W_BYTES - PARAM_BYTES - XCH_BYTES - kBarBytes;
     // a gather warp may run at most one ring phase ahead of the MMA warp (mbarrier parity), so the ring is
@@ -148,7 +148,7 @@ struct ConvCfg {
     static constexpr int NSTAGE = (AVAIL / STAGE_BYTES) > STAGE_CAP ? STAGE_CAP : (AVAIL / STAGE_BYTES);
     static_assert(PROD <= NSTAGE, "more gather warps than input stages");
     static_assert(NSTAGE >= 2, "need at least two input stages");
-    static constexpr int NACC = kEpiGroups;
+    static constexpr int NACC = NGRP;   // epilogue groups == TMEM accumulator stages == tiles in flight
     static constexpr int NMAIN = KXC == 1 ? 3 * COUT : KXC == 2 ? 2 * COUT : COUT;   // columns of the conv accumulator
     static constexpr int ACC_COLS = NMAIN + (SKIPG ? COUT : 0);
     static constexpr int TMEM_COLS = (NACC * ACC_COLS <= 32) ? 32 : (NACC * ACC_COLS <= 64) ? 64
@@ -156,7 +156,7 @@ struct ConvCfg {
     static_assert(NACC * ACC_COLS <= 512, "accumulators exceed TMEM");
     static_assert(NMAIN <= 256 && NMAIN % 16 == 0, "UMMA N");
     static constexpr int SMEM_BYTES = W_BYTES + NSTAGE * STAGE_BYTES + PARAM_BYTES + XCH_BYTES + kBarBytes;
-    static_assert((1 + 2 * NSTAGE + 2 * kEpiGroups) * 8 + 8 <= kBarBytes, "mbarrier block overflows its smem slot");
+    static_assert((1 + 2 * NSTAGE + 2 * NGRP) * 8 + 8 <= kBarBytes && NGRP >= 1 && 64 + 128 * kHalves * NGRP + 32 * (PROD > 0 ? PROD : 0) <= 1024, "mbarrier block overflows its smem slot");
     // warp 0 producer, warp 1 MMA issuer, NACC groups of 4 epilogue warps, then the gather warps
     static constexpr int THREADS = 64 + 128 * kHalves * NACC + 32 * PROD;
     // gather kind: 0 none, 1 nearest-x2 upsample of the 64 h3 channels (rb4.conv1), 2 im2col of the
@@ -173,6 +173,19 @@ struct ConvCfg {
     static constexpr int ROW1 = KXC == 1 ? 127 : 128;   // output rows are tile rows [ROW0, ROW1)
     static constexpr int CW = 16;              // channels per epilogue chunk
 };
+
+// Development aid (TDM_NVCC_DEFS=-DTDM_TIMELINE=<EPI>): CTA 0 of the kernels whose EPI matches records clock64() at
+// the pipeline events of its first 96 tiles into g_timeline[tile][event]; tools/timeline_probe.py prints the deltas.
+#ifdef TDM_TIMELINE
+__device__ long long g_timeline[96 * 16];
+#define TDM_TL(EPI_, it_, ev_)                                                                  \
+    do {                                                                                        \
+        if ((EPI_) == TDM_TIMELINE && blockIdx.x == 0 && (it_) < 96 && (threadIdx.x & 31) == 0) \
+            g_timeline[(it_) * 16 + (ev_)] = clock64();                                         \
+    } while (0)
+#else
+#define TDM_TL(EPI_, it_, ev_) do {} while (0)
+#endif
 
 template <int N>
 __device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]) {
@@ -211,11 +224,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, int KXC = 0, int PROD = 0, bool CPAR = false, int CIN2 = 0>
-__global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1) conv3x3_tc_kernel(const __grid_constant__ ConvArgs a) {
+template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, int KXC = 0, int PROD = 0, bool CPAR = false, int CIN2 = 0, int NGRP = kEpiGroups>
+__global__ void __launch_bounds__(64 + 128 * kHalves * NGRP + 32 * PROD, 1) conv3x3_tc_kernel(const __grid_constant__ ConvArgs a) {
     constexpr bool kPlain = (EPI == EPI_PLAIN || EPI == EPI_PLAIN_MASK);
     static_assert(!CPAR || (COUT <= 64 && !kPlain), "by-value channel parameters: forward epilogues, <= 64 channels");
-    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC, PROD, CIN2>;
+    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC, PROD, CIN2, NGRP>;
     static_assert(C::GK != 1 || (W == 28 && CIN == 96), "upsample gather serves rb4.conv1's concat input");
     static_assert(C::GK != 2 || (W == 28 && CIN == 32 && COUT == 32 && TAPS == 1 && KXC == 0), "im2col gather serves rb1.conv1");
     using G = Geo<W>;
@@ -237,7 +250,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
     float* s_sbias = s_par + 288;
     float* s_aux = s_par + 384;
     float* s_dot = s_par + 480;                       // [grp][tile parity][128] partial out-conv dots
-    float* s_xch = s_dot + kEpiGroups * 2 * 128;      // kx-combine boundary rows
+    float* s_xch = s_dot + C::NACC * 2 * 128;         // kx-combine boundary rows
     uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_dot) + C::XCH_BYTES);
     uint64_t* bar_w = bars;
     uint64_t* bar_full = bars + 1;
@@ -298,6 +311,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
             const uint32_t ph = (it / C::NSTAGE) & 1;
             if (lane == 0) {
                 mbar_wait(bar_empty + s, ph ^ 1);
+                TDM_TL(EPI, it, 0);
                 mbar_arrive_expect_tx(bar_full + s, C::BULK_PLANES * G::RT * 16);
             }
             __syncwarp();
@@ -317,26 +331,42 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
         constexpr uint32_t idesc_skip = make_idesc_bf16(128, COUT);
         mbar_wait(bar_w, 0);
         constexpr uint32_t B_LBO = (KXC ? 3 * COUT : COUT) * 16;
-        const uint64_t w_base = make_smem_desc(smem_u32(s_w), B_LBO, 128);
-        const uint64_t ws_base = make_smem_desc(smem_u32(s_w) + C::WCONV_BYTES, COUT * 16, 128);
+        // The MMAs of a tile are issued inside `if (elect_one())`: ptxas then keeps the descriptors in UNIFORM registers
+        // and every "base + constant" is one UIADD3.64 next to its UTCHMMA (2 SASS instructions per MMA).  Issued with
+        // the election inside each asm statement (or under `lane == 0`) every UTCHMMA dragged ~10 ELECT / R2UR / VOTEU
+        // instructions along to move its operands out of vector registers, and the issuing warp - not the tensor pipe -
+        // set the pace of the N = 32 layers (58 cycles per 40-cycle MMA; ncu source page, tools/micro).
+        const uint32_t w_addr = smem_u32(s_w);
+        const uint32_t in_addr0 = smem_u32(s_in);
+        const uint32_t tmem_u = tmem_base;
+        const uint64_t w_base = make_smem_desc(w_addr, B_LBO, 128);
+        const uint64_t ws_base = make_smem_desc(w_addr + C::WCONV_BYTES, COUT * 16, 128);
         int it = 0;
         for (int tile = blockIdx.x; tile < nt; tile += gridDim.x, ++it) {
             const int s = it % C::NSTAGE;
             const uint32_t ph = (it / C::NSTAGE) & 1;
             const int acc = it % C::NACC;
             const uint32_t aph = (it / C::NACC) & 1;
+            TDM_TL(EPI, it, 8);
+#ifndef TDM_DBG_NOWAIT   // timing experiment only (wrong results): the MMA warp never waits
             mbar_wait(bar_acce + acc, aph ^ 1);
+#endif
+            TDM_TL(EPI, it, 2);
+#ifndef TDM_DBG_NOWAIT
             mbar_wait(bar_full + s, ph);
+#endif
+            TDM_TL(EPI, it, 3);
             if constexpr (C::GK == 1 && TDM_GATHER_MODE != 0) fence_proxy_async_smem();   // cp.async (generic proxy) data -> async-proxy MMA reads
             tc_fence_after_sync();
-            const uint64_t in_base = make_smem_desc(smem_u32(s_in + s * C::STAGE_BYTES), G::RT * 16, 128);
-            const uint32_t d = tmem_base + acc * C::ACC_COLS;
+            const uint64_t in_base = make_smem_desc(in_addr0 + (uint32_t)s * C::STAGE_BYTES, G::RT * 16, 128);
+            const uint32_t d = tmem_u + acc * C::ACC_COLS;
+            if (elect_one()) {
             if constexpr (KXC == 1) {
 #pragma unroll
                 for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
                     for (int ks = 0; ks < CIN / 16; ++ks) {
-                        umma_bf16_elect(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp) * 16),
+                        umma_bf16(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp) * 16),
                                         desc_add(w_base, ((ky * C::NPL + 2 * ks) * 3 * COUT) * 16), idesc, (ky | ks) != 0);
                     }
                 }
@@ -347,9 +377,9 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
                 for (int ky = 0; ky < 3; ++ky) {
 #pragma unroll
                     for (int ks = 0; ks < CIN / 16; ++ks) {
-                        umma_bf16_elect(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp) * 16),
+                        umma_bf16(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp) * 16),
                                         desc_add(w_base, ((ky * C::NPL + 2 * ks) * 3 * COUT) * 16), idesc, (ky | ks) != 0);
-                        umma_bf16_elect(d + COUT, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp + 1) * 16),
+                        umma_bf16(d + COUT, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp + 1) * 16),
                                         desc_add(w_base, ((ky * C::NPL + 2 * ks) * 3 * COUT + 2 * COUT) * 16), idesc_skip, 1u);
                     }
                 }
@@ -362,7 +392,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
                     const int off = (TAPS == 1) ? 0 : (tap / 3 - 1) * G::Wp + (tap % 3 - 1);
 #pragma unroll
                     for (int ks = 0; ks < CIN / 16; ++ks) {
-                        umma_bf16_elect(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + off) * 16),
+                        umma_bf16(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + off) * 16),
                                         desc_add(w_base, ((tap * C::NPL + 2 * ks) * COUT) * 16), idesc, (tap | ks) != 0);
                     }
                 }
@@ -370,7 +400,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
                     // the extra input's 1x1 convolution lands in the same accumulator (centre tap, its own weights)
 #pragma unroll
                     for (int ks = 0; ks < CIN2 / 16; ++ks) {
-                        umma_bf16_elect(d, desc_add(in_base, (C::NPL + 2 * ks) * (G::RT * 16) + G::HALO * 16),
+                        umma_bf16(d, desc_add(in_base, (C::NPL + 2 * ks) * (G::RT * 16) + G::HALO * 16),
                                         desc_add(ws_base, ((2 * ks) * COUT) * 16), idesc, 1u);
                     }
                 }
@@ -378,14 +408,17 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
             if constexpr (SKIPG) {
 #pragma unroll
                 for (int ks = 0; ks < CIN / 16; ++ks) {
-                    umma_bf16_elect(d + C::NMAIN, desc_add(in_base, (2 * ks) * (G::RT * 16) + G::HALO * 16),
+                    umma_bf16(d + C::NMAIN, desc_add(in_base, (2 * ks) * (G::RT * 16) + G::HALO * 16),
                                     desc_add(ws_base, ((2 * ks) * COUT) * 16), idesc_skip, ks != 0);
                 }
             }
-            umma_commit_elect(bar_empty + s);   // smem stage reusable once these MMAs retire
-            umma_commit_elect(bar_accf + acc);  // accumulator complete
+            umma_commit(bar_empty + s);   // smem stage reusable once these MMAs retire
+            umma_commit(bar_accf + acc);  // accumulator complete
+            }
+            __syncwarp();
+            TDM_TL(EPI, it, 4);
         }
-    } else if (PROD != 0 && warp >= 2 + 4 * kHalves * kEpiGroups) {
+    } else if (PROD != 0 && warp >= 2 + 4 * kHalves * C::NACC) {
         // ===== gather producers (PROD warps): planes 0..7 of the tile = nearest-x2 upsample of the 14x14 source.
         //       Warp w owns tiles it = w (mod PROD) entirely; lane = smem row.  Measured on B200 @16384 (kernel us):
         //         TDM_GATHER_MODE 2  cp.async.ca (through L1), 2 warps   936   <- default
@@ -399,7 +432,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
         //       registers and no waiting: completion reaches the full barrier through
         //       cp.async.mbarrier.arrive.noinc (one arrival per lane), so a warp runs ahead as far as the ring
         //       has free stages. =====
-        const int pw = warp - (2 + 4 * kHalves * kEpiGroups);
+        const int pw = warp - (2 + 4 * kHalves * C::NACC);
         if constexpr (C::GK == 2) {
             // ===== im2col of the single-channel image (src/mnist.py:74 conv1 of rb1): tile row p gets the 3x3
             //       window of x around p as 32 "channels", so the 1 -> 32 convolution is one K = 32 GEMM:
@@ -606,6 +639,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
 
             // ---- phase B: drain the accumulator ----
             mbar_wait(bar_accf + grp, aph);
+            if (q == 0) TDM_TL(EPI, n * C::NACC + grp, 5);
             tc_fence_after_sync();
             float dot = 0.f;
             uint32_t mbits = 0;
@@ -627,6 +661,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
                         tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_acce + grp);
+                        if (q == 0) TDM_TL(EPI, n * C::NACC + grp, 7);
                     }
                     float4* xs = reinterpret_cast<float4*>(s_xch + (grp * 4 + q) * COUT + c0);   // per (group, quarter)
                     if (lane == 31) {
@@ -662,6 +697,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
                         tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_acce + grp);
+                        if (q == 0) TDM_TL(EPI, n * C::NACC + grp, 7);
                     }
                     // rows p-1 / p+1 are lanes -1 / +1; across the warp boundary they come through smem.
                     // Everything below is branch-free per channel (selects, broadcast loads): per-channel
@@ -705,6 +741,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
                         tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_acce + grp);
+                        if (q == 0) TDM_TL(EPI, n * C::NACC + grp, 7);
                     }
 #pragma unroll
                     for (int k = 0; k < CW; ++k) acc[k] = __uint_as_float(r1[k]);
@@ -818,6 +855,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
                 }
                 mbits = 0;
             }
+            if (q == 0) TDM_TL(EPI, n * C::NACC + grp, 6);
             if constexpr (EPI == EPI_FINAL) {
                 // the two halves each hold a partial dot of the 1x1 out conv: half 1 hands its part over
                 if constexpr (kHalves == 2) {
@@ -854,10 +892,10 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * kEpiGroups + 32 * PROD, 1
     if (warp == 2) tmem_dealloc<C::TMEM_COLS>(tmem_base);
 }
 
-template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, int KXC = 0, int PROD = 0, bool CPAR = false, int CIN2 = 0>
+template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, int KXC = 0, int PROD = 0, bool CPAR = false, int CIN2 = 0, int NGRP = kEpiGroups>
 static int launch_conv(const ConvArgs& a, cudaStream_t st, const char* name) {
-    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC, PROD, CIN2>;
-    auto kern = conv3x3_tc_kernel<W, CIN, COUT, EPI, SKIPG, TAPS, KXC, PROD, CPAR, CIN2>;
+    using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC, PROD, CIN2, NGRP>;
+    auto kern = conv3x3_tc_kernel<W, CIN, COUT, EPI, SKIPG, TAPS, KXC, PROD, CPAR, CIN2, NGRP>;
     static bool configured = false;
     if (!configured) {
         TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -872,9 +910,9 @@ static int launch_conv(const ConvArgs& a, cudaStream_t st, const char* name) {
 
 // Forward-pass launch: with a host mirror `hfp` of the flat fp32 parameters (the device copy is `fp`), the
 // per-channel vectors travel by value (CPAR); their host addresses follow from the device pointers in `a`.
-template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, int KXC = 0, int PROD = 0>
+template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, int KXC = 0, int PROD = 0, int NGRP = kEpiGroups>
 static int launch_conv_fwd(ConvArgs& a, const float* fp, const float* hfp, cudaStream_t st, const char* name) {
-    if (!hfp) return launch_conv<W, CIN, COUT, EPI, SKIPG, TAPS, KXC, PROD, false>(a, st, name);
+    if (!hfp) return launch_conv<W, CIN, COUT, EPI, SKIPG, TAPS, KXC, PROD, false, 0, NGRP>(a, st, name);
     auto mirror = [&](float* dst, const float* dev, int n) {
         if (dev) std::memcpy(dst, hfp + (dev - fp), (size_t)n * sizeof(float));
     };
@@ -883,7 +921,7 @@ static int launch_conv_fwd(ConvArgs& a, const float* fp, const float* hfp, cudaS
     if (SKIPG) mirror(a.cp.sbias, a.sbias, COUT);
     if (EPI == EPI_RES_X) { mirror(a.cp.aux, a.aux_w, 32); mirror(a.cp.aux + 32, a.aux_b, 32); }
     if (EPI == EPI_FINAL) { mirror(a.cp.aux, a.aux_w, 32); mirror(a.cp.aux + 32, a.aux_b, 1); }
-    return launch_conv<W, CIN, COUT, EPI, SKIPG, TAPS, KXC, PROD, true>(a, st, name);
+    return launch_conv<W, CIN, COUT, EPI, SKIPG, TAPS, KXC, PROD, true, 0, NGRP>(a, st, name);
 }
 
 }  // namespace tdm

@@ -29,6 +29,15 @@
 #include "conv_tc.cuh"
 #include "unet_ws.cuh"
 
+// epilogue groups (= tiles in flight) of the two nine-tap 32->32 convolutions, whose 32-column accumulators leave
+// TMEM room for more than the default four
+#ifndef TDM_G_RB1C2
+#define TDM_G_RB1C2 4
+#endif
+#ifndef TDM_G_RB4C2
+#define TDM_G_RB4C2 4
+#endif
+
 namespace tdm {
 
 // ---------------------------------------------------------------------------------------------
@@ -217,7 +226,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     a.out = ws + L.cat + 8 * L.ps28; a.out_ps = L.ps28;
     a.x = x; a.aux_w = fp + P::rb1_sw; a.aux_b = fp + P::rb1_sb; a.np = (int)L.np28;
     a.mask = mk(L.m2_1); a.mask_stride = L.np28;
-    if ((rc = launch_conv_fwd<28, 32, 32, EPI_RES_X, false, 9, KX::rb1c2>(a, fp, hfp, st, "rb1_conv2"))) return rc;
+    if ((rc = launch_conv_fwd<28, 32, 32, EPI_RES_X, false, 9, KX::rb1c2, 0, TDM_G_RB1C2>(a, fp, hfp, st, "rb1_conv2"))) return rc;
 
     // k3: pool h1 -> p1
     TDM_PROF(2);
@@ -291,7 +300,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     if (sa.train) { a.out = ws + L.h4; a.out_ps = L.ps28; }
     a.fuse_step = sa.fuse_step; a.z = sa.z; a.betas = sa.betas; a.alphas = sa.alphas;
     a.sqrt_om = sa.sqrt_om; a.seed = sa.seed; a.sample_offset = sa.sample_offset; a.step_id = sa.step_id;
-    if ((rc = launch_conv_fwd<28, 32, 32, EPI_FINAL, false, 9, KX::rb4c2>(a, fp, hfp, st, "rb4_conv2"))) return rc;
+    if ((rc = launch_conv_fwd<28, 32, 32, EPI_FINAL, false, 9, KX::rb4c2, 0, TDM_G_RB4C2>(a, fp, hfp, st, "rb4_conv2"))) return rc;
     TDM_PROF(9);
     return TDM_OK;
 }
@@ -324,6 +333,14 @@ extern "C" int tdm_unet_pack_weights(const float* flat_params, void* wpack, void
     TDM_CHECK_LAUNCH("tdm_unet_pack_weights");
     return TDM_OK;
 }
+
+#ifdef TDM_TIMELINE
+// development aid: copy the in-kernel timeline (conv_tc.cuh) to host memory
+extern "C" int tdm_debug_read_timeline(long long* host_out) {
+    TDM_CHECK_CUDA(cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * 96 * 16));
+    return TDM_OK;
+}
+#endif
 
 extern "C" int tdm_unet_forget_host_params(const void* wpack) {
     drop_host_params(wpack);
