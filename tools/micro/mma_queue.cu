@@ -116,6 +116,85 @@ __global__ void __launch_bounds__(64) kconv(long long* out, int tiles) {
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tm);
 }
+// the same conv-pattern issue loop while 16 other warps of the SM stream 16-byte global stores / loads
+// (what the epilogue warps do): does traffic through the L1 data path slow shared-memory-bound MMAs?
+template <int MODE>   // 0 idle, 1 STG.128 stream, 2 LDG.128 stream, 3 bulk g2s copies into a scratch smem area
+__global__ void __launch_bounds__(64 + 512) kconv_traffic(long long* out, int tiles, uint4* gbuf) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint32_t slot;
+    __shared__ __align__(8) uint64_t bars[16];
+    __shared__ volatile int done;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) tmem_alloc<512>(&slot);
+    if (threadIdx.x == 0) { for (int i = 0; i < 16; ++i) mbar_init(bars + i, 1); mbar_fence_init(); done = 0; }
+    for (int i = threadIdx.x; i < (4 * 12288 + 18432) / 4; i += 576) ((uint32_t*)smem)[i] = 0;
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tm = slot;
+    if (warp == 1) {
+        if (elect_one()) {
+            const uint64_t w_base = make_smem_desc(smem_u32(smem) + 4 * 12288, 512, 128);
+            constexpr uint32_t idesc = make_idesc_bf16(128, 32);
+            const long long t0 = clock64();
+            for (int t = 0; t < tiles; ++t) {
+                const uint64_t in_base = make_smem_desc(smem_u32(smem) + (t & 3) * 12288, 3072, 128);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks)
+                        umma_bf16(tm + (uint32_t)((t & 3) * 32), desc_add(in_base, (2 * ks) * 3072 + (32 + (tap / 3 - 1) * 29 + tap % 3 - 1) * 16),
+                                  desc_add(w_base, ((tap * 4 + 2 * ks) * 32) * 16), idesc, (tap | ks) != 0);
+                umma_commit(bars + ((2 * t) & 7));
+                umma_commit(bars + ((2 * t + 1) & 7));
+            }
+            umma_commit(bars + 15);
+            mbar_wait(bars + 15, 0);
+            out[blockIdx.x] = clock64() - t0;
+            done = 1;
+        }
+    } else if (warp >= 2 && MODE != 0) {
+        uint4* p = gbuf + (size_t)blockIdx.x * (1 << 16) + (warp - 2) * 4096 + lane;
+        uint4 v = make_uint4(warp, lane, 0, 0);
+        int i = 0;
+        uint32_t acc = 0;
+        if (MODE == 3 && warp == 2 && lane == 0) {   // one thread keeps 12 KB bulk copies coming (like the producer warp)
+            uint8_t* scratch = smem + 4 * 12288 + 18432;
+            uint32_t ph = 0;
+            while (!done) {
+                mbar_arrive_expect_tx(bars + 14, 12288);
+                bulk_g2s(scratch, reinterpret_cast<const uint8_t*>(gbuf) + (size_t)blockIdx.x * (1 << 20) + (i & 63) * 12288, 12288, bars + 14);
+                mbar_wait(bars + 14, ph);
+                ph ^= 1; ++i;
+            }
+        } else if (MODE != 3) {
+            while (!done) {
+                if (MODE == 1) p[(i & 127) * 32] = v;
+                else acc ^= p[(i & 127) * 32].x;
+                ++i;
+            }
+            if (acc == 0x12345u) p[0] = v;
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tm);
+}
+template <int MODE>
+void run_traffic(const char* what) {
+    long long* d; cudaMalloc(&d, 148 * sizeof(long long));
+    uint4* g; cudaMalloc(&g, (size_t)148 * (1 << 20)); cudaMemset(g, 0, (size_t)148 * (1 << 20));
+    cudaFuncSetAttribute(kconv_traffic<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
+    const int tiles = 512;
+    kconv_traffic<MODE><<<148, 576, 98304>>>(d, tiles, g); kconv_traffic<MODE><<<148, 576, 98304>>>(d, tiles, g);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h[148]; cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+    long long mx = 0; for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+    printf("conv-pattern tile on 148 SMs, other warps: %-28s %.1f cycles per tile %s\n", what, (double)mx / tiles, e == cudaSuccess ? "" : cudaGetErrorString(e));
+    cudaFree(d); cudaFree(g);
+}
+
 void run_conv() {
     long long* d; cudaMalloc(&d, sizeof(long long));
     cudaFuncSetAttribute(kconv, cudaFuncAttributeMaxDynamicSharedMemorySize, 98304);
@@ -155,5 +234,6 @@ void run() {
 int main() {
     run<32>(); run<128>();
     run_tile<32, 0>(); run_tile<32, 1>(); run_tile<32, 2>(); run_tile<96, 2>(); run_conv();
+    run_traffic<0>("idle"); run_traffic<1>("16 warps of STG.128"); run_traffic<2>("16 warps of LDG.128"); run_traffic<3>("12 KB bulk copies g2s");
     return 0;
 }
