@@ -339,85 +339,100 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * NGRP + 32 * PROD, 1) conv
         const uint32_t w_addr = smem_u32(s_w);
         const uint32_t in_addr0 = smem_u32(s_in);
         const uint32_t tmem_u = tmem_base;
-        const uint64_t w_base = make_smem_desc(w_addr, B_LBO, 128);
-        const uint64_t ws_base = make_smem_desc(w_addr + C::WCONV_BYTES, COUT * 16, 128);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < nt; tile += gridDim.x, ++it) {
-            const int s = it % C::NSTAGE;
-            const uint32_t ph = (it / C::NSTAGE) & 1;
-            const int acc = it % C::NACC;
-            const uint32_t aph = (it / C::NACC) & 1;
-            TDM_TL(EPI, it, 8);
-#ifndef TDM_DBG_NOWAIT   // timing experiment only (wrong results): the MMA warp never waits
-            mbar_wait(bar_acce + acc, aph ^ 1);
-#endif
-            TDM_TL(EPI, it, 2);
-#ifndef TDM_DBG_NOWAIT
-            mbar_wait(bar_full + s, ph);
-#endif
-            TDM_TL(EPI, it, 3);
-            if constexpr (C::GK == 1 && TDM_GATHER_MODE != 0) fence_proxy_async_smem();   // cp.async (generic proxy) data -> async-proxy MMA reads
-            tc_fence_after_sync();
-            const uint64_t in_base = make_smem_desc(in_addr0 + (uint32_t)s * C::STAGE_BYTES, G::RT * 16, 128);
-            const uint32_t d = tmem_u + acc * C::ACC_COLS;
-            if (elect_one()) {
-            if constexpr (KXC == 1) {
+        // ONE elected thread runs the whole persistent issue loop.  The waits for tile i+1 (accumulator free, input
+        // full) are taken in the middle of tile i's MMAs, while the pipe is busy with what is already queued (a
+        // thread can run ~7 MMAs ahead), so nothing but the two commits sits between the last MMA of a tile and the
+        // first MMA of the next.  Measured with the in-kernel timeline (tools/timeline_probe.py): with a per-tile
+        // "all lanes wait, elect, issue, __syncwarp" loop 475 of rb1.conv2's 1,160 cycles per tile passed between
+        // the last commit and the next first MMA - two already-satisfied mbarrier waits cost ~95 cycles each - and
+        // the pipe drained every tile.
+        if (elect_one()) {
+            auto wait_tile = [&](int itw) {
+                mbar_wait(bar_acce + itw % C::NACC, ((itw / C::NACC) & 1) ^ 1);
+                mbar_wait(bar_full + itw % C::NSTAGE, (itw / C::NSTAGE) & 1);
+            };
+            int it = 0;
+            if ((int)blockIdx.x < nt) wait_tile(0);
+            for (int tile = blockIdx.x; tile < nt; tile += gridDim.x, ++it) {
+                const int s = it % C::NSTAGE;
+                const int acc = it % C::NACC;
+                const bool more = tile + (int)gridDim.x < nt;
+                TDM_TL(EPI, it, 3);
+                if constexpr (C::GK == 1 && TDM_GATHER_MODE != 0) fence_proxy_async_smem();   // cp.async (generic proxy) data -> async-proxy MMA reads
+                tc_fence_after_sync();
+                const uint64_t in_base = make_smem_desc(in_addr0 + (uint32_t)s * C::STAGE_BYTES, G::RT * 16, 128);
+                // rebuilt per tile on purpose: kept across the loop the 18+ weight descriptors live in vector registers
+                // and cost two R2UR each per tile; rebuilt from the uniform address they are one UIADD3.64 apiece
+                uint32_t w_addr_t = w_addr;
+                asm volatile("" : "+r"(w_addr_t));   // opaque: keeps the compiler from hoisting the descriptors out of the loop
+                const uint64_t w_base = make_smem_desc(w_addr_t, B_LBO, 128);
+                const uint64_t ws_base = make_smem_desc(w_addr_t + C::WCONV_BYTES, COUT * 16, 128);
+                const uint32_t d = tmem_u + acc * C::ACC_COLS;
+                if constexpr (KXC == 1) {
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
+                    for (int ky = 0; ky < 3; ++ky) {
+                        if (ky == 2 && more) wait_tile(it + 1);
 #pragma unroll
-                    for (int ks = 0; ks < CIN / 16; ++ks) {
-                        umma_bf16(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp) * 16),
-                                        desc_add(w_base, ((ky * C::NPL + 2 * ks) * 3 * COUT) * 16), idesc, (ky | ks) != 0);
+                        for (int ks = 0; ks < CIN / 16; ++ks) {
+                            umma_bf16(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp) * 16),
+                                      desc_add(w_base, ((ky * C::NPL + 2 * ks) * 3 * COUT) * 16), idesc, (ky | ks) != 0);
+                        }
                     }
-                }
-            } else if constexpr (KXC == 2) {
-                // kx = 0,1 share one N = 2*COUT MMA (columns [Z0 | Z1], A at the centre column); kx = 2 is a plain
-                // tap accumulated into Z1 with A one row further.  Same weight image as the triple schedule.
+                } else if constexpr (KXC == 2) {
+                    // kx = 0,1 share one N = 2*COUT MMA (columns [Z0 | Z1], A at the centre column); kx = 2 is a plain
+                    // tap accumulated into Z1 with A one row further.  Same weight image as the triple schedule.
 #pragma unroll
-                for (int ky = 0; ky < 3; ++ky) {
+                    for (int ky = 0; ky < 3; ++ky) {
+                        if (ky == 2 && more) wait_tile(it + 1);
 #pragma unroll
-                    for (int ks = 0; ks < CIN / 16; ++ks) {
-                        umma_bf16(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp) * 16),
-                                        desc_add(w_base, ((ky * C::NPL + 2 * ks) * 3 * COUT) * 16), idesc, (ky | ks) != 0);
-                        umma_bf16(d + COUT, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp + 1) * 16),
-                                        desc_add(w_base, ((ky * C::NPL + 2 * ks) * 3 * COUT + 2 * COUT) * 16), idesc_skip, 1u);
+                        for (int ks = 0; ks < CIN / 16; ++ks) {
+                            umma_bf16(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp) * 16),
+                                      desc_add(w_base, ((ky * C::NPL + 2 * ks) * 3 * COUT) * 16), idesc, (ky | ks) != 0);
+                            umma_bf16(d + COUT, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp + 1) * 16),
+                                      desc_add(w_base, ((ky * C::NPL + 2 * ks) * 3 * COUT + 2 * COUT) * 16), idesc_skip, 1u);
+                        }
                     }
-                }
-            } else {
+                } else {
 #pragma unroll
-                for (int tap = 0; tap < TAPS; ++tap) {
+                    for (int tap = 0; tap < TAPS; ++tap) {
 #ifdef TDM_DBG_TAPS
-                    if (tap >= TDM_DBG_TAPS) break;   // timing experiment only (wrong results)
+                        if (tap >= TDM_DBG_TAPS) break;   // timing experiment only (wrong results)
 #endif
-                    const int off = (TAPS == 1) ? 0 : (tap / 3 - 1) * G::Wp + (tap % 3 - 1);
+                        if (TAPS == 9 && tap == 6 && more) wait_tile(it + 1);
+                        const int off = (TAPS == 1) ? 0 : (tap / 3 - 1) * G::Wp + (tap % 3 - 1);
+#pragma unroll
+                        for (int ks = 0; ks < CIN / 16; ++ks) {
+                            umma_bf16(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + off) * 16),
+                                      desc_add(w_base, ((tap * C::NPL + 2 * ks) * COUT) * 16), idesc, (tap | ks) != 0);
+                        }
+                        if (tap == 0) TDM_TL(EPI, it, 9);
+                        if (tap == 2) TDM_TL(EPI, it, 10);
+                        if (tap == 5) TDM_TL(EPI, it, 11);
+                        if (tap == 8) TDM_TL(EPI, it, 12);
+                    }
+                    if constexpr (CIN2 > 0) {
+                        // the extra input's 1x1 convolution lands in the same accumulator (centre tap, its own weights)
+#pragma unroll
+                        for (int ks = 0; ks < CIN2 / 16; ++ks) {
+                            umma_bf16(d, desc_add(in_base, (C::NPL + 2 * ks) * (G::RT * 16) + G::HALO * 16),
+                                      desc_add(ws_base, ((2 * ks) * COUT) * 16), idesc, 1u);
+                        }
+                    }
+                }
+                if constexpr (SKIPG) {
 #pragma unroll
                     for (int ks = 0; ks < CIN / 16; ++ks) {
-                        umma_bf16(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + off) * 16),
-                                        desc_add(w_base, ((tap * C::NPL + 2 * ks) * COUT) * 16), idesc, (tap | ks) != 0);
+                        umma_bf16(d + C::NMAIN, desc_add(in_base, (2 * ks) * (G::RT * 16) + G::HALO * 16),
+                                  desc_add(ws_base, ((2 * ks) * COUT) * 16), idesc_skip, ks != 0);
                     }
                 }
-                if constexpr (CIN2 > 0) {
-                    // the extra input's 1x1 convolution lands in the same accumulator (centre tap, its own weights)
-#pragma unroll
-                    for (int ks = 0; ks < CIN2 / 16; ++ks) {
-                        umma_bf16(d, desc_add(in_base, (C::NPL + 2 * ks) * (G::RT * 16) + G::HALO * 16),
-                                        desc_add(ws_base, ((2 * ks) * COUT) * 16), idesc, 1u);
-                    }
-                }
+                umma_commit(bar_empty + s);   // smem stage reusable once these MMAs retire
+                umma_commit(bar_accf + acc);  // accumulator complete
+                TDM_TL(EPI, it, 13);
+                if (TAPS == 1 && more) wait_tile(it + 1);   // two MMAs per tile: nothing to hide the waits behind
             }
-            if constexpr (SKIPG) {
-#pragma unroll
-                for (int ks = 0; ks < CIN / 16; ++ks) {
-                    umma_bf16(d + C::NMAIN, desc_add(in_base, (2 * ks) * (G::RT * 16) + G::HALO * 16),
-                                    desc_add(ws_base, ((2 * ks) * COUT) * 16), idesc_skip, ks != 0);
-                }
-            }
-            umma_commit(bar_empty + s);   // smem stage reusable once these MMAs retire
-            umma_commit(bar_accf + acc);  // accumulator complete
-            }
-            __syncwarp();
-            TDM_TL(EPI, it, 4);
         }
+        __syncwarp();
     } else if (PROD != 0 && warp >= 2 + 4 * kHalves * C::NACC) {
         // ===== gather producers (PROD warps): planes 0..7 of the tile = nearest-x2 upsample of the 14x14 source.
         //       Warp w owns tiles it = w (mod PROD) entirely; lane = smem row.  Measured on B200 @16384 (kernel us):

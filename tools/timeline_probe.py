@@ -31,10 +31,11 @@ lib.tdm_debug_read_timeline.argtypes = [ctypes.c_void_p]
 lib.tdm_debug_read_timeline.restype = ctypes.c_int
 assert lib.tdm_debug_read_timeline(buf) == 0
 tl = [[buf[i * 16 + e] for e in range(16)] for i in range(96)]
-names = {8: "top", 2: "accfree", 3: "full", 4: "issued", 0: "p.empty", 5: "e.accfull", 7: "e.release", 6: "e.done"}
-print("tile " + " ".join(f"{names[e]:>10s}" for e in (8, 2, 3, 4, 0, 5, 7, 6)) + "   (cycles since the previous tile was issued)")
-for i in range(8, 40):
-    ref = tl[i - 1][4]
-    print(f"{i:4d} " + " ".join(f"{tl[i][e] - ref:10d}" for e in (8, 2, 3, 4, 0, 5, 7, 6)))
-d = [tl[i][4] - tl[i - 1][4] for i in range(8, 90)]
-print("mean cycles per tile (issue to issue):", sum(d) / len(d))
+names = {8: "top", 2: "accfree", 3: "full", 9: "mma2", 10: "mma6", 11: "mma12", 12: "mma18", 13: "commits", 4: "issued", 0: "p.empty", 5: "e.accfull", 7: "e.release", 6: "e.done"}
+ORDER = (3, 9, 10, 11, 12, 13, 0, 5, 7, 6)
+print("tile " + " ".join(f"{names[e]:>10s}" for e in ORDER) + "   (cycles since the previous tile's commits)")
+for i in range(8, 28):
+    ref = tl[i - 1][13]
+    print(f"{i:4d} " + " ".join(f"{tl[i][e] - ref:10d}" for e in ORDER))
+d = [tl[i][13] - tl[i - 1][13] for i in range(8, 90)]
+print("mean cycles per tile (commit to commit):", sum(d) / len(d))
