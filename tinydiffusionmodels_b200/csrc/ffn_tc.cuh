@@ -157,11 +157,12 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: whole warp, one elected lane issues (tc05.cuh: warp-convergent issue) =====
+        // ===== MMA issuer: one elected thread runs the whole issue loop (conv_tc.cuh) =====
         constexpr uint32_t idesc1 = make_idesc_bf16(128, kFfnC);
         constexpr uint32_t idesc2 = make_idesc_bf16(128, kFfnD);
         const uint64_t a_base = make_smem_desc(smem_u32(sA), 2048, 128);
         const uint64_t p_base = make_smem_desc(smem_u32(sP), 2048, 128);
+        if (elect_one()) {
         int kit = 0, ti = 0;
         auto g1 = [&](int cg) {   // cg: chunk counter across tiles (buffer cg&1, use index cg>>1)
             const int buf = cg & 1;
@@ -175,11 +176,11 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
                 const uint32_t acc_flag = kb != 0;
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                    umma_bf16_elect(t_acc1 + buf * kFfnC, desc_add(a_base, (kb * 8 + 2 * ks) * 2048), desc_add(b_base, (2 * ks) * 2048),
+                    umma_bf16(t_acc1 + buf * kFfnC, desc_add(a_base, (kb * 8 + 2 * ks) * 2048), desc_add(b_base, (2 * ks) * 2048),
                                     idesc1, ks != 0 ? 1u : acc_flag);
-                umma_commit_multicast_elect(bar_empty + s, kAll);
+                umma_commit_multicast(bar_empty + s, kAll);
             }
-            umma_commit_elect(bar_acc1_full + buf);
+            umma_commit(bar_acc1_full + buf);
         };
         for (int mt = cluster_id * kFfnCluster + (int)crank; mt < m_tiles; mt += n_clusters * kFfnCluster, ++ti) {
             mbar_wait(bar_a_full, ti & 1);
@@ -200,18 +201,20 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
                     const uint32_t acc_flag = (c | kb) != 0;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks)
-                        umma_bf16_elect(t_acc2, desc_add(p_base, (kb * 8 + 2 * ks) * 2048), desc_add(b_base, (2 * ks) * 4096), idesc2,
+                        umma_bf16(t_acc2, desc_add(p_base, (kb * 8 + 2 * ks) * 2048), desc_add(b_base, (2 * ks) * 4096), idesc2,
                                         ks != 0 ? 1u : acc_flag);
-                    umma_commit_multicast_elect(bar_empty + s, kAll);
+                    umma_commit_multicast(bar_empty + s, kAll);
                 }
-                umma_commit_elect(bar_p_empty);                 // P may be overwritten once these MMAs retire
-                if (c == kFfnChunks - 1) umma_commit_elect(bar_acc2_full);
+                umma_commit(bar_p_empty);                 // P may be overwritten once these MMAs retire
+                if (c == kFfnChunks - 1) umma_commit(bar_acc2_full);
                 if (c + 2 < kFfnChunks) {
                     g1(cg + 2);
-                    if (c + 2 == kFfnChunks - 1) umma_commit_elect(bar_a_empty);   // last G1 of the tile: A may be reloaded
+                    if (c + 2 == kFfnChunks - 1) umma_commit(bar_a_empty);   // last G1 of the tile: A may be reloaded
                 }
             }
         }
+        }
+        __syncwarp();
     } else {
         // ===== epilogue groups: group g converts chunks c = g (mod 2) and finishes columns [128g, 128g+128) of the tile =====
         const int q = warp & 3;

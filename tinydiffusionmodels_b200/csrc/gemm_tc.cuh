@@ -124,8 +124,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: whole warp, one elected lane issues (tc05.cuh: warp-convergent issue) =====
+        // ===== MMA issuer: one elected thread runs the whole issue loop (conv_tc.cuh: descriptors stay in uniform
+        //       registers, no per-tile re-convergence) =====
         constexpr uint32_t idesc = make_idesc_bf16(kBM, kBN);
+        if (elect_one()) {
         int kit = 0, it = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
             const int mt = item / a.nsplit, sp = item - mt * a.nsplit;
@@ -146,13 +148,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                     const uint32_t acc_flag = kb != 0;
 #pragma unroll
                     for (int ks = 0; ks < kBK / 16; ++ks)
-                        umma_bf16_elect(d, desc_add(a_base, (2 * ks) * (kBM * 16)), desc_add(b_base, (2 * ks) * (kBN * 16)), idesc,
+                        umma_bf16(d, desc_add(a_base, (2 * ks) * (kBM * 16)), desc_add(b_base, (2 * ks) * (kBN * 16)), idesc,
                                         ks != 0 ? 1u : acc_flag);
-                    umma_commit_elect(bar_empty + s);
+                    umma_commit(bar_empty + s);
                 }
-                umma_commit_elect(bar_accf + acc);
+                umma_commit(bar_accf + acc);
             }
         }
+        }
+        __syncwarp();
     } else {
         // ===== epilogue groups =====
         const int q = warp & 3;

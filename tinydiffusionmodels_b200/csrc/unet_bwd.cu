@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const WgradArgs a) {
     } else if (warp == 1) {
         // whole warp, one elected lane issues (tc05.cuh: warp-convergent issue)
         constexpr uint32_t idesc = make_idesc_bf16(64, CX, 1, 1);
+        if (elect_one()) {   // one thread runs the whole issue loop (conv_tc.cuh: uniform-register descriptors, no per-tile re-convergence)
         int it = 0;
         for (int tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
             const int s = it % C::NSTAGE;
@@ -150,12 +151,14 @@ __global__ void __launch_bounds__(192, 1) wgrad_tc_kernel(const WgradArgs a) {
                 const uint32_t d = tmem_base + (tap < 5 ? tap * CX : ((16u << 16) + (tap - 5) * CX));
 #pragma unroll
                 for (int ks = 0; ks < kTile / 16; ++ks)
-                    umma_bf16_elect(d, desc_add(g_base, ks * 256), desc_add(x_base, (G::HALO + off + ks * 16) * 16), idesc,
+                    umma_bf16(d, desc_add(g_base, ks * 256), desc_add(x_base, (G::HALO + off + ks * 16) * 16), idesc,
                                     ks != 0 ? 1u : acc_flag);
             }
-            umma_commit_elect(bar_empty + s);
+            umma_commit(bar_empty + s);
         }
-        if (it > 0) umma_commit_elect(bar_done);
+        if (it > 0) umma_commit(bar_done);
+        }
+        __syncwarp();
     } else if ((int)blockIdx.x < a.nt) {
         // ===== one final flush: TMEM -> atomics into the flat gradient =====
         mbar_wait(bar_done, 0);
@@ -286,6 +289,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_dup_kernel(const WgradArgs a) {
         // whole warp, one elected lane issues (tc05.cuh: warp-convergent issue)
         constexpr uint32_t idesc128 = make_idesc_bf16(128, CX, 1, 1);
         constexpr uint32_t idesc64 = make_idesc_bf16(64, CX, 1, 1);
+        if (elect_one()) {   // one thread runs the whole issue loop (conv_tc.cuh: uniform-register descriptors, no per-tile re-convergence)
         int it = 0;
         for (int tile = blockIdx.x; tile < a.nt; tile += gridDim.x, ++it) {
             const int s = it % C::NSTAGE;
@@ -302,20 +306,22 @@ __global__ void __launch_bounds__(192, 1) wgrad_dup_kernel(const WgradArgs a) {
 #pragma unroll
                 for (int ks = 0; ks < kTile / 16; ++ks) {
                     const uint64_t ad = desc_add(g_base, ks * 256);
-                    umma_bf16_elect(tmem_base + ky * CX, ad, desc_add(x_base, (G::HALO + off + ks * 16) * 16), idesc128,
+                    umma_bf16(tmem_base + ky * CX, ad, desc_add(x_base, (G::HALO + off + ks * 16) * 16), idesc128,
                                     ks != 0 ? 1u : acc_flag);
                     if constexpr (CG == 64) {
                         // kx = 2 from copy 0 with the X window moved two rows on; ky = 0,1 share columns
                         // 3*CX.. through the lane-16 interleave of M = 64 accumulators, ky = 2 sits at 4*CX
                         const uint32_t d2 = tmem_base + (ky < 2 ? 3 * CX + ((uint32_t)(ky * 16) << 16) : 4 * CX);
-                        umma_bf16_elect(d2, ad, desc_add(x_base, (G::HALO + off + 2 + ks * 16) * 16), idesc64,
+                        umma_bf16(d2, ad, desc_add(x_base, (G::HALO + off + 2 + ks * 16) * 16), idesc64,
                                         ks != 0 ? 1u : acc_flag);
                     }
                 }
             }
-            umma_commit_elect(bar_empty + s);
+            umma_commit(bar_empty + s);
         }
-        if (it > 0) umma_commit_elect(bar_done);
+        if (it > 0) umma_commit(bar_done);
+        }
+        __syncwarp();
     } else if ((int)blockIdx.x < a.nt) {
         mbar_wait(bar_done, 0);
         tc_fence_after_sync();
