@@ -108,12 +108,18 @@ struct ConvArgs {
 constexpr int kEpiGroups = 4;  // epilogue warp groups == TMEM accumulator stages (tiles in flight)
 constexpr int kHalves = 1;     // warps per TMEM lane quarter inside a group (2: alternate 16-channel chunks)
 
+// When the MMA thread takes the waits for tile i+1: 0 = at the top of tile i+1, 1 = blocking in the middle of tile
+// i's MMAs, 2 = probed (test_wait) in the middle of tile i, blocking at the top of tile i+1 only if the probe failed.
+#ifndef TDM_PREWAIT
+#define TDM_PREWAIT 2
+#endif
 #ifndef TDM_MAX_STAGES
 #define TDM_MAX_STAGES 4
 #endif
 constexpr int kBarBytes = 512;               // smem reserved for the mbarriers + the TMEM base slot
 constexpr int kMaxStages = TDM_MAX_STAGES;   // input ring depth cap (bytes in flight per SM = stages x tile bytes)
 constexpr int kGatherPlanes = 8;   // planes built by the gather producers when PROD > 0 (the 64 h3 channels)
+constexpr int kSoloSmem = 115 * 1024;   // > (228 KB - 2 x 1 KB reserved) / 2
 #ifndef TDM_GATHER_WARPS
 #define TDM_GATHER_WARPS 2
 #endif
@@ -155,7 +161,12 @@ struct ConvCfg {
                                    : (NACC * ACC_COLS <= 128) ? 128 : (NACC * ACC_COLS <= 256) ? 256 : 512;
     static_assert(NACC * ACC_COLS <= 512, "accumulators exceed TMEM");
     static_assert(NMAIN <= 256 && NMAIN % 16 == 0, "UMMA N");
-    static constexpr int SMEM_BYTES = W_BYTES + NSTAGE * STAGE_BYTES + PARAM_BYTES + XCH_BYTES + kBarBytes;
+    static constexpr int SMEM_USED = W_BYTES + NSTAGE * STAGE_BYTES + PARAM_BYTES + XCH_BYTES + kBarBytes;
+    // Requested size: more than half an SM's shared memory, so that two of these persistent CTAs can never share an
+    // SM.  Under programmatic dependent launch the next kernel's CTAs are placed as SMs free up one by one; a small
+    // kernel (rb1.conv2: 74 KB, 55 registers) would land twice on the first free SMs and leave others empty, and
+    // with static tile striding the doubled-up SMs then set the kernel's time (measured: +9 % per reverse step).
+    static constexpr int SMEM_BYTES = SMEM_USED > kSoloSmem ? SMEM_USED : kSoloSmem;
     static_assert((1 + 2 * NSTAGE + 2 * NGRP) * 8 + 8 <= kBarBytes && NGRP >= 1 && 64 + 128 * kHalves * NGRP + 32 * (PROD > 0 ? PROD : 0) <= 1024, "mbarrier block overflows its smem slot");
     // warp 0 producer, warp 1 MMA issuer, NACC groups of 4 epilogue warps, then the gather warps
     static constexpr int THREADS = 64 + 128 * kHalves * NACC + 32 * PROD;
@@ -351,12 +362,24 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * NGRP + 32 * PROD, 1) conv
                 mbar_wait(bar_acce + itw % C::NACC, ((itw / C::NACC) & 1) ^ 1);
                 mbar_wait(bar_full + itw % C::NSTAGE, (itw / C::NSTAGE) & 1);
             };
+            auto prewait = [&](int itw, bool more) -> bool {
+#if TDM_PREWAIT == 1
+                if (more) wait_tile(itw);
+                return true;
+#elif TDM_PREWAIT == 2
+                return more && mbar_test(bar_acce + itw % C::NACC, ((itw / C::NACC) & 1) ^ 1) &&
+                       mbar_test(bar_full + itw % C::NSTAGE, (itw / C::NSTAGE) & 1);
+#else
+                return false;
+#endif
+            };
             int it = 0;
-            if ((int)blockIdx.x < nt) wait_tile(0);
+            bool ready = false;
             for (int tile = blockIdx.x; tile < nt; tile += gridDim.x, ++it) {
                 const int s = it % C::NSTAGE;
                 const int acc = it % C::NACC;
                 const bool more = tile + (int)gridDim.x < nt;
+                if (!ready) wait_tile(it);
                 TDM_TL(EPI, it, 3);
                 if constexpr (C::GK == 1 && TDM_GATHER_MODE != 0) fence_proxy_async_smem();   // cp.async (generic proxy) data -> async-proxy MMA reads
                 tc_fence_after_sync();
@@ -371,7 +394,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * NGRP + 32 * PROD, 1) conv
                 if constexpr (KXC == 1) {
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
-                        if (ky == 2 && more) wait_tile(it + 1);
+                        if (ky == 2) ready = prewait(it + 1, more);
 #pragma unroll
                         for (int ks = 0; ks < CIN / 16; ++ks) {
                             umma_bf16(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp) * 16),
@@ -383,7 +406,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * NGRP + 32 * PROD, 1) conv
                     // tap accumulated into Z1 with A one row further.  Same weight image as the triple schedule.
 #pragma unroll
                     for (int ky = 0; ky < 3; ++ky) {
-                        if (ky == 2 && more) wait_tile(it + 1);
+                        if (ky == 2) ready = prewait(it + 1, more);
 #pragma unroll
                         for (int ks = 0; ks < CIN / 16; ++ks) {
                             umma_bf16(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp) * 16),
@@ -398,7 +421,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * NGRP + 32 * PROD, 1) conv
 #ifdef TDM_DBG_TAPS
                         if (tap >= TDM_DBG_TAPS) break;   // timing experiment only (wrong results)
 #endif
-                        if (TAPS == 9 && tap == 6 && more) wait_tile(it + 1);
+                        if (TAPS == 9 && tap == 6) ready = prewait(it + 1, more);
                         const int off = (TAPS == 1) ? 0 : (tap / 3 - 1) * G::Wp + (tap % 3 - 1);
 #pragma unroll
                         for (int ks = 0; ks < CIN / 16; ++ks) {
@@ -429,7 +452,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * NGRP + 32 * PROD, 1) conv
                 umma_commit(bar_empty + s);   // smem stage reusable once these MMAs retire
                 umma_commit(bar_accf + acc);  // accumulator complete
                 TDM_TL(EPI, it, 13);
-                if (TAPS == 1 && more) wait_tile(it + 1);   // two MMAs per tile: nothing to hide the waits behind
+                if (TAPS == 1) ready = false;   // two MMAs per tile: nothing to hide the waits behind
             }
         }
         __syncwarp();

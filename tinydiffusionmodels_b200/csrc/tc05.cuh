@@ -55,6 +55,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe of a phase (test_wait never suspends the thread).
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU box.
 // ~4e9 cycles ≈ 2 s at 1.9 GHz, far beyond any legitimate wait in these kernels.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {

@@ -73,7 +73,7 @@ struct WgradCfg {
     static constexpr int NCOLS = (TAPS == 9 ? 5 : 1) * CX;
     static constexpr int TMEM_COLS = NCOLS <= 32 ? 32 : NCOLS <= 64 ? 64 : NCOLS <= 128 ? 128 : NCOLS <= 256 ? 256 : 512;
     static_assert(NCOLS <= 512, "TMEM");
-    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 512;
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 512 > kSoloSmem ? NSTAGE * STAGE_BYTES + 512 : kSoloSmem;   // one CTA per SM (conv_tc.cuh)
     static constexpr int THREADS = 192;
 };
 
@@ -223,7 +223,7 @@ struct WgradDupCfg {
     static constexpr int NCOLS = 3 * CX + (CG == 64 ? 2 * CX : 0);
     static constexpr int TMEM_COLS = NCOLS <= 128 ? 128 : NCOLS <= 256 ? 256 : 512;
     static_assert(NCOLS <= 512, "TMEM");
-    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 512;
+    static constexpr int SMEM_BYTES = NSTAGE * STAGE_BYTES + 512 > kSoloSmem ? NSTAGE * STAGE_BYTES + 512 : kSoloSmem;   // one CTA per SM (conv_tc.cuh)
     static constexpr int THREADS = 192;
 };
 
