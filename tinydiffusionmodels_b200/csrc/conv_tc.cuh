@@ -619,7 +619,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * NGRP + 32 * PROD, 1) conv
             const int y = r - 1;
 
             float ts = 0.f;
-            if ((EPI == EPI_CONV1 || EPI == EPI_PLAIN_MASK) && valid) ts = (float)__ldg(a.t + b) / 1000.0f;
+            if ((EPI == EPI_CONV1 || EPI == EPI_PLAIN_MASK) && valid) ts = (float)(int)__ldg(a.t + b) / 1000.0f;   // via int32 (I2F.S64 is a slow-path conversion)
             uint32_t mw[EPI == EPI_PLAIN_MASK ? (COUT + 31) / 32 : 1];
             if constexpr (EPI == EPI_PLAIN_MASK) {
 #pragma unroll
