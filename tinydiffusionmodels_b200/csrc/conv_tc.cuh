@@ -337,7 +337,7 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * NGRP + 32 * PROD, 1) conv
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: the whole warp runs this loop convergently, one elected lane issues =====
+        // ===== MMA issuer: one elected lane of this warp runs the persistent issue loop =====
         constexpr uint32_t idesc = make_idesc_bf16(128, C::NMAIN);
         constexpr uint32_t idesc_skip = make_idesc_bf16(128, COUT);
         mbar_wait(bar_w, 0);
@@ -350,10 +350,11 @@ __global__ void __launch_bounds__(64 + 128 * kHalves * NGRP + 32 * PROD, 1) conv
         const uint32_t w_addr = smem_u32(s_w);
         const uint32_t in_addr0 = smem_u32(s_in);
         const uint32_t tmem_u = tmem_base;
-        // ONE elected thread runs the whole persistent issue loop.  The waits for tile i+1 (accumulator free, input
-        // full) are taken in the middle of tile i's MMAs, while the pipe is busy with what is already queued (a
-        // thread can run ~7 MMAs ahead), so nothing but the two commits sits between the last MMA of a tile and the
-        // first MMA of the next.  Measured with the in-kernel timeline (tools/timeline_probe.py): with a per-tile
+        // ONE elected thread runs the whole persistent issue loop.  The barriers of tile i+1 (accumulator free, input
+        // full) are probed in the middle of tile i's MMAs, while the pipe is busy with what is already queued (a
+        // thread can run ~7 MMAs ahead); when the probe succeeds nothing but the two commits sits between the last MMA
+        // of a tile and the first MMA of the next, when it fails the thread finishes tile i first and blocks at the
+        // top of tile i+1 (TDM_PREWAIT).  Measured with the in-kernel timeline (tools/timeline_probe.py): with a per-tile
         // "all lanes wait, elect, issue, __syncwarp" loop 475 of rb1.conv2's 1,160 cycles per tile passed between
         // the last commit and the next first MMA - two already-satisfied mbarrier waits cost ~95 cycles each - and
         // the pipe drained every tile.
