@@ -398,8 +398,25 @@ def bench_train(dev, rank, world, batch, barrier, steps: int = 30, warmup: int =
     trainer.step(x_dev)
     launches = _lib.launch_count() - n0
     flops = 386_506_496 * batch   # fwd+bwd per image
+    # device-resident input pipeline: one epoch of MNIST-sized uint8 data, shuffled and
+    # normalised on the device in batches of `batch` (1 B read + 4 B written per pixel)
+    from tinydiffusionmodels_b200.data import DeviceImages
+
+    ds = DeviceImages(torch.randint(0, 256, (60000, 28, 28), dtype=torch.uint8), dev)
+    for _ in ds.batches(batch, seed=1, epoch=0, max_batches=8):
+        pass
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in ds.batches(batch, seed=1, epoch=1):
+        pass
+    e1.record()
+    torch.cuda.synchronize()
+    ms_epoch = e0.elapsed_time(e1)
     return {
         "metric": "unet_train_images_per_sec", "unit": "images/s",
+        "input_pipeline": {"images_per_s": 60000 / (ms_epoch * 1e-3), "gb_per_s": 60000 * 784 * 5 / (ms_epoch * 1e-3) / 1e9,
+                           "what": f"one 60,000-image epoch: device randperm + gather/normalise kernel per batch of {batch}"},
         "value": world * batch * steps / (ms * 1e-3),
         "e2e": {"value": world * batch * steps / (ms_e2e * 1e-3), "unit": "images/s",
                 "h2d_bytes_per_step": batch * 784 * 4, "d2h_bytes_per_step": 4},

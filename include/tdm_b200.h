@@ -84,6 +84,23 @@ int tdm_randn_philox(float* out, int64_t batch, int64_t inner, uint64_t seed,
 /* (clamp(x,-1,1)+1)/2, src/mnist.py:194. n elements fp32, out may alias x. */
 int tdm_to_unit_range(const float* x, float* out, int64_t n, void* stream);
 
+/* Input pipeline: replaces the host-side DataLoader transform of src/mnist.py:139-147
+ * (torchvision ToTensor = uint8 -> fp32 / 255, then Normalize = (x - mean) / std) for a dataset that is
+ * resident on the device as uint8 rows of row_elems pixels (row_elems % 4 == 0).  out[i] = normalised
+ * images[index[i]] for i < n; index == NULL means rows 0..n-1.  Bit-identical to the reference transform.
+ * Indices must address rows of `images` (not checked on the device). */
+int tdm_u8_gather_normalize(const uint8_t* images, const int64_t* index, float* out, int64_t n,
+                            int64_t row_elems, float mean, float stdv, void* stream);
+
+/* Output step: replaces torchvision.utils.save_image's pixel work at src/mnist.py:194-199 / 116-119:
+ * optional (clamp(x,-1,1)+1)/2 (from_signed != 0), make_grid(nrow, padding, pad_value 0) of n single-channel
+ * h x w fp32 images (channel tripled; n == 1 -> the image itself, no border) and the conversion
+ * mul(255).add(0.5).clamp(0,255).to(uint8), written as an HWC uint8 array of the shape
+ * tdm_image_grid_shape reports (host call, no GPU needed).  PNG encoding stays on the host. */
+int tdm_image_grid_shape(int64_t n, int h, int w, int nrow, int padding, int* out_h, int* out_w);
+int tdm_image_grid_u8(const float* x, uint8_t* grid_hwc, int64_t n, int h, int w, int nrow, int padding,
+                      int from_signed, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * MNIST UNet (src/mnist.py:45-87), bf16 tcgen05 implicit-GEMM convolutions, fp32 accumulate
  * ------------------------------------------------------------------------------------------- */

@@ -110,6 +110,46 @@ def to_unit_range(x: torch.Tensor) -> torch.Tensor:
 
 
 # ---------------------------------------------------------------------------------------------
+# input transform and output step — the pixel work of the third-party torchvision calls at
+# src/mnist.py:141-144 (ToTensor, Normalize) and :116-119 / :196-199 (utils.save_image).
+# torchvision is unpinned in requirements.txt; this container has 0.26.0.  Restated from its published
+# algorithm (transforms/functional.py::to_tensor, _functional_tensor.py::normalize, utils.py::make_grid /
+# save_image) and pinned by tests/golden/io_golden.pt, which tests/golden/make_golden_io.py records by
+# calling torchvision itself exactly as the reference does.
+# ---------------------------------------------------------------------------------------------
+def normalize_u8(images_u8: torch.Tensor, index: torch.Tensor | None = None, mean: float = 0.5,
+                 std: float = 0.5) -> torch.Tensor:
+    """(n, H, W) uint8 -> (n, 1, H, W) fp32: ToTensor (uint8 -> fp32, true division by 255) then
+    Normalize((mean,), (std,)) = sub(mean).div(std) (src/mnist.py:141-144)."""
+    rows = images_u8 if index is None else images_u8[index]
+    x = rows.to(torch.float32).div(255).unsqueeze(1)
+    m = torch.as_tensor([mean], dtype=torch.float32).view(-1, 1, 1)
+    sd = torch.as_tensor([std], dtype=torch.float32).view(-1, 1, 1)
+    return x.sub(m).div(sd)
+
+
+def image_grid_u8(x01: torch.Tensor, nrow: int = 8, padding: int = 2) -> torch.Tensor:
+    """The HWC uint8 array save_image(x01, nrow=nrow) passes to PIL (src/mnist.py:116-119,196-199): make_grid
+    (single channel tripled, pad_value 0, a lone image returned without border), then
+    mul(255).add(0.5).clamp(0,255) truncated to uint8."""
+    t = x01.to(torch.float32)
+    if t.size(1) == 1:
+        t = torch.cat((t, t, t), 1)
+    if t.size(0) == 1:
+        grid = t[0]
+    else:
+        nmaps = t.size(0)
+        xmaps = min(nrow, nmaps)
+        ymaps = int(math.ceil(float(nmaps) / xmaps))
+        height, width = t.size(2) + padding, t.size(3) + padding
+        grid = t.new_zeros((3, height * ymaps + padding, width * xmaps + padding))
+        for k in range(nmaps):
+            y, x = divmod(k, xmaps)
+            grid[:, y * height + padding: (y + 1) * height, x * width + padding: (x + 1) * width] = t[k]
+    return grid.mul(255).add(0.5).clamp(0, 255).permute(1, 2, 0).to(torch.uint8).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
 # training step — src/mnist.py:153-159 with AdamW defaults (torch.optim.AdamW(lr=1e-3))
 # ---------------------------------------------------------------------------------------------
 def mnist_loss_and_grads(sd: dict, x0: torch.Tensor, t: torch.Tensor, noise: torch.Tensor, tab: dict):

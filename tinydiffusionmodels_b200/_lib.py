@@ -28,6 +28,9 @@ SIGNATURES: dict[str, tuple] = {
     "tdm_timestep_advance": (c_int, [_P, c_int64, c_int64, _P]),
     "tdm_randn_philox": (c_int, [_P, c_int64, c_int64, c_uint64, c_uint64, c_uint32, _P]),
     "tdm_to_unit_range": (c_int, [_P, _P, c_int64, _P]),
+    "tdm_u8_gather_normalize": (c_int, [_P, _P, _P, c_int64, c_int64, c_float, c_float, _P]),
+    "tdm_image_grid_shape": (c_int, [c_int64, c_int, c_int, c_int, c_int, _P, _P]),
+    "tdm_image_grid_u8": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, c_int, c_int, _P]),
     "tdm_unet_param_count": (c_int64, []),
     "tdm_unet_wpack_bytes": (c_int64, []),
     "tdm_unet_workspace_bytes": (c_int64, [c_int64, c_int]),

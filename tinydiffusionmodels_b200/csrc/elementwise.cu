@@ -149,6 +149,71 @@ __global__ void add_i64_kernel(int64_t* __restrict__ t, int64_t n, int64_t delta
     if (i < n) t[i] += delta;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Input pipeline (src/mnist.py:139-147): the reference's DataLoader applies torchvision's
+// ToTensor (uint8 -> fp32, true division by 255) and Normalize ((x - mean) / std) to each image on
+// the host.  Here the uint8 dataset is resident in HBM and one pass gathers a (shuffled) batch and
+// normalises it.  A uint8 pixel has 256 possible values, so every block first builds the 256
+// results with the reference's exact op sequence (*_rn: no contraction) and the per-element work is
+// one shared-memory lookup: 1 byte read + 4 bytes written per pixel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+u8_gather_normalize_kernel(const uint8_t* __restrict__ images, const int64_t* __restrict__ index,
+                           float* __restrict__ out, int64_t n, int row_elems, float mean, float stdv) {
+    __shared__ float lut[256];
+    lut[threadIdx.x] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)threadIdx.x, 255.f), mean), stdv);
+    __syncthreads();
+    for (int64_t r = blockIdx.x; r < n; r += gridDim.x) {
+        const int64_t src = index ? index[r] : r;
+        const uint8_t* in = images + src * row_elems;
+        float* o = out + r * row_elems;
+        for (int j = threadIdx.x * 4; j < row_elems; j += 256 * 4) {
+            const uint32_t v = __ldcs(reinterpret_cast<const unsigned int*>(in + j));
+            float4 f;
+            f.x = lut[v & 0xff];
+            f.y = lut[(v >> 8) & 0xff];
+            f.z = lut[(v >> 16) & 0xff];
+            f.w = lut[v >> 24];
+            *reinterpret_cast<float4*>(o + j) = f;   // default policy: the training step reads it next
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Output step (src/mnist.py:194-199): (clamp(x,-1,1)+1)/2, torchvision.utils.save_image's make_grid
+// (single channel tripled, `padding` zero pixels around every image, nrow images per row) and its
+// float -> uint8 conversion mul(255).add_(0.5).clamp_(0,255).to(uint8), written as the HWC uint8
+// array PIL encodes.  One thread per grid pixel; only the uint8 grid crosses PCIe.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+image_grid_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ grid, int n, int h, int w,
+                     int xmaps, int padding, int gh, int gw, int from_signed) {
+    const int px = blockIdx.x * 256 + threadIdx.x;
+    if (px >= gh * gw) return;
+    const int gy = px / gw, gx = px - gy * gw;
+    float v = 0.f;   // make_grid's pad_value
+    bool inside = false;
+    int k = 0, iy = gy, ix = gx;
+    if (n == 1) {
+        inside = true;   // make_grid returns a single image as it is, without a border
+    } else {
+        const int ch = h + padding, cw = w + padding;
+        const int cy = gy / ch, cx = gx / cw;
+        iy = gy - cy * ch - padding;
+        ix = gx - cx * cw - padding;
+        k = cy * xmaps + cx;
+        inside = iy >= 0 && ix >= 0 && cx < xmaps && k < n;
+    }
+    if (inside) {
+        v = x[((int64_t)k * h + iy) * w + ix];
+        if (from_signed) v = __fdiv_rn(__fadd_rn(fminf(fmaxf(v, -1.f), 1.f), 1.f), 2.f);
+    }
+    v = fminf(fmaxf(__fadd_rn(__fmul_rn(v, 255.f), 0.5f), 0.f), 255.f);
+    const uint8_t b = (uint8_t)(int)v;   // truncation, like Tensor.to(torch.uint8)
+    uint8_t* o = grid + (int64_t)px * 3;
+    o[0] = b; o[1] = b; o[2] = b;
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline dim3 grid_for(int64_t batch, int64_t inner4) {
     return dim3((unsigned)batch, (unsigned)((inner4 + kChunk4 - 1) / kChunk4));
@@ -237,6 +302,52 @@ extern "C" int tdm_to_unit_range(const float* x, float* out, int64_t n, void* st
     unit_range_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0,
                         (cudaStream_t)stream>>>(x, out, n);
     TDM_CHECK_LAUNCH("tdm_to_unit_range");
+    return TDM_OK;
+}
+
+extern "C" int tdm_u8_gather_normalize(const uint8_t* images, const int64_t* index, float* out, int64_t n,
+                                       int64_t row_elems, float mean, float stdv, void* stream) {
+    TDM_CHECK_ARG(n >= 0 && row_elems > 0 && row_elems % 4 == 0 && row_elems <= (1 << 24),
+                  "tdm_u8_gather_normalize: row_elems must be a positive multiple of 4");
+    TDM_CHECK_ARG(stdv != 0.f, "tdm_u8_gather_normalize: std must be non-zero");
+    if (n == 0) return TDM_OK;
+    TDM_CHECK_ARG(images && out, "tdm_u8_gather_normalize: null pointer");
+    TDM_CHECK_ARG((reinterpret_cast<uintptr_t>(images) & 3u) == 0 && aligned16(out),
+                  "tdm_u8_gather_normalize: images must be 4-byte and out 16-byte aligned");
+    const int64_t cap = (int64_t)num_sms() * 8;
+    const unsigned grid = (unsigned)(n < cap ? n : cap);
+    u8_gather_normalize_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(images, index, out, n, (int)row_elems, mean, stdv);
+    TDM_CHECK_LAUNCH("tdm_u8_gather_normalize");
+    return TDM_OK;
+}
+
+extern "C" int tdm_image_grid_shape(int64_t n, int h, int w, int nrow, int padding, int* out_h, int* out_w) {
+    TDM_CHECK_ARG(n >= 1 && h >= 1 && w >= 1 && nrow >= 1 && padding >= 0 && out_h && out_w,
+                  "tdm_image_grid_shape: bad arguments");
+    if (n == 1) {
+        *out_h = h;
+        *out_w = w;
+        return TDM_OK;
+    }
+    const int64_t xmaps = nrow < n ? nrow : n;
+    const int64_t ymaps = (n + xmaps - 1) / xmaps;
+    const int64_t gh = (h + padding) * ymaps + padding, gw = (w + padding) * xmaps + padding;
+    TDM_CHECK_ARG(gh * gw < (1LL << 30), "tdm_image_grid_shape: grid too large");
+    *out_h = (int)gh;
+    *out_w = (int)gw;
+    return TDM_OK;
+}
+
+extern "C" int tdm_image_grid_u8(const float* x, uint8_t* grid_hwc, int64_t n, int h, int w, int nrow,
+                                 int padding, int from_signed, void* stream) {
+    int gh = 0, gw = 0;
+    if (int rc = tdm_image_grid_shape(n, h, w, nrow, padding, &gh, &gw)) return rc;
+    TDM_CHECK_ARG(x && grid_hwc, "tdm_image_grid_u8: null pointer");
+    const int xmaps = (int)(nrow < n ? nrow : n);
+    const int64_t px = (int64_t)gh * gw;
+    image_grid_u8_kernel<<<(unsigned)((px + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        x, grid_hwc, (int)n, h, w, xmaps, padding, gh, gw, from_signed);
+    TDM_CHECK_LAUNCH("tdm_image_grid_u8");
     return TDM_OK;
 }
 

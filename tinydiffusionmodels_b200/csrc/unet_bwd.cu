@@ -1021,17 +1021,12 @@ static int unet_backward_impl(const uint8_t* wp, const float* x, const int64_t* 
     c.red_plain = dflat + P::rb1_tb; c.red_ts = dflat + P::rb1_tw; c.red_masked = dflat + P::rb1_c1b;
     if ((rc = launch_conv<28, 32, 32, EPI_PLAIN_MASK, false, 9, KX::rb1c2>(c, st, "dgrad_rb1_c2"))) return rc;
     {
-        // exactly one resident wave: the blocks stride statically over the tiles, so a partial second wave (4 blocks
-        // per SM requested, 3 resident at 80 registers) would cost a whole extra block time
-        static int per_sm = 0;
-        if (!per_sm) {
-            TDM_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rb1_wgrad_kernel, 256, 0));
-            if (per_sm < 1) per_sm = 1;
-#ifdef TDM_RB1W_BLOCKS_PER_SM
-            per_sm = TDM_RB1W_BLOCKS_PER_SM;   // A/B aid
-#endif
-        }
-        const int grid = nt28 < per_sm * num_sms() ? nt28 : per_sm * num_sms();
+        // 4 blocks per SM requested although 3 are resident (80 registers): sizing the grid to exactly one resident
+        // wave (3 x SMs) is 1-2 % faster when every SM takes its 3 blocks at once, but under programmatic dependent
+        // launch the step time turned bimodal (presumably some SMs start with fewer than 3 and the left-over blocks
+        // then cost a whole extra block time:
+        // 0.644 / 0.707 ms training steps at B = 512); shorter blocks in 1.33 waves are the robust choice.
+        const int grid = nt28 < 4 * num_sms() ? nt28 : 4 * num_sms();
         launch_pdl(rb1_wgrad_kernel, dim3(grid), dim3(256), 0, st, ws + L.gh28, ws + L.go28, L.ps28, x, dflat + P::rb1_c1w,
                                                dflat + P::rb1_sw, B, nt28);
         TDM_CHECK_LAUNCH("rb1_wgrad");

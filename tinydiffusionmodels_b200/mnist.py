@@ -19,7 +19,6 @@ from __future__ import annotations
 import argparse
 import math
 import os
-import tempfile
 
 import torch
 import torch.nn as nn
@@ -204,19 +203,24 @@ def sample_loop(model: SimpleUNet, x: torch.Tensor, *, seed: int, sample_offset:
     return x
 
 
-def _save_grid(x01: torch.Tensor, samples_dir, filename: str):
-    """PNG grid through torchvision + utils.save_samples (I/O; same file names as the reference)."""
-    from torchvision import utils as tvutils
+def _encode_png(grid_u8_hwc) -> bytes:
+    """PNG bytes of an HWC uint8 array, through PIL exactly as torchvision.utils.save_image does."""
+    import io
 
-    nrow = int(math.sqrt(x01.shape[0]))
-    with tempfile.NamedTemporaryFile(suffix=".png", delete=False) as tmp:
-        tmp_name = tmp.name
-    try:
-        tvutils.save_image(x01, tmp_name, nrow=nrow)
-        with open(tmp_name, "rb") as f:
-            data = f.read()
-    finally:
-        os.unlink(tmp_name)
+    from PIL import Image
+
+    buf = io.BytesIO()
+    Image.fromarray(grid_u8_hwc).save(buf, format="png")
+    return buf.getvalue()
+
+
+def _save_grid(x: torch.Tensor, samples_dir, filename: str, *, from_signed: bool = False):
+    """The reference's ``save_image(x, nrow=int(sqrt(n)))`` + ``save_samples`` (src/mnist.py:116-124,196-209):
+    the clamp / grid / uint8 conversion runs on the device (``tdm_image_grid_u8``), only the uint8 grid is
+    copied to the host, PIL encodes it in memory (no temp file) - same bytes, same file names."""
+    nrow = int(math.sqrt(x.shape[0]))
+    grid = ops.image_grid_u8(x, nrow=nrow, padding=2, from_signed=from_signed)
+    data = _encode_png(grid.cpu().numpy())
     path = f"{samples_dir}/{filename}" if isinstance(samples_dir, str) else samples_dir / filename
     save_samples(data, path, mode="wb")
     return path
@@ -225,8 +229,7 @@ def _save_grid(x01: torch.Tensor, samples_dir, filename: str):
 def _generate(model, device, n_samples: int, seed: int | None = None) -> torch.Tensor:
     seed = _fresh_seed() if seed is None else seed
     x = ops.randn((n_samples, 1, 28, 28), device, seed=seed, sample_offset=0, stream_id=0)
-    x = sample_loop(model, x, seed=seed)
-    return ops.to_unit_range(x)
+    return sample_loop(model, x, seed=seed)   # x_0 in [-1, 1] (unclamped); the output step maps it to [0, 1]
 
 
 def sample_images(model: nn.Module, device: str, epoch: int, n_samples: int = 25, outdir: str = "samples"):
@@ -236,7 +239,7 @@ def sample_images(model: nn.Module, device: str, epoch: int, n_samples: int = 25
     try:
         with torch.no_grad():
             x = _generate(model, device, n_samples)
-            path = _save_grid(x.cpu(), samples_dir, f"epoch_{epoch:03d}.png")
+            path = _save_grid(x, samples_dir, f"epoch_{epoch:03d}.png", from_signed=True)
     finally:
         model.train(was_training)
     print(f"[epoch {epoch}] saved samples to {path}")
@@ -248,7 +251,7 @@ def sample(model: nn.Module, device: str, n_samples=25, ckpt_path="ckpt.pth", ou
     samples_dir = get_samples_dir(outdir)
     with torch.no_grad():
         x = _generate(model, device, n_samples)
-        path = _save_grid(x.cpu(), samples_dir, "samples.png")
+        path = _save_grid(x, samples_dir, "samples.png", from_signed=True)
     print(f"Saved samples to {path}")
 
 
@@ -288,17 +291,18 @@ def _batches(device, batch_size, synthetic, steps_per_epoch, epoch):
         for _ in range(steps_per_epoch or 469):
             yield torch.rand(batch_size, 1, 28, 28, device=device, generator=g) * 2 - 1
         return
-    from torch.utils.data import DataLoader
-    from torchvision import datasets, transforms
+    from .data import mnist_on_device
 
-    ds = datasets.MNIST("./data", train=True, download=True,
-                        transform=transforms.Compose([transforms.ToTensor(),
-                                                      transforms.Normalize((0.5,), (0.5,))]))
-    dl = DataLoader(ds, batch_size=batch_size, shuffle=True, num_workers=4, pin_memory=True)
-    for i, (x, _) in enumerate(dl):
-        if steps_per_epoch is not None and i >= steps_per_epoch:
-            break
-        yield x.to(device, non_blocking=True)
+    # the reference's DataLoader + ToTensor + Normalize((0.5,), (0.5,)) (src/mnist.py:139-147), with the uint8
+    # training set resident on the device: a permutation per epoch, one gather + normalise kernel per batch
+    dev = torch.empty(0, device=device).device   # resolved ("cuda" -> "cuda:0")
+    if dev not in _datasets:
+        _datasets[dev] = mnist_on_device(dev)
+    # like the reference's DataLoader, the visiting order follows torch's global seed (torch.manual_seed)
+    yield from _datasets[dev].batches(batch_size, seed=torch.initial_seed(), epoch=epoch, max_batches=steps_per_epoch)
+
+
+_datasets: dict = {}
 
 
 # ---------------------------------------------------------------------------------------------

@@ -100,3 +100,63 @@ def to_unit_range(x: torch.Tensor) -> torch.Tensor:
     _lib.check(_lib.load().tdm_to_unit_range(x.data_ptr(), out.data_ptr(), x.numel(),
                                              _lib.stream_ptr(x.device)), "tdm_to_unit_range")
     return out
+
+
+def normalize_u8(images: torch.Tensor, index: torch.Tensor | None = None, mean: float = 0.5,
+                 std: float = 0.5, out: torch.Tensor | None = None, *, check_index: bool = True) -> torch.Tensor:
+    """Gather rows of a device-resident uint8 image set and apply the reference's input transform,
+    ToTensor + Normalize((mean,), (std,)) (src/mnist.py:141-144), bit-identically.
+
+    ``images`` (N, H, W) or (N, 1, H, W) uint8 with H*W % 4 == 0; ``index`` int64 rows to take (``None`` =
+    all rows in order; range-checked on the host unless ``check_index=False``, which avoids the device
+    sync when the caller built the indices itself).  Returns (n, 1, H, W) fp32.
+    """
+    _need_cuda(images, index, out)
+    if images.dtype != torch.uint8:
+        raise ValueError("normalize_u8 expects a uint8 image tensor")
+    if images.dim() == 4 and images.shape[1] == 1:
+        images = images[:, 0]
+    if images.dim() != 3:
+        raise ValueError("normalize_u8 expects (N, H, W) or (N, 1, H, W) images")
+    images = images.contiguous()
+    total, h, w = images.shape
+    if index is not None:
+        index = _t64(index)
+        if check_index and index.numel() and (int(index.min()) < 0 or int(index.max()) >= total):
+            raise IndexError("normalize_u8: index out of range")
+    n = total if index is None else index.numel()
+    if out is None:
+        out = torch.empty((n, 1, h, w), dtype=torch.float32, device=images.device)
+    elif out.dtype != torch.float32 or out.numel() != n * h * w or not out.is_contiguous():
+        raise ValueError("normalize_u8: out must be a contiguous fp32 tensor of n*H*W elements")
+    _lib.check(_lib.load().tdm_u8_gather_normalize(images.data_ptr(), _lib.ptr(index), out.data_ptr(), n, h * w,
+                                                   float(mean), float(std), _lib.stream_ptr(images.device)),
+               "tdm_u8_gather_normalize")
+    return out
+
+
+def image_grid_shape(n: int, h: int, w: int, nrow: int, padding: int = 2) -> tuple[int, int]:
+    """(height, width) of the grid torchvision's make_grid builds for n single-channel h x w images."""
+    import ctypes
+
+    gh, gw = ctypes.c_int(), ctypes.c_int()
+    _lib.check(_lib.load().tdm_image_grid_shape(n, h, w, nrow, padding, ctypes.byref(gh), ctypes.byref(gw)),
+               "tdm_image_grid_shape")
+    return gh.value, gw.value
+
+
+def image_grid_u8(x: torch.Tensor, nrow: int = 8, padding: int = 2, *, from_signed: bool = False) -> torch.Tensor:
+    """The uint8 HWC array ``torchvision.utils.save_image(x, nrow=nrow, padding=padding)`` hands to PIL
+    (src/mnist.py:116-119,194-199), built on the device.  ``x`` (n, 1, H, W) fp32 in [0, 1]; with
+    ``from_signed`` the map (clamp(x,-1,1)+1)/2 of src/mnist.py:194 is applied first."""
+    _need_cuda(x)
+    if x.dim() != 4 or x.shape[1] != 1 or x.shape[0] < 1:
+        raise ValueError("image_grid_u8 expects a non-empty (n, 1, H, W) tensor")
+    x = _f32c(x)
+    n, _, h, w = x.shape
+    gh, gw = image_grid_shape(n, h, w, nrow, padding)
+    grid = torch.empty((gh, gw, 3), dtype=torch.uint8, device=x.device)
+    _lib.check(_lib.load().tdm_image_grid_u8(x.data_ptr(), grid.data_ptr(), n, h, w, nrow, padding,
+                                             1 if from_signed else 0, _lib.stream_ptr(x.device)),
+               "tdm_image_grid_u8")
+    return grid
