@@ -49,21 +49,61 @@ class DeviceImages:
         return torch.randperm(len(self), device=self.device, generator=g)
 
     def batches(self, batch_size: int, *, seed: int = 0, epoch: int = 0, shuffle: bool = True,
-                max_batches: int | None = None) -> Iterator[torch.Tensor]:
-        """Yield (b, 1, H, W) fp32 batches of one epoch."""
-        if batch_size < 1:
-            raise ValueError("batch_size must be positive")
+                max_batches: int | None = None, rank: int | None = None, world: int | None = None
+                ) -> Iterator[torch.Tensor]:
+        """Yield this rank's (b, 1, H, W) fp32 batches of one epoch (``batch_size`` images per rank and step).
+
+        Data parallel: every rank slices the same permutation (rank 0's, broadcast once per epoch) and takes its own
+        part of each global batch of ``world * batch_size`` images (``rank_batch_slices``), so the ranks see disjoint
+        data and take the same number of steps; no image data ever crosses a GPU boundary.  ``rank`` / ``world`` default to the
+        initialised ``torch.distributed`` group, else to a single process.
+        """
+        if rank is None or world is None:
+            rank, world = _rank_world()
         order = self.permutation(seed, epoch) if shuffle else None
-        n = len(self)
-        for i, start in enumerate(range(0, n, batch_size)):
+        if order is not None and world > 1:
+            import torch.distributed as dist
+
+            if dist.is_available() and dist.is_initialized():
+                dist.broadcast(order, src=0)   # once per epoch, 8 B per image: every rank slices rank 0's order
+        for i, (lo, hi) in enumerate(rank_batch_slices(len(self), batch_size, rank, world)):
             if max_batches is not None and i >= max_batches:
                 return
-            stop = min(start + batch_size, n)
-            if order is None:
-                idx = torch.arange(start, stop, device=self.device)
-            else:
-                idx = order[start:stop]
+            idx = torch.arange(lo, hi, device=self.device) if order is None else order[lo:hi]
             yield ops.normalize_u8(self.images, idx, self.mean, self.std, check_index=False)
+
+
+def rank_batch_slices(n: int, batch_size: int, rank: int = 0, world: int = 1) -> list[tuple[int, int]]:
+    """Positions [lo, hi) of the epoch's visiting order that ``rank`` takes at each step.
+
+    Step k covers the global batch [k*G, min((k+1)*G, n)) with G = world * batch_size, split contiguously over the
+    ranks (``dist.shard_range``: sizes differ by at most one).  The last, partial global batch is kept like the
+    reference's ``drop_last=False`` (src/mnist.py:146) unless it holds fewer images than there are ranks - every
+    rank must take part in every step's gradient exchange, so a step some rank would enter empty-handed is dropped.
+    """
+    from .dist import shard_range
+
+    if batch_size < 1:
+        raise ValueError("batch_size must be positive")
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world {rank}/{world}")
+    out = []
+    g = batch_size * world
+    for start in range(0, n, g):
+        size = min(g, n - start)
+        if size < world:
+            break
+        lo, hi = shard_range(size, rank, world)
+        out.append((start + lo, start + hi))
+    return out
+
+
+def _rank_world() -> tuple[int, int]:
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
 
 
 def mnist_on_device(device, root: str = "./data", train: bool = True, download: bool = True) -> DeviceImages:

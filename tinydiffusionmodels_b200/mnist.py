@@ -287,7 +287,9 @@ def train(model: nn.Module, device: str, epochs: int = 5, batch_size: int = 128,
 
 def _batches(device, batch_size, synthetic, steps_per_epoch, epoch):
     if synthetic:
-        g = torch.Generator(device=device).manual_seed(1234 + epoch)
+        from .data import _rank_world
+
+        g = torch.Generator(device=device).manual_seed(1234 + epoch + 7919 * _rank_world()[0])   # ranks see different data
         for _ in range(steps_per_epoch or 469):
             yield torch.rand(batch_size, 1, 28, 28, device=device, generator=g) * 2 - 1
         return
