@@ -90,7 +90,35 @@ def test_checkpoint_round_trip_with_reference_format(tmp_path):
     m.load_state_dict(load_checkpoint(str(src), "cpu"))
     dst = tmp_path / "ours.pth"
     save_checkpoint(m.state_dict(), str(dst))
-    back = torch.load(dst, map_location="cpu")
+    back = torch.load(dst, map_location="cpu", weights_only=True)
     assert list(back.keys()) == list(ref_sd.keys())
     for k, v in ref_sd.items():
         assert back[k].dtype == v.dtype and back[k].shape == v.shape and torch.equal(back[k], v), k
+
+
+def test_text_checkpoint_round_trip_with_reference_format(tmp_path):
+    """src/shakespeare.py:311-341 writes {'diffusion_model', 'rounding_fn', ['embedding_fn'], 'epoch', ...}; the
+    state_dicts in text_golden.pt come from the real reference classes.  Such a file loads into our modules and
+    the same dictionary layout written from our modules carries identical keys, shapes, dtypes and values."""
+    from tinydiffusionmodels_b200.shakespeare import LearnedEmbedding, LearnedRounding, TinyTransformer
+    from tinydiffusionmodels_b200.utils import load_checkpoint, save_checkpoint
+
+    gt = torch.load(GOLD / "text_golden.pt", weights_only=False)
+    ref_ckpt = {"diffusion_model": gt["model_sd"], "rounding_fn": gt["rounding_sd"], "embedding_fn": gt["emb_sd"],
+                "epoch": 3, "final_training": True}
+    src = tmp_path / "text_ref.pth"
+    torch.save(ref_ckpt, src)
+    ck = load_checkpoint(str(src), "cpu")
+    model, rnd, emb = TinyTransformer(gt["dim"]), LearnedRounding(gt["dim"], gt["V"]), LearnedEmbedding(gt["V"], gt["dim"])
+    model.load_state_dict(ck["diffusion_model"])
+    rnd.load_state_dict(ck["rounding_fn"])
+    emb.load_state_dict(ck["embedding_fn"])
+    dst = tmp_path / "text_ours.pth"
+    save_checkpoint({"diffusion_model": model.state_dict(), "rounding_fn": rnd.state_dict(),
+                     "embedding_fn": emb.state_dict(), "epoch": 3, "final_training": True}, str(dst))
+    back = torch.load(dst, map_location="cpu", weights_only=True)   # plain tensors only: nothing of the module is pickled
+    assert list(back) == list(ref_ckpt) and back["epoch"] == 3 and back["final_training"] is True
+    for part in ("diffusion_model", "rounding_fn", "embedding_fn"):
+        assert list(back[part]) == list(ref_ckpt[part])
+        for k, v in ref_ckpt[part].items():
+            assert back[part][k].dtype == v.dtype and back[part][k].shape == v.shape and torch.equal(back[part][k], v), k

@@ -97,14 +97,14 @@ class TinyTransformer(nn.Module):
         self.dim = dim
         self._engines: dict = {}
 
-    def _version(self) -> int:
+    def _param_version(self) -> int:
         return sum(p._version for p in self.parameters())
 
     def engine(self, batch: int, seq_len: int) -> TextEngine:
         p0 = next(self.parameters())
         if not p0.is_cuda:
             raise _lib.TdmError("TinyTransformer runs on CUDA only (no CPU fallback): call .to('cuda')")
-        key = (batch, seq_len, p0.device, self._version(), p0.data_ptr())
+        key = (batch, seq_len, p0.device, self._param_version(), p0.data_ptr())
         if key not in self._engines:
             self._engines.clear()
             self._engines[key] = TextEngine(self.state_dict(), p0.device, batch, seq_len)
