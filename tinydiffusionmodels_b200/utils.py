@@ -59,13 +59,11 @@ def upload_to_gcs(local_path: str, gcs_path: str) -> None:
 @contextlib.contextmanager
 def _scratch_file(suffix: str, mode: str = "w+b"):
     """A named temp file that is always unlinked, whatever happens inside the block."""
-    tmp = tempfile.NamedTemporaryFile(mode=mode, suffix=suffix, delete=False)
-    try:
-        yield tmp
-    finally:
-        with contextlib.suppress(Exception):
-            tmp.close()
-        os.unlink(tmp.name)
+    with tempfile.NamedTemporaryFile(mode=mode, suffix=suffix, delete=False) as tmp:
+        try:
+            yield tmp
+        finally:
+            os.unlink(tmp.name)   # still open here: unlinking an open file is fine on POSIX
 
 
 def load_checkpoint(ckpt_path: PathLike, device: str) -> dict:
