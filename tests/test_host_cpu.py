@@ -84,3 +84,81 @@ def test_cli_parsers_keep_reference_flags(capsys):
     for mod in (m, t):
         with pytest.raises(TdmError):
             mod.main([])          # no CUDA device -> loud failure, never a silent CPU path
+
+
+def test_text_training_schedules_known_values():
+    """Host-side schedules of src/shakespeare.py:159-172 (pure functions; the text training loop itself is out of
+    scope): warm-up ramp, cosine decay, eta_min floor, linear rounding-weight decay."""
+    from src.shakespeare import dynamic_rounding_weight_schedule, get_cosine_schedule_with_warmup
+
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=2.0)
+    sched = get_cosine_schedule_with_warmup(opt, num_warmup_steps=4, num_training_steps=12, eta_min=0.1)
+    lrs = []
+    for _ in range(13):
+        lrs.append(opt.param_groups[0]["lr"])
+        opt.step()
+        sched.step()
+    assert lrs[:5] == [0.0, 0.5, 1.0, 1.5, 2.0]
+    assert lrs[8] == pytest.approx(2.0 * 0.5) and lrs[12] == pytest.approx(2.0 * 0.1)      # midpoint, floor
+    assert all(a >= b for a, b in zip(lrs[4:], lrs[5:]))
+    assert dynamic_rounding_weight_schedule(0, 10) == 1.0
+    assert dynamic_rounding_weight_schedule(10, 10) == pytest.approx(0.1)
+    assert dynamic_rounding_weight_schedule(5, 10, 2.0, 1.0) == 1.5
+
+
+def test_eval_mode_restores_the_previous_mode():
+    from src.mnist import eval_mode
+
+    m = torch.nn.Dropout()
+    m.train()
+    with eval_mode(m):
+        assert not m.training
+    assert m.training
+    m.eval()
+    with pytest.raises(RuntimeError):
+        with eval_mode(m):
+            raise RuntimeError("boom")
+    assert not m.training
+
+
+@pytest.mark.reference
+def test_public_surface_matches_the_live_reference():
+    """Every public function / class / constant the reference's two modules define exists here under the same name,
+    with the same positional parameters and defaults (ours may add keyword parameters after them).  Not mirrored
+    on purpose: the text training loop and its data preparation."""
+    import inspect
+    import math
+
+    from tests.golden.make_golden import import_reference
+
+    ref_m, ref_t = import_reference()
+    import src.mnist as our_m
+    import src.shakespeare as our_t
+
+    not_mirrored = {"shakespeare": {"train", "load_text_dataset", "tokenize_corpus"}, "mnist": set()}
+    third_party = ("torch", "tqdm", "transformers", "datasets", "math", "os", "pathlib", "typing", "google",
+                   "argparse", "contextlib", "torchvision")
+    for name, ref, ours in (("mnist", ref_m, our_m), ("shakespeare", ref_t, our_t)):
+        for n, obj in vars(ref).items():
+            if n.startswith("_") or inspect.ismodule(obj) or n in not_mirrored[name]:
+                continue
+            if (inspect.isfunction(obj) or inspect.isclass(obj)) and obj.__module__.split(".")[0] in third_party:
+                continue
+            assert hasattr(ours, n), f"src.{name}.{n} is missing"
+            if inspect.isfunction(obj):
+                want = [(p.name, p.default) for p in inspect.signature(obj).parameters.values()]
+                got = [(p.name, p.default) for p in inspect.signature(getattr(ours, n)).parameters.values()]
+                assert got[:len(want)] == want, f"src.{name}.{n}: {got} vs {want}"
+                assert all(d is not inspect.Parameter.empty for _, d in got[len(want):]), n   # extras are optional
+    # the two schedule helpers agree exactly with the reference over a whole run
+    for warm, total, eta in ((0, 10, 0), (5, 50, 0.0), (100, 1000, 0.05), (7, 7, 0)):
+        o1 = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1e-3)
+        o2 = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1e-3)
+        s1 = ref_t.get_cosine_schedule_with_warmup(o1, warm, total, eta)
+        s2 = our_t.get_cosine_schedule_with_warmup(o2, warm, total, eta)
+        for _ in range(total + 3):
+            assert o1.param_groups[0]["lr"] == o2.param_groups[0]["lr"]
+            o1.step(); o2.step(); s1.step(); s2.step()
+    for e in range(0, 11):
+        assert ref_t.dynamic_rounding_weight_schedule(e, 10, 0.7, 0.05) == our_t.dynamic_rounding_weight_schedule(e, 10, 0.7, 0.05)
+    assert math.isclose(our_t.dynamic_rounding_weight_schedule(3, 10), 0.73)

@@ -17,6 +17,7 @@ There is no CPU path: tensors must live on a CUDA device and the library must be
 from __future__ import annotations
 
 import argparse
+import contextlib
 import math
 import os
 
@@ -203,6 +204,17 @@ def sample_loop(model: SimpleUNet, x: torch.Tensor, *, seed: int, sample_offset:
     return x
 
 
+@contextlib.contextmanager
+def eval_mode(module: nn.Module):
+    """Run a block with ``module`` in eval mode and put its previous mode back (ref src/mnist.py:89-96)."""
+    was_training = module.training
+    module.eval()
+    try:
+        yield
+    finally:
+        module.train(was_training)
+
+
 def _encode_png(grid_u8_hwc) -> bytes:
     """PNG bytes of an HWC uint8 array, through PIL exactly as torchvision.utils.save_image does."""
     import io
@@ -234,14 +246,9 @@ def _generate(model, device, n_samples: int, seed: int | None = None) -> torch.T
 
 def sample_images(model: nn.Module, device: str, epoch: int, n_samples: int = 25, outdir: str = "samples"):
     samples_dir = get_samples_dir(outdir)
-    was_training = model.training
-    model.eval()
-    try:
-        with torch.no_grad():
-            x = _generate(model, device, n_samples)
-            path = _save_grid(x, samples_dir, f"epoch_{epoch:03d}.png", from_signed=True)
-    finally:
-        model.train(was_training)
+    with eval_mode(model), torch.no_grad():
+        x = _generate(model, device, n_samples)
+        path = _save_grid(x, samples_dir, f"epoch_{epoch:03d}.png", from_signed=True)
     print(f"[epoch {epoch}] saved samples to {path}")
 
 

@@ -15,6 +15,7 @@ party (transformers) and stays a torch module.
 from __future__ import annotations
 
 import argparse
+import math
 import os
 from pathlib import Path
 
@@ -27,6 +28,29 @@ from .text_engine import Rounder, TextEngine
 from .utils import get_samples_dir, load_checkpoint, save_samples
 
 HF_TOKEN = os.getenv("HF_TOKEN")
+
+
+# ---- host-side training schedules (ref src/shakespeare.py:159-172) ---------------------------------------------
+# The text *training* loop is not part of this path; these two pure functions of it are, because
+# code written against the reference imports them and they cost nothing to keep identical.
+def get_cosine_schedule_with_warmup(optimizer, num_warmup_steps, num_training_steps, eta_min=0):
+    """``LambdaLR`` factor: linear ramp 0 -> 1 over the warm-up steps, then half a cosine down to ``eta_min``."""
+    warm = float(max(1, num_warmup_steps))
+    span = float(max(1, num_training_steps - num_warmup_steps))
+
+    def factor(step):
+        if step < num_warmup_steps:
+            return float(step) / warm
+        progress = float(step - num_warmup_steps) / span
+        return max(eta_min, 0.5 * (1.0 + math.cos(math.pi * progress)))
+
+    return torch.optim.lr_scheduler.LambdaLR(optimizer, factor)
+
+
+def dynamic_rounding_weight_schedule(epoch, total_epochs, initial_weight=1.0, final_weight=0.1):
+    """Weight of the rounding (cross-entropy) loss, interpolated linearly over the epochs."""
+    progress = epoch / total_epochs
+    return initial_weight * (1 - progress) + final_weight * progress
 T = 1_000
 _tables = make_schedule(T)
 betas = _tables.betas
