@@ -150,6 +150,11 @@ def test_public_surface_matches_the_live_reference():
                 got = [(p.name, p.default) for p in inspect.signature(getattr(ours, n)).parameters.values()]
                 assert got[:len(want)] == want, f"src.{name}.{n}: {got} vs {want}"
                 assert all(d is not inspect.Parameter.empty for _, d in got[len(want):]), n   # extras are optional
+            if inspect.isclass(obj):
+                for meth in ("__init__", "forward"):
+                    want = [(p.name, p.default) for p in inspect.signature(getattr(obj, meth)).parameters.values()]
+                    got = [(p.name, p.default) for p in inspect.signature(getattr(getattr(ours, n), meth)).parameters.values()]
+                    assert got[:len(want)] == want, f"src.{name}.{n}.{meth}: {got} vs {want}"
     # the two schedule helpers agree exactly with the reference over a whole run
     for warm, total, eta in ((0, 10, 0), (5, 50, 0.0), (100, 1000, 0.05), (7, 7, 0)):
         o1 = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1e-3)
