@@ -51,3 +51,26 @@ def test_product_package_never_imports_the_oracle():
         for f in (ROOT / base).rglob("*.py"):
             text = f.read_text()
             assert "import oracle" not in text and "from oracle" not in text, f
+
+
+def test_tensor_core_kernels_carry_tcgen05_and_bulk_copy_sass():
+    """Static proof that the hot kernels are tcgen05 / TMEM / TMA-engine code and not a SIMT or mma.sync stand-in:
+    every convolution, weight-gradient, GEMM, FFN and attention kernel in the built library issues UTCHMMA
+    (tcgen05.mma), reads its accumulator with LDTM (tcgen05.ld) and is fed by UBLKCP (cp.async.bulk)."""
+    import shutil
+    import sys
+    from pathlib import Path
+
+    if not (shutil.which("cuobjdump") and shutil.which("c++filt")):
+        pytest.skip("cuobjdump / c++filt not on PATH")
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    from sass_mnemonics import kernel_mnemonics
+
+    table = kernel_mnemonics()
+    hot = {n: c for n, c in table.items()
+           if n.split("<")[0] in ("conv3x3_tc_kernel", "wgrad_dup_kernel", "wgrad_tc_kernel", "gemm_tc_kernel",
+                                  "ffn_tc_kernel", "attn_tc_kernel")}
+    assert len(hot) >= 30
+    for name, c in hot.items():
+        assert c["UTCHMMA"] > 0 and c["LDTM"] > 0 and c["UBLKCP"] > 0 and c["UTCBAR"] > 0, (name, dict(c))
+    assert not any("HMMA." in n for n in table)      # sanity: names are kernels, not instructions
