@@ -219,14 +219,15 @@ def run_ours(args) -> None:
             graph.replay()
         _lib.check(lib.tdm_to_unit_range(x.data_ptr(), out01.data_ptr(), x.numel(), _lib.stream_ptr(dev)), "unit")
 
+    x_e2e = torch.empty_like(x)
+
     def trajectory_e2e():
-        """Host x_T -> device, T reverse steps, [0,1] images -> host."""
-        x.copy_(host_in, non_blocking=True)
-        t_buf.fill_(T_STEPS - 1)
-        for _ in range(T_STEPS):
-            graph.replay()
-        _lib.check(lib.tdm_to_unit_range(x.data_ptr(), out01.data_ptr(), x.numel(), _lib.stream_ptr(dev)), "unit")
-        host_out.copy_(out01, non_blocking=True)
+        """The call a user makes (tinydiffusionmodels_b200.mnist.sample_loop, the loop of src/mnist.py:190-194) on
+        host data: pinned x_T -> device, T reverse steps through the public API (it keeps the captured step per
+        (model, batch, seed) and replays it), clamp + [0,1] map, images -> pinned host memory."""
+        x_e2e.copy_(host_in, non_blocking=True)
+        sample_loop(model, x_e2e, seed=seed, sample_offset=offset)
+        host_out.copy_(ops.to_unit_range(x_e2e), non_blocking=True)
 
     def barrier():
         if world > 1:
@@ -305,10 +306,19 @@ def run_ours(args) -> None:
         "step_dram_bytes": step_traffic, "step_hbm_frac": step_hbm_frac,
     }
 
+    peaks_all = {"hbm_gbs": float(peaks["hbm_gbs"]), "tf_sustained": peak_tf, "source": peak_src}
+    # ---- BASELINE.json configs[2]: the batch sweep (and configs[0]'s batch 64), bounded to a few reverse steps ----
+    sweep = None if args.no_extras else bench_sweep(model, dev, seed, offset, world)
+    # ---- the reference's own eager PyTorch path on this B200 ----
+    gpu_eager = None if (args.no_extras or rank != 0) else bench_gpu_eager(dev, (64, B))
     # ---- secondary metric: UNet train images/s (BASELINE.json configs[1]), data-parallel ------
-    train = bench_train(dev, rank, world, args.train_batch, barrier)
+    train = bench_train(dev, rank, world, args.train_batch, barrier, peaks_all)
+    # BASELINE.json configs[1] as written: global batch 512 over 8 GPUs = 64 images per GPU
+    train64 = None if args.no_extras else bench_train(dev, rank, world, 64, barrier, peaks_all, pipeline=False)
     # ---- secondary metric: Shakespeare sampler sequences/s (BASELINE.json configs[3], [4]) -----
-    text = bench_text(dev, rank, world, args.text_batch, barrier) if not args.no_text else None
+    text = bench_text(dev, rank, world, args.text_batch, barrier, peaks_all) if not args.no_text else None
+    text2048 = (bench_text(dev, rank, world, max(64, args.text_batch // 4), barrier, peaks_all, dim=2048)
+                if not (args.no_text or args.no_extras) else None)
 
     if rank != 0:
         if world > 1:
@@ -321,6 +331,14 @@ def run_ours(args) -> None:
         sec_per_rstep, cores = cpu_reverse_steps(64, 20, warm=3)
         cpu_baseline = {"value": 64 / (sec_per_rstep * T_STEPS), "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "20 of 1000 reverse steps at batch 64 (oracle port of src/mnist.py:167-180), extrapolated x50"}
+        if not args.no_extras:
+            train["cpu_baseline"] = cpu_train_baseline(cores)
+            if train64 is not None:
+                train64["cpu_baseline"] = train["cpu_baseline"]
+            if text is not None:
+                text["cpu_baseline"] = cpu_text_baseline(cores, 256)
+            if text2048 is not None:
+                text2048["cpu_baseline"] = cpu_text_baseline(cores, 2048)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -340,14 +358,174 @@ def run_ours(args) -> None:
         "cpu_baseline": cpu_baseline,
         "clocks": clocks,
         "train": train,
+        "train_global512_per8": train64,
         "text": text,
+        "text_dim2048": text2048,
+        "sweep": sweep,
+        "gpu_eager_baseline": gpu_eager,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def bench_train(dev, rank, world, batch, barrier, steps: int = 30, warmup: int = 5) -> dict:
+def _event_ms(torch, fn, n: int) -> float:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def bench_sweep(model, dev, seed, offset, world, sizes=(64, 1024, 4096, 16384, 65536, 262144)) -> dict:
+    """BASELINE.json configs[0] (batch 64) and configs[2] (1K-256K samples per GPU): graph-replayed reverse steps
+    through the same engine, a BOUNDED number of steps per size (the full T=1000 trajectory at 256K samples alone
+    would take a minute); samples/s = samples / (1000 x measured ms per reverse step).  Sizes above the engine's
+    chunk (mnist.SAMPLE_CHUNK) run as sequential chunks on one workspace, exactly as sample_loop does."""
+    import torch
+
+    from tinydiffusionmodels_b200 import _lib
+    from tinydiffusionmodels_b200.mnist import SAMPLE_CHUNK
+
+    lib = _lib.load()
+    out = {}
+    for n in sizes:
+        chunk = min(n, SAMPLE_CHUNK)
+        nchunks = (n + chunk - 1) // chunk
+        eng = model.engine(chunk)
+        eng._prep(chunk)
+        x = torch.randn(chunk, 1, 28, 28, device=dev)
+        t = torch.full((chunk,), T_STEPS - 1, dtype=torch.int64, device=dev)
+
+        def one():
+            eng.p_sample(x, t, None, out=x, seed=seed, sample_offset=offset)
+            _lib.check(lib.tdm_timestep_advance(t.data_ptr(), chunk, -1, _lib.stream_ptr(dev)), "advance")
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            one()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            one()
+        reps = 200 if n <= 1024 else 40 if n <= 16384 else 12
+        for _ in range(5):
+            g.replay()
+        t.fill_(T_STEPS - 1)
+        ms = _event_ms(torch, g.replay, reps) * nchunks
+        out[str(n)] = {"samples_per_s": world * n / (ms * 1e-3 * T_STEPS), "ms_per_reverse_step": ms,
+                       "reverse_steps_timed": reps, "chunks": nchunks}
+        del g, x, t
+    out["note"] = ("per GPU; x world GPUs (weak scaling, no collective); bounded sample of the T=1000 trajectory: "
+                   "graph-replayed reverse steps, extrapolated x1000")
+    return out
+
+
+def bench_gpu_eager(dev, batches) -> dict:
+    """The reference's own path on this B200 (src/mnist.py:224-233 picks `cuda`): the oracle port of p_sample - the
+    same ATen/cuDNN ops the reference dispatches - run eagerly on the GPU, in fp32 (TF32 off), with TF32 convolutions,
+    and under bf16 autocast.  A baseline leg like cpu_baseline: never the product path."""
+    import torch
+    from oracle import ddpm_oracle as O
+    from tests.helpers import random_unet_state_dict
+
+    sd = {k: v.to(dev) for k, v in random_unet_state_dict(0).items()}
+    tab = {k: (v.to(dev) if hasattr(v, "to") else v) for k, v in O.make_tables().items()}
+    res = {}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for b in batches:
+            x = torch.randn(b, 1, 28, 28, device=dev)
+            z = torch.randn_like(x)
+            t = torch.full((b,), 500, dtype=torch.long, device=dev)
+            row = {}
+            for mode in ("fp32", "tf32", "bf16_autocast"):
+                torch.backends.cudnn.allow_tf32 = mode != "fp32"
+                torch.backends.cuda.matmul.allow_tf32 = mode != "fp32"
+
+                def step():
+                    with torch.no_grad():
+                        if mode == "bf16_autocast":
+                            with torch.autocast("cuda", dtype=torch.bfloat16):
+                                eps = O.unet_forward(sd, x, t)
+                            return O.reverse_step(x, eps.float(), t, z, tab)
+                        return O.mnist_p_sample(sd, x, t, z, tab)
+
+                for _ in range(3):
+                    step()
+                torch.cuda.synchronize()
+                ms = _event_ms(torch, step, 10 if b > 1024 else 50)
+                row[mode] = {"ms_per_reverse_step": ms, "samples_per_s": b / (ms * 1e-3 * T_STEPS)}
+            res[str(b)] = row
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    res["note"] = ("PyTorch eager (cuDNN/ATen) on the same B200, oracle port of src/mnist.py:167-180 including the "
+                   "reference's per-step host sync on `t[0] == 0`; 10-50 reverse steps timed with CUDA events, extrapolated x1000")
+    return res
+
+
+def cpu_train_baseline(cores: int) -> dict:
+    """Reference inner training step (src/mnist.py:153-159) on the host cores: oracle loss + autograd + AdamW, B=512."""
+    import torch
+    from oracle import ddpm_oracle as O
+    from tests.helpers import random_unet_state_dict
+
+    torch.set_num_threads(cores)
+    sd = random_unet_state_dict(0)
+    tab = O.make_tables()
+    g = torch.Generator().manual_seed(0)
+    b = 512
+    x0 = torch.rand(b, 1, 28, 28, generator=g) * 2 - 1
+    flat = {k: (v.clone(), torch.zeros_like(v), torch.zeros_like(v)) for k, v in sd.items()}
+
+    def step(k):
+        t = torch.randint(0, T_STEPS, (b,), generator=g)
+        noise = torch.randn(b, 1, 28, 28, generator=g)
+        cur = {n: p for n, (p, _, _) in flat.items()}
+        _, grads = O.mnist_loss_and_grads(cur, x0, t, noise, tab)
+        for n, (p, m, v) in flat.items():
+            flat[n] = O.adamw_step(p, grads[n], m, v, k)
+
+    step(1)
+    t0 = time.perf_counter()
+    n = 3
+    for k in range(n):
+        step(k + 2)
+    dt = (time.perf_counter() - t0) / n
+    return {"value": b / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{n} optimizer steps at batch {b} after 1 warm-up (oracle port of src/mnist.py:153-159: q_sample, UNet, MSE, backward, AdamW)"}
+
+
+def cpu_text_baseline(cores: int, dim: int) -> dict:
+    """Reference text reverse step (src/shakespeare.py:343-352) on the host cores, n=5, L=64 (the reference's sampling
+    job), bounded to a few of the 1000 steps."""
+    import torch
+    from oracle import ddpm_oracle as O
+    from tinydiffusionmodels_b200.shakespeare import TinyTransformer
+
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone() for k, v in TinyTransformer(dim).state_dict().items()}
+    tab = O.make_tables()
+    n, L = 5, 64
+    x = torch.randn(n, L, dim)
+    nsteps = 20 if dim == 256 else 5
+    with torch.no_grad():
+        for i in range(2):
+            x = O.text_p_sample(sd, x, torch.full((n,), 999 - i, dtype=torch.long), torch.randn_like(x), tab)
+        t0 = time.perf_counter()
+        for i in range(nsteps):
+            x = O.text_p_sample(sd, x, torch.full((n,), 997 - i, dtype=torch.long), torch.randn_like(x), tab)
+        dt = (time.perf_counter() - t0) / nsteps
+    return {"value": n / (dt * T_STEPS), "unit": "sequences/s", "cores": cores, "kind": "port",
+            "sample": f"{nsteps} of 1000 reverse steps at n={n}, L={L}, dim={dim} (oracle port of src/shakespeare.py:343-352), "
+                      f"extrapolated; rounding not included"}
+
+
+def bench_train(dev, rank, world, batch, barrier, peaks, steps: int = 30, warmup: int = 5, pipeline: bool = True) -> dict:
     """UNet DDPM training step (src/mnist.py:153-159) on synthetic U(-1,1) images, `batch` per GPU,
     gradients summed inside the optimizer kernel over peer-mapped buffers when world > 1 (NCCL all-reduce if the
     ranks cannot map each other).  Device-resident and host-fed variants."""
@@ -402,21 +580,29 @@ def bench_train(dev, rank, world, batch, barrier, steps: int = 30, warmup: int =
     # normalised on the device in batches of `batch` (1 B read + 4 B written per pixel)
     from tinydiffusionmodels_b200.data import DeviceImages
 
-    ds = DeviceImages(torch.randint(0, 256, (60000, 28, 28), dtype=torch.uint8), dev)
-    for _ in ds.batches(batch, seed=1, epoch=0, max_batches=8):
-        pass
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in ds.batches(batch, seed=1, epoch=1):
-        pass
-    e1.record()
-    torch.cuda.synchronize()
-    ms_epoch = e0.elapsed_time(e1)
+    input_pipeline = None
+    if pipeline:
+        ds = DeviceImages(torch.randint(0, 256, (60000, 28, 28), dtype=torch.uint8), dev)
+        for _ in ds.batches(batch, seed=1, epoch=0, max_batches=8, rank=0, world=1):
+            pass
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in ds.batches(batch, seed=1, epoch=1, rank=0, world=1):
+            pass
+        e1.record()
+        torch.cuda.synchronize()
+        ms_epoch = e0.elapsed_time(e1)
+        input_pipeline = {"images_per_s": 60000 / (ms_epoch * 1e-3), "gb_per_s": 60000 * 784 * 5 / (ms_epoch * 1e-3) / 1e9,
+                          "what": f"one 60,000-image epoch: device randperm + gather/normalise kernel per batch of {batch}"}
+    tf = flops / (ms / steps * 1e-3) / 1e12
     return {
         "metric": "unet_train_images_per_sec", "unit": "images/s",
-        "input_pipeline": {"images_per_s": 60000 / (ms_epoch * 1e-3), "gb_per_s": 60000 * 784 * 5 / (ms_epoch * 1e-3) / 1e9,
-                           "what": f"one 60,000-image epoch: device randperm + gather/normalise kernel per batch of {batch}"},
+        "input_pipeline": input_pipeline,
+        "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": tf / peaks["tf_sustained"], "traffic": None,
+                     "what": "whole training step (34 launches): 386,506,496 FLOP/image fwd+bwd (BASELINE.md section 3) / "
+                             "step time, against the sustained bf16 peak"},
         "value": world * batch * steps / (ms * 1e-3),
         "e2e": {"value": world * batch * steps / (ms_e2e * 1e-3), "unit": "images/s",
                 "h2d_bytes_per_step": batch * 784 * 4, "d2h_bytes_per_step": 4},
@@ -431,7 +617,7 @@ def bench_train(dev, rank, world, batch, barrier, steps: int = 30, warmup: int =
     }
 
 
-def bench_text(dev, rank, world, batch, barrier, rsteps: int = 100) -> dict:
+def bench_text(dev, rank, world, batch, barrier, peaks, rsteps: int = 100, dim: int = 256, vocab: int = 256_000) -> dict:
     """Shakespeare embedding-space sampler (src/shakespeare.py:355-426): TinyTransformer(256), L=64,
     `batch` sequences per GPU.  Times `rsteps` graph-replayed reverse steps (of the T=1000 loop) and
     the learned-rounding argmax at V=256,000; sequences/s = batch / (1000*step + rounding)."""
@@ -443,7 +629,9 @@ def bench_text(dev, rank, world, batch, barrier, rsteps: int = 100) -> dict:
     from tinydiffusionmodels_b200.text_engine import Rounder
 
     torch.manual_seed(0)
-    dim, L, V = 256, 64, 256_000
+    L, V = 64, vocab
+    if dim != 256:
+        rsteps = 30
     model = TinyTransformer(dim).to(dev).eval()
     eng = model.engine(batch, L)
     x = torch.randn(batch, L, dim, device=dev)
@@ -496,11 +684,23 @@ def bench_text(dev, rank, world, batch, barrier, rsteps: int = 100) -> dict:
     tot = torch.tensor([1000 * ms_step + ms_round], device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    flop_tok = 8_060_928
+    flop_tok = 8_060_928 if dim == 256 else 3 * (8 * dim * dim + 4 * L * dim + 8 * 2048 * dim)
+    den_tf = flop_tok * L * batch / (ms_step * 1e-3) / 1e12
+    rnd_tf = 2.0 * dim * V * L * batch / (ms_round * 1e-3) / 1e12
+    mix_bytes = batch * V * 4 + (dim * V * 2)                 # fp32 AR logits once + the bf16 rounding matrix once
+    mix_gbs = mix_bytes / (ms_mix * 1e-3) / 1e9
     return {
+        "roofline": {"bound": "tensor", "achieved": den_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": den_tf / peaks["tf_sustained"], "traffic": None,
+                     "what": "denoiser reverse step: algorithmic FLOP/token-step (BASELINE.md section 3) x tokens / step time",
+                     "rounding": {"bound": "tensor", "achieved": rnd_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                                  "frac": rnd_tf / peaks["tf_sustained"], "what": f"2*dim*V FLOP/token, {L * batch} tokens, V={V}"},
+                     "guided_mix": {"bound": "hbm", "achieved": mix_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                    "frac": mix_gbs / peaks["hbm_gbs"],
+                                    "what": f"one position of guided_generate at {batch} sequences: fp32 AR logits ({batch}xV) + bf16 W (VxD) read once"}},
         "metric": "shakespeare_sequences_per_sec_T1000", "unit": "sequences/s",
         "value": world * batch / (float(tot.item()) * 1e-3),
-        "config": {"workload": f"TinyTransformer(dim=256, depth 3, 4 heads), L=64, {batch} sequences per GPU, "
+        "config": {"workload": f"TinyTransformer(dim={dim}, depth 3, 4 heads), L=64, {batch} sequences per GPU, "
                                f"T=1000 reverse steps + learned rounding argmax over V={V}; random-init weights"},
         "ms_per_reverse_step": ms_step, "reverse_steps_timed": rsteps, "ms_rounding": ms_round,
         "denoiser_tflops": flop_tok * L * batch / (ms_step * 1e-3) / 1e12,
@@ -519,6 +719,8 @@ def main():
     ap.add_argument("--train-batch", type=int, default=512, help="training images per GPU per step")
     ap.add_argument("--text-batch", type=int, default=512, help="text sequences per GPU (secondary metric)")
     ap.add_argument("--no-text", action="store_true", help="skip the text secondary metric")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sweep / eager-PyTorch / dim-2048 / 64-per-GPU training legs and their CPU baselines")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -258,6 +258,19 @@ int tdm_round_argmax(const float* x_rows, int64_t rows, int dim, const void* w_p
                      int64_t ar_ld, float alpha, float temperature, int64_t* out_idx, float* out_val,
                      void* workspace, int64_t workspace_bytes, void* stream);
 
+/* LearnedRounding.forward (src/shakespeare.py:93-102): out_logits[r][v] = x_r . W_v + bias_v as fp32, row-major
+ * with leading dimension out_ld >= vocab (cosine=1: x_r . E_v / |x_r| with a pre-normalised table, bias = NULL).
+ * Same operands and workspace (tdm_round_workspace_bytes) as tdm_round_argmax; the samplers never call this -
+ * they fuse the GEMM with the argmax - it exists for callers that want the logits themselves (training losses). */
+int tdm_linear_logits(const float* x_rows, int64_t rows, int dim, const void* w_planes, int64_t vocab,
+                      int64_t vocab_padded, const float* bias, int cosine, float* out_logits, int64_t out_ld,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
+/* LearnedEmbedding.forward (src/shakespeare.py:71-80): out_rows[i][:] = table[ids[i]][:] (fp32, dim % 4 == 0).
+ * An id outside [0, vocab) writes a zero row and sets *bad_flag (device int, nullable) to 1. */
+int tdm_embedding_gather(const float* table, int64_t vocab, int dim, const int64_t* ids, int64_t n,
+                         float* out_rows, int* bad_flag, void* stream);
+
 /* Measurement aid (bench.py roofline): one fused p_sample with CUDA events recorded on `stream`
  * between its nine launches; SYNCHRONISES on the last event and writes the nine per-kernel
  * durations in milliseconds to host_ms9 (order: rb1.conv1, rb1.conv2, avgpool, rb2.conv1,

@@ -96,6 +96,7 @@ def test_rank_batch_slices_partition_every_global_batch():
                 assert all(hi > lo for lo, hi in spans)                    # nobody enters a step empty-handed
                 assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))  # contiguous, disjoint
                 assert max(hi - lo for lo, hi in spans) <= bs
+                assert len({hi - lo for lo, hi in spans}) == 1             # equal local batches: equal-weight mean, disjoint noise keys
                 covered.append((spans[0][0], spans[-1][1]))
             assert covered[0][0] == 0 and all(a[1] == b[0] for a, b in zip(covered, covered[1:]))
             assert n - covered[-1][1] < world                              # only a < world remainder is dropped

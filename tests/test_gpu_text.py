@@ -190,3 +190,60 @@ def test_guided_generate(cuda, learned):
         upto = int(low[0]) if len(low) else L
         assert torch.equal(got[bi, :upto], ref[bi, :upto]), f"sequence {bi} diverges before position {upto}"
     print("exact prefix lengths ok; full-sequence agreement", float((got == ref).float().mean()))
+
+
+# ---- the two module forwards the samplers never call (ref src/shakespeare.py:71-80, 93-102) ------------------------
+@pytest.mark.parametrize("vocab", [8192, 5000, 257])
+def test_learned_rounding_forward_returns_logits(cuda, vocab):
+    """LearnedRounding.forward = decoder(x): fp32 logits from the tcgen05 GEMM (bf16 products, fp32 accumulation).
+    Tolerance: |x.w| error <= 2^-8 * sum|x_i w_i| (two bf16 roundings per product); asserted as max-abs <= 0.08
+    (the margin the token tests use) and rel-rms <= 5e-3 against the fp32 oracle, the oracle itself pinned to the
+    reference's own logits by tests/test_oracle.py (golden `learned_logits`)."""
+    torch.manual_seed(7)
+    dim = 256
+    rounding = LearnedRounding(dim, vocab)
+    x = torch.randn(3, 17, dim) * 4                      # 51 rows: a partial 128-row tile
+    ref = O.learned_logits(x, rounding.decoder.weight.detach(), rounding.decoder.bias.detach())
+    with torch.no_grad():
+        got = rounding.to(cuda)(x.to(cuda))
+    assert got.shape == ref.shape and got.dtype == torch.float32
+    got = got.cpu()
+    print(f"V={vocab}: logits rel-rms {rel_rms(got, ref):.2e} max-abs {float((got - ref).abs().max()):.3e}")
+    assert rel_rms(got, ref) < 5e-3 and float((got - ref).abs().max()) < 0.08
+    assert torch.equal(got.argmax(-1), round_to_tokens(x.to(cuda), rounding, None, True, True).cpu())   # same GEMM as the fused argmax
+
+
+def test_learned_embedding_forward_is_an_exact_gather(cuda):
+    torch.manual_seed(8)
+    emb = LearnedEmbedding(1000, 256)
+    ids = torch.randint(0, 1000, (4, 33))
+    want = emb.embeddings.weight.detach()[ids]
+    with torch.no_grad():
+        got = emb.to(cuda)(ids.to(cuda))
+    assert torch.equal(got.cpu(), want)                 # bit-exact: a copy
+    assert emb(torch.empty(0, 5, dtype=torch.long, device=cuda)).shape == (0, 5, 256)
+    with pytest.raises(IndexError):
+        emb(torch.tensor([[0, 1000]], device=cuda))
+
+
+def test_rounding_at_the_benchmarked_vocabulary(cuda):
+    """V = 256,000 (Gemma's vocabulary, the size bench.py times), n = 5 sequences of L = 64: learned and cosine
+    rounding bit-exact wherever the fp32 top-2 margin exceeds the stated tolerance."""
+    torch.manual_seed(9)
+    dim, vocab = 256, 256_000
+    rounding = LearnedRounding(dim, vocab)
+    emb = LearnedEmbedding(vocab, dim)
+    x = torch.randn(5, 64, dim) * 4
+    logits = O.learned_logits(x, rounding.decoder.weight.detach(), rounding.decoder.bias.detach())
+    sims = O.cosine_logits(x, emb.embeddings.weight.detach())
+    got = round_to_tokens(x.to(cuda), rounding.to(cuda), emb.to(cuda), True, True).cpu()
+    _margin_check(got, logits, 0.08, "learned V=256000")
+    got_c = round_to_tokens(x.to(cuda), rounding, emb, False, True).cpu()
+    _margin_check(got_c, sims, 4e-3, "cosine V=256000")
+    assert int(got.max()) < vocab and int(got_c.max()) < vocab
+    # and the guided mix at this size: one position, AR logits from a seeded table
+    ar = torch.randn(5, vocab) * 2
+    mixed = 0.7 * ar + 0.3 * logits[:, 0]               # src/shakespeare.py:449-466 at temperature 1
+    r = Rounder(cuda)
+    gm = r.argmax(x[:, 0].to(cuda), weight=rounding.decoder.weight, bias=rounding.decoder.bias, ar_logits=ar.to(cuda), alpha=0.3).cpu()
+    _margin_check(gm, mixed, 0.05, "guided mix V=256000")

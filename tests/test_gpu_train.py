@@ -161,3 +161,49 @@ def test_fused_gradient_exchange_two_gpus():
                         "--master-addr", "127.0.0.1", "--master-port", "29547", str(root / "tools" / "peer_train_check.py")],
                        capture_output=True, text=True, timeout=600, cwd=root)
     assert "PEER_CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("world", [1, 2, 5, 8])
+def test_fused_exchange_adamw_is_bit_exact_one_step(cuda, world):
+    """The gradient exchange fused into the optimizer kernel (adamw_kernel<PEER>), one step, EXACT: `world` peer
+    buffers (all on this GPU - the kernel only sees addresses) hold seeded gradients, every "rank" runs
+    tdm_adamw_flat_peer, and its parameters / moments must be bit-equal to tdm_adamw_flat on the rank-ordered fp32
+    sum ((0 + g0) + g1) + ... - the sum order the kernel documents, the same on every rank, which is what keeps the
+    replicas bit-identical.  The flags are pre-set to the step index, so no rank waits for another."""
+    import ctypes
+
+    from tinydiffusionmodels_b200 import _lib
+    lib = _lib.load()
+    n = 181_473
+    g = torch.Generator().manual_seed(50 + world)
+    p0 = torch.randn(n, generator=g).to(cuda)
+    m0 = (torch.randn(n, generator=g) * 1e-2).to(cuda)
+    v0 = (torch.rand(n, generator=g) * 1e-3).to(cuda)
+    grads = [(torch.randn(n, generator=g) * (10.0 ** (r % 3 - 1))).to(cuda) for r in range(world)]   # mixed magnitudes: order matters
+    nbytes = int(lib.tdm_peer_buffer_bytes(n))
+    bufs = [torch.zeros(nbytes, dtype=torch.uint8, device=cuda) for _ in range(world)]
+    kstep = 3                                              # slot parity 1
+    off = int(lib.tdm_peer_grad_offset(n, kstep & 1))
+    for r in range(world):
+        bufs[r][:512].view(torch.int64)[:world] = kstep    # flags[q] = "rank q finished gradient k"
+        bufs[r][off:off + 4 * n].view(torch.float32).copy_(grads[r])
+    bases = (ctypes.c_void_p * world)(*[b.data_ptr() for b in bufs])
+    step = torch.full((1,), kstep, dtype=torch.int64, device=cuda)
+    hp = dict(lr=1e-3, b1=0.9, b2=0.999, eps=1e-8, wd=0.01)
+    # reference: plain AdamW on the rank-ordered sum
+    gsum = torch.zeros(n, device=cuda)
+    for r in range(world):
+        gsum = gsum + grads[r]
+    pr, mr, vr = p0.clone(), m0.clone(), v0.clone()
+    _lib.check(lib.tdm_adamw_flat(pr.data_ptr(), gsum.data_ptr(), mr.data_ptr(), vr.data_ptr(), n, hp["lr"], hp["b1"], hp["b2"],
+                                  hp["eps"], hp["wd"], 1.0 / world, step.data_ptr(), _lib.stream_ptr(cuda)), "tdm_adamw_flat")
+    for rank in range(world):
+        p, m, v = p0.clone(), m0.clone(), v0.clone()
+        _lib.check(lib.tdm_adamw_flat_peer(p.data_ptr(), m.data_ptr(), v.data_ptr(), n, hp["lr"], hp["b1"], hp["b2"], hp["eps"],
+                                           hp["wd"], 1.0 / world, step.data_ptr(), bases, world, rank,
+                                           _lib.stream_ptr(cuda)), "tdm_adamw_flat_peer")
+        torch.cuda.synchronize()
+        assert torch.equal(p, pr) and torch.equal(m, mr) and torch.equal(v, vr), f"rank {rank} of {world} differs"
+    # and against torch's own AdamW arithmetic on the same sum (rtol: the oracle's op order differs in the last bit)
+    po, mo, vo = O.adamw_step(p0.cpu(), (gsum / world).cpu(), m0.cpu(), v0.cpu(), kstep, lr=hp["lr"])[:3]
+    torch.testing.assert_close(pr.cpu(), po, rtol=2e-6, atol=1e-7)

@@ -28,6 +28,8 @@ def test_shard_range_is_a_balanced_partition(n, world):
 def test_rank_batch_slices_cover_the_epoch_once(n, bs, world):
     per_rank = [rank_batch_slices(n, bs, r, world) for r in range(world)]
     assert len({len(p) for p in per_rank}) == 1
+    for k in range(len(per_rank[0])):
+        assert len({per_rank[r][k][1] - per_rank[r][k][0] for r in range(world)}) == 1   # equal local batches per step
     seen = sorted(s for p in per_rank for s in p)
     assert all(hi > lo and hi - lo <= bs for lo, hi in seen)
     assert all(a[1] == b[0] for a, b in zip(seen, seen[1:]))            # disjoint and gap-free

@@ -60,6 +60,8 @@ SIGNATURES: dict[str, tuple] = {
     "tdm_text_p_sample": (c_int, [ctypes.POINTER(_P), c_int, _P, c_int64, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_uint64, c_uint64, c_uint32, _P]),
     "tdm_round_workspace_bytes": (c_int64, [c_int64, c_int, c_int64]),
     "tdm_round_argmax": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int64, _P, c_int, _P, c_int64, c_float, c_float, _P, _P, _P, c_int64, _P]),
+    "tdm_linear_logits": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int64, _P, c_int, _P, c_int64, _P, c_int64, _P]),
+    "tdm_embedding_gather": (c_int, [_P, c_int64, c_int, _P, c_int64, _P, _P, _P]),
     "tdm_unet_profile_p_sample": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, ctypes.POINTER(c_float), _P]),
 }
 

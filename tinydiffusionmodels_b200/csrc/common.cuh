@@ -1,5 +1,6 @@
 // common.cuh — error plumbing, launch accounting and the counter-based RNG shared by all kernels.
 #pragma once
+#include <atomic>
 #include <cstdlib>
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -79,6 +80,21 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     } while (0)
 
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: set it once per (kernel instantiation,
+// device ordinal), lock-free (a racing thread at worst sets it twice).  The static lives in the enclosing
+// function, i.e. one mask per template instantiation of the launcher.
+#define TDM_SET_MAX_DYN_SMEM(kern, bytes)                                                              \
+    do {                                                                                               \
+        static std::atomic<unsigned long long> done__{0ull};                                           \
+        int dev__ = 0;                                                                                 \
+        TDM_CHECK_CUDA(cudaGetDevice(&dev__));                                                         \
+        const unsigned long long bit__ = 1ull << (dev__ & 63);                                         \
+        if (!(done__.load(std::memory_order_acquire) & bit__)) {                                       \
+            TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)); \
+            done__.fetch_or(bit__, std::memory_order_release);                                         \
+        }                                                                                              \
+    } while (0)
 
 // ---- Philox4x32-10 (Salmon et al. 2011), hand-rolled so the numpy oracle can mirror it --------
 // counter = (c0, c1, c2, c3), key = (k0, k1).  Same constants as Random123 / cuRAND.

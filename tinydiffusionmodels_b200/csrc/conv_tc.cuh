@@ -935,11 +935,7 @@ template <int W, int CIN, int COUT, int EPI, bool SKIPG, int TAPS = 9, int KXC =
 static int launch_conv(const ConvArgs& a, cudaStream_t st, const char* name) {
     using C = ConvCfg<W, CIN, COUT, SKIPG, TAPS, KXC, PROD, CIN2, NGRP>;
     auto kern = conv3x3_tc_kernel<W, CIN, COUT, EPI, SKIPG, TAPS, KXC, PROD, CPAR, CIN2, NGRP>;
-    static bool configured = false;
-    if (!configured) {
-        TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured = true;
-    }
+    TDM_SET_MAX_DYN_SMEM(kern, C::SMEM_BYTES);
     const int nt = (a.np + C::TSTRIDE - 1) / C::TSTRIDE;
     const int grid = nt < num_sms() ? nt : num_sms();
     launch_pdl(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, a);

@@ -375,11 +375,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
 }
 
 static int launch_ffn(const FfnArgs& a, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        TDM_CHECK_CUDA(cudaFuncSetAttribute(ffn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFfnSmem));
-        configured = true;
-    }
+    TDM_SET_MAX_DYN_SMEM(ffn_tc_kernel, kFfnSmem);
     const int m_tiles = a.Mp / 128;
     TDM_CHECK_ARG(m_tiles % kFfnCluster == 0, "ffn_fused: row tiles (%d) must be a multiple of the cluster size", m_tiles);
     int grid = m_tiles < num_sms() ? m_tiles : num_sms();

@@ -11,6 +11,8 @@
 //   GE_RES_LN  N == 256 only: bias + fp32 residual, then LayerNorm of the whole row in the epilogue
 //              (row = one thread; the pre-LN values are parked back in the accumulator's TMEM columns
 //              between the statistics pass and the normalise pass) -> fp32 + bf16 planes
+//   GE_LOGITS  bias (+ row scale) -> fp32 row-major [M][n_valid]: the logits LearnedRounding.forward returns
+//              (src/shakespeare.py:93-102); the samplers never take this path
 //   GE_ARGMAX  running (max, argmax) over N, optionally mixed with AR logits — the logits are
 //              never written (src/shakespeare.py:389-390, 398-401, 451-467)
 #pragma once
@@ -19,7 +21,7 @@
 
 namespace tdm {
 
-enum : int { GE_BF16 = 0, GE_RES_F32 = 1, GE_ARGMAX = 2, GE_RES_LN = 3 };
+enum : int { GE_BF16 = 0, GE_RES_F32 = 1, GE_ARGMAX = 2, GE_RES_LN = 3, GE_LOGITS = 4 };
 
 constexpr int kBM = 128, kBN = 256, kBK = 64;
 constexpr int kGemmStages = 4;
@@ -59,6 +61,9 @@ struct GemmArgs {
     float* part_val;         // [2*nsplit][Mp]
     int64_t* part_idx;
     int nsplit;              // work items per row tile (== N/256 for the plain epilogues)
+    // GE_LOGITS
+    float* logits;           // [M][logits_ld] fp32 row-major
+    int64_t logits_ld;
 };
 
 template <int EPI>
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
             float best4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
             int best4_i[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
             float rs = 1.f;
-            if (EPI == GE_ARGMAX && a.row_scale && rvalid) rs = __ldg(a.row_scale + row);
+            if ((EPI == GE_ARGMAX || EPI == GE_LOGITS) && a.row_scale && rvalid) rs = __ldg(a.row_scale + row);
             for (int nt = n0; nt < n1; ++nt, ++it) {
                 if ((it & 1) != grp) continue;
                 const uint32_t aph = (n_mine++) & 1;
@@ -244,6 +249,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                             vb[pj * 4 + 3] = __float_as_uint(v3);
                         }
                         tmem_st32(taddr + c0, vb);
+                    } else if constexpr (EPI == GE_LOGITS) {
+                        float* orow = a.logits + (int64_t)row * a.logits_ld + nb;
+                        const bool vec = (a.logits_ld & 3) == 0 && nb + 32 <= a.n_valid;   // 16-byte aligned, whole chunk valid
+#pragma unroll
+                        for (int k4 = 0; k4 < 8; ++k4) {
+                            float v[4];   // shuffles stay outside the row-validity branch (all lanes take part)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                v[k] = __uint_as_float(r[k4 * 4 + k]) * rs + __shfl_sync(0xffffffffu, bias_l, k4 * 4 + k);
+                            if (rvalid) {
+                                if (vec) {
+                                    *reinterpret_cast<float4*>(orow + k4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        if (nb + k4 * 4 + k < a.n_valid) orow[k4 * 4 + k] = v[k];
+                                }
+                            }
+                        }
                     } else {
                         const float* arow = (a.ar && rvalid) ? a.ar + (int64_t)row * a.ar_ld : nullptr;
                         const bool full = nb + 32 <= a.n_valid;   // tile-uniform: only the last tile of a padded vocabulary is partial
@@ -323,11 +347,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
 template <int EPI>
 static int launch_gemm(const GemmArgs& a, cudaStream_t st, const char* name) {
     auto kern = gemm_tc_kernel<EPI>;
-    static bool configured = false;
-    if (!configured) {
-        TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-        configured = true;
-    }
+    TDM_SET_MAX_DYN_SMEM(kern, kGemmSmem);
     TDM_CHECK_ARG(EPI != GE_RES_LN || a.N == kBN, "%s: fused LayerNorm needs N == 256", name);
     TDM_CHECK_ARG(a.Mp % kBM == 0 && a.N % kBN == 0 && a.K % kBK == 0 && a.K > 0 && a.nsplit > 0,
                   "%s: bad GEMM shape M=%d Mp=%d N=%d K=%d", name, a.M, a.Mp, a.N, a.K);

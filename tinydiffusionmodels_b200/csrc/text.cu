@@ -487,11 +487,7 @@ template <int L, int HD>
 static int launch_attn(const uint8_t* qkv, int64_t ps, int D, int heads, int64_t B, uint8_t* out, cudaStream_t st) {
     using C = AttnCfg<L, HD>;
     auto kern = attn_tc_kernel<L, HD>;
-    static bool configured = false;
-    if (!configured) {
-        TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-        configured = true;
-    }
+    TDM_SET_MAX_DYN_SMEM(kern, C::SMEM);
     launch_pdl(kern, dim3((unsigned)(B * heads)), dim3(128), C::SMEM, st, qkv, ps, D, heads, out, ps);
     TDM_CHECK_LAUNCH("attention");
     return TDM_OK;
@@ -725,5 +721,61 @@ extern "C" int tdm_round_argmax(const float* x_rows, int64_t rows, int dim, cons
     if ((rc = launch_gemm<GE_ARGMAX>(g, st, "round_argmax"))) return rc;
     argmax_merge_kernel<<<(M + 127) / 128, 128, 0, st>>>(pv, pi, 2 * nsplit, M, Mp, out_idx, out_val);
     TDM_CHECK_LAUNCH("argmax_merge");
+    return TDM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LearnedRounding.forward / LearnedEmbedding.forward (src/shakespeare.py:71-80, 93-102): the two module calls
+// the samplers never make (they fuse the GEMM with the argmax) but code written against the reference does
+// ---------------------------------------------------------------------------------------------
+extern "C" int tdm_linear_logits(const float* x_rows, int64_t rows, int dim, const void* w_planes, int64_t vocab,
+                                 int64_t vocab_padded, const float* bias, int cosine, float* out_logits, int64_t out_ld,
+                                 void* workspace, int64_t workspace_bytes, void* stream) {
+    TDM_CHECK_ARG(x_rows && w_planes && out_logits && workspace, "tdm_linear_logits: null pointer");
+    TDM_CHECK_ARG(rows > 0 && dim % 128 == 0 && vocab > 0 && vocab_padded % kBN == 0 && vocab_padded >= vocab && out_ld >= vocab,
+                  "tdm_linear_logits: bad shape rows=%lld dim=%d vocab=%lld/%lld ld=%lld", (long long)rows, dim,
+                  (long long)vocab, (long long)vocab_padded, (long long)out_ld);
+    TDM_CHECK_ARG(workspace_bytes >= tdm_round_workspace_bytes(rows, dim, vocab), "tdm_linear_logits: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int M = (int)rows, Mp = (M + 127) / 128 * 128;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+    uint8_t* xp = ws;
+    const int64_t o = ((int64_t)(dim / 8) * Mp * 16 + 255) / 256 * 256;
+    float* rnorm = reinterpret_cast<float*>(ws + o);
+    rows_to_planes_kernel<<<Mp / 32, 256, 0, st>>>(x_rows, M, Mp, dim, 1, nullptr, nullptr, nullptr, nullptr, nullptr, xp,
+                                                   rnorm);
+    TDM_CHECK_LAUNCH("logits: rows_to_planes");
+    GemmArgs g{};
+    g.a = xp; g.a_ps = (int64_t)Mp * 16; g.w = reinterpret_cast<const uint8_t*>(w_planes); g.w_ps = vocab_padded * 16;
+    g.bias = bias; g.M = M; g.Mp = Mp; g.N = (int)vocab_padded; g.n_valid = (int)vocab; g.K = dim;
+    g.row_scale = cosine ? rnorm : nullptr;   // cosine similarity: the table in w_planes is pre-normalised
+    g.nsplit = (int)(vocab_padded / kBN);
+    g.logits = out_logits; g.logits_ld = out_ld;
+    return launch_gemm<GE_LOGITS>(g, st, "linear_logits");
+}
+
+__global__ void embedding_gather_kernel(const float* __restrict__ table, const int64_t* __restrict__ ids, int64_t n,
+                                        int64_t vocab, int dim4, float* __restrict__ out, int* __restrict__ bad) {
+    const float4* t4 = reinterpret_cast<const float4*>(table);
+    float4* o4 = reinterpret_cast<float4*>(out);
+    for (int64_t row = blockIdx.x; row < n; row += gridDim.x) {
+        const int64_t id = ids[row];
+        if (id < 0 || id >= vocab) {   // nn.Embedding raises: report it, write zeros
+            if (threadIdx.x == 0 && bad) atomicExch(bad, 1);
+            for (int j = threadIdx.x; j < dim4; j += blockDim.x) o4[row * dim4 + j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            continue;
+        }
+        for (int j = threadIdx.x; j < dim4; j += blockDim.x) o4[row * dim4 + j] = __ldg(t4 + id * dim4 + j);
+    }
+}
+
+extern "C" int tdm_embedding_gather(const float* table, int64_t vocab, int dim, const int64_t* ids, int64_t n,
+                                    float* out_rows, int* bad_flag, void* stream) {
+    TDM_CHECK_ARG(table && ids && out_rows && vocab > 0 && dim > 0 && dim % 4 == 0 && n >= 0,
+                  "tdm_embedding_gather: bad arguments");
+    if (n == 0) return TDM_OK;
+    const unsigned grid = (unsigned)(n < 148 * 16 ? n : 148 * 16);
+    embedding_gather_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(table, ids, n, vocab, dim / 4, out_rows, bad_flag);
+    TDM_CHECK_LAUNCH("tdm_embedding_gather");
     return TDM_OK;
 }

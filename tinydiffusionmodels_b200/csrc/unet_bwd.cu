@@ -371,11 +371,7 @@ template <int W, int CG, int CX, bool SKIPW = false>
 static int launch_wgrad_dup(WgradArgs a, int64_t np, cudaStream_t st, const char* name) {
     using C = WgradDupCfg<W, CG, CX>;
     auto kern = wgrad_dup_kernel<W, CG, CX, SKIPW>;
-    static bool configured = false;
-    if (!configured) {
-        TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured = true;
-    }
+    TDM_SET_MAX_DYN_SMEM(kern, C::SMEM_BYTES);
     a.nt = (int)((np + 2 + kTile - 1) / kTile);   // two rows past np so the shifted copies reach the last positions
     const int grid = a.nt < num_sms() ? a.nt : num_sms();
     launch_pdl(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, a);
@@ -387,11 +383,7 @@ template <int W, int CG, int CX, int TAPS>
 static int launch_wgrad(const WgradArgs& a, cudaStream_t st, const char* name) {
     using C = WgradCfg<W, CG, CX, TAPS>;
     auto kern = wgrad_tc_kernel<W, CG, CX, TAPS>;
-    static bool configured = false;
-    if (!configured) {
-        TDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured = true;
-    }
+    TDM_SET_MAX_DYN_SMEM(kern, C::SMEM_BYTES);
     const int grid = a.nt < num_sms() ? a.nt : num_sms();
     launch_pdl(kern, dim3(grid), dim3(C::THREADS), C::SMEM_BYTES, st, a);
     TDM_CHECK_LAUNCH(name);
@@ -815,7 +807,7 @@ __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
              float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps, float wd,
              float grad_scale, const int64_t* __restrict__ step, PeerBases peers, int world, int rank,
-             int64_t grad_off0, int64_t grad_slot_floats) {
+             int64_t grad_off0, int64_t grad_slot_floats, long long timeout_cycles) {
     pdl_wait();   // PDL (common.cuh): first statement, nothing before it touches global memory
     pdl_launch_dependents();
     __shared__ float s_c[2];
@@ -835,7 +827,7 @@ adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restri
             const uint64_t* mine = reinterpret_cast<const uint64_t*>(peers.base[rank]) + r;
             const long long t0 = clock64();
             while (ld_acquire_sys(mine) < (uint64_t)kstep) {
-                if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer died; fail loudly instead of hanging
+                if (clock64() - t0 > timeout_cycles) {   // a peer died; fail loudly instead of hanging (peer_timeout_cycles)
                     printf("tdm adamw_peer: rank %d timed out waiting for rank %d at step %lld\n", rank, r, (long long)kstep);
                     __trap();
                 }
@@ -1066,12 +1058,27 @@ extern "C" int tdm_adamw_flat(float* params, const float* grads, float* exp_avg,
     if (n == 0) return TDM_OK;
     launch_pdl(adamw_kernel<false>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
                params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, grad_scale, step_dev,
-               PeerBases{}, 1, 0, (int64_t)0, (int64_t)0);
+               PeerBases{}, 1, 0, (int64_t)0, (int64_t)0, 0LL);
     TDM_CHECK_LAUNCH("tdm_adamw_flat");
     return TDM_OK;
 }
 
 extern "C" int64_t tdm_peer_grad_offset(int64_t n, int parity);
+
+// How long a rank spins for its peers' "gradient k complete" flags before it traps.  Ranks may legitimately be
+// far apart at step 1 (dataset decode, graph capture), so the default is minutes, not seconds;
+// TDM_PEER_TIMEOUT_S overrides it.  Counted in SM clocks at a nominal 2 GHz.
+static long long peer_timeout_cycles() {
+    static const long long cycles = [] {
+        double secs = 300.0;
+        if (const char* e = std::getenv("TDM_PEER_TIMEOUT_S")) {
+            const double v = std::atof(e);
+            if (v > 0.0) secs = v;
+        }
+        return (long long)(secs * 2.0e9);
+    }();
+    return cycles;
+}
 
 extern "C" int tdm_adamw_flat_peer(float* params, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                                    float beta1, float beta2, float eps, float weight_decay, float grad_scale,
@@ -1090,7 +1097,7 @@ extern "C" int tdm_adamw_flat_peer(float* params, float* exp_avg, float* exp_avg
     const int64_t slot = (tdm_peer_grad_offset(n, 1) - off0) / 4;
     launch_pdl(adamw_kernel<true>, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream,
                params, (const float*)nullptr, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, grad_scale,
-               step_dev, pb, world, rank, off0, slot);
+               step_dev, pb, world, rank, off0, slot, peer_timeout_cycles());
     TDM_CHECK_LAUNCH("tdm_adamw_flat_peer");
     return TDM_OK;
 }

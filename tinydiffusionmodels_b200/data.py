@@ -76,10 +76,11 @@ class DeviceImages:
 def rank_batch_slices(n: int, batch_size: int, rank: int = 0, world: int = 1) -> list[tuple[int, int]]:
     """Positions [lo, hi) of the epoch's visiting order that ``rank`` takes at each step.
 
-    Step k covers the global batch [k*G, min((k+1)*G, n)) with G = world * batch_size, split contiguously over the
-    ranks (``dist.shard_range``: sizes differ by at most one).  The last, partial global batch is kept like the
-    reference's ``drop_last=False`` (src/mnist.py:146) unless it holds fewer images than there are ranks - every
-    rank must take part in every step's gradient exchange, so a step some rank would enter empty-handed is dropped.
+    Step k covers the global batch [k*G, min((k+1)*G, n)) with G = world * batch_size, split contiguously and
+    EVENLY over the ranks.  The last, partial global batch is kept like the reference's ``drop_last=False``
+    (src/mnist.py:146), trimmed to a multiple of ``world`` (at most world-1 images of an epoch are skipped): every
+    rank must take part in every step's gradient exchange with the same local batch, because the optimizer
+    averages the ranks' mean gradients with equal weights and the training noise is keyed on rank*b + row.
     """
     from .dist import shard_range
 
@@ -91,7 +92,8 @@ def rank_batch_slices(n: int, batch_size: int, rank: int = 0, world: int = 1) ->
     g = batch_size * world
     for start in range(0, n, g):
         size = min(g, n - start)
-        if size < world:
+        size -= size % world
+        if size == 0:
             break
         lo, hi = shard_range(size, rank, world)
         out.append((start + lo, start + hi))

@@ -89,6 +89,7 @@ class SimpleUNet(nn.Module):
         self._flat_grad: torch.Tensor | None = None
         self._engine: UNetEngine | None = None
         self._trainer = None
+        self._weights_generation = 0   # bumped by every raw-pointer update of the flat parameters (UNetTrainer.step)
 
     # -- flat parameter storage ------------------------------------------------------------
     def _is_flat(self) -> bool:
@@ -142,7 +143,11 @@ class SimpleUNet(nn.Module):
         if e is None or e.device != flat.device or e.max_batch < batch:
             e = UNetEngine(flat.device, max(batch, 1))
             self._engine = e
-        e.ensure_packed(flat)
+        # key on everything that can change the weights: writes through the parameter views (load_state_dict,
+        # torch.optim) bump the views' version counters, the fused trainer / graph replays write through raw
+        # pointers and bump _weights_generation instead (flat._version sees neither)
+        e.ensure_packed(flat, (flat.data_ptr(), flat._version, sum(p._version for p in self.parameters()),
+                               self._weights_generation))
         return e
 
     def forward(self, x, t):
@@ -161,46 +166,95 @@ def p_sample(model, x, t):
     return model.engine(x.shape[0]).p_sample(x, t, None, seed=_fresh_seed())
 
 
+# Samples one engine workspace holds at a time: larger batches run as sequential chunks (a sample's trajectory
+# depends only on its global index, so chunking cannot change a bit of the result).  The activations of a reverse
+# step take < 1 MB per sample, so a chunk is < 32 GB of the 180 GB of HBM.
+SAMPLE_CHUNK = 32768
+
+
 @torch.no_grad()
 def sample_loop(model: SimpleUNet, x: torch.Tensor, *, seed: int, sample_offset: int = 0,
-                steps: int = timesteps, use_graph: bool = True) -> torch.Tensor:
-    """Run ``steps`` reverse steps (t = steps-1 .. 0) in place on ``x`` and return it (pre-clamp).
+                steps: int = timesteps, use_graph: bool = True, noise: torch.Tensor | None = None) -> torch.Tensor:
+    """Run ``steps`` reverse steps (t = steps-1 .. 0) in place on ``x`` and return it (pre-clamp)
+    (ref src/mnist.py:190-194).
 
     Row b's trajectory depends only on (seed, sample_offset + b): the batch may be sharded over
     any number of GPUs / calls and the union of the results is bit-identical.
+
+    ``noise`` (optional, ``(steps, B, 1, 28, 28)`` on the device) injects the per-step posterior noise:
+    ``noise[i]`` is used at timestep ``i`` (row 0 is never read: the reference adds none at t = 0) -
+    the parity tests feed the oracle's noise through the same captured, device-timestep loop.
+
+    The captured reverse step is cached on the model's engine per (batch, seed, sample_offset): a second call
+    with the same key only copies ``x`` into the graph's buffer and replays.
     """
     n = x.shape[0]
     if n == 0:
         return x
+    if n > SAMPLE_CHUNK:
+        for lo in range(0, n, SAMPLE_CHUNK):
+            hi = min(n, lo + SAMPLE_CHUNK)
+            xc = x[lo:hi]
+            if not xc.is_contiguous():
+                raise ValueError("sample_loop: x must be contiguous")
+            sample_loop(model, xc, seed=seed, sample_offset=sample_offset + lo, steps=steps, use_graph=use_graph,
+                        noise=None if noise is None else noise[:, lo:hi])
+        return x
     eng = model.engine(n)
     lib = eng.lib
     dev = x.device
-    t_buf = torch.full((n,), steps - 1, device=dev, dtype=torch.int64)
+    if noise is not None:
+        if noise.shape[0] < steps or noise.shape[1] != n or noise.device != dev:
+            raise ValueError("noise must be (steps, B, 1, 28, 28) on the device of x")
+        noise = noise.float().contiguous().view(noise.shape[0], -1)
 
-    def one_step():
-        eng.p_sample(x, t_buf, None, out=x, seed=seed, sample_offset=sample_offset)
+    def one_step(xb, t_buf, zs):
+        z = None
+        if zs is not None:
+            z = zs.index_select(0, t_buf[:1]).view(-1)   # row t of the noise, picked on the device
+        eng.p_sample(xb, t_buf, z, out=xb, seed=seed, sample_offset=sample_offset)
         _lib.check(lib.tdm_timestep_advance(t_buf.data_ptr(), n, -1, _lib.stream_ptr(dev)),
                    "tdm_timestep_advance")
 
     if not use_graph or steps < 4:
+        t_buf = torch.full((n,), steps - 1, device=dev, dtype=torch.int64)
+        xb = x if x.is_contiguous() and x.dtype == torch.float32 else x.float().contiguous()
         for _ in range(steps):
-            one_step()
+            one_step(xb, t_buf, noise)
+        if xb is not x:
+            x.copy_(xb)
         return x
-    # warm-up outside capture on scratch state (lazy kernel attribute setup, workspace zeroing)
-    x_keep, t_keep = x.clone(), t_buf.clone()
-    side = torch.cuda.Stream(device=dev)
-    side.wait_stream(torch.cuda.current_stream(dev))
-    with torch.cuda.stream(side):
-        one_step()
-    torch.cuda.current_stream(dev).wait_stream(side)
-    x.copy_(x_keep)
-    t_buf.copy_(t_keep)
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        one_step()
-    # capture does not execute: state is still (x_T, steps-1)
+    eng._prep(n)   # a cached graph must not replay into a workspace last laid out for another batch
+    key = (n, int(seed), int(sample_offset), None if noise is None else tuple(noise.shape))
+    hit = eng._loops.get(key)
+    if hit is None:
+        xb = torch.empty(n, 1, 28, 28, device=dev, dtype=torch.float32)
+        t_buf = torch.empty(n, dtype=torch.int64, device=dev)
+        zs = None if noise is None else torch.empty_like(noise)
+        xb.copy_(x)
+        t_buf.fill_(steps - 1)
+        if zs is not None:
+            zs.copy_(noise)
+        # warm-up outside capture on scratch state (lazy kernel attribute setup)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            one_step(xb, t_buf, zs)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            one_step(xb, t_buf, zs)   # capture does not execute
+        while len(eng._loops) >= 8:   # a handful of (batch, seed) keys stay warm; older ones are dropped
+            eng._loops.pop(next(iter(eng._loops)))
+        hit = eng._loops[key] = (graph, xb, t_buf, zs)
+    graph, xb, t_buf, zs = hit
+    xb.copy_(x)
+    t_buf.fill_(steps - 1)
+    if zs is not None:
+        zs.copy_(noise)
     for _ in range(steps):
         graph.replay()
+    x.copy_(xb)
     return x
 
 
@@ -275,8 +329,15 @@ def train(model: nn.Module, device: str, epochs: int = 5, batch_size: int = 128,
     network on the benchmark boxes)."""
     from .unet_train import UNetTrainer
 
+    from .data import _rank_world
+
     if "AIP_MODEL_DIR" in os.environ:
         ckpt_path = get_vertex_checkpoint_path("image-model.pth")
+    rank, world = _rank_world()
+    if not synthetic:
+        # decode (and, on rank 0 only, download) the dataset BEFORE the trainer exists: the ranks next meet inside the
+        # optimizer kernel's flag wait, which must not also have to cover a dataset download
+        _dataset_for(device, rank, world)
     trainer = UNetTrainer(model, lr=lr, max_batch=batch_size)
     for epoch in range(epochs):
         running, seen = None, 0
@@ -287,9 +348,12 @@ def train(model: nn.Module, device: str, epochs: int = 5, batch_size: int = 128,
             if (step + 1) % log_every == 0:
                 print(f"Epoch {epoch + 1}/{epochs} step {step + 1}: loss={float(running) / seen:.4f}")
                 running, seen = None, 0
-        if sample_every_epoch:
+        if sample_every_epoch and rank == 0:   # the replicas are bit-identical: one of them draws the samples
             sample_images(model, device, epoch + 1, samples_per_epoch)
-    save_checkpoint(model.state_dict(), ckpt_path)
+    if rank == 0:
+        save_checkpoint(model.state_dict(), ckpt_path)
+    if world > 1:
+        torch.distributed.barrier()   # nobody reads the checkpoint before rank 0 has written it
 
 
 def _batches(device, batch_size, synthetic, steps_per_epoch, epoch):
@@ -304,14 +368,29 @@ def _batches(device, batch_size, synthetic, steps_per_epoch, epoch):
 
     # the reference's DataLoader + ToTensor + Normalize((0.5,), (0.5,)) (src/mnist.py:139-147), with the uint8
     # training set resident on the device: a permutation per epoch, one gather + normalise kernel per batch
-    dev = torch.empty(0, device=device).device   # resolved ("cuda" -> "cuda:0")
-    if dev not in _datasets:
-        _datasets[dev] = mnist_on_device(dev)
+    from .data import _rank_world
+
+    ds = _dataset_for(device, *_rank_world())
     # like the reference's DataLoader, the visiting order follows torch's global seed (torch.manual_seed)
-    yield from _datasets[dev].batches(batch_size, seed=torch.initial_seed(), epoch=epoch, max_batches=steps_per_epoch)
+    yield from ds.batches(batch_size, seed=torch.initial_seed(), epoch=epoch, max_batches=steps_per_epoch)
 
 
 _datasets: dict = {}
+
+
+def _dataset_for(device, rank: int = 0, world: int = 1):
+    """The uint8 training set resident on ``device`` (cached).  With several ranks sharing ``./data``, rank 0
+    downloads / decodes first and the others read the finished files after a barrier."""
+    from .data import mnist_on_device
+
+    dev = torch.empty(0, device=device).device   # resolved ("cuda" -> "cuda:0")
+    if dev not in _datasets:
+        if world > 1 and rank != 0:
+            torch.distributed.barrier()
+        _datasets[dev] = mnist_on_device(dev, download=(rank == 0))
+        if world > 1 and rank == 0:
+            torch.distributed.barrier()
+    return _datasets[dev]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -335,6 +414,14 @@ def main(argv=None):
     if not torch.cuda.is_available():
         raise _lib.TdmError("tinydiffusionmodels_b200 needs a CUDA (sm_100a) device; there is no CPU path")
     device = "cuda"
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # torchrun: one process per GPU, data-parallel training (gradient exchange inside the optimizer kernel)
+        from . import dist as tdist
+
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        device = f"cuda:{local}"
+        tdist.init_from_env(device=torch.device(device))
     if args.seed is not None:
         torch.manual_seed(args.seed)
     model = SimpleUNet().to(device)
@@ -342,7 +429,7 @@ def main(argv=None):
     if args.train:
         train(model, device, epochs=args.epochs, batch_size=args.batch_size, ckpt_path=args.ckpt,
               synthetic=args.synthetic, steps_per_epoch=args.steps_per_epoch)
-    if args.sample:
+    if args.sample and (not torch.distributed.is_initialized() or torch.distributed.get_rank() == 0):
         sample(model, device, n_samples=args.n_samples, ckpt_path=args.ckpt)
     if not args.train and not args.sample:
         print("Nothing to do. Pass --train or --sample.")

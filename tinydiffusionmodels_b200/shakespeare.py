@@ -6,7 +6,7 @@
 * ``sample`` / ``sample_diffusion_embeddings``     (ref :355-426)  -> graph-replayed reverse loop,
                                                                       fused rounding GEMM + argmax
 * ``guided_generate``                              (ref :429-470)  -> fused diff-logit GEMM + AR mix + argmax
-* ``LearnedEmbedding`` / ``LearnedRounding``       (ref :46-102)   parameter containers (weight ABI)
+* ``LearnedEmbedding`` / ``LearnedRounding``       (ref :46-102)   weight ABI + forward (gather kernel / logits GEMM)
 
 Text *training* (ref :122-341) is outside this build's hot path: the modules raise
 instead of silently running PyTorch kernels.  The base LM inside ``guided_generate`` is third
@@ -88,7 +88,22 @@ class LearnedEmbedding(nn.Module):
                 self.embeddings.weight.copy_(proj(pretrained_embeddings))
 
     def forward(self, token_ids):
-        raise _lib.TdmError("embedding lookup belongs to text training, which this build does not accelerate")
+        """embeddings[token_ids] (ref :71-80) - one gather kernel; inference only (no autograd graph)."""
+        w = self.embeddings.weight
+        if not w.is_cuda:
+            raise _lib.TdmError("LearnedEmbedding runs on CUDA only (no CPU fallback): call .to('cuda')")
+        ids = token_ids.to(device=w.device, dtype=torch.int64).contiguous()
+        out = torch.empty(*ids.shape, self.embed_dim, dtype=torch.float32, device=w.device)
+        if ids.numel() == 0:
+            return out
+        bad = torch.zeros(1, dtype=torch.int32, device=w.device)
+        lib = _lib.load()
+        _lib.check(lib.tdm_embedding_gather(w.detach().float().contiguous().data_ptr(), self.vocab_size, self.embed_dim,
+                                            ids.data_ptr(), ids.numel(), out.data_ptr(), bad.data_ptr(),
+                                            _lib.stream_ptr(w.device)), "tdm_embedding_gather")
+        if int(bad):   # nn.Embedding raises IndexError on an out-of-range id; so do we (this read synchronises)
+            raise IndexError("index out of range in LearnedEmbedding")
+        return out
 
     def get_embedding_matrix(self):
         return self.embeddings.weight
@@ -103,8 +118,13 @@ class LearnedRounding(nn.Module):
         self.decoder = nn.Linear(embed_dim, vocab_size)
 
     def forward(self, embeddings):
-        raise _lib.TdmError("LearnedRounding logits are never materialised here: use sample()/guided_generate(), "
-                            "which fuse the GEMM with the argmax")
+        """logits = decoder(embeddings), fp32 (..., V) (ref :93-102): the tcgen05 GEMM with a bias epilogue that
+        writes the logits (bf16 products, fp32 accumulation).  The samplers do not call this - they fuse the same
+        GEMM with the argmax (``Rounder.argmax``) so the (rows, V) logits never reach HBM.  Inference only."""
+        w = self.decoder.weight
+        if not w.is_cuda:
+            raise _lib.TdmError("LearnedRounding runs on CUDA only (no CPU fallback): call .to('cuda')")
+        return _rounder(w.device).logits(embeddings.to(w.device), weight=w, bias=self.decoder.bias)
 
 
 class TinyTransformer(nn.Module):

@@ -183,3 +183,27 @@ class Rounder:
                                              self._ws.numel(), _lib.stream_ptr(self.device)), "tdm_round_argmax")
         idx = idx.view(lead)
         return (idx, val.view(lead)) if return_values else idx
+
+    def logits(self, x: torch.Tensor, *, weight: torch.Tensor, bias: torch.Tensor | None = None,
+               cosine: bool = False) -> torch.Tensor:
+        """x.W^T + b (or the cosine similarities) as an fp32 (..., V) tensor - what ``LearnedRounding.forward``
+        returns (ref src/shakespeare.py:93-102).  bf16 tensor-core products, fp32 accumulation."""
+        if not x.is_cuda:
+            raise _lib.TdmError("rounding needs CUDA tensors (no CPU fallback)")
+        lead = x.shape[:-1]
+        dim = x.shape[-1]
+        xr = x.reshape(-1, dim).float().contiguous()
+        rows = xr.shape[0]
+        vocab = weight.shape[0]
+        if rows == 0:
+            return torch.empty(*lead, vocab, dtype=torch.float32, device=self.device)
+        wp = self._pack(weight, cosine)
+        need = int(self.lib.tdm_round_workspace_bytes(rows, dim, vocab))
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        out = torch.empty(rows, vocab, dtype=torch.float32, device=self.device)
+        b = None if (bias is None or cosine) else bias.detach().to(self.device, torch.float32).contiguous()
+        _lib.check(self.lib.tdm_linear_logits(xr.data_ptr(), rows, dim, wp.data_ptr(), vocab, _pad256(vocab), _lib.ptr(b),
+                                              int(cosine), out.data_ptr(), vocab, self._ws.data_ptr(), self._ws.numel(),
+                                              _lib.stream_ptr(self.device)), "tdm_linear_logits")
+        return out.view(*lead, vocab)

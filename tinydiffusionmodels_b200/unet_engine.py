@@ -72,9 +72,10 @@ class UNetEngine:
         self._ws_batch = None  # the plane strides depend on the batch: re-zero when it changes
         self.sched: Schedule = schedule_on(self.device)
         self._packed_from = None
+        self._loops: dict = {}   # captured reverse-step graphs of sample_loop, keyed by (batch, seed, offset, noise?)
 
     # -- weights ---------------------------------------------------------------------------
-    def load_flat(self, flat: torch.Tensor) -> None:
+    def load_flat(self, flat: torch.Tensor, key=None) -> None:
         if flat.numel() != PARAM_COUNT or flat.dtype != torch.float32 or not flat.is_cuda:
             raise ValueError("flat params must be a CUDA fp32 vector of 181,473 elements")
         flat = flat.contiguous()
@@ -84,7 +85,8 @@ class UNetEngine:
         _lib.check(self.lib.tdm_unet_pack_weights_host(flat.data_ptr(), host.data_ptr(), self.wpack.data_ptr(),
                                                        _lib.stream_ptr(self.device)),
                    "tdm_unet_pack_weights_host")
-        self._packed_from = (flat.data_ptr(), flat._version)
+        self._packed_from = (flat.data_ptr(), flat._version) if key is None else key
+        self._loops.clear()   # captured loops carry the old per-channel vectors in their launch arguments
 
     def __del__(self):
         try:
@@ -95,9 +97,14 @@ class UNetEngine:
     def load_state_dict(self, sd: dict) -> None:
         self.load_flat(flatten_state_dict(sd, self.device))
 
-    def ensure_packed(self, flat: torch.Tensor) -> None:
-        if self._packed_from != (flat.data_ptr(), flat._version):
-            self.load_flat(flat)
+    def ensure_packed(self, flat: torch.Tensor, key=None) -> None:
+        """Re-pack when ``key`` changed.  ``flat._version`` alone is NOT a usable key: the fused trainer and the
+        CUDA-graph replays write the flat vector through raw pointers, and ``load_state_dict`` / ``torch.optim``
+        write through the parameter *views*, whose version counters are their own - the caller (SimpleUNet.engine)
+        folds those and its own weight-generation counter into ``key``."""
+        want = (flat.data_ptr(), flat._version) if key is None else key
+        if self._packed_from != want:
+            self.load_flat(flat, key)
 
     # -- compute ---------------------------------------------------------------------------
     def _prep(self, batch: int) -> None:

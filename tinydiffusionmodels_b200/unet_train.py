@@ -119,6 +119,15 @@ class PeerGrads:
         """Device address of this rank's gradient slot for (1-based) step ``step_k``."""
         return self.own + int(self.lib.tdm_peer_grad_offset(self.n, step_k & 1))
 
+    def grad_view(self, step_k: int) -> torch.Tensor:
+        """The same slot as an fp32 tensor aliasing the raw allocation (``__cuda_array_interface__``)."""
+        class _Raw:
+            pass
+        raw = _Raw()
+        raw.__cuda_array_interface__ = {"shape": (self.n,), "typestr": "<f4", "data": (self.grad_ptr(step_k), False),
+                                        "version": 2, "strides": None}
+        return torch.as_tensor(raw, device=self.device)
+
     def close(self) -> None:
         for p in getattr(self, "_imported", []):
             self.lib.tdm_peer_close(p)
@@ -178,6 +187,13 @@ class UNetTrainer:
             self.rank = torch.distributed.get_rank(process_group)
         else:
             self.rank = 0
+        if self.world > 1:
+            # the replicas must START bit-identical (the rank-ordered gradient sum keeps them so): rank 0's
+            # parameters win, whatever seed the other ranks constructed their model with
+            torch.distributed.broadcast(self.flat, src=0, group=process_group)
+            self.engine.pack(self.flat)
+            if hasattr(model, "_weights_generation"):
+                model._weights_generation += 1
         self.loss = torch.zeros(1, device=dev)
         self._bufs = {}
         self._graph_cache = {}
@@ -308,6 +324,10 @@ class UNetTrainer:
             self._update()
         self.iteration += 1
         self._k += 1
+        # the kernels wrote the flat parameters through raw pointers: no torch version counter moved, so tell the
+        # model that its sampling engine's packed copy (and host mirror) is stale
+        if hasattr(self.model, "_weights_generation"):
+            self.model._weights_generation += 1
         return self.loss[0].clone()   # the buffer is overwritten by the next step
 
 

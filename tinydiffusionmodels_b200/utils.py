@@ -1,9 +1,10 @@
 """Checkpoint / sample I/O with the reference's call signatures (src/utils.py:11-141).
 
 Out of scope for acceleration (pure I/O) but part of the drop-in surface the
-entry points call.  Two behavioural differences, both additive: google-cloud-storage is imported
-lazily (the reference imports it at module import, which fails where it is not installed), and
-``load_checkpoint`` passes ``weights_only=False`` only for dict-of-dict text checkpoints' sake.
+entry points call.  One behavioural difference, additive: google-cloud-storage is imported
+lazily (the reference imports it at module import, which fails where it is not installed).
+``load_checkpoint`` calls ``torch.load(path, map_location=device)`` exactly as the reference does
+(torch's default ``weights_only`` applies; both checkpoint formats are plain tensor dicts).
 """
 from __future__ import annotations
 

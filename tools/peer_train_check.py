@@ -47,7 +47,64 @@ def run(mode: str, use_graph: bool):
     return flat, losses, e0.elapsed_time(e1) / 50
 
 
-ok = True
+def exact_one_step() -> bool:
+    """One optimizer step with the REAL cross-GPU exchange, exact: every rank writes a seeded gradient into its
+    peer slot, runs tdm_adamw_flat_peer (flags + loads over NVLink), and must end bit-equal to tdm_adamw_flat on the
+    rank-ordered sum of the all-gathered gradients - and, the replicas being what matters, bit-equal across ranks.
+    Also reported: agreement with NCCL's all_reduce (bit-equal for 2 ranks, where the sum order cannot differ)."""
+    from tinydiffusionmodels_b200 import _lib
+    from tinydiffusionmodels_b200.unet_train import PeerGrads
+    lib = _lib.load()
+    n = 181_473
+    peer = PeerGrads(lib, dev, n)
+    okv = torch.tensor([1 if peer.ok else 0], device=dev, dtype=torch.int32)
+    dist.all_reduce(okv, op=dist.ReduceOp.MIN)
+    if int(okv) != 1:
+        if rank == 0:
+            print("exact one-step: peer mapping unavailable:", peer.error)
+        return False
+    good = True
+    g0 = torch.Generator().manual_seed(1)
+    p0 = torch.randn(n, generator=g0).to(dev)
+    m0 = (torch.randn(n, generator=g0) * 1e-2).to(dev)
+    v0 = (torch.rand(n, generator=g0) * 1e-3).to(dev)
+    p, m, v = p0.clone(), m0.clone(), v0.clone()
+    pr, mr, vr = p0.clone(), m0.clone(), v0.clone()
+    step = torch.ones(1, dtype=torch.int64, device=dev)
+    for k in (1, 2, 3):                                     # both gradient slots, the flags advancing
+        gk = torch.Generator().manual_seed(1000 * k + rank)
+        mine = (torch.randn(n, generator=gk) * (10.0 ** (rank % 3 - 1))).to(dev)
+        peer.grad_view(k).copy_(mine)
+        step.fill_(k)
+        _lib.check(lib.tdm_adamw_flat_peer(p.data_ptr(), m.data_ptr(), v.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8, 0.01,
+                                           1.0 / world, step.data_ptr(), peer.bases, world, rank, _lib.stream_ptr(dev)), "peer adamw")
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine)
+        gsum = torch.zeros(n, device=dev)
+        for r in range(world):
+            gsum = gsum + gathered[r]
+        _lib.check(lib.tdm_adamw_flat(pr.data_ptr(), gsum.data_ptr(), mr.data_ptr(), vr.data_ptr(), n, 1e-3, 0.9, 0.999, 1e-8,
+                                      0.01, 1.0 / world, step.data_ptr(), _lib.stream_ptr(dev)), "local adamw")
+        torch.cuda.synchronize()
+        same = torch.equal(p, pr) and torch.equal(m, mr) and torch.equal(v, vr)
+        nc = mine.clone()
+        dist.all_reduce(nc)
+        nccl_same = torch.equal(nc, gsum)
+        allp = [torch.empty_like(p) for _ in range(world)]
+        dist.all_gather(allp, p)
+        replicas = all(torch.equal(allp[0], a) for a in allp)
+        flag = torch.tensor([1 if (same and replicas) else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            print(f"exact one-step k={k}: fused exchange == rank-ordered sum + AdamW (bit-equal on every rank): {bool(int(flag))}; "
+                  f"replicas bit-identical: {replicas}; NCCL all_reduce sum bit-equal to the rank-ordered sum: {nccl_same}")
+        good = good and bool(int(flag))
+    dist.barrier()
+    peer.close()
+    return good
+
+
+ok = exact_one_step()
 for use_graph in (False, True):
     pf, pl, pms = run("peer", use_graph)
     nf, nl, nms = run("nccl", use_graph)
