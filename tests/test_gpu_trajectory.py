@@ -15,9 +15,11 @@ Tolerances (stated).  The kernels multiply in bf16 with fp32 accu
 activations in bf16; one eps evaluation differs from fp32 by <= 1e-2 of its rms (test_gpu_unet.py).  A reverse step
 scales that error by beta_t / sqrt(1 - acp_t) <= 0.02, so
   per step (re-synchronised):  atol 2e-3 on x_{t-1}                                      [same bar as test_gpu_unet]
-  6 golden steps end to end:   rel-rms <= 5e-3 of the trajectory's rms, max <= 4e-2 rms
-  60 Philox steps end to end:  rel-rms <= 2e-2
-  trained net, T = 1000:       rel-rms <= 5e-2 on the pre-clamp x_0, mean |pixel| error <= 2e-2 on the [0,1] image
+  6 golden steps end to end:   rel-rms <= 1e-3 of the trajectory's rms, max <= 1e-2 rms   [measured 3.8e-5 / 1.3e-4]
+  60 Philox steps end to end:  rel-rms <= 5e-3                                            [measured 2.2e-4]
+  trained net, T = 1000:       rel-rms <= 2e-2 on the pre-clamp x_0, mean |pixel| error <= 5e-3 on the [0,1] image
+                                                                                          [measured 3.2e-3 / 6.3e-4;
+                                                  a bf16-autocast run of the fp32 oracle drifts 1.2e-2 / 2.6e-3]
 """
 from pathlib import Path
 
@@ -51,7 +53,7 @@ def test_golden_six_step_trajectory_through_the_captured_loop(cuda):
     rms = want.pow(2).mean().sqrt()
     err_rms, err_max = rel_rms(got, want), float((got - want).abs().max() / rms)
     print(f"golden traj6 (graph loop): rel-rms {err_rms:.2e} max/rms {err_max:.2e}")
-    assert err_rms < 5e-3 and err_max < 4e-2
+    assert err_rms < 1e-3 and err_max < 1e-2
     # eager loop == graph loop, bit for bit
     eager = sample_loop(m, x_T.to(cuda).clone(), seed=0, steps=6, noise=zs.to(cuda), use_graph=False).cpu()
     assert torch.equal(eager, got)
@@ -81,7 +83,7 @@ def test_philox_loop_60_steps_matches_oracle(cuda):
     torch.testing.assert_close(xin.cpu(), x0, rtol=0, atol=2e-5)
     got = sample_loop(m, xin.clone(), seed=seed, sample_offset=off, steps=steps).cpu()
     print(f"60-step Philox loop: rel-rms {rel_rms(got, want):.2e} (rms {float(want.pow(2).mean().sqrt()):.3f})")
-    assert rel_rms(got, want) < 2e-2
+    assert rel_rms(got, want) < 5e-3
     # a second call replays the cached graph: same bits; so do the eager loop and any sharding
     assert torch.equal(sample_loop(m, xin.clone(), seed=seed, sample_offset=off, steps=steps).cpu(), got)
     assert torch.equal(sample_loop(m, xin.clone(), seed=seed, sample_offset=off, steps=steps, use_graph=False).cpu(), got)
@@ -128,7 +130,7 @@ def test_trained_checkpoint_full_T1000_final_sample(cuda):
     img_err = float((O.to_unit_range(got) - O.to_unit_range(want)).abs().mean())
     print(f"trained net, T=1000, B=8: final x_0 rms {rms:.3f}, rel-rms vs oracle {e:.2e}, mean |image| error {img_err:.2e}")
     assert torch.isfinite(got).all() and rms < 50.0       # the trained trajectory stays bounded
-    assert e < 5e-2 and img_err < 2e-2
+    assert e < 2e-2 and img_err < 5e-3
 
 
 def test_sampling_after_weight_updates_uses_the_new_weights(cuda):
