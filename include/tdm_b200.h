@@ -116,6 +116,7 @@ int64_t tdm_unet_workspace_bytes(int64_t batch, int for_backward);
  * rb1.conv1.bias, rb1.conv2.weight, ..., out.weight, out.bias; conv weights OIHW) into the
  * kernel-side packed image (bf16 [tap][Cin/8][Cout][8] planes + fp32 biases). */
 int tdm_unet_pack_weights(const float* flat_params, void* wpack, void* stream);
+
 /* Same, and additionally registers a HOST copy of the flat parameters (181,473 floats, copied into
  * library-owned memory) for this `wpack` buffer.  While a mirror is registered, tdm_unet_forward /
  * tdm_unet_p_sample pass the per-channel epilogue vectors (conv / skip biases, time-embedding weight
@@ -129,15 +130,23 @@ int tdm_unet_pack_weights_host(const float* flat_params, const float* flat_param
                                void* stream);
 int tdm_unet_forget_host_params(const void* wpack);
 
+/* Sampling schedule switch (process-wide): 1 (default; TDM_UNFUSED=1 in the environment starts at 0) runs each 28x28
+ * ResidualBlock as ONE kernel whose conv1 output stays in shared memory (csrc/resblock_tc.cuh; needs the host mirror
+ * of tdm_unet_pack_weights_host); 0 runs the layer-by-layer kernels, which leave every intermediate (t1, t4, s4) in
+ * the workspace for the per-layer parity tests.  Returns the previous setting.  Training always runs layer by layer
+ * (the backward pass needs the intermediates). */
+int tdm_unet_set_fused(int on);
+
 /* The workspace must be zero-filled once after allocation (guard rows), then may be reused
  * for the same batch size; zero it again before using it with a different batch size. */
 
 /* Test/debug aid: workspace layout for `batch` as 16 int64 written to HOST memory:
  * {tiles28, tiles14, plane_stride28, plane_stride14, off_t1, off_cat, off_p1, off_t2, off_s2,
- *  off_h2, off_t3, off_t4, off_s4, total_bytes, off_h3, 0}.  Activation tensor [C][pos] lives at
+ *  off_h2, off_t3, off_t4, off_s4, total_bytes, off_h3, GUARD28}.  Activation tensor [C][pos] lives at
  * off + (c/8)*plane_stride + (GUARD + pos)*16 + (c%8)*2 with pos(b,y,x) = b*S + (y+1)*(W+1) + x,
- * S = (W+1)^2, GUARD = 40 (W=28) or 24 (W=14).  In the sampling path rb3's output stays at 14x14
- * (off_h3) and channels 0..63 of the concat buffer are not materialised. */
+ * S = (W+1)^2, GUARD = GUARD28 = 168 (W=28) or 24 (W=14).  In the sampling path rb3's output stays at 14x14
+ * (off_h3) and channels 0..63 of the concat buffer are not materialised; with the fused blocks
+ * (tdm_unet_set_fused) t1, t4 and s4 are not materialised either. */
 int tdm_unet_debug_layout(int64_t batch, int64_t* host_out16);
 
 /* SimpleUNet.forward(x, t) (src/mnist.py:76-87).  x: [batch,1,28,28] fp32, t: [batch] int64,

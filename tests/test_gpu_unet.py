@@ -18,6 +18,16 @@ RMS_TOL = 1.0e-2
 MAX_TOL = 8.0e-2
 
 
+@pytest.fixture
+def unfused():
+    """Run the layer-by-layer kernels (every intermediate lands in the workspace) for the duration of a test."""
+    from tinydiffusionmodels_b200 import _lib
+    lib = _lib.load()
+    prev = lib.tdm_unet_set_fused(0)
+    yield
+    lib.tdm_unet_set_fused(prev)
+
+
 def _oracle_intermediates(sd, x, t):
     import torch.nn.functional as F
     tt = (t.float() / 1000).view(-1, 1, 1, 1)
@@ -43,7 +53,7 @@ def _oracle_intermediates(sd, x, t):
 
 
 @pytest.mark.parametrize("batch", [1, 3, 64])
-def test_unet_forward_matches_oracle(cuda, batch):
+def test_unet_forward_matches_oracle(cuda, batch, unfused):
     sd = random_unet_state_dict(0)
     g = torch.Generator().manual_seed(10 + batch)
     x = torch.randn(batch, 1, 28, 28, generator=g)
@@ -129,7 +139,7 @@ def _forward_without_mirror(eng, sd, x, t, cuda):
     return out
 
 
-def test_host_mirror_path_is_bit_identical_to_smem_path(cuda):
+def test_host_mirror_path_is_bit_identical_to_smem_path(cuda, unfused):
     """Per-channel vectors by value (constant bank, tdm_unet_pack_weights_host) vs staged in shared
     memory (tdm_unet_pack_weights): same arithmetic, so the outputs must be equal bit for bit."""
     sd = random_unet_state_dict(3)
@@ -163,7 +173,7 @@ def test_repack_drops_a_stale_host_mirror(cuda):
     assert rel_rms(got_a.cpu(), O.unet_forward(sd_a, x, t)) < RMS_TOL
 
 
-def test_first_conv_keeps_fp32_like_precision(cuda):
+def test_first_conv_keeps_fp32_like_precision(cuda, unfused):
     """rb1.conv1 runs on the tensor pipe as hi/lo bf16 products (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo):
     its output is then rounded to bf16 once, so it must sit at the bf16 rounding floor (2^-9 relative),
     well below the 2e-2 per-layer bar - also for inputs far outside the unit range."""
@@ -181,3 +191,40 @@ def test_first_conv_keeps_fp32_like_precision(cuda):
     ref = F.relu(F.conv2d(x, sd["rb1.conv1.weight"], sd["rb1.conv1.bias"], padding=1))
     ref = ref + F.linear(tt, sd["rb1.time_emb.weight"], sd["rb1.time_emb.bias"]).view(9, -1, 1, 1)
     assert rel_rms(got, ref) < 3e-3
+
+
+@pytest.mark.parametrize("batch", [1, 2, 7, 64, 300])
+def test_fused_blocks_match_layer_by_layer_and_oracle(cuda, batch):
+    """The fused 28x28 blocks (conv1 -> shared memory -> conv2 in one kernel, csrc/resblock_tc.cuh) against the
+    layer-by-layer kernels and the fp32 oracle.  Same bf16 operands and the same fp32 accumulators; only the order
+    in which the taps are accumulated differs (ky = 1 first), so the two CUDA schedules agree to ~1e-3 of the output
+    rms, far inside the 1e-2 bar against the oracle.  Batches chosen so that a CTA band is shorter than, equal to
+    and much longer than the four-slot ring, and so that the last tile is ragged."""
+    from tinydiffusionmodels_b200 import _lib
+    lib = _lib.load()
+    sd = random_unet_state_dict(31)
+    g = torch.Generator().manual_seed(900 + batch)
+    x = torch.randn(batch, 1, 28, 28, generator=g)
+    t = torch.randint(0, 1000, (batch,), generator=g)
+    z = torch.randn(batch, 1, 28, 28, generator=g)
+    eng = UNetEngine(cuda, batch)
+    eng.load_state_dict(sd)
+    prev = lib.tdm_unet_set_fused(1)
+    try:
+        fused = eng.forward(x.to(cuda), t.to(cuda)).cpu()
+        fused_step = eng.p_sample(x.to(cuda), t.to(cuda), z.to(cuda)).cpu()
+        again = eng.forward(x.to(cuda), t.to(cuda)).cpu()
+        lib.tdm_unet_set_fused(0)
+        plain = eng.forward(x.to(cuda), t.to(cuda)).cpu()
+        plain_step = eng.p_sample(x.to(cuda), t.to(cuda), z.to(cuda)).cpu()
+    finally:
+        lib.tdm_unet_set_fused(prev)
+    assert torch.equal(fused, again)                       # deterministic
+    ref = O.unet_forward(sd, x, t)
+    rms = ref.pow(2).mean().sqrt()
+    print(f"B={batch}: fused vs layer-by-layer rel-rms {rel_rms(fused, plain):.2e}; fused vs oracle {rel_rms(fused, ref):.2e}, "
+          f"max/rms {float((fused - ref).abs().max() / rms):.2e}")
+    assert rel_rms(fused, plain) < 3e-3
+    assert rel_rms(fused, ref) < RMS_TOL and float((fused - ref).abs().max() / rms) < MAX_TOL
+    torch.testing.assert_close(fused_step, O.mnist_p_sample(sd, x, t, z, TAB), rtol=0, atol=2e-3)
+    torch.testing.assert_close(fused_step, plain_step, rtol=0, atol=1e-3)

@@ -38,6 +38,7 @@ SIGNATURES: dict[str, tuple] = {
     "tdm_unet_pack_weights": (c_int, [_P, _P, _P]),
     "tdm_unet_pack_weights_host": (c_int, [_P, _P, _P, _P]),
     "tdm_unet_forget_host_params": (c_int, [_P]),
+    "tdm_unet_set_fused": (c_int, [c_int]),
     "tdm_unet_forward": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P]),
     "tdm_unet_p_sample": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_uint64, c_uint64, c_uint32, _P]),
     "tdm_unet_forward_train": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, _P]),

@@ -28,6 +28,7 @@
 #include "unet_layout.cuh"
 #include "conv_tc.cuh"
 #include "unet_ws.cuh"
+#include "resblock_tc.cuh"
 
 // epilogue groups (= tiles in flight) of the two nine-tap 32->32 convolutions, whose 32-column accumulators leave
 // TMEM room for more than the default four
@@ -185,6 +186,18 @@ static void drop_host_params(const void* wpack) {
 // ---------------------------------------------------------------------------------------------
 // optional per-kernel timing (bench.py's roofline): events recorded between the nine launches
 static thread_local cudaEvent_t* g_prof = nullptr;
+
+// The 28x28 residual blocks as single kernels (resblock_tc.cuh) unless TDM_UNFUSED=1 / tdm_unet_set_fused(0).
+static std::atomic<int> g_fused{-1};
+static bool fused_blocks_enabled() {
+    int v = g_fused.load(std::memory_order_relaxed);
+    if (v < 0) {
+        const char* e = std::getenv("TDM_UNFUSED");
+        v = (e && e[0] == '1') ? 0 : 1;
+        g_fused.store(v, std::memory_order_relaxed);
+    }
+    return v != 0;
+}
 #define TDM_PROF(i)                                   \
     do {                                              \
         if (g_prof) cudaEventRecord(g_prof[i], st);   \
@@ -274,6 +287,32 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
         if ((rc = launch_conv_fwd<14, 64, 64, EPI_RES, false, 9, KX::rb3c2>(a, fp, hfp, st, "rb3_conv2"))) return rc;
     }
 
+    // k8 + k9 fused (sampling with a host mirror): the whole rb4 block + out conv + reverse step in one kernel,
+    // t4 and s4 stay in shared memory (resblock_tc.cuh).  TDM_UNFUSED=1 keeps the layer-by-layer kernels (the
+    // per-layer parity tests read t4 / s4 back from the workspace).
+    if (!sa.train && hfp && fused_blocks_enabled()) {
+        TDM_PROF(7);
+        RbArgs r{};
+        r.in = ws + L.cat + 8 * L.ps28; r.in_ps = L.ps28;
+        r.in2 = ws + L.h3; r.in2_ps = L.ps14;
+        r.w1 = wp + WP::rb4_c1; r.wsk = wp + WP::rb4_sk; r.w2 = wp + WP::rb4_c2;
+        r.t = t; r.x = sa.fuse_step ? x : nullptr; r.fout = fout;
+        r.z = sa.z; r.betas = sa.betas; r.alphas = sa.alphas; r.sqrt_om = sa.sqrt_om;
+        r.seed = sa.seed; r.sample_offset = sa.sample_offset; r.step_id = sa.step_id; r.fuse_step = sa.fuse_step;
+        r.np = (int)L.np28; r.batch = B;
+        std::memcpy(r.cp.bias1, hfp + P::rb4_c1b, 32 * sizeof(float));
+        std::memcpy(r.cp.tw, hfp + P::rb4_tw, 32 * sizeof(float));
+        std::memcpy(r.cp.tb, hfp + P::rb4_tb, 32 * sizeof(float));
+        std::memcpy(r.cp.sbias, hfp + P::rb4_sb, 32 * sizeof(float));
+        std::memcpy(r.cp.bias2, hfp + P::rb4_c2b, 32 * sizeof(float));
+        std::memcpy(r.cp.aux, hfp + P::out_w, 32 * sizeof(float));
+        r.cp.aux[32] = hfp[P::out_b];
+        if ((rc = launch_resblock_rb4(r, st))) return rc;
+        TDM_PROF(8);
+        TDM_PROF(9);
+        return TDM_OK;
+    }
+
     // k8: rb4.conv1 (+skip) -> t4, s4
     TDM_PROF(7);
     a = ConvArgs{}; a.t = t; a.batch = B; a.np = (int)L.np28;
@@ -320,7 +359,7 @@ extern "C" int tdm_unet_debug_layout(int64_t batch, int64_t* host_out16) {
     TDM_CHECK_ARG(batch > 0 && host_out16, "tdm_unet_debug_layout: bad arguments");
     const UNetWs w = make_ws(batch, false);
     const int64_t v[16] = {w.nt28, w.nt14, w.ps28, w.ps14, w.t1, w.cat, w.p1, w.t2,
-                           w.s2,   w.h2,   w.t3,   w.t4,   w.s4, w.total, w.h3, 0};
+                           w.s2,   w.h2,   w.t3,   w.t4,   w.s4, w.total, w.h3, Geo<28>::GUARD};
     for (int i = 0; i < 16; ++i) host_out16[i] = v[i];
     return TDM_OK;
 }
@@ -341,6 +380,12 @@ extern "C" int tdm_debug_read_timeline(long long* host_out) {
     return TDM_OK;
 }
 #endif
+
+extern "C" int tdm_unet_set_fused(int on) {
+    const int prev = fused_blocks_enabled() ? 1 : 0;
+    g_fused.store(on ? 1 : 0, std::memory_order_relaxed);
+    return prev;
+}
 
 extern "C" int tdm_unet_forget_host_params(const void* wpack) {
     drop_host_params(wpack);

@@ -24,9 +24,11 @@ struct Geo {
     static constexpr int S = (W_ + 1) * (W_ + 1);
     static constexpr int HALO = (W_ == 28) ? 32 : 16;  // >= Wp + 1
     static constexpr int RT = kTile + 2 * HALO;        // smem rows per plane per tile
-    static constexpr int GUARD = HALO + 8;             // zero rows in front of position 0 in HBM
-    static constexpr int TAIL = HALO + kTile;          // zero rows after the last tile (kx-combined
-                                                       // tiles overlap and may start up to 127 rows late)
+    // zero rows in front of position 0 / behind the last tile in HBM (never written).  The fused 28x28 blocks
+    // (resblock_tc.cuh) stream 126-row tiles and compute one halo tile on either side of a CTA's band, so their
+    // input reads reach 126 + 1 + HALO rows before position 0 and up to 126 + 158 rows past the last position.
+    static constexpr int GUARD = (W_ == 28) ? 168 : HALO + 8;
+    static constexpr int TAIL = (W_ == 28) ? 296 : HALO + kTile;   // (kx-combined tiles overlap and may start up to 127 rows late)
     static_assert(HALO >= Wp + 1, "halo must cover the largest tap offset");
 };
 
@@ -34,8 +36,8 @@ __host__ __device__ inline int64_t num_tiles(int64_t batch, int S) {
     return (batch * S + kTile - 1) / kTile;
 }
 // rows allocated per plane: GUARD | nt*128 positions | TAIL
-__host__ __device__ inline int64_t plane_rows(int64_t batch, int S, int halo) {
-    return num_tiles(batch, S) * kTile + (halo + 8) + (halo + kTile);
+__host__ __device__ inline int64_t plane_rows(int64_t batch, int S, int guard, int tail) {
+    return num_tiles(batch, S) * kTile + guard + tail;
 }
 
 // ---- flat fp32 parameter vector (reference state_dict order) -----------------

@@ -27,8 +27,8 @@ static inline UNetWs make_ws(int64_t batch, bool for_backward) {
     w.nt14 = num_tiles(batch, Geo<14>::S);
     w.np28 = w.nt28 * kTile;
     w.np14 = w.nt14 * kTile;
-    w.ps28 = plane_rows(batch, Geo<28>::S, Geo<28>::HALO) * 16;
-    w.ps14 = plane_rows(batch, Geo<14>::S, Geo<14>::HALO) * 16;
+    w.ps28 = plane_rows(batch, Geo<28>::S, Geo<28>::GUARD, Geo<28>::TAIL) * 16;
+    w.ps14 = plane_rows(batch, Geo<14>::S, Geo<14>::GUARD, Geo<14>::TAIL) * 16;
     int64_t o = 0;
     auto take = [&](int64_t bytes) {
         int64_t at = o;

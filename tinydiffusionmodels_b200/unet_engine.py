@@ -189,7 +189,7 @@ def read_activation(engine: UNetEngine, name: str, batch: int) -> torch.Tensor:
     ps = {28: v[2], 14: v[3]}
     off = {**dict(zip(_WS_NAMES, v[4:13])), "h3": v[14]}[name]
     w, c = _WS_GEOM[name]
-    halo = (32 if w == 28 else 16) + 8   # GUARD rows in front of position 0
+    halo = v[15] if w == 28 else 24       # GUARD rows in front of position 0 (unet_layout.cuh)
     wp, s = w + 1, (w + 1) * (w + 1)
     rows = ps[w] // 16
     raw = engine.ws[off: off + (c // 8) * ps[w]].view(torch.bfloat16).view(c // 8, rows, 8)
