@@ -220,10 +220,27 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     const int nt14 = (int)L.nt14;
     int rc;
 
-    // k1: rb1.conv1 (1 -> 32) + ReLU + time bias -> t1, on the tensor pipe: gather warps build the im2col of x
-    TDM_PROF(0);
+    const bool fused = !sa.train && hfp && fused_blocks_enabled();
     auto mk = [&](int64_t off) { return sa.train ? reinterpret_cast<uint32_t*>(ws + off) : nullptr; };
     ConvArgs a{};
+    if (fused) {
+        // k1 + k2 fused: the whole rb1 block in one kernel (resblock_tc.cuh), t1 stays in shared memory -> h1
+        TDM_PROF(0);
+        RbArgs r{};
+        r.x = x; r.t = t; r.w1 = wp + WP::rb1_c1; r.w2 = wp + WP::rb1_c2;
+        r.out = ws + L.cat + 8 * L.ps28; r.out_ps = L.ps28;
+        r.np = (int)L.np28; r.batch = B;
+        std::memcpy(r.cp.bias1, hfp + P::rb1_c1b, 32 * sizeof(float));
+        std::memcpy(r.cp.tw, hfp + P::rb1_tw, 32 * sizeof(float));
+        std::memcpy(r.cp.tb, hfp + P::rb1_tb, 32 * sizeof(float));
+        std::memcpy(r.cp.sbias, hfp + P::rb1_sb, 32 * sizeof(float));
+        std::memcpy(r.cp.bias2, hfp + P::rb1_c2b, 32 * sizeof(float));
+        std::memcpy(r.cp.aux, hfp + P::rb1_sw, 32 * sizeof(float));
+        if ((rc = launch_resblock<RB_KIND_RB1>(r, st, "rb1_fused"))) return rc;
+        TDM_PROF(1);
+    } else {
+    // k1: rb1.conv1 (1 -> 32) + ReLU + time bias -> t1, on the tensor pipe: gather warps build the im2col of x
+    TDM_PROF(0);
     a.t = t; a.batch = B; a.np = (int)L.np28;
     a.x = x; a.w = wp + WP::rb1_c1; a.bias = fp + P::rb1_c1b; a.tw = fp + P::rb1_tw; a.tb = fp + P::rb1_tb;
     a.out = ws + L.t1; a.out_ps = L.ps28;
@@ -240,6 +257,8 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     a.x = x; a.aux_w = fp + P::rb1_sw; a.aux_b = fp + P::rb1_sb; a.np = (int)L.np28;
     a.mask = mk(L.m2_1); a.mask_stride = L.np28;
     if ((rc = launch_conv_fwd<28, 32, 32, EPI_RES_X, false, 9, KX::rb1c2, 0, TDM_G_RB1C2>(a, fp, hfp, st, "rb1_conv2"))) return rc;
+
+    }
 
     // k3: pool h1 -> p1
     TDM_PROF(2);
@@ -290,7 +309,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
     // k8 + k9 fused (sampling with a host mirror): the whole rb4 block + out conv + reverse step in one kernel,
     // t4 and s4 stay in shared memory (resblock_tc.cuh).  TDM_UNFUSED=1 keeps the layer-by-layer kernels (the
     // per-layer parity tests read t4 / s4 back from the workspace).
-    if (!sa.train && hfp && fused_blocks_enabled()) {
+    if (fused) {
         TDM_PROF(7);
         RbArgs r{};
         r.in = ws + L.cat + 8 * L.ps28; r.in_ps = L.ps28;
@@ -307,7 +326,7 @@ int unet_forward_impl(const uint8_t* wp, const float* x, const int64_t* t, float
         std::memcpy(r.cp.bias2, hfp + P::rb4_c2b, 32 * sizeof(float));
         std::memcpy(r.cp.aux, hfp + P::out_w, 32 * sizeof(float));
         r.cp.aux[32] = hfp[P::out_b];
-        if ((rc = launch_resblock_rb4(r, st))) return rc;
+        if ((rc = launch_resblock<RB_KIND_RB4>(r, st, "rb4_fused"))) return rc;
         TDM_PROF(8);
         TDM_PROF(9);
         return TDM_OK;

@@ -1,6 +1,6 @@
 """In-kernel timeline of the fused rb4 block (development aid).
 
-Build with  TDM_NVCC_DEFS=-DTDM_TIMELINE=100 python -m tinydiffusionmodels_b200.build --force , then
+Build with  TDM_NVCC_DEFS=-DTDM_TIMELINE=104 (rb4) or 101 (rb1) python -m tinydiffusionmodels_b200.build --force , then
     python tools/fused_timeline.py [batch]
 CTA 0 records clock64() per step: MMA thread (step top, acc2 free, acc1 free, input full, conv1 issued, t full,
 conv2 issued), epilogue 1 (acc1 full seen, released, t written), epilogue 2 (acc2 full seen, done), gather
