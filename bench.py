@@ -271,37 +271,35 @@ def run_ours(args) -> None:
     per_kernel = []
     t_buf.fill_(500)
     for i in range(8):
-        per_kernel.append(eng.profile_p_sample(x, t_buf, seed=seed))
+        per_kernel.append(eng.profile_kernels(x, t_buf, seed=seed))
     per_kernel = per_kernel[2:]
-    kms = [statistics.mean(k[i] for k in per_kernel) for i in range(9)]
-    names = UNetEngine.KERNEL_NAMES
-    flops = UNetEngine.KERNEL_FLOPS_PER_IMAGE
-    top = max(range(9), key=lambda i: kms[i])
+    names = [k[0] for k in per_kernel[0]]
+    flops = [k[1] for k in per_kernel[0]]
+    nk = len(names)
+    kms = [statistics.mean(k[i][2] for k in per_kernel) for i in range(nk)]
+    top = max(range(nk), key=lambda i: kms[i])
     peaks, peak_src = _peaks()
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
     achieved_tf = flops[top] * B / (kms[top] * 1e-3) / 1e12
     step_ms_sum = sum(kms)
-    traffic = None
-    tfile = ROOT / "profiles" / "r01_traffic_rb4_conv1.json"
-    if tfile.exists():
-        tj = json.loads(tfile.read_text())
-        if tj.get("kernel") == names[top] and tj.get("batch") == B:
-            traffic = tj["dram_bytes_per_launch"]   # dram read+write of one launch, ncu --set full
-    # whole reverse step against the HBM roofline of the per-layer design: DRAM bytes ncu counted for every kernel of
-    # one step (profiles/r01_traffic_step.json) / the live per-kernel times / the measured copy bandwidth
-    step_traffic = step_hbm_frac = None
-    sfile = ROOT / "profiles" / "r01_traffic_step.json"
+    # DRAM traffic from the committed ncu captures of this build (profiles/r02_traffic_step.json: per-kernel
+    # dram__bytes_read.sum + dram__bytes_write.sum of one reverse step at this batch)
+    traffic = step_traffic = step_hbm_frac = None
+    sfile = ROOT / "profiles" / "r02_traffic_step.json"
     if sfile.exists():
         sj = json.loads(sfile.read_text())
-        if sj.get("batch") == B:
+        if sj.get("batch") == B and sj.get("fused") == eng.fused():
             step_traffic = sj["dram_bytes_per_step"]
             step_hbm_frac = step_traffic / (step_ms_sum * 1e-3) / (float(peaks["hbm_gbs"]) * 1e9)
+            traffic = sj.get("per_kernel", {}).get(names[top])
     roofline = {
         "bound": "tensor", "kernel": names[top], "achieved": achieved_tf, "peak": peak_tf,
         "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
         "peak_source": f"{peak_src} bf16_tflops_sustained (kernel timed inside a long step)",
         "kernel_ms": {n: round(v, 4) for n, v in zip(names, kms)},
         "kernel_share_of_step": round(kms[top] / step_ms_sum, 4),
+        "kernel_tflops": {n: round(f * B / (v * 1e-3) / 1e12, 1) for n, f, v in zip(names, flops, kms) if f},
+        "fused_blocks": eng.fused(),
         "whole_unet_tflops": FLOPS_PER_IMAGE_STEP * B / (step_ms_sum * 1e-3) / 1e12,
         "step_dram_bytes": step_traffic, "step_hbm_frac": step_hbm_frac,
     }

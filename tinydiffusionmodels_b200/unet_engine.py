@@ -156,6 +156,28 @@ class UNetEngine:
     KERNEL_FLOPS_PER_IMAGE = (451_584, 14_450_688 + 50_176, 0, 7_225_344 + 802_816, 14_450_688, 14_450_688,
                               14_450_688, 43_352_064 + 4_816_896, 14_450_688 + 50_176)
 
+    def fused(self) -> bool:
+        """Whether sampling launches run the 28x28 residual blocks as single kernels (tdm_unet_set_fused)."""
+        prev = int(self.lib.tdm_unet_set_fused(1))
+        self.lib.tdm_unet_set_fused(prev)
+        return bool(prev)
+
+    def kernel_table(self) -> list[tuple[str, int]]:
+        """(name, algorithmic FLOPs per image) of every launch of one sampling step, in launch order."""
+        f = dict(zip(self.KERNEL_NAMES, self.KERNEL_FLOPS_PER_IMAGE))
+        if not self.fused():
+            return list(f.items())
+        return [("rb1_fused", f["rb1_conv1"] + f["rb1_conv2"]), ("avgpool", 0), ("rb2_conv1", f["rb2_conv1"]),
+                ("rb2_conv2", f["rb2_conv2"]), ("rb3_conv1", f["rb3_conv1"]), ("rb3_conv2", f["rb3_conv2"]),
+                ("rb4_fused_out_step", f["rb4_conv1"] + f["rb4_conv2_out_step"])]
+
+    def profile_kernels(self, x: torch.Tensor, t: torch.Tensor, seed: int = 0) -> list[tuple[str, int, float]]:
+        """(name, FLOPs per image, milliseconds) per launch of one fused p_sample (CUDA events between the launches)."""
+        ms = self.profile_p_sample(x, t, seed)
+        if self.fused():   # the event slots of the launches a fused block absorbed are empty
+            ms = [ms[0], ms[2], ms[3], ms[4], ms[5], ms[6], ms[7]]
+        return [(n, fl, v) for (n, fl), v in zip(self.kernel_table(), ms)]
+
     def profile_p_sample(self, x: torch.Tensor, t: torch.Tensor, seed: int = 0) -> list[float]:
         """Per-kernel milliseconds of one fused p_sample (CUDA events between the launches)."""
         import ctypes
