@@ -73,7 +73,7 @@ struct RbArgs {
 };
 
 constexpr int kTS = 126;            // tile stride of the fused block (both convolutions)
-constexpr int kRingSlots = 4;
+constexpr int kRingSlots = 4;        // rb4 (shared memory is full); rb1 uses Rb1Cfg::RING_SLOTS
 constexpr int kRingMargin = 40;     // mirrored rows in front of / behind the ring (>= 1 + Wp + 1 = 31)
 constexpr int kRingRows = kRingMargin + kRingSlots * kTS + kRingMargin;   // 584
 
@@ -88,6 +88,8 @@ struct Rb4Cfg {
     static constexpr int W1_MID = NPL * 128 * 16;                    // ky = 1 block with the skip rows: [12][128][8]
     static constexpr int W1_BYTES = 2 * W1_SIDE + W1_MID;            // 61,440
     static constexpr int W2_BYTES = 9 * 32 * 32 * 2;                 // 18,432
+    static constexpr int RING_SLOTS = kRingSlots, LAG = 3;           // conv2(j) is issued at step j + LAG; slots >= LAG + 1
+    static constexpr int RING_ROWS = kRingRows;
     static constexpr int RING_BYTES = 4 * kRingRows * 16;            // t: 4 planes x 584 rows
     static constexpr int STASH_BYTES = 4 * kRingSlots * kTS * 16;    // skip: 4 planes x 504 rows
     static constexpr int XCH_BYTES = 2 * 2 * 4 * 2 * 16 * 4;         // [tile parity][half][quarter][up|down][16 fp32]
@@ -117,7 +119,11 @@ struct Rb1Cfg {
     static constexpr int XWIN_FLOATS = 256;                          // fp32 window of x per tile (<= 189 pixels + alignment)
     static constexpr int W1_BYTES = 32 * 32 * 2;                     // [4][32][8] hi/hi/lo tap terms (unet_fwd.cu pack)
     static constexpr int W2_BYTES = 9 * 32 * 32 * 2;
-    static constexpr int RING_BYTES = 4 * kRingRows * 16;
+    // one more ring slot than rb4 and conv2 one step further behind: the t tile conv2 waits for was finished a whole
+    // step earlier, so the epilogue-1 latency (~800 cycles, of a ~1,000-cycle step) is off the MMA thread's path
+    static constexpr int RING_SLOTS = 5, LAG = 4;
+    static constexpr int RING_ROWS = kRingMargin + RING_SLOTS * kTS + kRingMargin;   // 710
+    static constexpr int RING_BYTES = 4 * RING_ROWS * 16;
     static constexpr int STASH_BYTES = 0;
     static constexpr int XCH_BYTES = 0;
     static constexpr int PROD = 4;                                   // im2col warps
@@ -297,8 +303,16 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
             // the top of every step the four already-satisfied waits cost ~600 cycles per step during which the
             // pipe drained (in-kernel timeline, tools/fused_timeline.py: rb1 1,580 cycles per step for 800 of MMAs).
             bool ok_full = false, ok_a2 = false, ok_tf = false;
-            for (int s = 0; s < n1 + 3; ++s) {
-                const int j = s - 3;
+            int tf_taken = -1;   // t-full phases are taken strictly in tile order, each exactly once
+            auto take_tfull = [&](int upto) {
+                for (; tf_taken < upto; ++tf_taken) {
+                    const int i = tf_taken + 1;
+                    if (!(ok_tf && i == upto)) mbar_wait(bar_tfull + (i & 1), (i >> 1) & 1);
+                }
+                ok_tf = false;
+            };
+            for (int s = 0; s < n1 + C::LAG; ++s) {
+                const int j = s - C::LAG;
                 TDM_TL(100 + KIND, s, 0);
                 // the accumulator conv2(j) will write: taking its release HERE (before conv1(s) is issued) is what
                 // orders epilogue 2 of conv2(j-2) - the reader of stash slot (s-4)%4 - before that slot's next
@@ -307,8 +321,9 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                 TDM_TL(100 + KIND, s, 1);
                 if (s < n1) {
                     const int st = s % C::NSTAGE;
-                    // (no "accumulator free" wait: epilogue 1 of tile s-2 arrived on t-full only after its TMEM reads,
-                    // and the t-full of tile s-2 was taken at step s-1)
+                    // "accumulator 1 free" = t-full of tile s-2: epilogue 1 arrives on it only after its TMEM reads.
+                    // Taking it here also keeps each t-full barrier at most one phase ahead of this thread.
+                    if (s >= 2) take_tfull(s - 2);
                     if (!ok_full) mbar_wait(bar_full + st, (s / C::NSTAGE) & 1);
                     TDM_TL(100 + KIND, s, 3);
                     if constexpr (kRb4) fence_proxy_async_smem();   // cp.async (generic proxy) rows -> async-proxy MMA reads
@@ -330,7 +345,7 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                         for (int ks = 0; ks < C::CIN / 16; ++ks)
                             umma_bf16(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO - G::Wp) * 16),
                                       desc_add(wa, (2 * ks) * 1536), idesc_side, 1u);
-                        if (s >= 1) ok_tf = mbar_test(bar_tfull + ((s - 1) & 1), ((s - 1) >> 1) & 1);
+                        if (s >= 1 && tf_taken == s - 2) ok_tf = mbar_test(bar_tfull + ((s - 1) & 1), ((s - 1) >> 1) & 1);
 #pragma unroll
                         for (int ks = 0; ks < C::CIN / 16; ++ks)
                             umma_bf16(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + G::Wp) * 16),
@@ -347,9 +362,9 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                     umma_commit(bar_acc1f + (s & 1));
                     TDM_TL(100 + KIND, s, 4);
                 }
-                if (s >= 1 && s - 1 < n1) {
-                    // t of tile s-1 is in the ring (epilogue-1 threads fenced their generic-proxy stores)
-                    if (!ok_tf) mbar_wait(bar_tfull + ((s - 1) & 1), ((s - 1) >> 1) & 1);
+                if (j >= 0 && j < n2) {
+                    // conv2(j) reads t of tiles j .. j+2 (epilogue-1 threads fenced their generic-proxy stores)
+                    take_tfull(j + 2);
                     TDM_TL(100 + KIND, s, 5);
                 }
                 ok_full = ok_a2 = ok_tf = false;
@@ -359,8 +374,8 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                     asm volatile("" : "+r"(w_t));
                     const uint64_t w_base = make_smem_desc(w_t, 32 * 16, 128);
                     // centre tile = local conv1 tile j+1 in ring slot (j+1)%4; tile row 0 = ring row slot*126 - 1
-                    const uint32_t row0 = kRingMargin + ((j + 1) & 3) * kTS - 1;
-                    const uint64_t t_base = make_smem_desc(ring_addr + row0 * 16, kRingRows * 16, 128);
+                    const uint32_t row0 = kRingMargin + ((j + 1) % C::RING_SLOTS) * kTS - 1;
+                    const uint64_t t_base = make_smem_desc(ring_addr + row0 * 16, C::RING_ROWS * 16, 128);
                     const uint32_t d = tmem_base + 2 * C::ACC1_COLS + (j & 1) * C::ACC2_COLS;
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
@@ -368,12 +383,11 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                         // next step's barriers, one probe at a time with a few MMAs queued behind each
                         if (tap == 3 && s + 1 < n1) ok_full = mbar_test(bar_full + (s + 1) % C::NSTAGE, ((s + 1) / C::NSTAGE) & 1);
                         if (tap == 6 && j + 1 < n2) ok_a2 = mbar_test(bar_acc2e + ((j + 1) & 1), (((j + 1) >> 1) & 1) ^ 1);
-                        if (!kRb4 && tap == 8 && s < n1) ok_tf = mbar_test(bar_tfull + (s & 1), (s >> 1) & 1);
 #pragma unroll
                         for (int ks = 0; ks < 2; ++ks) {
                             // off may be negative: add it as a signed row count to the 14-bit address field (never borrows:
                             // the ring sits far above shared-memory address 0)
-                            umma_bf16(d, t_base + (uint64_t)(int64_t)(off + (2 * ks) * kRingRows),
+                            umma_bf16(d, t_base + (uint64_t)(int64_t)(off + (2 * ks) * C::RING_ROWS),
                                       desc_add(w_base, ((tap * 4 + 2 * ks) * 32) * 16), idesc_c2, (tap | ks) != 0);
                         }
                     }
@@ -566,11 +580,11 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                     v[k] = fmaxf(__uint_as_float(d1[k]) + a.cp.bias1[c0 + k], 0.f) + fmaf(a.cp.tw[c0 + k], ts, a.cp.tb[c0 + k]);
             }
             if (owned) {
-                const int slot = i & 3;
+                const int slot = i % C::RING_SLOTS;
                 const int rrow = slot * kTS + (trow - 1);              // ring row (without the margin)
                 uint8_t* tdst = s_ring + (size_t)(kRingMargin + rrow) * 16;
                 // mirror: the first rows of slot 0 again behind the ring, the last rows of slot 3 again in front of it
-                const int mirror = (rrow < kRingMargin) ? kRingSlots * kTS : (rrow >= kRingSlots * kTS - kRingMargin) ? -kRingSlots * kTS : 0;
+                const int mirror = (rrow < kRingMargin) ? C::RING_SLOTS * kTS : (rrow >= C::RING_SLOTS * kTS - kRingMargin) ? -C::RING_SLOTS * kTS : 0;
 #pragma unroll
                 for (int pj = 0; pj < 2; ++pj) {
                     uint4 o;
@@ -579,8 +593,8 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                     o.z = valid ? pack_bf16x2(v[pj * 8 + 4], v[pj * 8 + 5]) : 0u;
                     o.w = valid ? pack_bf16x2(v[pj * 8 + 6], v[pj * 8 + 7]) : 0u;
                     const int plane = half * 2 + pj;
-                    *reinterpret_cast<uint4*>(tdst + (size_t)plane * (kRingRows * 16)) = o;
-                    if (mirror) *reinterpret_cast<uint4*>(tdst + (size_t)plane * (kRingRows * 16) + mirror * 16) = o;
+                    *reinterpret_cast<uint4*>(tdst + (size_t)plane * (C::RING_ROWS * 16)) = o;
+                    if (mirror) *reinterpret_cast<uint4*>(tdst + (size_t)plane * (C::RING_ROWS * 16) + mirror * 16) = o;
                     if constexpr (kRb4) {
                         // 1x1 skip of the block input (src/mnist.py:61), kept as bf16 like the layer-by-layer path's s4
                         uint4 o2;
@@ -645,7 +659,7 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                 if (valid) xin = __ldg(a.x + (int64_t)b * 784 + y * 28 + cc);
             }
             mbar_wait(bar_acc2f + grp, (j >> 1) & 1);
-            if (q == 2) TDM_TL(100 + KIND, j + 3, 10);
+            if (q == 2) TDM_TL(100 + KIND, j + C::LAG, 10);
             tc_fence_after_sync();
             uint4 rv[4];
             if constexpr (kRb4) {
@@ -703,7 +717,7 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                     }
                 }
             }
-            if (q == 2) TDM_TL(100 + KIND, j + 3, 11);
+            if (q == 2) TDM_TL(100 + KIND, j + C::LAG, 11);
         }
     }
     }
