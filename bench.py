@@ -682,6 +682,36 @@ def bench_text(dev, rank, world, batch, barrier, peaks, rsteps: int = 100, dim: 
     tot = torch.tensor([1000 * ms_step + ms_round], device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    guided = None
+    if dim == 256:
+        # BASELINE.json configs[4] end to end: guided_generate (src/shakespeare.py:429-470) with a random-init 4-layer
+        # Gemma standing in for google/gemma-2b-it (no hub access), stepped through its KV cache vs the reference's
+        # full-prefix re-forward; 64 sequences x 64 positions, V = 256,000
+        try:
+            from transformers import GemmaConfig, GemmaForCausalLM
+
+            from tinydiffusionmodels_b200.shakespeare import LearnedEmbedding, _SyntheticTokenizer, guided_generate
+
+            gb = 64
+            cfg = GemmaConfig(vocab_size=V, hidden_size=256, intermediate_size=1024, num_hidden_layers=4, num_attention_heads=4,
+                              num_key_value_heads=1, head_dim=64, max_position_embeddings=256)
+            lm = GemmaForCausalLM(cfg).to(dev).eval()
+            zg = z[:gb].contiguous()
+            embf = LearnedEmbedding(8, dim)   # unused with learned rounding
+            res = {}
+            for mode, kv in (("kv_cached", True), ("full_prefix", False)):
+                guided_generate(lm, rf, _SyntheticTokenizer(), embf, zg[:, :4].contiguous(), alpha=0.3, use_kv_cache=kv)   # warm-up
+                torch.cuda.synchronize()
+                e0.record()
+                guided_generate(lm, rf, _SyntheticTokenizer(), embf, zg, alpha=0.3, use_kv_cache=kv)
+                e1.record()
+                torch.cuda.synchronize()
+                res[mode] = {"ms": e0.elapsed_time(e1), "sequences_per_s": world * gb / (e0.elapsed_time(e1) * 1e-3)}
+            guided = {"what": f"guided_generate end to end, {gb} sequences x {L} positions, V={V}, random-init 4-layer Gemma "
+                              "stand-in (hidden 256) as the base LM; includes the LM forward and the host-side decode", **res}
+            del lm
+        except Exception as e:   # noqa: BLE001  (transformers missing or incompatible: the leg is optional)
+            guided = {"unavailable": str(e)[:200]}
     flop_tok = 8_060_928 if dim == 256 else 3 * (8 * dim * dim + 4 * L * dim + 8 * 2048 * dim)
     den_tf = flop_tok * L * batch / (ms_step * 1e-3) / 1e12
     rnd_tf = 2.0 * dim * V * L * batch / (ms_round * 1e-3) / 1e12
@@ -702,7 +732,7 @@ def bench_text(dev, rank, world, batch, barrier, peaks, rsteps: int = 100, dim: 
                                f"T=1000 reverse steps + learned rounding argmax over V={V}; random-init weights"},
         "ms_per_reverse_step": ms_step, "reverse_steps_timed": rsteps, "ms_rounding": ms_round,
         "denoiser_tflops": flop_tok * L * batch / (ms_step * 1e-3) / 1e12,
-        "guided_mix_ms_per_position": ms_mix, "gpu_launches_per_reverse_step": int(launches),
+        "guided_mix_ms_per_position": ms_mix, "guided_generate_e2e": guided, "gpu_launches_per_reverse_step": int(launches),
         "dtype": "bf16 (fp32 residual stream, LayerNorm, softmax, accumulation)",
     }
 

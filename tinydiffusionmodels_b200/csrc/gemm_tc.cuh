@@ -28,7 +28,11 @@ constexpr int kGemmStages = 4;
 constexpr int kGemmStageA = kBM * kBK * 2;   // 16 KB
 constexpr int kGemmStageB = kBN * kBK * 2;   // 32 KB
 constexpr int kGemmStage = kGemmStageA + kGemmStageB;
-constexpr int kGemmSmem = kGemmStages * kGemmStage + 1024;
+// GE_ARGMAX with AR logits: each epilogue warp transposes 32 rows x 32 columns of the fp32 AR logits through its own
+// padded shared-memory tile (coalesced 128-byte row reads in, one row per lane out)
+constexpr int kArTileFloats = 32 * 33;
+constexpr int kGemmSmemBase = kGemmStages * kGemmStage + 1024;
+constexpr int kGemmSmem = kGemmSmemBase + 8 * kArTileFloats * 4;
 constexpr int kGemmThreads = 64 + 2 * 128;
 
 struct GemmArgs {
@@ -269,16 +273,34 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                             }
                         }
                     } else {
-                        const float* arow = (a.ar && rvalid) ? a.ar + (int64_t)row * a.ar_ld : nullptr;
                         const bool full = nb + 32 <= a.n_valid;   // tile-uniform: only the last tile of a padded vocabulary is partial
+                        // AR logits of this warp's 32 rows x these 32 columns.  Read row-wise - thread = row, 32 consecutive
+                        // floats each - every load instruction touches 32 different 128-byte lines (1,024 LSU wavefronts per
+                        // chunk; the guided mix ran at 0.15 of the HBM roofline on exactly this).  Instead the warp reads one
+                        // ROW per instruction (lane = column: one coalesced 128-byte request) and turns the tile through
+                        // shared memory (row stride 33 words: conflict-free both ways).
+                        float* art = reinterpret_cast<float*>(smem + kGemmSmemBase) + (warp - 2) * kArTileFloats;
+                        if (a.ar) {
+                            const int row0 = mt * kBM + q * 32;
+                            const int ncol = nb + lane;
+                            const bool cok = full || ncol < a.n_valid;
+                            __syncwarp();   // the previous chunk's reads of the tile are done
+#pragma unroll 8
+                            for (int rr = 0; rr < 32; ++rr) {
+                                float av = 0.f;
+                                if (cok && row0 + rr < a.M) av = __ldg(a.ar + (int64_t)(row0 + rr) * a.ar_ld + ncol);
+                                art[rr * 33 + lane] = av;
+                            }
+                            __syncwarp();
+                        }
 #pragma unroll
                         for (int k = 0; k < 32; ++k) {
                             const int n = nb + k;
                             float v = __uint_as_float(r[k]) * rs + __shfl_sync(0xffffffffu, bias_l, k);
-                            if (arow) {
+                            if (a.ar) {
                                 // src/shakespeare.py:449-466: both logit sets divided by the temperature,
                                 // then mixed (1-alpha)*ar + alpha*diff
-                                v = (1.0f - a.alpha) * (__ldg(arow + (full || n < a.n_valid ? n : 0)) * a.inv_temp) + a.alpha * (v * a.inv_temp);
+                                v = (1.0f - a.alpha) * (art[lane * 33 + k] * a.inv_temp) + a.alpha * (v * a.inv_temp);
                             }
                             if (!full && n >= a.n_valid) v = -INFINITY;
                             if (v > best4[k & 3]) {   // strict: first (lowest) index wins ties, as torch.argmax

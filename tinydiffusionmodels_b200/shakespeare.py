@@ -215,10 +215,42 @@ def sample(model, rounding_fn, embedding_fn, tokenizer, device, n_samples=4, seq
         return texts
 
 
+class _LMStepper:
+    """AR logits of the next position (ref :447-449).
+
+    The reference re-runs the base LM over the whole prefix at every position - O(L^2) per sequence.  An LM that
+    implements the Hugging Face cache protocol (``use_cache=True`` / ``past_key_values``) is fed only the newest token
+    against its cached keys and values, O(L) per sequence, with the same logits up to fp rounding; any other callable
+    gets exactly the reference's call.  The LM itself stays a third-party torch module.
+    """
+
+    def __init__(self, base_lm, use_kv_cache: bool = True):
+        self.lm = base_lm
+        self.mode = None if use_kv_cache else "prefix"
+        self.cache = None
+
+    def __call__(self, input_ids: torch.Tensor, pos: int) -> torch.Tensor:
+        if self.mode is None:   # probe once, on the first position
+            try:
+                out = self.lm(input_ids[:, :pos + 1], use_cache=True)
+                self.cache = getattr(out, "past_key_values", None)
+                self.mode = "cache" if self.cache is not None else "prefix"
+                return out.logits[:, -1, :]
+            except TypeError:   # a plain callable(input_ids)
+                self.mode = "prefix"
+        if self.mode == "cache":
+            out = self.lm(input_ids[:, pos:pos + 1], past_key_values=self.cache, use_cache=True)
+            self.cache = out.past_key_values
+            return out.logits[:, -1, :]
+        return self.lm(input_ids[:, :pos + 1]).logits[:, -1, :]
+
+
 def guided_generate(base_lm, rounding_fn, tokenizer, embedding_fn, diff_z, alpha=0.5, max_len=128,
-                    temperature=1.0, use_learned_rounding=True, use_learned_embeddings=True):
+                    temperature=1.0, use_learned_rounding=True, use_learned_embeddings=True, *, use_kv_cache=True):
     """Greedy AR decoding steered by the diffusion embeddings (ref :429-470).  Per position the
-    diffusion logits, the (1-alpha)/alpha mix with the AR logits and the argmax are one kernel."""
+    diffusion logits, the (1-alpha)/alpha mix with the AR logits and the argmax are one kernel; the base LM is
+    stepped incrementally through its KV cache when it has one (``_LMStepper``; ``use_kv_cache=False`` forces the
+    reference's full-prefix re-forward)."""
     device = diff_z.device
     B, L, _ = diff_z.shape
     r = _rounder(device)
@@ -229,9 +261,10 @@ def guided_generate(base_lm, rounding_fn, tokenizer, embedding_fn, diff_z, alpha
     else:
         emb = embedding_fn.get_embedding_matrix() if use_learned_embeddings else embedding_fn
         kw = dict(weight=emb, cosine=True)
+    lm_step = _LMStepper(base_lm, use_kv_cache)
     with torch.no_grad():
         for pos in range(L):
-            ar_logits = base_lm(input_ids[:, :pos + 1]).logits[:, -1, :]          # third-party LM forward
+            ar_logits = lm_step(input_ids, pos)                                   # third-party LM forward
             nxt = r.argmax(diff_z[:, pos, :], ar_logits=ar_logits, alpha=alpha, temperature=temperature, **kw)
             input_ids[:, pos + 1] = nxt
     return tokenizer.batch_decode(input_ids[:, 1:], skip_special_tokens=True)
@@ -262,8 +295,10 @@ class _SyntheticLM(nn.Module):
     def get_input_embeddings(self):
         return self.emb
 
-    def forward(self, input_ids):
+    def forward(self, input_ids, past_key_values=None, use_cache=False):
         import types
+        if use_cache:   # a bigram LM's whole "cache" is the newest token: only its logits are needed (and computed)
+            return types.SimpleNamespace(logits=self.out(self.emb(input_ids[:, -1:])), past_key_values=("bigram",))
         return types.SimpleNamespace(logits=self.out(self.emb(input_ids)))
 
 
