@@ -91,17 +91,54 @@ def unet_forward(sd: dict, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
     return F.conv2d(h4, sd["out.weight"], sd["out.bias"])    # :87
 
 
-def mnist_p_sample(sd: dict, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor | None, tab: dict):
-    return reverse_step(x, unet_forward(sd, x, t), t, z, tab)
+def _bf16(v: torch.Tensor) -> torch.Tensor:
+    return v.to(torch.bfloat16).to(torch.float32)
 
 
-def mnist_sample_loop(sd: dict, x_T: torch.Tensor, zs, tab: dict, steps: int = T) -> torch.Tensor:
+def unet_forward_bf16_points(sd: dict, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    """The same network (src/mnist.py:76-87) in fp32 arithmetic, but with every value the CUDA path keeps in bf16
+    rounded to bf16 at the same point: the weights of every tensor-core convolution (all but rb1.conv1, which the
+    kernels split into hi/lo terms, and rb1's 1x1 skip, which is fp32 in an epilogue) and the stored activations t1, h1,
+    pool(h1), t2, s2, h2, t3, h3, t4.  Biases, time embeddings, accumulation, rb4's 1x1 skip and the out conv stay fp32,
+    as in the kernels.  Test infrastructure: it shows that the CUDA-vs-fp32 gap IS the operand dtype (the CUDA path sits
+    an order of magnitude closer to this than to unet_forward) and bounds what a different summation order adds."""
+    q = _bf16
+    tt = (t.float() / T).view(-1, 1, 1, 1)
+    bsz = t.shape[0]
+
+    def temb(p):
+        return F.linear(tt, sd[f"{p}.time_emb.weight"], sd[f"{p}.time_emb.bias"]).view(bsz, -1, 1, 1)
+
+    def block(p, xin, first_fp32=False, skip_out_bf16=False, skip_fp32=False):
+        w1 = sd[f"{p}.conv1.weight"] if first_fp32 else q(sd[f"{p}.conv1.weight"])
+        tmid = q(F.relu(F.conv2d(xin, w1, sd[f"{p}.conv1.bias"], padding=1)) + temb(p))
+        h = F.relu(F.conv2d(tmid, q(sd[f"{p}.conv2.weight"]), sd[f"{p}.conv2.bias"], padding=1))
+        if f"{p}.skip.weight" in sd:
+            sw = sd[f"{p}.skip.weight"] if skip_fp32 else q(sd[f"{p}.skip.weight"])
+            sk = F.conv2d(xin, sw, sd[f"{p}.skip.bias"])
+            return h + (q(sk) if skip_out_bf16 else sk)
+        return h + xin
+
+    h1 = q(block("rb1", x, first_fp32=True, skip_fp32=True))
+    p1 = q(F.avg_pool2d(h1, 2))
+    h2 = q(block("rb2", p1, skip_out_bf16=True))
+    h3 = q(block("rb3", h2))
+    cat = torch.cat([F.interpolate(h3, scale_factor=2, mode="nearest"), h1], dim=1)
+    h4 = block("rb4", cat)
+    return F.conv2d(h4, sd["out.weight"], sd["out.bias"])
+
+
+def mnist_p_sample(sd: dict, x: torch.Tensor, t: torch.Tensor, z: torch.Tensor | None, tab: dict, forward=None):
+    return reverse_step(x, (forward or unet_forward)(sd, x, t), t, z, tab)
+
+
+def mnist_sample_loop(sd: dict, x_T: torch.Tensor, zs, tab: dict, steps: int = T, forward=None) -> torch.Tensor:
     """src/mnist.py:190-194 with x_T and the per-step noises injected. zs[i] is the noise used at
-    timestep i (unused for i == 0). Returns the pre-clamp x_0."""
+    timestep i (unused for i == 0). Returns the pre-clamp x_0.  `forward` swaps the denoiser (unet_forward_bf16_points)."""
     x = x_T
     for i in reversed(range(steps)):
         t = torch.full((x.shape[0],), i, dtype=torch.long)
-        x = mnist_p_sample(sd, x, t, None if i == 0 else zs[i], tab)
+        x = mnist_p_sample(sd, x, t, None if i == 0 else zs[i], tab, forward)
     return x
 
 

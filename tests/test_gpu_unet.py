@@ -228,3 +228,22 @@ def test_fused_blocks_match_layer_by_layer_and_oracle(cuda, batch):
     assert rel_rms(fused, ref) < RMS_TOL and float((fused - ref).abs().max() / rms) < MAX_TOL
     torch.testing.assert_close(fused_step, O.mnist_p_sample(sd, x, t, z, TAB), rtol=0, atol=2e-3)
     torch.testing.assert_close(fused_step, plain_step, rtol=0, atol=1e-3)
+
+
+def test_gap_to_the_fp32_oracle_is_the_operand_dtype(cuda):
+    """The CUDA forward against the oracle that rounds to bf16 at the kernels' own rounding points
+    (oracle.unet_forward_bf16_points): it must sit several times closer to that than to the fp32 oracle - what is left
+    is the summation order inside the tensor core and the hi/lo split of rb1.conv1.  This is the evidence that the
+    1e-2 parity bar is the dtype the north star asks for and not a hidden bug."""
+    sd = random_unet_state_dict(77)
+    g = torch.Generator().manual_seed(78)
+    x = torch.randn(64, 1, 28, 28, generator=g)
+    t = torch.randint(0, 1000, (64,), generator=g)
+    eng = UNetEngine(cuda, 64)
+    eng.load_state_dict(sd)
+    got = eng.forward(x.to(cuda), t.to(cuda)).cpu()
+    ref, ref_q = O.unet_forward(sd, x, t), O.unet_forward_bf16_points(sd, x, t)
+    e, e_q, d = rel_rms(got, ref), rel_rms(got, ref_q), rel_rms(ref_q, ref)
+    print(f"CUDA vs fp32 oracle {e:.2e}; CUDA vs bf16-rounding-point oracle {e_q:.2e}; that oracle vs fp32 {d:.2e}")
+    assert e < RMS_TOL
+    assert e_q < 0.5 * e and e_q < 1.5e-3                 # measured 3.1e-3 (fp32) / 5.9e-4 (rounding points)
