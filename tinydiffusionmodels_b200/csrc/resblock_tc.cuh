@@ -117,6 +117,7 @@ struct Rb4Cfg {
     static constexpr int RING_BYTES = 4 * RING_ROWS * 16;            // t: 4 planes
     static constexpr int XCH_BYTES = 2 * 2 * 4 * 2 * 16 * 4;         // [tile parity][half][quarter][up|down][16 fp32]
     static constexpr int PROD = 2;                                   // gather warps
+    static constexpr int B_ISSUERS = 1;                              // warp 0
     static constexpr int EPI1_WARPS = 8, EPI2_WARPS = 8;
     static constexpr int THREADS = 32 * (2 + EPI1_WARPS + EPI2_WARPS + PROD);
     // TMEM: [0,192) conv1 accumulator stages [kx0 | kx1 | kx2], [192,256) conv2 stages, [256,448) the 1x1 skip of the
@@ -154,7 +155,10 @@ struct Rb1Cfg {
     static constexpr int XCH_BYTES = 0;
     static constexpr int PROD = 4;                                   // im2col warps
     static constexpr int EPI1_WARPS = 8, EPI2_WARPS = 8;
-    static constexpr int THREADS = 32 * (2 + EPI1_WARPS + EPI2_WARPS + PROD + 1);   // + issuer B's warp
+    // rb1's conv1 is two small MMAs, so issuer A's turn is too short to hide issuer B's scalar prologue (~700 cycles per
+    // tile next to ~700 of MMA issue): TWO B issuers take alternate steps (one accumulator stage each)
+    static constexpr int B_ISSUERS = 2;
+    static constexpr int THREADS = 32 * (2 + EPI1_WARPS + EPI2_WARPS + PROD + B_ISSUERS);   // 24 warps
     static constexpr int ACC1_COLS = 32, ACC2_COLS = 32, SKIP_SLOTS = 1;
     static constexpr int OFF_ACC2 = 2 * ACC1_COLS, OFF_SKIP = 0;
     static constexpr int TMEM_COLS = 128;
@@ -172,6 +176,21 @@ struct Rb1Cfg {
 
 template <int KIND> struct RbCfgOf { using type = Rb4Cfg; };
 template <> struct RbCfgOf<RB_KIND_RB1> { using type = Rb1Cfg; };
+
+// Waits of the fused blocks: TDM_RB_WAIT_OOL=1 keeps only the first probe inline and calls the shared out-of-line retry
+// loop (tc05.cuh: mbar_wait_slow) - the fused kernels have ~35 wait sites and their code size is an instruction-cache
+// concern (at 55 KB of SASS 39 % of all stall samples were no_inst; at 41 KB 1.9 %).
+#ifndef TDM_RB_WAIT_OOL
+#define TDM_RB_WAIT_OOL 1
+#endif
+__device__ __forceinline__ void rb_wait(uint64_t* bar, uint32_t parity) {
+#if TDM_RB_WAIT_OOL
+    if (mbar_try_wait(bar, parity)) return;
+    mbar_wait_slow(smem_u32(bar), parity, TDM_PARK_NS);
+#else
+    mbar_wait(bar, parity);
+#endif
+}
 
 // Poll a turn token until it reaches `want` (bounded: a protocol bug must trap, not hang the box).
 __device__ __forceinline__ void tok_wait(volatile uint32_t* t, uint32_t want) {
@@ -236,7 +255,12 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 40);
     static_assert(C::RING_SLOTS <= 6 && C::NSTAGE <= 4, "barrier layout");
 
-    const int warp = threadIdx.x >> 5;
+    // TDM_WARP_REV=1 assigns the roles from the highest hardware warp id down (TMEM lane quarters follow the hardware id)
+#ifndef TDM_WARP_REV
+#define TDM_WARP_REV 0
+#endif
+    const int hw_warp = threadIdx.x >> 5;
+    const int warp = TDM_WARP_REV ? C::THREADS / 32 - 1 - hw_warp : hw_warp;
     const int lane = threadIdx.x & 31;
 
     // ---- this CTA's band: conv2 / output tiles [j0, j1), conv1 tiles [j0-1, j1+1) ----
@@ -279,20 +303,20 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
     const uint32_t tmem_base = *s_tmem;
 
     // ===== MMA issuer B (one elected thread): conv2(s - LAG), reading t of tiles j .. j+2 from the ring =====
-    auto issue_conv2 = [&]() {
+    auto issue_conv2 = [&](const int first) {
         constexpr uint32_t idesc_c2 = make_idesc_bf16(128, 32);
-        mbar_wait(bar_w, 0);
+        rb_wait(bar_w, 0);
         const uint32_t w2_addr = smem_u32(s_w2), ring_addr = smem_u32(s_ring);
         int tf_taken = -1;   // t-full phases are taken strictly in tile order
-        for (int s = 0; s < n1 + C::LAG; ++s) {
+        for (int s = first; s < n1 + C::LAG; s += C::B_ISSUERS) {
             const int j = s - C::LAG;
             const bool work = j >= 0 && j < n2;
             if (work) {
-                mbar_wait(bar_acc2e + (j & 1), ((j >> 1) & 1) ^ 1);   // epilogue 2 of conv2(j-2) has drained the accumulator
+                rb_wait(bar_acc2e + (j & 1), ((j >> 1) & 1) ^ 1);   // epilogue 2 of conv2(j-2) has drained the accumulator
                 // conv2(j) reads t of tiles j .. j+2 (epilogue-1 threads fenced their generic-proxy stores)
                 for (; tf_taken < j + 2; ++tf_taken) {
                     const int i = tf_taken + 1;
-                    mbar_wait(bar_tring + i % C::RING_SLOTS, (i / C::RING_SLOTS) & 1);
+                    rb_wait(bar_tring + i % C::RING_SLOTS, (i / C::RING_SLOTS) & 1);
                 }
             }
             TDM_TL(100 + KIND, s, 5);
@@ -324,7 +348,7 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
             TDM_TL(100 + KIND, s, 6);
         }
     };
-    constexpr int kIssuerBWarp = kRb4 ? 0 : C::THREADS / 32 - 1;
+    constexpr int kIssuerBWarp = kRb4 ? 0 : C::THREADS / 32 - C::B_ISSUERS;
 
     if (n2 > 0) {
     if (warp == 0) {
@@ -343,7 +367,7 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
         }
         if constexpr (kRb4) {
             __syncwarp();
-            if (elect_one()) issue_conv2();
+            if (elect_one()) issue_conv2(0);
             __syncwarp();
         } else {
             // rb1: the window of x (fp32, contiguous in [B][784]) that the 3x3 neighbourhoods of tile rows
@@ -352,7 +376,7 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                 for (int i = 0; i < n1; ++i) {
                     const int s = i % C::NSTAGE;
                     const uint32_t ph = (i / C::NSTAGE) & 1;
-                    mbar_wait(bar_xw_empty + s, ph ^ 1);
+                    rb_wait(bar_xw_empty + s, ph ^ 1);
                     const int64_t pos0 = (int64_t)(Tb + i) * kTS - 1;
                     const int64_t lo = rb_pixel_lower_bound(pos0 - 30, a.batch) & ~(int64_t)3;          // 16-byte aligned
                     int64_t hi = (rb_pixel_lower_bound(pos0 + 128 + 30, a.batch) + 3) & ~(int64_t)3;
@@ -368,8 +392,8 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                 }
             }
         }
-    } else if (!kRb4 && warp == kIssuerBWarp) {
-        if (elect_one()) issue_conv2();
+    } else if (!kRb4 && warp >= kIssuerBWarp) {
+        if (elect_one()) issue_conv2(warp - kIssuerBWarp);
         __syncwarp();
     } else if (warp == 1) {
         // ===== MMA issuer A: conv1(s) =====
@@ -377,7 +401,7 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
             constexpr uint32_t idesc_side = make_idesc_bf16(128, 96);
             constexpr uint32_t idesc_c2 = make_idesc_bf16(128, 32);
             (void)idesc_side; (void)idesc_c2;
-            mbar_wait(bar_w, 0);
+            rb_wait(bar_w, 0);
             const uint32_t w1_addr = smem_u32(s_w1), in_addr = smem_u32(s_in);
             for (int s = 0; s < n1 + C::LAG; ++s) {
                 const int j = s - C::LAG;
@@ -387,10 +411,16 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                     // the accumulator conv2(j) will write: taking its release HERE (before conv1(s) is issued) is what
                     // orders epilogue 2 of conv2(j-2) - the reader of stash slot (s-4)%4 - before that slot's next
                     // writer, the epilogue of conv1(s)
-                    if (j >= 0 && j < n2) mbar_wait(bar_acc2e + (j & 1), ((j >> 1) & 1) ^ 1);
+                    if (j >= 0 && j < n2) rb_wait(bar_acc2e + (j & 1), ((j >> 1) & 1) ^ 1);
+#ifdef TDM_TL_FINE
+                    TDM_TL(100 + KIND, s, 14);
+#endif
                     // "accumulator 1 free" = t-full of tile s-2: epilogue 1 arrives on it only after its TMEM reads
-                    if (s >= 2) mbar_wait(bar_tfull + (s & 1), ((s - 2) >> 1) & 1);
-                    mbar_wait(bar_full + st, (s / C::NSTAGE) & 1);
+                    if (s >= 2) rb_wait(bar_tfull + (s & 1), ((s - 2) >> 1) & 1);
+#ifdef TDM_TL_FINE
+                    TDM_TL(100 + KIND, s, 15);
+#endif
+                    rb_wait(bar_full + st, (s / C::NSTAGE) & 1);
                     if constexpr (kRb4) fence_proxy_async_smem();   // cp.async (generic proxy) rows -> async-proxy MMA reads
                 }
                 TDM_TL(100 + KIND, s, 1);
@@ -447,7 +477,7 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
         for (int i = 0; i < n1; ++i) {
             const int s = i % C::NSTAGE;
             const uint32_t ph = (i / C::NSTAGE) & 1;
-            mbar_wait(bar_empty + s, ph ^ 1);
+            rb_wait(bar_empty + s, ph ^ 1);
             if (pw == 0) TDM_TL(100 + KIND, i, 12);
             uint8_t* st = s_in + s * C::STAGE_BYTES;
             // planes 8..11 (the 32 skip channels h1) arrive by bulk copy, issued here: warp 0 is issuer B
@@ -500,8 +530,8 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
         for (int i = pw; i < n1; i += C::PROD) {
             const int s = i % C::NSTAGE;
             const uint32_t ph = (i / C::NSTAGE) & 1;
-            mbar_wait(bar_empty + s, ph ^ 1);      // the MMAs that read this stage last have retired
-            mbar_wait(bar_xw_full + s, ph);        // this tile's window of x has landed
+            rb_wait(bar_empty + s, ph ^ 1);      // the MMAs that read this stage last have retired
+            rb_wait(bar_xw_full + s, ph);        // this tile's window of x has landed
             TDM_TL(100 + KIND, i, 12);
             uint8_t* st = s_in + s * C::STAGE_BYTES;
             const float* xw = reinterpret_cast<const float*>(smem + Rb1Cfg::OFF_XWIN) + s * Rb1Cfg::XWIN_FLOATS;
@@ -556,7 +586,7 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
         }
     } else if (warp < 2 + C::EPI1_WARPS) {
         // ===== epilogue 1: every tile; warp = (TMEM lane quarter q, channel half) =====
-        const int q = warp & 3;
+        const int q = hw_warp & 3;
         const int half = (warp - 2) >> 2;
         const int c0 = half * 16;
         for (int i = 0; i < n1; ++i) {
@@ -575,7 +605,7 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
             float ts = 0.f;
             if (valid) ts = (float)(int)__ldg(a.t + b) / 1000.0f;
 
-            mbar_wait(bar_acc1f + acc, (i >> 1) & 1);
+            rb_wait(bar_acc1f + acc, (i >> 1) & 1);
             if (warp == 2) TDM_TL(100 + KIND, i, 7);
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC1_COLS;
@@ -604,7 +634,9 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                                                 __uint_as_float(d2[4 * k + 2]), __uint_as_float(d2[4 * k + 3]));
                 }
                 named_bar_sync(1 + half, 128);   // the four quarter warps of this channel half
+#ifndef TDM_TL_FINE
                 if (warp == 2) TDM_TL(100 + KIND, i, 14);
+#endif
                 // q == 0 / q == 3: tile rows 0 / 127 are never output rows, any finite value will do
                 const float4* xprev = reinterpret_cast<const float4*>(xbuf + (q > 0 ? q - 1 : 0) * 32);
                 const float4* xnext = reinterpret_cast<const float4*>(xbuf + (q < 3 ? q + 1 : 3) * 32 + 16);
@@ -650,7 +682,9 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                     if (mirror) *reinterpret_cast<uint4*>(tdst + (size_t)plane * (C::RING_ROWS * 16) + mirror * 16) = o;
                 }
             }
+#ifndef TDM_TL_FINE
             if (warp == 2) TDM_TL(100 + KIND, i, 15);
+#endif
             fence_proxy_async_smem();   // this thread's generic-proxy stores -> visible to conv2's async-proxy reads
             tc_fence_before_sync();     // ... and its TMEM reads ordered before the arrival that also frees the accumulator
             __syncwarp();
@@ -662,7 +696,7 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
         }
     } else {
         // ===== epilogue 2: group g = tiles j = g (mod 2); warp = TMEM lane quarter =====
-        const int q = warp & 3;
+        const int q = hw_warp & 3;
         const int grp = (warp - (2 + C::EPI1_WARPS)) >> 2;
         for (int j = grp; j < n2; j += 2) {
             const int trow = q * 32 + lane;
@@ -702,7 +736,7 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
             } else {
                 if (valid) xin = __ldg(a.x + (int64_t)b * 784 + y * 28 + cc);
             }
-            mbar_wait(bar_acc2f + grp, (j >> 1) & 1);
+            rb_wait(bar_acc2f + grp, (j >> 1) & 1);
             if (q == 2) TDM_TL(100 + KIND, j + C::LAG, 10);
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::OFF_ACC2 + grp * C::ACC2_COLS;

@@ -141,13 +141,34 @@ static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t p
         }
     }
 }
+// TDM_WAIT_OOL=1 (set by a kernel's translation unit before including this header) keeps only the first probe
+// inline.  Measured both ways: out of line everywhere made the plain convolution kernels 20-25 % SLOWER (rb2.conv1
+// 208 -> 260 us at 16,384 images: the call clobbers the registers the persistent loops keep live), so the default is
+// the inlined loop.
+#ifndef TDM_WAIT_OOL
+#define TDM_WAIT_OOL 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (TDM_WAIT_TEST ? mbar_test(bar, parity) : mbar_try_wait(bar, parity)) return;
+    if (mbar_try_wait(bar, parity)) return;
+#if TDM_WAIT_OOL
     mbar_wait_slow(smem_u32(bar), parity, TDM_PARK_NS);
+#else
+    const long long t0 = clock64();
+#if TDM_PARK_NS > 0
+    while (!mbar_try_wait_hint(bar, parity, TDM_PARK_NS)) {
+#else
+    while (!mbar_try_wait(bar, parity)) {
+#endif
+        if (clock64() - t0 > 4000000000LL) {
+            printf("tdm: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
+#endif
 }
 // The polling form, for the one thread whose wake-up latency is on the critical path (the MMA issuer).
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-    if (TDM_WAIT_TEST ? mbar_test(bar, parity) : mbar_try_wait(bar, parity)) return;
+    if (mbar_try_wait(bar, parity)) return;
     mbar_wait_slow(smem_u32(bar), parity, 0u);
 }
 
