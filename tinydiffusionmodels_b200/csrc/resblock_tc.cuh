@@ -4,8 +4,7 @@
 //     out = relu(conv2(t) + b2) + skip(in)          conv2 on tcgen05, its A operand read from SHARED MEMORY
 //
 // The intermediate t (and the 1x1 skip of rb4) never reach HBM: conv1's epilogue writes t as bf16 planes into a
-// ring of shared-memory tiles, which is exactly the operand layout conv2's MMAs read at their nine row offsets; rb4's
-// 1x1 skip is computed next to conv1 and simply STAYS IN TMEM (a ring of 32-column slots) until epilogue 2 adds it.
+// ring of shared-memory tiles, which is exactly the operand layout conv2's MMAs read at their nine row offsets.
 // Layer by layer the reverse step moved 13.4 GB at 16,384 images (profiles/r01_traffic_step.json), 130x the
 // algorithmic bytes, because t1/t4/s4 round-tripped HBM; this removes 324 KB of the 818 KB per image-step.
 //
@@ -13,51 +12,30 @@
 // Both convolutions use tiles of stride kTS = 126 positions (tile T = positions [126T-1, 126T+127), rows 1..126
 // are its output rows) so that conv1's kx-triple schedule and conv2's nine-tap schedule see the same tiles:
 //
-//   warp 0       weights once; rb1: per tile the bulk-copied fp32 window of x the tile's 3x3 neighbourhoods fall into;
-//                rb4: then issuer B (below)
-//   warp 1       MMA issuer A, one elected thread: conv1(s) (rb4: + the 1x1 skip of the same rows into its TMEM slot)
-//   issuer B     (rb4: warp 0, rb1: the last warp), one elected thread: conv2(s-LAG)
-//                  The two issuers take turns on the tensor pipe in the fixed order  conv1(s), conv2(s-LAG), conv1(s+1), ...
-//                  (a shared-memory turn counter each way), and each does its own waits, fences and descriptor arithmetic
-//                  while the other one's MMAs execute: with ONE thread doing both, that scalar prologue (~100 dependent
-//                  instructions and a proxy fence, 500-800 cycles) sat between every two MMA bursts and the pipe idled
-//                  (in-kernel timeline: rb4 2,940 cycles per tile for 1,776 of MMAs, rb1 1,620 for 800).
+//   warp 0       producer: weights once; per tile the bulk-copied input (rb4: the 32 skip channels h1 as planes;
+//                rb1: the fp32 window of x the tile's 3x3 neighbourhoods fall into)
+//   warp 1       MMA issuer, one elected thread.  Step s:  conv1(s)  then  conv2(s-3)
 //                  conv2(j) reads t of tiles j, j+1, j+2 (local indices; the band's first and last conv1 tiles
-//                  are halo tiles), so it runs LAG = 4 steps behind: the chain conv1(s-1) -> epilogue 1 (~2,000 cycles)
-//                  -> conv2 -> turn -> conv1(s+2) then spans three steps instead of two
+//                  are halo tiles), so it runs three steps behind: the tensor pipe works on conv1(s) while the
+//                  epilogue of conv1(s-1) is still converting
 //   warps 2..9   epilogue 1 (8 warps = 4 TMEM lane quarters x 2 channel halves), every tile: TMEM -> kx shift-add,
-//                bias, ReLU, time embedding -> bf16 planes into the t ring
-//   warps 10..17 epilogue 2 (2 groups x 4 warps, alternating tiles): TMEM -> bias, ReLU, + skip (rb4: from its TMEM slot,
-//                fp32), 1x1 out conv, reverse step with in-kernel Philox noise (rb4) / + 1x1 skip of x -> h1 planes (rb1)
-//   warps 18..   gather warps: the nearest-x2 upsample of the 14x14 rb3 output into the input stage, both warps on every
-//                tile, and the bulk copies of its 32 skip channels h1 (rb4) /
+//                bias, ReLU, time embedding -> bf16 planes into the t ring (+ the skip rows into the stash ring)
+//   warps 10..17 epilogue 2 (2 groups x 4 warps, alternating tiles): TMEM -> bias, ReLU, + skip, 1x1 out conv,
+//                reverse step with in-kernel Philox noise (rb4) / + 1x1 skip of x -> h1 planes (rb1)
+//   warps 18..   gather warps: the nearest-x2 upsample of the 14x14 rb3 output into the input stage (rb4) /
 //                the im2col rows of the single-channel image, hi/lo bf16 terms, built from the staged window (rb1)
 //
-// Ring safety needs no barriers of its own - the tensor pipe executes in issue order and the turn exchange fixes that
-// order:  the t ring has LAG + 1 = 5 tile slots; tile i's last reader is conv2(i), issued at step i + LAG BEFORE
-// conv1(i + LAG + 1), and epilogue 1 of tile i + 5 (the next writer of the slot) only starts when conv1(i + 5) has
-// completed.  The TMEM skip slot of tile i is read by epilogue 2 of conv2(i-1) before it releases its accumulator;
-// issuer A takes that release BEFORE it issues the conv1 that reuses the slot (LAG + 2 slots).  (Fully independent
-// issuers were tried and were slower: conv1 ran ahead, conv2's MMAs queued behind two tiles of conv1's in the pipe,
-// and the epilogues waited on each other through the ring.)
-//
-// What bounds rb4 now (in-kernel timeline, cycles per 126-row tile: 2,780; MMA law 1,968): shared-memory bandwidth - the
-// MMAs' operand reads take the port for exactly their own duration whenever N < 128, and the input-stage fills, the
-// t-ring stores and the kx shuffles of epilogue 1 share it (the 42 MMAs of a tile then run at 66 cycles each instead
-// of 47) - and, at about the same level, the turnaround of the two input stages.  Removing MMAs (timing experiments
-// TDM_EXP) changes the tile time by less than 6 %.
+// Ring safety needs no barriers of its own - the tensor pipe executes in issue order and the MMA thread is the
+// sequencer:  the t ring has 4 tile slots; tile i's last reader is conv2(i), issued at step i+3 BEFORE conv1(i+4),
+// and epilogue 1 of tile i+4 (the next writer of the slot) only starts when conv1(i+4) has completed.  The stash
+// slot of tile i is read by epilogue 2 of conv2(i-1) before it releases its accumulator; the MMA thread takes that
+// release (it needs it for conv2(i+1) anyway) BEFORE it issues conv1(i+4).
 #pragma once
 #include "conv_tc.cuh"
 
 namespace tdm {
 
 enum : int { RB_KIND_RB1 = 1, RB_KIND_RB4 = 4 };
-
-// timing experiments (WRONG results; development aid): 1 = conv2 issues one tap instead of nine,
-// 4 = rb4's conv1 issues only its ky = 1 row, 6 = rb4 issues no skip MMAs, 7 = epilogue 1 skips its kx shuffles
-#ifndef TDM_EXP
-#define TDM_EXP 0
-#endif
 
 struct RbChanPar {
     float bias1[32];
@@ -95,7 +73,9 @@ struct RbArgs {
 };
 
 constexpr int kTS = 126;            // tile stride of the fused block (both convolutions)
+constexpr int kRingSlots = 4;        // rb4 (shared memory is full); rb1 uses Rb1Cfg::RING_SLOTS
 constexpr int kRingMargin = 40;     // mirrored rows in front of / behind the ring (>= 1 + Wp + 1 = 31)
+constexpr int kRingRows = kRingMargin + kRingSlots * kTS + kRingMargin;   // 584
 
 struct Rb4Cfg {
     using G = Geo<28>;
@@ -104,38 +84,30 @@ struct Rb4Cfg {
     static constexpr int GATHER_PLANES = 8, BULK_PLANES = 4;
     static constexpr int STAGE_BYTES = NPL * G::RT * 16;             // 36,864
     static constexpr int NSTAGE = 2;
-    static constexpr int W1_KY = NPL * 96 * 16;                      // one kernel row, kx-triple: [12][96][8] bf16
-    static constexpr int WSK_BYTES = NPL * 32 * 16;                  // 1x1 skip: [12][32][8]
-    static constexpr int W1_BYTES = 3 * W1_KY + WSK_BYTES;           // 61,440
+    static constexpr int W1_SIDE = NPL * 96 * 16;                    // ky = 0 / ky = 2 block: [12][96][8] bf16
+    static constexpr int W1_MID = NPL * 128 * 16;                    // ky = 1 block with the skip rows: [12][128][8]
+    static constexpr int W1_BYTES = 2 * W1_SIDE + W1_MID;            // 61,440
     static constexpr int W2_BYTES = 9 * 32 * 32 * 2;                 // 18,432
-    // conv2(j) is issued at step j + LAG and needs t of tiles j .. j+2: the dependency chain conv1(s-1) -> epilogue 1
-    // (~2,200 cycles) -> conv2 -> token -> conv1(s+2) spans LAG - 1 steps, and at LAG = 3 it, not the tensor pipe, set
-    // the pace (in-kernel timeline).  The fifth ring slot became affordable when the 1x1 skip stopped being stashed
-    // in shared memory (32 KB): it now stays in TMEM until epilogue 2 wants it (SKIP_SLOTS below).
-    static constexpr int RING_SLOTS = 5, LAG = 4;                    // slots >= LAG + 1
-    static constexpr int RING_ROWS = kRingMargin + RING_SLOTS * kTS + kRingMargin;   // 710
-    static constexpr int RING_BYTES = 4 * RING_ROWS * 16;            // t: 4 planes
+    static constexpr int RING_SLOTS = kRingSlots, LAG = 3;           // conv2(j) is issued at step j + LAG; slots >= LAG + 1
+    static constexpr int RING_ROWS = kRingRows;
+    static constexpr int RING_BYTES = 4 * kRingRows * 16;            // t: 4 planes x 584 rows
+    static constexpr int STASH_BYTES = 4 * kRingSlots * kTS * 16;    // skip: 4 planes x 504 rows
     static constexpr int XCH_BYTES = 2 * 2 * 4 * 2 * 16 * 4;         // [tile parity][half][quarter][up|down][16 fp32]
     static constexpr int PROD = 2;                                   // gather warps
-    static constexpr int B_ISSUERS = 1;                              // warp 0
     static constexpr int EPI1_WARPS = 8, EPI2_WARPS = 8;
     static constexpr int THREADS = 32 * (2 + EPI1_WARPS + EPI2_WARPS + PROD);
-    // TMEM: [0,192) conv1 accumulator stages [kx0 | kx1 | kx2], [192,256) conv2 stages, [256,448) the 1x1 skip of the
-    // last SKIP_SLOTS conv1 tiles: written by conv1(i)'s issuer at step i, read by epilogue 2 of conv2(i-1), which is
-    // issued at step i - 1 + LAG and has released its accumulator by step i + LAG + 1 < i + SKIP_SLOTS
-    static constexpr int ACC1_COLS = 96, ACC2_COLS = 32, SKIP_SLOTS = LAG + 2;
-    static constexpr int OFF_ACC2 = 2 * ACC1_COLS, OFF_SKIP = OFF_ACC2 + 2 * ACC2_COLS;
-    static constexpr int TMEM_COLS = 512;
-    static_assert(OFF_SKIP + SKIP_SLOTS * 32 <= TMEM_COLS, "TMEM layout");
+    static constexpr int ACC1_COLS = 128, ACC2_COLS = 32;
+    static constexpr int TMEM_COLS = 512;                            // 2 x 128 + 2 x 32 = 320 -> next power of two
     static constexpr int OFF_W1 = 0;
     static constexpr int OFF_W2 = OFF_W1 + W1_BYTES;
     static constexpr int OFF_IN = OFF_W2 + W2_BYTES;
     static constexpr int OFF_RING = OFF_IN + NSTAGE * STAGE_BYTES;
-    static constexpr int OFF_XCH = OFF_RING + RING_BYTES;
+    static constexpr int OFF_STASH = OFF_RING + RING_BYTES;
+    static constexpr int OFF_XCH = OFF_STASH + STASH_BYTES;
     static constexpr int OFF_BAR = OFF_XCH + XCH_BYTES;
-    static constexpr int SMEM_BYTES = OFF_BAR + 512;
+    static constexpr int SMEM_BYTES = OFF_BAR + 256;
     static_assert(SMEM_BYTES <= 227 * 1024, "fused rb4 exceeds shared memory");
-    static constexpr int FULL_ARRIVALS = 1 + PROD * 32;              // bulk issuer + one cp.async arrival per gather lane
+    static constexpr int FULL_ARRIVALS = 1 + 32;                     // bulk issuer + one cp.async arrival per gather lane
 };
 
 struct Rb1Cfg {
@@ -152,57 +124,28 @@ struct Rb1Cfg {
     static constexpr int RING_SLOTS = 5, LAG = 4;
     static constexpr int RING_ROWS = kRingMargin + RING_SLOTS * kTS + kRingMargin;   // 710
     static constexpr int RING_BYTES = 4 * RING_ROWS * 16;
+    static constexpr int STASH_BYTES = 0;
     static constexpr int XCH_BYTES = 0;
     static constexpr int PROD = 4;                                   // im2col warps
     static constexpr int EPI1_WARPS = 8, EPI2_WARPS = 8;
-    // rb1's conv1 is two small MMAs, so issuer A's turn is too short to hide issuer B's scalar prologue (~700 cycles per
-    // tile next to ~700 of MMA issue): TWO B issuers take alternate steps (one accumulator stage each)
-    static constexpr int B_ISSUERS = 2;
-    static constexpr int THREADS = 32 * (2 + EPI1_WARPS + EPI2_WARPS + PROD + B_ISSUERS);   // 24 warps
-    static constexpr int ACC1_COLS = 32, ACC2_COLS = 32, SKIP_SLOTS = 1;
-    static constexpr int OFF_ACC2 = 2 * ACC1_COLS, OFF_SKIP = 0;
+    static constexpr int THREADS = 32 * (2 + EPI1_WARPS + EPI2_WARPS + PROD);
+    static constexpr int ACC1_COLS = 32, ACC2_COLS = 32;
     static constexpr int TMEM_COLS = 128;
     static constexpr int OFF_W1 = 0;
     static constexpr int OFF_W2 = OFF_W1 + W1_BYTES;
     static constexpr int OFF_IN = OFF_W2 + W2_BYTES;
     static constexpr int OFF_XWIN = OFF_IN + NSTAGE * STAGE_BYTES;
     static constexpr int OFF_RING = OFF_XWIN + NSTAGE * XWIN_FLOATS * 4;
-    static constexpr int OFF_XCH = OFF_RING + RING_BYTES;
+    static constexpr int OFF_STASH = OFF_RING + RING_BYTES;
+    static constexpr int OFF_XCH = OFF_STASH;
     static constexpr int OFF_BAR = OFF_XCH;
-    static constexpr int SMEM_USED = OFF_BAR + 512;
+    static constexpr int SMEM_USED = OFF_BAR + 256;
     static constexpr int SMEM_BYTES = SMEM_USED > kSoloSmem ? SMEM_USED : kSoloSmem;   // one CTA per SM (conv_tc.cuh)
     static constexpr int FULL_ARRIVALS = 1;                          // the im2col warp that built the stage
 };
 
 template <int KIND> struct RbCfgOf { using type = Rb4Cfg; };
 template <> struct RbCfgOf<RB_KIND_RB1> { using type = Rb1Cfg; };
-
-// Waits of the fused blocks: TDM_RB_WAIT_OOL=1 keeps only the first probe inline and calls the shared out-of-line retry
-// loop (tc05.cuh: mbar_wait_slow) - the fused kernels have ~35 wait sites and their code size is an instruction-cache
-// concern (at 55 KB of SASS 39 % of all stall samples were no_inst; at 41 KB 1.9 %).
-#ifndef TDM_RB_WAIT_OOL
-#define TDM_RB_WAIT_OOL 1
-#endif
-__device__ __forceinline__ void rb_wait(uint64_t* bar, uint32_t parity) {
-#if TDM_RB_WAIT_OOL
-    if (mbar_try_wait(bar, parity)) return;
-    mbar_wait_slow(smem_u32(bar), parity, TDM_PARK_NS);
-#else
-    mbar_wait(bar, parity);
-#endif
-}
-
-// Poll a turn token until it reaches `want` (bounded: a protocol bug must trap, not hang the box).
-__device__ __forceinline__ void tok_wait(volatile uint32_t* t, uint32_t want) {
-    if (*t >= want) return;
-    uint32_t spins = 0;
-    while (*t < want) {
-        if (++spins > 400000000u) {
-            printf("tdm: issuer token wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-            __trap();
-        }
-    }
-}
 
 // Index of the first real pixel at or after position `pos` in the [B][784] fp32 image array (monotone in pos):
 // pad rows / pad columns map to the next pixel.  Used to bound the window of x a tile's 3x3 neighbourhoods touch.
@@ -233,6 +176,7 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
     uint8_t* s_w2 = smem + C::OFF_W2;
     uint8_t* s_in = smem + C::OFF_IN;
     uint8_t* s_ring = smem + C::OFF_RING;
+    uint8_t* s_stash = smem + C::OFF_STASH;
     float* s_xch = reinterpret_cast<float*>(smem + C::OFF_XCH);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
     uint64_t* bar_xw_full = bars + 24;            // rb1: NSTAGE (x window landed)
@@ -245,22 +189,9 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
     uint64_t* bar_tfull = bar_acc1e + 2;          // 2
     uint64_t* bar_acc2f = bar_tfull + 2;          // 2
     uint64_t* bar_acc2e = bar_acc2f + 2;          // 2
-    // turn tokens of the two MMA issuers: plain shared-memory counters polled with volatile loads.  They order instruction
-    // ISSUE only (no data passes through them), and an mbarrier hand-off cost 330-400 cycles each way (in-kernel timeline).
-    volatile uint32_t* tok = reinterpret_cast<volatile uint32_t*>(bars + 42);   // [0] B -> A: steps B has issued, [1] A -> B
-    // "t of tile i is in the ring", for issuer B: one barrier per ring slot.  (bar_tfull's two barriers serve issuer A as
-    // "accumulator 1 free"; B first looks LAG steps after A and would find them two phases on.)  Slot i % SLOTS cannot
-    // complete its next phase before B has issued conv2(i): the slot's next writer waits, through A, for that.
-    uint64_t* bar_tring = bars + 32;              // RING_SLOTS (<= 6)
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 40);
-    static_assert(C::RING_SLOTS <= 6 && C::NSTAGE <= 4, "barrier layout");
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc2e + 2);
 
-    // TDM_WARP_REV=1 assigns the roles from the highest hardware warp id down (TMEM lane quarters follow the hardware id)
-#ifndef TDM_WARP_REV
-#define TDM_WARP_REV 0
-#endif
-    const int hw_warp = threadIdx.x >> 5;
-    const int warp = TDM_WARP_REV ? C::THREADS / 32 - 1 - hw_warp : hw_warp;
+    const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
     // ---- this CTA's band: conv2 / output tiles [j0, j1), conv1 tiles [j0-1, j1+1) ----
@@ -289,9 +220,6 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
             mbar_init(bar_acc2f + i, 1);
             mbar_init(bar_acc2e + i, 4);
         }
-        for (int i = 0; i < C::RING_SLOTS; ++i) mbar_init(bar_tring + i, C::EPI1_WARPS);
-        tok[0] = 0u;
-        tok[1] = 0u;
         mbar_fence_init();
     }
     if (warp == 2) tmem_alloc<C::TMEM_COLS>(s_tmem);
@@ -302,63 +230,20 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
     tc_fence_after_sync();
     const uint32_t tmem_base = *s_tmem;
 
-    // ===== MMA issuer B (one elected thread): conv2(s - LAG), reading t of tiles j .. j+2 from the ring =====
-    auto issue_conv2 = [&](const int first) {
-        constexpr uint32_t idesc_c2 = make_idesc_bf16(128, 32);
-        rb_wait(bar_w, 0);
-        const uint32_t w2_addr = smem_u32(s_w2), ring_addr = smem_u32(s_ring);
-        int tf_taken = -1;   // t-full phases are taken strictly in tile order
-        for (int s = first; s < n1 + C::LAG; s += C::B_ISSUERS) {
-            const int j = s - C::LAG;
-            const bool work = j >= 0 && j < n2;
-            if (work) {
-                rb_wait(bar_acc2e + (j & 1), ((j >> 1) & 1) ^ 1);   // epilogue 2 of conv2(j-2) has drained the accumulator
-                // conv2(j) reads t of tiles j .. j+2 (epilogue-1 threads fenced their generic-proxy stores)
-                for (; tf_taken < j + 2; ++tf_taken) {
-                    const int i = tf_taken + 1;
-                    rb_wait(bar_tring + i % C::RING_SLOTS, (i / C::RING_SLOTS) & 1);
-                }
-            }
-            TDM_TL(100 + KIND, s, 5);
-            tok_wait(tok + 1, (uint32_t)s + 1u);                      // issuer A has issued conv1(s)
-            TDM_TL(100 + KIND, s, 2);
-            if (work) {
-                tc_fence_after_sync();
-                uint32_t w_t = w2_addr;
-                asm volatile("" : "+r"(w_t));   // rebuild the descriptors per tile from a uniform address (conv_tc.cuh)
-                const uint64_t w_base = make_smem_desc(w_t, 32 * 16, 128);
-                // centre tile = local conv1 tile j+1 in ring slot (j+1) % SLOTS; tile row 0 = ring row slot*126 - 1
-                const uint32_t row0 = kRingMargin + ((j + 1) % C::RING_SLOTS) * kTS - 1;
-                const uint64_t t_base = make_smem_desc(ring_addr + row0 * 16, C::RING_ROWS * 16, 128);
-                const uint32_t d = tmem_base + C::OFF_ACC2 + (j & 1) * C::ACC2_COLS;
-#pragma unroll
-                for (int tap = (TDM_EXP == 1 ? 4 : 0); tap < (TDM_EXP == 1 ? 5 : 9); ++tap) {
-                    const int off = (tap / 3 - 1) * G::Wp + (tap % 3 - 1);
-#pragma unroll
-                    for (int ks = 0; ks < 2; ++ks) {
-                        // off may be negative: add it as a signed row count to the 14-bit address field (never borrows:
-                        // the ring sits far above shared-memory address 0)
-                        umma_bf16(d, t_base + (uint64_t)(int64_t)(off + (2 * ks) * C::RING_ROWS),
-                                  desc_add(w_base, ((tap * 4 + 2 * ks) * 32) * 16), idesc_c2, ((TDM_EXP == 1 ? tap - 4 : tap) | ks) != 0);
-                    }
-                }
-                umma_commit(bar_acc2f + (j & 1));
-            }
-            tok[0] = (uint32_t)s + 1u;   // issuer A's turn
-            TDM_TL(100 + KIND, s, 6);
-        }
-    };
-    constexpr int kIssuerBWarp = kRb4 ? 0 : C::THREADS / 32 - C::B_ISSUERS;
-
     if (n2 > 0) {
     if (warp == 0) {
         // ===== producer: weights once, then the bulk-copied input of every conv1 tile =====
         if (lane == 0) {
             mbar_arrive_expect_tx(bar_w, C::W1_BYTES + C::W2_BYTES);
             if constexpr (kRb4) {
-                // conv1, kx-triple: three kernel rows [12][96][8], then the 1x1 skip [12][32][8]
-                for (int ky = 0; ky < 3; ++ky) bulk_g2s(s_w1 + ky * Rb4Cfg::W1_KY, a.w1 + ky * Rb4Cfg::W1_KY, Rb4Cfg::W1_KY, bar_w);
-                bulk_g2s(s_w1 + 3 * Rb4Cfg::W1_KY, a.wsk, Rb4Cfg::WSK_BYTES, bar_w);
+                // conv1: ky = 0 and ky = 2 blocks as they are ([12][96][8]); the ky = 1 block gets the 32 skip rows
+                // behind its 96 (one N = 128 MMA per K step yields the three kx partials AND the 1x1 skip)
+                bulk_g2s(s_w1, a.w1, Rb4Cfg::W1_SIDE, bar_w);
+                bulk_g2s(s_w1 + Rb4Cfg::W1_SIDE + Rb4Cfg::W1_MID, a.w1 + 2 * Rb4Cfg::W1_SIDE, Rb4Cfg::W1_SIDE, bar_w);
+                for (int k = 0; k < Rb4Cfg::NPL; ++k) {
+                    bulk_g2s(s_w1 + Rb4Cfg::W1_SIDE + k * 2048, a.w1 + Rb4Cfg::W1_SIDE + k * 1536, 1536, bar_w);
+                    bulk_g2s(s_w1 + Rb4Cfg::W1_SIDE + k * 2048 + 1536, a.wsk + k * 512, 512, bar_w);
+                }
             } else {
                 bulk_g2s(s_w1, a.w1, C::W1_BYTES, bar_w);
             }
@@ -366,9 +251,21 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
             bulk_g2s(s_w2 + 16384, a.w2 + 16384, C::W2_BYTES - 16384, bar_w);
         }
         if constexpr (kRb4) {
-            __syncwarp();
-            if (elect_one()) issue_conv2(0);
-            __syncwarp();
+            for (int i = 0; i < n1; ++i) {
+                const int s = i % C::NSTAGE;
+                const uint32_t ph = (i / C::NSTAGE) & 1;
+                if (lane == 0) {
+                    mbar_wait(bar_empty + s, ph ^ 1);
+                    mbar_arrive_expect_tx(bar_full + s, Rb4Cfg::BULK_PLANES * G::RT * 16);
+                }
+                __syncwarp();
+                if (lane < Rb4Cfg::BULK_PLANES) {
+                    // smem row 0 = global position 126*T - 1 - HALO; the buffers start at row -GUARD
+                    const int64_t row = (int64_t)(Tb + i) * kTS - 1 - G::HALO + G::GUARD;
+                    bulk_g2s(s_in + s * C::STAGE_BYTES + (Rb4Cfg::GATHER_PLANES + lane) * (G::RT * 16),
+                             a.in + lane * a.in_ps + row * 16, G::RT * 16, bar_full + s);
+                }
+            }
         } else {
             // rb1: the window of x (fp32, contiguous in [B][784]) that the 3x3 neighbourhoods of tile rows
             // [126T-1, 126T+127) fall into: pixels lower_bound(pos0 - 30) .. lower_bound(pos0 + 128 + 30)
@@ -376,7 +273,7 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                 for (int i = 0; i < n1; ++i) {
                     const int s = i % C::NSTAGE;
                     const uint32_t ph = (i / C::NSTAGE) & 1;
-                    rb_wait(bar_xw_empty + s, ph ^ 1);
+                    mbar_wait(bar_xw_empty + s, ph ^ 1);
                     const int64_t pos0 = (int64_t)(Tb + i) * kTS - 1;
                     const int64_t lo = rb_pixel_lower_bound(pos0 - 30, a.batch) & ~(int64_t)3;          // 16-byte aligned
                     int64_t hi = (rb_pixel_lower_bound(pos0 + 128 + 30, a.batch) + 3) & ~(int64_t)3;
@@ -392,41 +289,44 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                 }
             }
         }
-    } else if (!kRb4 && warp >= kIssuerBWarp) {
-        if (elect_one()) issue_conv2(warp - kIssuerBWarp);
-        __syncwarp();
     } else if (warp == 1) {
-        // ===== MMA issuer A: conv1(s) =====
+        // ===== MMA issuer =====
         if (elect_one()) {
+            constexpr uint32_t idesc_mid = make_idesc_bf16(128, 128);
             constexpr uint32_t idesc_side = make_idesc_bf16(128, 96);
             constexpr uint32_t idesc_c2 = make_idesc_bf16(128, 32);
-            (void)idesc_side; (void)idesc_c2;
-            rb_wait(bar_w, 0);
-            const uint32_t w1_addr = smem_u32(s_w1), in_addr = smem_u32(s_in);
+            mbar_wait(bar_w, 0);
+            const uint32_t w1_addr = smem_u32(s_w1), w2_addr = smem_u32(s_w2);
+            const uint32_t in_addr = smem_u32(s_in), ring_addr = smem_u32(s_ring);
+            // The barriers of step s+1 are PROBED (test_wait) between the MMAs of step s, while the pipe works through
+            // what is already queued; a step only blocks on a barrier whose probe failed.  With blocking waits at
+            // the top of every step the four already-satisfied waits cost ~600 cycles per step during which the
+            // pipe drained (in-kernel timeline, tools/fused_timeline.py: rb1 1,580 cycles per step for 800 of MMAs).
+            bool ok_full = false, ok_a2 = false, ok_tf = false;
+            int tf_taken = -1;   // t-full phases are taken strictly in tile order, each exactly once
+            auto take_tfull = [&](int upto) {
+                for (; tf_taken < upto; ++tf_taken) {
+                    const int i = tf_taken + 1;
+                    if (!(ok_tf && i == upto)) mbar_wait(bar_tfull + (i & 1), (i >> 1) & 1);
+                }
+                ok_tf = false;
+            };
             for (int s = 0; s < n1 + C::LAG; ++s) {
                 const int j = s - C::LAG;
-                const int st = s % C::NSTAGE;
                 TDM_TL(100 + KIND, s, 0);
-                if (s < n1) {
-                    // the accumulator conv2(j) will write: taking its release HERE (before conv1(s) is issued) is what
-                    // orders epilogue 2 of conv2(j-2) - the reader of stash slot (s-4)%4 - before that slot's next
-                    // writer, the epilogue of conv1(s)
-                    if (j >= 0 && j < n2) rb_wait(bar_acc2e + (j & 1), ((j >> 1) & 1) ^ 1);
-#ifdef TDM_TL_FINE
-                    TDM_TL(100 + KIND, s, 14);
-#endif
-                    // "accumulator 1 free" = t-full of tile s-2: epilogue 1 arrives on it only after its TMEM reads
-                    if (s >= 2) rb_wait(bar_tfull + (s & 1), ((s - 2) >> 1) & 1);
-#ifdef TDM_TL_FINE
-                    TDM_TL(100 + KIND, s, 15);
-#endif
-                    rb_wait(bar_full + st, (s / C::NSTAGE) & 1);
-                    if constexpr (kRb4) fence_proxy_async_smem();   // cp.async (generic proxy) rows -> async-proxy MMA reads
-                }
+                // the accumulator conv2(j) will write: taking its release HERE (before conv1(s) is issued) is what
+                // orders epilogue 2 of conv2(j-2) - the reader of stash slot (s-4)%4 - before that slot's next
+                // writer, the epilogue of conv1(s)
+                if (j >= 0 && j < n2 && !ok_a2) mbar_wait(bar_acc2e + (j & 1), ((j >> 1) & 1) ^ 1);
                 TDM_TL(100 + KIND, s, 1);
-                tok_wait(tok + 0, (uint32_t)s);                       // issuer B has issued conv2 of step s-1
-                TDM_TL(100 + KIND, s, 3);
                 if (s < n1) {
+                    const int st = s % C::NSTAGE;
+                    // "accumulator 1 free" = t-full of tile s-2: epilogue 1 arrives on it only after its TMEM reads.
+                    // Taking it here also keeps each t-full barrier at most one phase ahead of this thread.
+                    if (s >= 2) take_tfull(s - 2);
+                    if (!ok_full) mbar_wait(bar_full + st, (s / C::NSTAGE) & 1);
+                    TDM_TL(100 + KIND, s, 3);
+                    if constexpr (kRb4) fence_proxy_async_smem();   // cp.async (generic proxy) rows -> async-proxy MMA reads
                     tc_fence_after_sync();
                     uint32_t w_t = w1_addr;
                     asm volatile("" : "+r"(w_t));   // rebuild the descriptors per tile from a uniform address (conv_tc.cuh)
@@ -434,22 +334,22 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                     if constexpr (kRb4) {
                         const uint64_t in_base = make_smem_desc(in_addr + (uint32_t)st * C::STAGE_BYTES, G::RT * 16, 128);
                         const uint64_t wa = make_smem_desc(w_t, 96 * 16, 128);
-                        const uint64_t wk = make_smem_desc(w_t + 3 * Rb4Cfg::W1_KY, 32 * 16, 128);
-                        // one N = 96 MMA per kernel row and K step yields the three kx partials [kx0 | kx1 | kx2]
+                        const uint64_t wb = make_smem_desc(w_t + Rb4Cfg::W1_SIDE, 128 * 16, 128);
+                        const uint64_t wc = make_smem_desc(w_t + Rb4Cfg::W1_SIDE + Rb4Cfg::W1_MID, 96 * 16, 128);
+                        // ky = 1 first: its N = 128 MMAs initialise all four column groups [kx0 | kx1 | kx2 | skip]
 #pragma unroll
-                        for (int ky = (TDM_EXP == 4 ? 1 : 0); ky < (TDM_EXP == 4 ? 2 : 3); ++ky)
+                        for (int ks = 0; ks < C::CIN / 16; ++ks)
+                            umma_bf16(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + G::HALO * 16),
+                                      desc_add(wb, (2 * ks) * 2048), idesc_mid, ks != 0);
 #pragma unroll
-                            for (int ks = 0; ks < C::CIN / 16; ++ks)
-                                umma_bf16(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + (ky - 1) * G::Wp) * 16),
-                                          desc_add(wa, ky * Rb4Cfg::W1_KY + (2 * ks) * 1536), idesc_side,
-                                          ((TDM_EXP == 4 ? ky - 1 : ky) | ks) != 0);
-                        // the 1x1 skip of the block input (src/mnist.py:61) into its own TMEM slot: it stays there until
-                        // epilogue 2 of conv2(s-1) adds it, LAG steps from now
-                        const uint32_t dsk = tmem_base + C::OFF_SKIP + (s % C::SKIP_SLOTS) * 32;
+                        for (int ks = 0; ks < C::CIN / 16; ++ks)
+                            umma_bf16(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO - G::Wp) * 16),
+                                      desc_add(wa, (2 * ks) * 1536), idesc_side, 1u);
+                        if (s >= 1 && tf_taken == s - 2) ok_tf = mbar_test(bar_tfull + ((s - 1) & 1), ((s - 1) >> 1) & 1);
 #pragma unroll
-                        for (int ks = 0; ks < (TDM_EXP == 6 ? 0 : C::CIN / 16); ++ks)
-                            umma_bf16(dsk, desc_add(in_base, (2 * ks) * (G::RT * 16) + G::HALO * 16),
-                                      desc_add(wk, (2 * ks) * 512), idesc_c2, ks != 0);
+                        for (int ks = 0; ks < C::CIN / 16; ++ks)
+                            umma_bf16(d, desc_add(in_base, (2 * ks) * (G::RT * 16) + (G::HALO + G::Wp) * 16),
+                                      desc_add(wc, (2 * ks) * 1536), idesc_side, 1u);
                     } else {
                         // rb1.conv1 as a K = 32 GEMM over the im2col rows (hi/lo bf16 tap terms, conv_tc.cuh)
                         const uint64_t in_base = make_smem_desc(in_addr + (uint32_t)st * C::STAGE_BYTES, kTile * 16, 128);
@@ -460,40 +360,56 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                     }
                     umma_commit(bar_empty + st);
                     umma_commit(bar_acc1f + (s & 1));
+                    TDM_TL(100 + KIND, s, 4);
                 }
-                tok[1] = (uint32_t)s + 1u;   // issuer B's turn
-                TDM_TL(100 + KIND, s, 4);
+                if (j >= 0 && j < n2) {
+                    // conv2(j) reads t of tiles j .. j+2 (epilogue-1 threads fenced their generic-proxy stores)
+                    take_tfull(j + 2);
+                    TDM_TL(100 + KIND, s, 5);
+                }
+                ok_full = ok_a2 = ok_tf = false;
+                if (j >= 0 && j < n2) {
+                    tc_fence_after_sync();
+                    uint32_t w_t = w2_addr;
+                    asm volatile("" : "+r"(w_t));
+                    const uint64_t w_base = make_smem_desc(w_t, 32 * 16, 128);
+                    // centre tile = local conv1 tile j+1 in ring slot (j+1)%4; tile row 0 = ring row slot*126 - 1
+                    const uint32_t row0 = kRingMargin + ((j + 1) % C::RING_SLOTS) * kTS - 1;
+                    const uint64_t t_base = make_smem_desc(ring_addr + row0 * 16, C::RING_ROWS * 16, 128);
+                    const uint32_t d = tmem_base + 2 * C::ACC1_COLS + (j & 1) * C::ACC2_COLS;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int off = (tap / 3 - 1) * G::Wp + (tap % 3 - 1);
+                        // next step's barriers, one probe at a time with a few MMAs queued behind each
+                        if (tap == 3 && s + 1 < n1) ok_full = mbar_test(bar_full + (s + 1) % C::NSTAGE, ((s + 1) / C::NSTAGE) & 1);
+                        if (tap == 6 && j + 1 < n2) ok_a2 = mbar_test(bar_acc2e + ((j + 1) & 1), (((j + 1) >> 1) & 1) ^ 1);
+#pragma unroll
+                        for (int ks = 0; ks < 2; ++ks) {
+                            // off may be negative: add it as a signed row count to the 14-bit address field (never borrows:
+                            // the ring sits far above shared-memory address 0)
+                            umma_bf16(d, t_base + (uint64_t)(int64_t)(off + (2 * ks) * C::RING_ROWS),
+                                      desc_add(w_base, ((tap * 4 + 2 * ks) * 32) * 16), idesc_c2, (tap | ks) != 0);
+                        }
+                    }
+                    umma_commit(bar_acc2f + (j & 1));
+                    TDM_TL(100 + KIND, s, 6);
+                }
             }
         }
         __syncwarp();
     } else if (warp >= 2 + C::EPI1_WARPS + C::EPI2_WARPS) {
         const int pw = warp - (2 + C::EPI1_WARPS + C::EPI2_WARPS);
         if constexpr (kRb4) {
-        // ===== gather warps: planes 0..7 of the input stage = nearest-x2 upsample of h3 (src/mnist.py:83).  BOTH warps work
-        //       on every tile (alternate 32-row blocks).  A stage's turnaround (issue ~2,000 cycles + ~1,400 to land) is one
-        //       of the two things that bound this kernel (the other: shared-memory bandwidth, MMA operand reads + everything
-        //       else).  Tried and measured, no gain: six gather warps, three (warp 0 included), an L2 prefetch of the next
-        //       tiles' h3 lines, staging h3 by bulk copy and expanding it shared -> shared (slower: 3,100 cycles per tile) =====
-        for (int i = 0; i < n1; ++i) {
+        // ===== gather warps: planes 0..7 of the input stage = nearest-x2 upsample of h3 (src/mnist.py:83) =====
+        for (int i = pw; i < n1; i += C::PROD) {
             const int s = i % C::NSTAGE;
             const uint32_t ph = (i / C::NSTAGE) & 1;
-            rb_wait(bar_empty + s, ph ^ 1);
-            if (pw == 0) TDM_TL(100 + KIND, i, 12);
+            mbar_wait(bar_empty + s, ph ^ 1);
+            TDM_TL(100 + KIND, i, 12);
             uint8_t* st = s_in + s * C::STAGE_BYTES;
-            // planes 8..11 (the 32 skip channels h1) arrive by bulk copy, issued here: warp 0 is issuer B
-            if (pw == 0) {
-                if (lane == 0) mbar_arrive_expect_tx(bar_full + s, Rb4Cfg::BULK_PLANES * G::RT * 16);
-                __syncwarp();
-                if (lane < Rb4Cfg::BULK_PLANES) {
-                    // smem row 0 = global position 126*T - 1 - HALO; the buffers start at row -GUARD
-                    const int64_t row = (int64_t)(Tb + i) * kTS - 1 - G::HALO + G::GUARD;
-                    bulk_g2s(st + (Rb4Cfg::GATHER_PLANES + lane) * (G::RT * 16), a.in + lane * a.in_ps + row * 16,
-                             G::RT * 16, bar_full + s);
-                }
-            }
             const int pos0 = (Tb + i) * kTS - 1 - G::HALO;   // may be negative
-            // lane's first row decoded once; every further row is 64 positions on: (row, column) += (2, 6) with carries
-            int pos = pos0 + pw * 32 + lane;
+            // lane's first row decoded once; every further row is 32 positions on: (row, column) += (1, 3) with carries
+            int pos = pos0 + lane;
             int b = 0, rw = 0, c = 0;
             {
                 const int pp = pos < 0 ? pos + G::S : pos;   // pos0 >= -160-S never happens: tiles start at T >= -1
@@ -504,7 +420,7 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                 if (pos < 0) b -= 1;
             }
 #pragma unroll 1
-            for (int r = pw * 32 + lane; r < G::RT; r += 32 * C::PROD) {
+            for (int r = lane; r < G::RT; r += 32) {
                 const uint8_t* src = a.in2;   // any valid address when the row is zero-filled
                 uint32_t nbytes = 0;
                 if (b >= 0 && b < a.batch && rw >= 1 && c < G::W) {
@@ -515,13 +431,12 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
 #pragma unroll
                 for (int pl = 0; pl < Rb4Cfg::GATHER_PLANES; ++pl)
                     cp_async16<true>(st + pl * (G::RT * 16) + r * 16, nbytes ? src + pl * a.in2_ps : src, nbytes);
-                static_assert(C::PROD == 2 || !kRb4, "row stepping below assumes two gather warps (64 positions per step)");
-                c += 6; rw += 2;   // 64 = 2 * 29 + 6
+                c += 3; rw += 1;
                 if (c >= G::Wp) { c -= G::Wp; rw += 1; }
                 if (rw >= G::Wp) { rw -= G::Wp; b += 1; }
             }
             cp_async_arrive_noinc(bar_full + s);
-            if (pw == 0) TDM_TL(100 + KIND, i, 13);
+            TDM_TL(100 + KIND, i, 13);
         }
         } else {
         // ===== im2col warps (rb1): tile row p gets the 3x3 window of x around p as 32 "channels" (conv_tc.cuh:
@@ -530,8 +445,8 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
         for (int i = pw; i < n1; i += C::PROD) {
             const int s = i % C::NSTAGE;
             const uint32_t ph = (i / C::NSTAGE) & 1;
-            rb_wait(bar_empty + s, ph ^ 1);      // the MMAs that read this stage last have retired
-            rb_wait(bar_xw_full + s, ph);        // this tile's window of x has landed
+            mbar_wait(bar_empty + s, ph ^ 1);      // the MMAs that read this stage last have retired
+            mbar_wait(bar_xw_full + s, ph);        // this tile's window of x has landed
             TDM_TL(100 + KIND, i, 12);
             uint8_t* st = s_in + s * C::STAGE_BYTES;
             const float* xw = reinterpret_cast<const float*>(smem + Rb1Cfg::OFF_XWIN) + s * Rb1Cfg::XWIN_FLOATS;
@@ -586,7 +501,7 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
         }
     } else if (warp < 2 + C::EPI1_WARPS) {
         // ===== epilogue 1: every tile; warp = (TMEM lane quarter q, channel half) =====
-        const int q = hw_warp & 3;
+        const int q = warp & 3;
         const int half = (warp - 2) >> 2;
         const int c0 = half * 16;
         for (int i = 0; i < n1; ++i) {
@@ -605,16 +520,18 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
             float ts = 0.f;
             if (valid) ts = (float)(int)__ldg(a.t + b) / 1000.0f;
 
-            rb_wait(bar_acc1f + acc, (i >> 1) & 1);
+            mbar_wait(bar_acc1f + acc, (i >> 1) & 1);
             if (warp == 2) TDM_TL(100 + KIND, i, 7);
             tc_fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC1_COLS;
             float v[16];
+            uint32_t sk[16];
             if constexpr (kRb4) {
                 uint32_t d0[16], d1[16], d2[16];
                 tmem_ld16(taddr + c0, d0);
                 tmem_ld16(taddr + 32 + c0, d1);
                 tmem_ld16(taddr + 64 + c0, d2);
+                tmem_ld16(taddr + 96 + c0, sk);
                 tmem_ld_wait();
                 if (warp == 2) TDM_TL(100 + KIND, i, 8);
                 // out[p] = Y0[p-1] + Y1[p] + Y2[p+1]: neighbour rows are neighbour lanes; across a warp boundary they
@@ -634,9 +551,7 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                                                 __uint_as_float(d2[4 * k + 2]), __uint_as_float(d2[4 * k + 3]));
                 }
                 named_bar_sync(1 + half, 128);   // the four quarter warps of this channel half
-#ifndef TDM_TL_FINE
                 if (warp == 2) TDM_TL(100 + KIND, i, 14);
-#endif
                 // q == 0 / q == 3: tile rows 0 / 127 are never output rows, any finite value will do
                 const float4* xprev = reinterpret_cast<const float4*>(xbuf + (q > 0 ? q - 1 : 0) * 32);
                 const float4* xnext = reinterpret_cast<const float4*>(xbuf + (q < 3 ? q + 1 : 3) * 32 + 16);
@@ -648,8 +563,8 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         const int k = 4 * k4 + jj;
-                        const float up = TDM_EXP == 7 ? __uint_as_float(d0[k]) : __shfl_up_sync(0xffffffffu, __uint_as_float(d0[k]), 1);
-                        const float dn = TDM_EXP == 7 ? __uint_as_float(d2[k]) : __shfl_down_sync(0xffffffffu, __uint_as_float(d2[k]), 1);
+                        const float up = __shfl_up_sync(0xffffffffu, __uint_as_float(d0[k]), 1);
+                        const float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(d2[k]), 1);
                         const float accv = (first ? pus[jj] : up) + __uint_as_float(d1[k]) + (last ? pds[jj] : dn);
                         // src/mnist.py:57-59: relu(conv1 + b) + time_emb(t)
                         v[k] = fmaxf(accv + a.cp.bias1[c0 + k], 0.f) + fmaf(a.cp.tw[c0 + k], ts, a.cp.tb[c0 + k]);
@@ -680,23 +595,30 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
                     const int plane = half * 2 + pj;
                     *reinterpret_cast<uint4*>(tdst + (size_t)plane * (C::RING_ROWS * 16)) = o;
                     if (mirror) *reinterpret_cast<uint4*>(tdst + (size_t)plane * (C::RING_ROWS * 16) + mirror * 16) = o;
+                    if constexpr (kRb4) {
+                        // 1x1 skip of the block input (src/mnist.py:61), kept as bf16 like the layer-by-layer path's s4
+                        uint4 o2;
+                        uint32_t* ow = &o2.x;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int ch = c0 + pj * 8 + 2 * k;
+                            ow[k] = pack_bf16x2(__uint_as_float(sk[pj * 8 + 2 * k]) + a.cp.sbias[ch],
+                                                __uint_as_float(sk[pj * 8 + 2 * k + 1]) + a.cp.sbias[ch + 1]);
+                        }
+                        *reinterpret_cast<uint4*>(s_stash + (size_t)rrow * 16 + (size_t)plane * (kRingSlots * kTS * 16)) = o2;
+                    }
                 }
             }
-#ifndef TDM_TL_FINE
             if (warp == 2) TDM_TL(100 + KIND, i, 15);
-#endif
             fence_proxy_async_smem();   // this thread's generic-proxy stores -> visible to conv2's async-proxy reads
             tc_fence_before_sync();     // ... and its TMEM reads ordered before the arrival that also frees the accumulator
             __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(bar_tfull + acc);
-                mbar_arrive(bar_tring + i % C::RING_SLOTS);
-            }
+            if (lane == 0) mbar_arrive(bar_tfull + acc);
             if (warp == 2) TDM_TL(100 + KIND, i, 9);
         }
     } else {
         // ===== epilogue 2: group g = tiles j = g (mod 2); warp = TMEM lane quarter =====
-        const int q = hw_warp & 3;
+        const int q = warp & 3;
         const int grp = (warp - (2 + C::EPI1_WARPS)) >> 2;
         for (int j = grp; j < n2; j += 2) {
             const int trow = q * 32 + lane;
@@ -736,18 +658,21 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
             } else {
                 if (valid) xin = __ldg(a.x + (int64_t)b * 784 + y * 28 + cc);
             }
-            rb_wait(bar_acc2f + grp, (j >> 1) & 1);
+            mbar_wait(bar_acc2f + grp, (j >> 1) & 1);
             if (q == 2) TDM_TL(100 + KIND, j + C::LAG, 10);
             tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + C::OFF_ACC2 + grp * C::ACC2_COLS;
+            uint4 rv[4];
+            if constexpr (kRb4) {
+                // the skip rows of this tile: written by epilogue 1 of local conv1 tile j+1 (slot (j+1)%4) long before
+                // conv2(j) could be issued.  Read BEFORE the accumulator is released (see the MMA warp).
+                const int srow = ((j + 1) & 3) * kTS + (trow >= 1 && trow <= kTS ? trow - 1 : 0);
+#pragma unroll
+                for (int pl = 0; pl < 4; ++pl)
+                    rv[pl] = *reinterpret_cast<const uint4*>(s_stash + (size_t)pl * (kRingSlots * kTS * 16) + (size_t)srow * 16);
+            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 2 * C::ACC1_COLS + grp * C::ACC2_COLS;
             uint32_t r1[32];
             tmem_ld32(taddr, r1);
-            uint32_t sk[kRb4 ? 32 : 1];
-            if constexpr (kRb4) {
-                // the 1x1 skip of these rows: left in TMEM by conv1 of local tile j+1.  Read BEFORE the accumulator is
-                // released: that release is what lets issuer A reuse the skip slot SKIP_SLOTS tiles on.
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + C::OFF_SKIP + ((j + 1) % C::SKIP_SLOTS) * 32, sk);
-            }
             tmem_ld_wait();
             tc_fence_before_sync();
             __syncwarp();
@@ -755,10 +680,18 @@ __global__ void __launch_bounds__(RbCfgOf<KIND>::type::THREADS, 1) resblock_tc_k
             if constexpr (kRb4) {
                 float dot = 0.f;
 #pragma unroll
-                for (int ch = 0; ch < 32; ++ch) {
-                    // src/mnist.py:60-61 then the 1x1 out conv (:87)
-                    const float v = fmaxf(__uint_as_float(r1[ch]) + a.cp.bias2[ch], 0.f) + (__uint_as_float(sk[ch]) + a.cp.sbias[ch]);
-                    dot = fmaf(a.cp.aux[ch], v, dot);
+                for (int pl = 0; pl < 4; ++pl) {
+                    const uint32_t* rw = &rv[pl].x;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float2 f = unpack_bf16x2(rw[k]);
+                        const int ch = pl * 8 + 2 * k;
+                        // src/mnist.py:60-61 then the 1x1 out conv (:87)
+                        const float v0 = fmaxf(__uint_as_float(r1[ch]) + a.cp.bias2[ch], 0.f) + f.x;
+                        const float v1 = fmaxf(__uint_as_float(r1[ch + 1]) + a.cp.bias2[ch + 1], 0.f) + f.y;
+                        dot = fmaf(a.cp.aux[ch], v0, dot);
+                        dot = fmaf(a.cp.aux[ch + 1], v1, dot);
+                    }
                 }
                 if (valid) {
                     const float eps = dot + a.cp.aux[32];

@@ -67,109 +67,18 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// try_wait with a suspend-time hint: the hardware parks the warp until the phase completes or the hint (ns) elapses,
-// instead of returning after its short default limit.
-__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
-        : "memory");
-    return ok != 0;
-}
 // Bounded wait: a protocol bug must surface as a trapped launch, never as a hung GPU box.
 // ~4e9 cycles ≈ 2 s at 1.9 GHz, far beyond any legitimate wait in these kernels.
-//
-// The waiting warp is PARKED (suspend-time hint), not spinning: in the fused residual-block kernels the default
-// try_wait loop (try_wait, clock64, compare, branch) was 42 % (rb4) / 24 % (rb1) of all warp instructions issued
-// (ncu source page, profiles/r02_ncu_src_fused_hotspots.txt) - issue slots taken from the epilogue warps that bound
-// the kernel.  TDM_PARK_NS=0 restores the polling loop.
-#ifndef TDM_PARK_NS
-#define TDM_PARK_NS 20000
-#endif
-// The retry loop lives in ONE out-of-line function: inlined at every wait site (loop, clock64 bookkeeping, printf
-// and trap) it was ~25 instructions x ~30 sites of cold code in the fused residual-block kernels, whose 55 KB of SASS
-// then thrashed the instruction cache (ncu: 39 % of all stall samples were no_inst; 1.9 % at 41 KB).
-// TDM_WAIT_TEST=1: poll with the non-blocking test_wait and back off with nanosleep instead of the (potentially
-// blocking) try_wait.
-#ifndef TDM_WAIT_TEST
-#define TDM_WAIT_TEST 0
-#endif
-#ifndef TDM_WAIT_SLEEP_NS
-#define TDM_WAIT_SLEEP_NS 32
-#endif
-static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity, uint32_t park_ns) {
-    const long long t0 = clock64();
-    for (;;) {
-        uint32_t ok;
-#if TDM_WAIT_TEST
-        asm volatile(
-            "{\n\t.reg .pred P;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, P;\n\t}"
-            : "=r"(ok)
-            : "r"(bar_addr), "r"(parity)
-            : "memory");
-        if (ok) return;
-        if (park_ns) __nanosleep(TDM_WAIT_SLEEP_NS);
-#else
-        if (park_ns) {
-            asm volatile(
-                "{\n\t.reg .pred P;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
-                "selp.u32 %0, 1, 0, P;\n\t}"
-                : "=r"(ok)
-                : "r"(bar_addr), "r"(parity), "r"(park_ns)
-                : "memory");
-        } else {
-            asm volatile(
-                "{\n\t.reg .pred P;\n\t"
-                "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
-                "selp.u32 %0, 1, 0, P;\n\t}"
-                : "=r"(ok)
-                : "r"(bar_addr), "r"(parity)
-                : "memory");
-        }
-        if (ok) return;
-#endif
-        if (clock64() - t0 > 4000000000LL) {
-            printf("tdm: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
-            __trap();
-        }
-    }
-}
-// TDM_WAIT_OOL=1 (set by a kernel's translation unit before including this header) keeps only the first probe
-// inline.  Measured both ways: out of line everywhere made the plain convolution kernels 20-25 % SLOWER (rb2.conv1
-// 208 -> 260 us at 16,384 images: the call clobbers the registers the persistent loops keep live), so the default is
-// the inlined loop.
-#ifndef TDM_WAIT_OOL
-#define TDM_WAIT_OOL 0
-#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-#if TDM_WAIT_OOL
-    mbar_wait_slow(smem_u32(bar), parity, TDM_PARK_NS);
-#else
     const long long t0 = clock64();
-#if TDM_PARK_NS > 0
-    while (!mbar_try_wait_hint(bar, parity, TDM_PARK_NS)) {
-#else
     while (!mbar_try_wait(bar, parity)) {
-#endif
         if (clock64() - t0 > 4000000000LL) {
-            printf("tdm: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+            printf("tdm: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x,
+                   (int)threadIdx.x);
             __trap();
         }
     }
-#endif
-}
-// The polling form, for the one thread whose wake-up latency is on the critical path (the MMA issuer).
-__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    mbar_wait_slow(smem_u32(bar), parity, 0u);
 }
 
 // ---------------------------------------------------------------------------------------------
