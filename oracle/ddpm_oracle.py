@@ -99,7 +99,7 @@ def unet_forward_bf16_points(sd: dict, x: torch.Tensor, t: torch.Tensor) -> torc
     """The same network (src/mnist.py:76-87) in fp32 arithmetic, but with every value the CUDA path keeps in bf16
     rounded to bf16 at the same point: the weights of every tensor-core convolution (all but rb1.conv1, which the
     kernels split into hi/lo terms, and rb1's 1x1 skip, which is fp32 in an epilogue) and the stored activations t1, h1,
-    pool(h1), t2, s2, h2, t3, h3, t4.  Biases, time embeddings, accumulation, rb4's 1x1 skip and the out conv stay fp32,
+    pool(h1), t2, s2, h2, t3, h3, t4, s4.  Biases, time embeddings, accumulation and the out conv stay fp32,
     as in the kernels.  Test infrastructure: it shows that the CUDA-vs-fp32 gap IS the operand dtype (the CUDA path sits
     an order of magnitude closer to this than to unet_forward) and bounds what a different summation order adds."""
     q = _bf16
@@ -124,7 +124,7 @@ def unet_forward_bf16_points(sd: dict, x: torch.Tensor, t: torch.Tensor) -> torc
     h2 = q(block("rb2", p1, skip_out_bf16=True))
     h3 = q(block("rb3", h2))
     cat = torch.cat([F.interpolate(h3, scale_factor=2, mode="nearest"), h1], dim=1)
-    h4 = block("rb4", cat)
+    h4 = block("rb4", cat, skip_out_bf16=True)
     return F.conv2d(h4, sd["out.weight"], sd["out.bias"])
 
 

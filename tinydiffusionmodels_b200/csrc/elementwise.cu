@@ -128,17 +128,18 @@ randn_kernel(float* __restrict__ out, uint32_t inner4, uint64_t seed, uint64_t s
 
 __global__ void __launch_bounds__(256)
 unit_range_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n) {
-    // (clamp(x,-1,1) + 1) / 2 with the reference's op order (src/mnist.py:194)
+    // (clamp(x,-1,1) + 1) / 2 with the reference's op order (src/mnist.py:194).  The division by two is a multiplication by
+    // 0.5 (exact either way, same bits); as an IEEE division it made this 55 instructions per element (ncu, round 2).
     int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4;
     if (i + 3 < n) {
         float4 v = ldcs4(x + i);
-        v.x = __fdiv_rn(__fadd_rn(fminf(fmaxf(v.x, -1.f), 1.f), 1.f), 2.f);
-        v.y = __fdiv_rn(__fadd_rn(fminf(fmaxf(v.y, -1.f), 1.f), 1.f), 2.f);
-        v.z = __fdiv_rn(__fadd_rn(fminf(fmaxf(v.z, -1.f), 1.f), 1.f), 2.f);
-        v.w = __fdiv_rn(__fadd_rn(fminf(fmaxf(v.w, -1.f), 1.f), 1.f), 2.f);
+        v.x = __fmul_rn(__fadd_rn(fminf(fmaxf(v.x, -1.f), 1.f), 1.f), 0.5f);
+        v.y = __fmul_rn(__fadd_rn(fminf(fmaxf(v.y, -1.f), 1.f), 1.f), 0.5f);
+        v.z = __fmul_rn(__fadd_rn(fminf(fmaxf(v.z, -1.f), 1.f), 1.f), 0.5f);
+        v.w = __fmul_rn(__fadd_rn(fminf(fmaxf(v.w, -1.f), 1.f), 1.f), 0.5f);
         stcs4(out + i, v);
     } else {
-        for (; i < n; ++i) out[i] = __fdiv_rn(__fadd_rn(fminf(fmaxf(x[i], -1.f), 1.f), 1.f), 2.f);
+        for (; i < n; ++i) out[i] = __fmul_rn(__fadd_rn(fminf(fmaxf(x[i], -1.f), 1.f), 1.f), 0.5f);
     }
 }
 
