@@ -46,7 +46,7 @@ enum : int { EPI_CONV1 = 0, EPI_RES = 1, EPI_RES_X = 2, EPI_RES_UP = 3, EPI_FINA
 
 // Per-channel epilogue parameters BY VALUE (CPAR = true).  Kernel arguments live in the constant bank, so a
 // compile-time-indexed a.cp.bias[ch] is a c[0x0][..] operand of the FADD itself: no load instruction and,
-// what matters, no shared-memory wavefront.  ncu (profiles/r01_ncu_full_unet_convs_B16384_f.csv): the
+// what matters, no shared-memory wavefront.  ncu (capture F of round 1, a scratch capture - DESIGN.md section 6): the
 // broadcast LDS.128 of these vectors cost ~8 wavefronts each (4 "ideal" + bank conflicts with the MMA's own
 // operand reads) and kept l1tex__data_pipe_lsu_wavefronts at 80-90 % in rb1.conv2 / rb2.conv1 / rb4.conv1.
 // The values must be known on the host at launch: the sampling engines register a host mirror of the flat
