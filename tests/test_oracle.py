@@ -12,6 +12,7 @@ import torch
 
 from oracle import ddpm_oracle as O
 from oracle import philox as PX
+from tests.helpers import random_unet_state_dict, rel_rms
 
 GOLD = Path(__file__).resolve().parent / "golden"
 
@@ -176,3 +177,42 @@ def test_oracle_matches_live_reference_unet():
         want = model(x, t)
     got = O.unet_forward(model.state_dict(), x, t)
     torch.testing.assert_close(got, want, rtol=0, atol=1e-6)
+
+
+def test_rounding_point_oracle_is_the_fp32_oracle_plus_bf16_rounding():
+    """oracle.unet_forward_bf16_points (the checker the GPU parity tests use to show that the CUDA-vs-fp32 gap is the
+    operand dtype) must BE the fp32 network with bf16 rounding and nothing else: with the rounding switched off it is
+    the fp32 oracle bit for bit, with it on it moves by the few 1e-3 that bf16 operands cost."""
+    sd = random_unet_state_dict(5)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(6, 1, 28, 28, generator=g)
+    t = torch.randint(0, 1000, (6,), generator=g)
+    want = O.unet_forward(sd, x, t)
+    keep = O._bf16
+    try:
+        O._bf16 = lambda v: v                      # rounding off: same graph, same op order as unet_forward
+        same = O.unet_forward_bf16_points(sd, x, t)
+    finally:
+        O._bf16 = keep
+    torch.testing.assert_close(same, want, rtol=0, atol=2e-6)
+    got = O.unet_forward_bf16_points(sd, x, t)
+    e = rel_rms(got, want)
+    assert 2e-4 < e < 6e-3, e
+
+
+def test_trained_checkpoint_fixture_is_the_reference_format():
+    """tests/golden/mnist_trained.pt (made by make_trained.py from the reference's own model): reference state_dict
+    keys and shapes, a loss that went down, and a denoiser that actually denoises on the oracle."""
+    ck = torch.load(GOLD / "mnist_trained.pt")
+    sd = ck["state_dict"]
+    ref_keys = torch.load(GOLD / "mnist_golden.pt")["state_dict"]
+    assert list(sd.keys()) == list(ref_keys.keys())
+    assert all(sd[k].shape == ref_keys[k].shape and sd[k].dtype == torch.float32 for k in sd)
+    assert ck["loss_last"] < 0.1 * ck["loss_first"]
+    g = torch.Generator().manual_seed(1)
+    x0 = torch.zeros(4, 1, 28, 28) - 1.0
+    x0[:, :, 10:18, 10:18] = 1.0
+    t = torch.full((4,), 300, dtype=torch.long)
+    noise = torch.randn(x0.shape, generator=g)
+    eps = O.unet_forward(sd, O.q_sample(x0, t, noise, O.make_tables()), t)
+    assert float((eps - noise).pow(2).mean()) < 0.5 * float(noise.pow(2).mean())
