@@ -183,6 +183,36 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
             int best4_i[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
             float rs = 1.f;
             if ((EPI == GE_ARGMAX || EPI == GE_LOGITS) && a.row_scale && rvalid) rs = __ldg(a.row_scale + row);
+            // GE_ARGMAX with AR logits: the NEXT 32-column chunk of this warp's 32 AR rows is kept in flight in registers
+            // (32 coalesced 128-byte row reads per lane) while the current chunk is mixed and compared.  Loaded chunk by
+            // chunk on demand, each chunk was four dependent batches of eight loads at HBM latency: the guided mix ran at
+            // 0.20 (512 sequences) - 0.55 (128) of the HBM roofline, latency-bound in this epilogue.
+            // (two chunks ahead, in two register sets: the chunk loop is unrolled by two for this epilogue so that the
+            // sets are addressed statically)
+            constexpr int kSub = EPI == GE_ARGMAX ? 2 : 1;
+            float nx[kSub][EPI == GE_ARGMAX ? 32 : 1];
+            auto ar_load = [&](float (&dst)[EPI == GE_ARGMAX ? 32 : 1], int nt_, int c0_) {
+                if constexpr (EPI == GE_ARGMAX) {
+                    const int row0 = mt * kBM + q * 32;
+                    const int ncol = nt_ * kBN + c0_ + lane;
+                    const bool cok = ncol < a.n_valid;
+                    const float* p = a.ar + (int64_t)row0 * a.ar_ld + ncol;   // one pointer, stepped by the row pitch
+                    if (row0 + 32 <= a.M) {          // warp-uniform: all 32 rows exist (the usual case)
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr, p += a.ar_ld) dst[rr] = cok ? __ldg(p) : 0.f;
+                    } else {
+#pragma unroll
+                        for (int rr = 0; rr < 32; ++rr, p += a.ar_ld) dst[rr] = (cok && row0 + rr < a.M) ? __ldg(p) : 0.f;
+                    }
+                }
+            };
+            if (EPI == GE_ARGMAX && a.ar) {
+                int nt_first = n0 + ((grp - (it & 1)) & 1);     // this group's first tile of the item
+                if (nt_first < n1) {
+                    ar_load(nx[0], nt_first, 0);
+                    ar_load(nx[kSub - 1], nt_first, 32);
+                }
+            }
             for (int nt = n0; nt < n1; ++nt, ++it) {
                 if ((it & 1) != grp) continue;
                 const uint32_t aph = (n_mine++) & 1;
@@ -190,7 +220,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                 tc_fence_after_sync();
                 float ln_sum = 0.f, ln_sq = 0.f;
 #pragma unroll 1
-                for (int c0 = 0; c0 < kBN; c0 += 32) {
+                for (int c00 = 0; c00 < kBN; c00 += 32 * kSub) {
+#pragma unroll
+                for (int hsub = 0; hsub < kSub; ++hsub) {
+                    const int c0 = c00 + 32 * hsub;
                     uint32_t r[32];
                     tmem_ld32(taddr + c0, r);
                     // lane l fetches the bias of column c0 + l (one coalesced 128 B load); columns get it by shuffle
@@ -281,34 +314,48 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                         // shared memory (row stride 33 words: conflict-free both ways).
                         float* art = reinterpret_cast<float*>(smem + kGemmSmemBase) + (warp - 2) * kArTileFloats;
                         if (a.ar) {
-                            const int row0 = mt * kBM + q * 32;
-                            const int ncol = nb + lane;
-                            const bool cok = full || ncol < a.n_valid;
                             __syncwarp();   // the previous chunk's reads of the tile are done
-#pragma unroll 8
-                            for (int rr = 0; rr < 32; ++rr) {
-                                float av = 0.f;
-                                if (cok && row0 + rr < a.M) av = __ldg(a.ar + (int64_t)(row0 + rr) * a.ar_ld + ncol);
-                                art[rr * 33 + lane] = av;
-                            }
-                            __syncwarp();
-                        }
+                            // lane = column here: the column's bias term (and -inf for the padding columns of the last
+                            // vocabulary tile) goes in with the AR logit, so the row-wise pass needs no shuffle and no
+                            // validity select per element
+                            const float cb = (full || nb + lane < a.n_valid) ? a.alpha * a.inv_temp * bias_l : -INFINITY;
+                            const float car = (1.0f - a.alpha) * a.inv_temp;
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) {
-                            const int n = nb + k;
-                            float v = __uint_as_float(r[k]) * rs + __shfl_sync(0xffffffffu, bias_l, k);
-                            if (a.ar) {
-                                // src/shakespeare.py:449-466: both logit sets divided by the temperature,
-                                // then mixed (1-alpha)*ar + alpha*diff
-                                v = (1.0f - a.alpha) * (art[lane * 33 + k] * a.inv_temp) + a.alpha * (v * a.inv_temp);
+                            for (int rr = 0; rr < 32; ++rr) art[rr * 33 + lane] = fmaf(car, nx[hsub][rr], cb);
+                            __syncwarp();
+                            // this register set is free: the chunk after the next one (of this tile, or of this group's next tile)
+                            if (c0 + 64 < kBN) ar_load(nx[hsub], nt, c0 + 64);
+                            else if (nt + 2 < n1) ar_load(nx[hsub], nt + 2, c0 + 64 - kBN);
+                        }
+                        // src/shakespeare.py:449-466: both logit sets divided by the temperature, then mixed
+                        // (1-alpha)*ar + alpha*diff.  The constants are folded per thread (row) and per chunk (bias):
+                        //   v = c_dot * dot + (c_ar * ar + bias_s),  c_ar = (1-alpha)/T,  c_dot = alpha*rs/T,  bias_s = alpha*bias/T
+                        // (the bracket is formed when the AR chunk is turned through shared memory) - two FMAs per element
+                        // instead of six multiplies and adds; the value differs from the reference's op order in the last
+                        // bit, which the token parity bar (exact where the top-2 margin allows) absorbs
+                        if (a.ar) {   // (kernel-uniform: two copies of the loop, no select per element)
+                            const float c_dot = a.alpha * a.inv_temp * rs;
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) {
+                                const float v = fmaf(c_dot, __uint_as_float(r[k]), art[lane * 33 + k]);
+                                if (v > best4[k & 3]) {   // strict: first (lowest) index wins ties, as torch.argmax
+                                    best4[k & 3] = v;
+                                    best4_i[k & 3] = nb + k;
+                                }
                             }
-                            if (!full && n >= a.n_valid) v = -INFINITY;
-                            if (v > best4[k & 3]) {   // strict: first (lowest) index wins ties, as torch.argmax
-                                best4[k & 3] = v;
-                                best4_i[k & 3] = n;
+                        } else {
+                            const float bias_s = (full || nb + lane < a.n_valid) ? bias_l : -INFINITY;
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) {
+                                const float v = fmaf(rs, __uint_as_float(r[k]), __shfl_sync(0xffffffffu, bias_s, k));
+                                if (v > best4[k & 3]) {
+                                    best4[k & 3] = v;
+                                    best4_i[k & 3] = nb + k;
+                                }
                             }
                         }
                     }
+                }
                 }
                 if constexpr (EPI == GE_RES_LN) {
                     // pass 2 of 2: normalise (nn.LayerNorm: biased variance, eps inside the sqrt), write both formats
