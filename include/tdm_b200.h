@@ -280,6 +280,47 @@ int tdm_linear_logits(const float* x_rows, int64_t rows, int dim, const void* w_
 int tdm_embedding_gather(const float* table, int64_t vocab, int dim, const int64_t* ids, int64_t n,
                          float* out_rows, int* bad_flag, void* stream);
 
+/* ---- Shakespeare training step (src/shakespeare.py:221-250): row f2 of the scope table -----------------------
+ * All parameters live in ONE flat fp32 buffer; `offsets` is a HOST array of float offsets into it (and into the
+ * gradient buffer of the same layout): 12 per encoder layer in tdm_text_forward's order (weights here are the plain
+ * fp32 nn.Linear matrices), then time_emb.weight [dim], time_emb.bias [dim], decoder.weight [vocab][dim],
+ * decoder.bias [vocab], embeddings.weight [vocab][dim] (offset -1: the embedding table is not trained and is passed
+ * as emb_table instead - the reference's use_learned_embeddings=False, src/shakespeare.py:227-228). */
+int64_t tdm_text_train_workspace_bytes(int64_t batch, int seq_len, int dim, int depth, int64_t vocab);
+int64_t tdm_text_train_wpack_bytes(int dim, int depth, int64_t vocab);
+
+/* bf16 operand forms of every weight matrix (forward and transposed) from the flat parameters; call after every
+ * optimiser step. */
+int tdm_text_train_pack(const float* flat_params, const int64_t* offsets, int dim, int depth, int64_t vocab,
+                        void* wpack, int64_t wpack_bytes, void* stream);
+
+/* One evaluation of the training objective on a batch of token ids (batch, seq_len):
+ *   x0 = table[ids]; t ~ U{0..999} (t_in: injected, else Philox); noise ~ N(0,1) (noise_in: injected (batch,
+ *   seq_len, dim), else Philox keyed like tdm_q_sample_philox with stream id = *step_dev);
+ *   noise_pred = TinyTransformer(q_sample(x0, t, noise), t) with dropout_p applied at the module's five dropout
+ *   sites when grads != NULL (train mode; masks are Philox bits keyed (seed, *step_dev, site, element), see
+ *   oracle/text_train_oracle.py); losses[0] = mse(noise_pred, noise), losses[1] = cross_entropy(x0 W^T + b, ids),
+ *   losses[2] = losses[0] + *rounding_weight_dev * losses[1]   (src/shakespeare.py:226-244).
+ * grads != NULL: also the gradient of losses[2] w.r.t. every parameter, written (not accumulated) into grads.
+ * grads == NULL: eval mode (no dropout, no backward) - the validation pass (src/shakespeare.py:268-287).
+ * The (batch*seq_len, vocab) logits are never materialised. */
+int tdm_text_train_step(const float* flat_params, float* grads, const int64_t* offsets, const void* wpack,
+                        const float* emb_table, const int64_t* token_ids, const int64_t* t_in, const float* noise_in,
+                        const float* sqrt_acp, const float* sqrt_om_acp, void* workspace, int64_t workspace_bytes,
+                        int64_t batch, int seq_len, int dim, int depth, int64_t vocab, float dropout_p,
+                        const float* rounding_weight_dev, uint64_t seed, uint64_t sample_offset,
+                        const int64_t* step_dev, float* losses, void* stream);
+
+/* torch.optim.AdamW's update (src/shakespeare.py:196) over a flat buffer with the learning rate read from the device
+ * (the cosine / warm-up schedule of src/shakespeare.py:159-167 changes it every step of a replayed graph).  The betas
+ * are doubles because torch rounds beta and 1 - beta to fp32 separately. */
+int tdm_adamw_flat_lr(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      const float* lr_dev, double beta1, double beta2, float eps, float weight_decay, float grad_scale,
+                      const int64_t* step_dev, void* stream);
+
+/* Test aid: byte offsets of the training workspace's tensors (24 values, see text_train.cu). */
+int tdm_text_train_debug_layout(int64_t batch, int seq_len, int dim, int depth, int64_t vocab, int64_t* out);
+
 /* Measurement aid (bench.py roofline): one fused p_sample with CUDA events recorded on `stream`
  * between its nine launches; SYNCHRONISES on the last event and writes the nine per-kernel
  * durations in milliseconds to host_ms9 (order: rb1.conv1, rb1.conv2, avgpool, rb2.conv1,

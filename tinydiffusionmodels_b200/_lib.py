@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import re
-from ctypes import c_char_p, c_float, c_int, c_int64, c_uint32, c_uint64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_uint32, c_uint64, c_void_p
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
@@ -63,6 +63,13 @@ SIGNATURES: dict[str, tuple] = {
     "tdm_round_argmax": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int64, _P, c_int, _P, c_int64, c_float, c_float, _P, _P, _P, c_int64, _P]),
     "tdm_linear_logits": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int64, _P, c_int, _P, c_int64, _P, c_int64, _P]),
     "tdm_embedding_gather": (c_int, [_P, c_int64, c_int, _P, c_int64, _P, _P, _P]),
+    "tdm_text_train_workspace_bytes": (c_int64, [c_int64, c_int, c_int, c_int, c_int64]),
+    "tdm_text_train_wpack_bytes": (c_int64, [c_int, c_int, c_int64]),
+    "tdm_text_train_pack": (c_int, [_P, ctypes.POINTER(c_int64), c_int, c_int, c_int64, _P, c_int64, _P]),
+    "tdm_text_train_step": (c_int, [_P, _P, ctypes.POINTER(c_int64), _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int,
+                                    c_int, c_int, c_int64, c_float, _P, c_uint64, c_uint64, _P, _P, _P]),
+    "tdm_adamw_flat_lr": (c_int, [_P, _P, _P, _P, c_int64, _P, c_double, c_double, c_float, c_float, c_float, _P, _P]),
+    "tdm_text_train_debug_layout": (c_int, [c_int64, c_int, c_int, c_int, c_int64, ctypes.POINTER(c_int64)]),
     "tdm_unet_profile_p_sample": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_uint64, ctypes.POINTER(c_float), _P]),
 }
 

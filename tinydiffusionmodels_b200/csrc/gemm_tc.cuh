@@ -15,13 +15,18 @@
 //              (src/shakespeare.py:93-102); the samplers never take this path
 //   GE_ARGMAX  running (max, argmax) over N, optionally mixed with AR logits — the logits are
 //              never written (src/shakespeare.py:389-390, 398-401, 451-467)
+// Training (text_train.cu; src/shakespeare.py:221-250) adds a K split for GE_LOGITS (few output tiles, long
+// reductions: partial s of an item goes to its own fp32 slab, summed by a small kernel afterwards), ReLU / an fp32
+// addend for GE_LOGITS, and the two halves of the fused Linear(dim, V) + cross-entropy:
+//   GE_LSE     online (max, sum exp) per row over the item's vocabulary range + the target's logit; logits never written
+//   GE_DLOGITS (softmax - onehot) * scale -> bf16 planes (the A operand of the two gradient GEMMs)
 #pragma once
 #include "common.cuh"
 #include "tc05.cuh"
 
 namespace tdm {
 
-enum : int { GE_BF16 = 0, GE_RES_F32 = 1, GE_ARGMAX = 2, GE_RES_LN = 3, GE_LOGITS = 4 };
+enum : int { GE_BF16 = 0, GE_RES_F32 = 1, GE_ARGMAX = 2, GE_RES_LN = 3, GE_LOGITS = 4, GE_LSE = 5, GE_DLOGITS = 6 };
 
 constexpr int kBM = 128, kBN = 256, kBK = 64;
 constexpr int kGemmStages = 4;
@@ -68,7 +73,37 @@ struct GemmArgs {
     // GE_LOGITS
     float* logits;           // [M][logits_ld] fp32 row-major
     int64_t logits_ld;
+    const float* logits_add; // optional fp32 [M][logits_ld] added to the result (gradient of a residual branch)
+    // K split (GE_LOGITS only): items = row tiles x nsplit x ksplit; split s > 0 writes its partial sums (no bias, no
+    // addend) to logits + s * split_stride
+    int ksplit;              // 0 or 1: the whole K in one item
+    int64_t split_stride;    // floats
+    // GE_LSE / GE_DLOGITS: the fused Linear + cross-entropy (F.cross_entropy of src/shakespeare.py:241)
+    const int64_t* target;   // [M] class index per row
+    float* part_sum;         // GE_LSE: [2*nsplit][Mp] sum exp(v - part_val); part_val holds the running maxima
+    float* tgt_logit;        // GE_LSE: [M] logit of the target class
+    const float* lse;        // GE_DLOGITS: [M] log-sum-exp per row
+    const float* dev_scale;  // GE_DLOGITS: device scalar multiplying the gradient (the rounding-loss weight), or null
+    float scale;             // GE_DLOGITS: host factor (1 / rows)
 };
+
+// one work item of the persistent loop: a row tile, a range of column tiles and a range of K blocks
+struct GemmItem {
+    int mt, sp, ks, n0, n1, kb0, kb1;
+};
+__device__ __forceinline__ GemmItem gemm_item(const GemmArgs& a, int item, int n_tiles, int kblocks) {
+    GemmItem w;
+    const int ksplit = a.ksplit > 1 ? a.ksplit : 1;
+    const int rest = item / ksplit;
+    w.ks = item - rest * ksplit;
+    w.mt = rest / a.nsplit;
+    w.sp = rest - w.mt * a.nsplit;
+    w.n0 = (int)((int64_t)w.sp * n_tiles / a.nsplit);
+    w.n1 = (int)((int64_t)(w.sp + 1) * n_tiles / a.nsplit);
+    w.kb0 = (int)((int64_t)w.ks * kblocks / ksplit);
+    w.kb1 = (int)((int64_t)(w.ks + 1) * kblocks / ksplit);
+    return w;
+}
 
 template <int EPI>
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs a) {
@@ -102,17 +137,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
 
     const int m_tiles = a.Mp / kBM;
     const int n_tiles = a.N / kBN;
-    const int items = m_tiles * a.nsplit;
+    const int items = m_tiles * a.nsplit * (a.ksplit > 1 ? a.ksplit : 1);
     const int kblocks = a.K / kBK;
 
     if (warp == 0) {
         // ===== producer =====
         int kit = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int mt = item / a.nsplit, sp = item - mt * a.nsplit;
-            const int n0 = (int)((int64_t)sp * n_tiles / a.nsplit), n1 = (int)((int64_t)(sp + 1) * n_tiles / a.nsplit);
-            for (int nt = n0; nt < n1; ++nt) {
-                for (int kb = 0; kb < kblocks; ++kb, ++kit) {
+            const GemmItem w = gemm_item(a, item, n_tiles, kblocks);
+            const int mt = w.mt;
+            for (int nt = w.n0; nt < w.n1; ++nt) {
+                for (int kb = w.kb0; kb < w.kb1; ++kb, ++kit) {
                     const int s = kit % kGemmStages;
                     const uint32_t ph = (kit / kGemmStages) & 1;
                     if (lane == 0) {
@@ -139,14 +174,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
         if (elect_one()) {
         int kit = 0, it = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int mt = item / a.nsplit, sp = item - mt * a.nsplit;
-            const int n0 = (int)((int64_t)sp * n_tiles / a.nsplit), n1 = (int)((int64_t)(sp + 1) * n_tiles / a.nsplit);
-            for (int nt = n0; nt < n1; ++nt, ++it) {
+            const GemmItem w = gemm_item(a, item, n_tiles, kblocks);
+            for (int nt = w.n0; nt < w.n1; ++nt, ++it) {
                 const int acc = it & 1;
                 const uint32_t aph = (it >> 1) & 1;
                 mbar_wait(bar_acce + acc, aph ^ 1);
                 const uint32_t d = tmem_base + acc * kBN;
-                for (int kb = 0; kb < kblocks; ++kb, ++kit) {
+                for (int kb = w.kb0; kb < w.kb1; ++kb, ++kit) {
                     const int s = kit % kGemmStages;
                     const uint32_t ph = (kit / kGemmStages) & 1;
                     mbar_wait(bar_full + s, ph);
@@ -154,7 +188,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                     const uint32_t a_addr = smem_u32(smem + s * kGemmStage);
                     const uint64_t a_base = make_smem_desc(a_addr, kBM * 16, 128);
                     const uint64_t b_base = make_smem_desc(a_addr + kGemmStageA, kBN * 16, 128);
-                    const uint32_t acc_flag = kb != 0;
+                    const uint32_t acc_flag = kb != w.kb0;
 #pragma unroll
                     for (int ks = 0; ks < kBK / 16; ++ks)
                         umma_bf16(d, desc_add(a_base, (2 * ks) * (kBM * 16)), desc_add(b_base, (2 * ks) * (kBN * 16)), idesc,
@@ -173,10 +207,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + grp * kBN;
         int it = 0, n_mine = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int mt = item / a.nsplit, sp = item - mt * a.nsplit;
-            const int n0 = (int)((int64_t)sp * n_tiles / a.nsplit), n1 = (int)((int64_t)(sp + 1) * n_tiles / a.nsplit);
+            const GemmItem w = gemm_item(a, item, n_tiles, kblocks);
+            const int mt = w.mt, sp = w.sp, n0 = w.n0, n1 = w.n1;
             const int row = mt * kBM + q * 32 + lane;
             const bool rvalid = row < a.M;
+            // GE_LSE: running maximum and sum of exp over this item's columns; GE_LSE / GE_DLOGITS: the row's target class
+            float lse_m = -INFINITY, lse_s = 0.f, tgt_v = 0.f;
+            bool tgt_hit = false;
+            int tgt = -1;
+            float row_lse = 0.f, gscale = 0.f;
+            if constexpr (EPI == GE_LSE || EPI == GE_DLOGITS) {
+                if (rvalid) tgt = (int)__ldg(a.target + row);
+            }
+            if constexpr (EPI == GE_DLOGITS) {
+                if (rvalid) row_lse = __ldg(a.lse + row);
+                gscale = a.scale * (a.dev_scale ? __ldg(a.dev_scale) : 1.0f);
+            }
             // four independent running maxima (columns k % 4): one serial compare/select chain over all
             // 256 columns of a tile is a ~2000-cycle dependency chain per thread
             float best4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -227,7 +273,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                     uint32_t r[32];
                     tmem_ld32(taddr + c0, r);
                     // lane l fetches the bias of column c0 + l (one coalesced 128 B load); columns get it by shuffle
-                    const float bias_l = a.bias ? __ldg(a.bias + nt * kBN + c0 + lane) : 0.f;
+                    const float bias_l = (a.bias && (EPI != GE_LOGITS || w.ks == 0)) ? __ldg(a.bias + nt * kBN + c0 + lane) : 0.f;
                     tmem_ld_wait();
                     if (EPI != GE_RES_LN && c0 + 32 == kBN) {
                         tc_fence_before_sync();
@@ -287,14 +333,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                         }
                         tmem_st32(taddr + c0, vb);
                     } else if constexpr (EPI == GE_LOGITS) {
-                        float* orow = a.logits + (int64_t)row * a.logits_ld + nb;
+                        float* orow = a.logits + (int64_t)w.ks * a.split_stride + (int64_t)row * a.logits_ld + nb;
+                        const float* arow = (a.logits_add && w.ks == 0) ? a.logits_add + (int64_t)row * a.logits_ld + nb : nullptr;
                         const bool vec = (a.logits_ld & 3) == 0 && nb + 32 <= a.n_valid;   // 16-byte aligned, whole chunk valid
 #pragma unroll
                         for (int k4 = 0; k4 < 8; ++k4) {
                             float v[4];   // shuffles stay outside the row-validity branch (all lanes take part)
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
+                            for (int k = 0; k < 4; ++k) {
                                 v[k] = __uint_as_float(r[k4 * 4 + k]) * rs + __shfl_sync(0xffffffffu, bias_l, k4 * 4 + k);
+                                if (a.relu) v[k] = fmaxf(v[k], 0.f);
+                            }
+                            if (rvalid && arow) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (vec || nb + k4 * 4 + k < a.n_valid) v[k] += __ldg(arow + k4 * 4 + k);
+                            }
                             if (rvalid) {
                                 if (vec) {
                                     *reinterpret_cast<float4*>(orow + k4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
@@ -304,6 +358,51 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                                         if (nb + k4 * 4 + k < a.n_valid) orow[k4 * 4 + k] = v[k];
                                 }
                             }
+                        }
+                    } else if constexpr (EPI == GE_LSE) {
+                        // logits of this row x these 32 columns (padding columns -> -inf): fold into the running
+                        // (max, sum exp) pair, keep the target's logit when it falls in this chunk
+                        const bool full = nb + 32 <= a.n_valid;
+                        float v[32];
+                        float cmax = -INFINITY;
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) {
+                            v[k] = __uint_as_float(r[k]) + __shfl_sync(0xffffffffu, bias_l, k);
+                            if (!full && nb + k >= a.n_valid) v[k] = -INFINITY;
+                            cmax = fmaxf(cmax, v[k]);
+                            if (nb + k == tgt) {
+                                tgt_v = v[k];
+                                tgt_hit = true;
+                            }
+                        }
+                        if (cmax > -INFINITY) {
+                            if (cmax > lse_m) {
+                                lse_s *= __expf(lse_m - cmax);   // exp(-inf) = 0 on the first chunk
+                                lse_m = cmax;
+                            }
+                            float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                            for (int k = 0; k < 32; ++k) s4[k & 3] += __expf(v[k] - lse_m);
+                            lse_s += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+                        }
+                    } else if constexpr (EPI == GE_DLOGITS) {
+                        // d loss / d logits = (softmax - onehot) * scale, zero for padding rows and columns (both are
+                        // reduction indices of the gradient GEMMs that read these planes)
+                        const bool full = nb + 32 <= a.n_valid;
+#pragma unroll
+                        for (int pj = 0; pj < 4; ++pj) {
+                            float gk[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const int n = nb + pj * 8 + k;
+                                const float v = __uint_as_float(r[pj * 8 + k]) + __shfl_sync(0xffffffffu, bias_l, pj * 8 + k);
+                                float p = __expf(v - row_lse);
+                                if (n == tgt) p -= 1.0f;
+                                gk[k] = (rvalid && (full || n < a.n_valid)) ? p * gscale : 0.f;
+                            }
+                            const uint4 o = make_uint4(pack_bf16x2(gk[0], gk[1]), pack_bf16x2(gk[2], gk[3]),
+                                                       pack_bf16x2(gk[4], gk[5]), pack_bf16x2(gk[6], gk[7]));
+                            *reinterpret_cast<uint4*>(a.out_bf16 + (int64_t)(nb / 8 + pj) * a.ob_ps + (int64_t)row * 16) = o;
                         }
                     } else {
                         const bool full = nb + 32 <= a.n_valid;   // tile-uniform: only the last tile of a padded vocabulary is partial
@@ -390,6 +489,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                     }
                 }
             }
+            if constexpr (EPI == GE_LSE) {
+                const int64_t slot = (int64_t)(sp * 2 + grp) * a.Mp + row;
+                a.part_val[slot] = lse_m;
+                a.part_sum[slot] = lse_s;
+                if (tgt_hit) a.tgt_logit[row] = tgt_v;
+            }
             if constexpr (EPI == GE_ARGMAX) {
                 float best = best4[0];
                 int bi = best4_i[0];
@@ -420,7 +525,8 @@ static int launch_gemm(const GemmArgs& a, cudaStream_t st, const char* name) {
     TDM_CHECK_ARG(EPI != GE_RES_LN || a.N == kBN, "%s: fused LayerNorm needs N == 256", name);
     TDM_CHECK_ARG(a.Mp % kBM == 0 && a.N % kBN == 0 && a.K % kBK == 0 && a.K > 0 && a.nsplit > 0,
                   "%s: bad GEMM shape M=%d Mp=%d N=%d K=%d", name, a.M, a.Mp, a.N, a.K);
-    const int items = (a.Mp / kBM) * a.nsplit;
+    TDM_CHECK_ARG(a.ksplit <= 1 || EPI == GE_LOGITS, "%s: the K split exists for the fp32 row-major epilogue only", name);
+    const int items = (a.Mp / kBM) * a.nsplit * (a.ksplit > 1 ? a.ksplit : 1);
     const int grid = items < num_sms() ? items : num_sms();
     launch_pdl(kern, dim3(grid), dim3(kGemmThreads), kGemmSmem, st, a);
     TDM_CHECK_LAUNCH(name);

@@ -1,5 +1,5 @@
 """Shakespeare embedding-space text diffusion on B200 — host mirror of the reference's
-``src/shakespeare.py`` for the *sampling* paths named by the north star:
+``src/shakespeare.py``: the *sampling* paths named by the north star and (row f2) the training loop:
 
 * ``q_sample`` / ``p_sample``                      (ref src/shakespeare.py:37-44, 343-352)
 * ``TinyTransformer.forward`` (eval)               (ref :105-120)  -> tcgen05 GEMMs + attention
@@ -8,9 +8,12 @@
 * ``guided_generate``                              (ref :429-470)  -> fused diff-logit GEMM + AR mix + argmax
 * ``LearnedEmbedding`` / ``LearnedRounding``       (ref :46-102)   weight ABI + forward (gather kernel / logits GEMM)
 
-Text *training* (ref :122-341) is outside this build's hot path: the modules raise
-instead of silently running PyTorch kernels.  The base LM inside ``guided_generate`` is third
-party (transformers) and stays a torch module.
+* ``train`` (+ ``load_text_dataset`` / ``tokenize_corpus``) (ref :122-341) -> ``text_train.TextTrainer``: the whole
+                                                                      step as one replayed CUDA graph
+
+The modules' own ``forward`` stay inference-only (no autograd graph is ever built): training goes through ``train``,
+whose backward pass is hand-written CUDA.  The base LM inside ``guided_generate`` is third party (transformers) and
+stays a torch module.
 """
 from __future__ import annotations
 
@@ -31,8 +34,6 @@ HF_TOKEN = os.getenv("HF_TOKEN")
 
 
 # ---- host-side training schedules (ref src/shakespeare.py:159-172) ---------------------------------------------
-# The text *training* loop is not part of this path; these two pure functions of it are, because
-# code written against the reference imports them and they cost nothing to keep identical.
 def get_cosine_schedule_with_warmup(optimizer, num_warmup_steps, num_training_steps, eta_min=0):
     """``LambdaLR`` factor: linear ramp 0 -> 1 over the warm-up steps, then half a cosine down to ``eta_min``."""
     warm = float(max(1, num_warmup_steps))
@@ -157,9 +158,112 @@ class TinyTransformer(nn.Module):
     def forward(self, x: torch.Tensor, t: torch.Tensor):
         if self.training or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
                              and x.requires_grad):
-            raise _lib.TdmError("TinyTransformer here is inference-only (eval + no_grad); text training is "
-                                "outside this build's hot path")
+            raise _lib.TdmError("TinyTransformer.forward is inference-only (eval + no_grad): training runs through "
+                                "shakespeare.train / text_train.TextTrainer, whose backward pass is CUDA, not autograd")
         return self.engine(x.shape[0], x.shape[1]).forward(x, t)
+
+
+def load_text_dataset():
+    """The raw Shakespeare corpus as one string (ref :122-125; needs the HF hub)."""
+    from datasets import load_dataset
+
+    ds = load_dataset("tiny_shakespeare", trust_remote_code=True)
+    return "\n\n".join(ds["train"]["text"] + ds["test"]["text"] + ds["validation"]["text"])
+
+
+def tokenize_corpus(text: str, tokenizer, seq_len: int, val_split=0.1):
+    """Tokenise the corpus once, cut it into (n_chunks, seq_len) rows, random train/val split (ref :128-157)."""
+    from torch.utils.data import random_split
+
+    ids = tokenizer(text, add_special_tokens=False, return_attention_mask=False, return_tensors="pt").input_ids.squeeze(0)
+    n_chunks = ids.size(0) // seq_len
+    chunks = ids[: n_chunks * seq_len].view(n_chunks, seq_len)
+    n_val = int(n_chunks * val_split)
+    return random_split(chunks, [n_chunks - n_val, n_val])
+
+
+def _mean_losses(sums, n):
+    return {k: v / max(n, 1) for k, v in zip(("diff", "round", "total"), sums)}
+
+
+def train(model, rounding_fn, embedding_fn, data_loader, val_loader, device, ckpt_path="text_ckpt.pth", epochs=1,
+          lr=1e-4, weight_decay=1e-4, rounding_weight=1.0, use_learned_embeddings=True, patience=5,
+          use_lr_scheduling=True, warmup_steps=100, *, seed=None, log_every=50):
+    """The reference's training loop (ref :174-341) with the step on the device: per batch one replayed CUDA graph
+    (forward, both losses, backward, AdamW, weight re-pack; ``text_train.TextTrainer``), the cosine / warm-up learning
+    rate and the per-epoch rounding weight written to device scalars, validation in eval mode, best / final
+    checkpoints in the reference's format.  Losses are accumulated on the device and read once per ``log_every`` steps
+    (the reference's per-step ``.item()`` calls would serialise the stream)."""
+    from .text_train import TextTrainer
+    from .utils import get_vertex_checkpoint_path, save_checkpoint
+
+    first = next(iter(data_loader))
+    batch, seq_len = int(first.shape[0]), int(first.shape[1])
+    tr = TextTrainer(model, rounding_fn, embedding_fn, device, batch, seq_len, lr=lr, weight_decay=weight_decay,
+                     use_learned_embeddings=use_learned_embeddings, seed=_fresh_seed() if seed is None else seed)
+    total_steps = len(data_loader) * epochs
+    warm = float(max(1, warmup_steps))
+    span = float(max(1, total_steps - warmup_steps))
+
+    def lr_at(k):   # LambdaLR factor of get_cosine_schedule_with_warmup, evaluated for optimiser step k (0-based)
+        if not use_lr_scheduling:
+            return lr
+        if k < warmup_steps:
+            return lr * float(k) / warm
+        return lr * max(0, 0.5 * (1.0 + math.cos(math.pi * float(k - warmup_steps) / span)))
+
+    best_val, bad_epochs, k = float("inf"), 0, 0
+    for epoch in range(epochs):
+        rw = dynamic_rounding_weight_schedule(epoch, epochs, rounding_weight)
+        acc = torch.zeros(3, device=tr.device)
+        n_tr = 0
+        for token_ids in data_loader:
+            if tuple(token_ids.shape) != (batch, seq_len):
+                continue   # a ragged last batch would need a second captured graph; it is skipped (stated in DESIGN.md)
+            acc += tr.step(token_ids, lr=lr_at(k), rounding_weight=rw)
+            k += 1
+            n_tr += 1
+            if log_every and n_tr % log_every == 0:
+                d, r, t_ = (acc / n_tr).tolist()
+                print(f"Epoch {epoch + 1}/{epochs} step {n_tr}: diff={d:.4f} round={r:.4f} total={t_:.4f} rw={rw:.3f} lr={lr_at(k):.2e}")
+        train_losses = _mean_losses((acc / max(n_tr, 1)).tolist(), 1)
+        model.eval(); rounding_fn.eval()
+        vacc = torch.zeros(3, device=tr.device)
+        n_val = 0
+        for token_ids in val_loader:
+            if tuple(token_ids.shape) != (batch, seq_len):
+                continue
+            vacc += tr.evaluate(token_ids)
+            n_val += 1
+        val_losses = _mean_losses((vacc / max(n_val, 1)).tolist(), 1)
+        print(f"Epoch {epoch + 1}/{epochs}:")
+        print(f"  Train: diff={train_losses['diff']:.4f}, round={train_losses['round']:.4f}, total={train_losses['total']:.4f}")
+        print(f"  Val:   diff={val_losses['diff']:.4f}, round={val_losses['round']:.4f}, total={val_losses['total']:.4f}")
+        print(f"  Rounding weight: {rw:.3f}")
+        if n_val == 0 or val_losses["total"] < best_val:
+            best_val = val_losses["total"] if n_val else best_val
+            bad_epochs = 0
+            best_path = ckpt_path.replace(".pth", "_best.pth")
+            ck = {"diffusion_model": model.state_dict(), "rounding_fn": rounding_fn.state_dict(), "epoch": epoch,
+                  "val_loss": best_val}
+            if use_learned_embeddings:
+                ck["embedding_fn"] = embedding_fn.state_dict()
+            save_checkpoint(ck, best_path)
+            print(f"  New best validation loss! Saved to {best_path}")
+        else:
+            bad_epochs += 1
+            if bad_epochs >= patience:
+                print(f"  Early stopping triggered after {patience} epochs without improvement")
+                break
+    tr.sync_modules()
+    final_path = get_vertex_checkpoint_path("text-model.pth") if "AIP_MODEL_DIR" in os.environ else ckpt_path
+    print(f"✔ Saving final checkpoint to {final_path}...")
+    ck = {"diffusion_model": model.state_dict(), "rounding_fn": rounding_fn.state_dict(), "epoch": epochs,
+          "final_training": True}
+    if use_learned_embeddings:
+        ck["embedding_fn"] = embedding_fn.state_dict()
+    save_checkpoint(ck, final_path)
+    return tr
 
 
 def p_sample(model, x, t):
@@ -339,8 +443,6 @@ def main(argv=None):
     print(f"Device: {device}")
     if args.seed is not None:
         torch.manual_seed(args.seed)
-    if args.train:
-        raise _lib.TdmError("text training is outside this build's hot path (SURVEY.md §8f); use the reference")
 
     if args.synthetic:
         tokenizer = _SyntheticTokenizer()
@@ -360,6 +462,23 @@ def main(argv=None):
         embedding_fn = pretrained
     diff_model = TinyTransformer(embed_dim, dropout=args.dropout).to(device)
     rounding_fn = LearnedRounding(embed_dim, vocab_size).to(device)
+
+    if args.train:
+        from torch.utils.data import DataLoader
+        if args.synthetic:   # no HF hub: a synthetic corpus of random ids, enough to exercise the whole loop
+            gen = torch.Generator().manual_seed(0 if args.seed is None else args.seed)
+            chunks = torch.randint(0, vocab_size, (args.batch_size * 12, args.seq_len), generator=gen)
+            n_val = max(args.batch_size, int(chunks.shape[0] * args.val_split) // args.batch_size * args.batch_size)
+            train_chunks, val_chunks = chunks[n_val:], chunks[:n_val]
+        else:
+            train_chunks, val_chunks = tokenize_corpus(load_text_dataset(), tokenizer, args.seq_len, args.val_split)
+        train_dl = DataLoader(train_chunks, batch_size=args.batch_size, shuffle=True)
+        val_dl = DataLoader(val_chunks, batch_size=args.batch_size, shuffle=False)
+        print(f"Training on {len(train_chunks)} chunks, validating on {len(val_chunks)} chunks")
+        train(diff_model, rounding_fn, embedding_fn, train_dl, val_dl, device, args.ckpt, epochs=args.epochs, lr=args.lr,
+              weight_decay=args.weight_decay, rounding_weight=args.rounding_weight,
+              use_learned_embeddings=args.use_learned_embeddings, patience=args.patience,
+              use_lr_scheduling=args.use_lr_scheduling, warmup_steps=args.warmup_steps, seed=args.seed)
 
     def load():
         nonlocal embedding_fn
