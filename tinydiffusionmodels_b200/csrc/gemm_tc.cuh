@@ -85,6 +85,8 @@ struct GemmArgs {
     const float* lse;        // GE_DLOGITS: [M] log-sum-exp per row
     const float* dev_scale;  // GE_DLOGITS: device scalar multiplying the gradient (the rounding-loss weight), or null
     float scale;             // GE_DLOGITS: host factor (1 / rows)
+    uint8_t* out_bf16_t;     // GE_DLOGITS: the same values transposed, bf16 planes along the ROW index [Mp/8][obt_rows][8]
+    int64_t obt_rows;        //             (the A operand of dW = dlogits^T . X), or null
 };
 
 // one work item of the persistent loop: a row tile, a range of column tiles and a range of K blocks
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
     const int n_tiles = a.N / kBN;
     const int items = m_tiles * a.nsplit * (a.ksplit > 1 ? a.ksplit : 1);
     const int kblocks = a.K / kBK;
+    const bool a_resident = kblocks == kGemmStages && a.ksplit <= 1;
 
     if (warp == 0) {
         // ===== producer =====
@@ -147,16 +150,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
             const GemmItem w = gemm_item(a, item, n_tiles, kblocks);
             const int mt = w.mt;
             for (int nt = w.n0; nt < w.n1; ++nt) {
+                // K == 4 blocks (width 256) and no K split: k-block kb always lands in ring slot kb, so the item's A tile
+                // (128 rows x 256, 64 KB) is loaded once, with the first column tile, and stays in the slots' A halves
+                // for every further column tile - 128 KB instead of 192 KB of L2 reads per tile, which is what the
+                // vocabulary-sized GEMMs (AI 87 FLOP/B with A re-read) are bound by
+                const bool load_a = !a_resident || nt == w.n0;
                 for (int kb = w.kb0; kb < w.kb1; ++kb, ++kit) {
                     const int s = kit % kGemmStages;
                     const uint32_t ph = (kit / kGemmStages) & 1;
                     if (lane == 0) {
                         mbar_wait(bar_empty + s, ph ^ 1);
-                        mbar_arrive_expect_tx(bar_full + s, kGemmStage);
+                        mbar_arrive_expect_tx(bar_full + s, load_a ? kGemmStage : kGemmStageB);
                     }
                     __syncwarp();
                     uint8_t* st = smem + s * kGemmStage;
                     if (lane < 8) {
+                        if (load_a)
                         bulk_g2s(st + lane * (kBM * 16), a.a + (int64_t)(kb * 8 + lane) * a.a_ps + (int64_t)mt * (kBM * 16),
                                  kBM * 16, bar_full + s);
                     } else if (lane < 16) {
@@ -345,9 +354,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                                 if (a.relu) v[k] = fmaxf(v[k], 0.f);
                             }
                             if (rvalid && arow) {
+                                if (vec) {
+                                    const float4 ad = __ldg(reinterpret_cast<const float4*>(arow + k4 * 4));
+                                    v[0] += ad.x; v[1] += ad.y; v[2] += ad.z; v[3] += ad.w;
+                                } else {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    if (vec || nb + k4 * 4 + k < a.n_valid) v[k] += __ldg(arow + k4 * 4 + k);
+                                    for (int k = 0; k < 4; ++k)
+                                        if (nb + k4 * 4 + k < a.n_valid) v[k] += __ldg(arow + k4 * 4 + k);
+                                }
                             }
                             if (rvalid) {
                                 if (vec) {
@@ -389,6 +403,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                         // d loss / d logits = (softmax - onehot) * scale, zero for padding rows and columns (both are
                         // reduction indices of the gradient GEMMs that read these planes)
                         const bool full = nb + 32 <= a.n_valid;
+                        float* art = reinterpret_cast<float*>(smem + kGemmSmemBase) + (warp - 2) * kArTileFloats;
+                        if (a.out_bf16_t) __syncwarp();   // the previous chunk's reads of the tile are done
 #pragma unroll
                         for (int pj = 0; pj < 4; ++pj) {
                             float gk[8];
@@ -403,6 +419,25 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                             const uint4 o = make_uint4(pack_bf16x2(gk[0], gk[1]), pack_bf16x2(gk[2], gk[3]),
                                                        pack_bf16x2(gk[4], gk[5]), pack_bf16x2(gk[6], gk[7]));
                             *reinterpret_cast<uint4*>(a.out_bf16 + (int64_t)(nb / 8 + pj) * a.ob_ps + (int64_t)row * 16) = o;
+                            if (a.out_bf16_t) {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) art[lane * 33 + pj * 8 + k] = gk[k];
+                            }
+                        }
+                        if (a.out_bf16_t) {
+                            // the same 32 x 32 block with lane = column: eight consecutive rows (tokens) of one column are
+                            // one 16-byte plane row; the warp's 32 columns make each store 512 contiguous bytes
+                            __syncwarp();
+                            const int64_t rp0 = (int64_t)(mt * kBM + q * 32) / 8;
+#pragma unroll
+                            for (int g8 = 0; g8 < 4; ++g8) {
+                                float tv[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) tv[j] = art[(g8 * 8 + j) * 33 + lane];
+                                *reinterpret_cast<uint4*>(a.out_bf16_t + ((rp0 + g8) * a.obt_rows + nb + lane) * 16) =
+                                    make_uint4(pack_bf16x2(tv[0], tv[1]), pack_bf16x2(tv[2], tv[3]), pack_bf16x2(tv[4], tv[5]),
+                                               pack_bf16x2(tv[6], tv[7]));
+                            }
                         }
                     } else {
                         const bool full = nb + 32 <= a.n_valid;   // tile-uniform: only the last tile of a padded vocabulary is partial

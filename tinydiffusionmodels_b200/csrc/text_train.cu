@@ -12,8 +12,8 @@
 //     ("k-planes" [K/8][rows][8] along the reduction index) by two small packing kernels;
 //   * the (M, V) logits are never written: pass 1 (GE_LSE) keeps an online (max, sum exp) per row and picks up
 //     the target's logit, pass 2 (GE_DLOGITS) recomputes the logits and writes d loss / d logits as bf16
-//     planes, which are the A operand of dX0 = dlogits . W (K split over the SMs) and, transposed in 8x8
-//     blocks, of dW = dlogits^T . X0;
+//     planes in both orientations (the second one turned through shared memory in the epilogue): the A operands
+//     of dX0 = dlogits . W (K split over the SMs) and of dW = dlogits^T . X0;
 //   * dropout masks are never stored: they are a pure function (Philox4x32-10) of (seed, step, site, element)
 //     and are recomputed in the backward pass — the oracle regenerates the same bits in numpy;
 //   * LayerNorm, attention (L <= 128 keys per sequence: 4*L*D FLOP per token, 2 % of the encoder) and the
@@ -164,37 +164,6 @@ __global__ void pack_mplanes_kernel(const float* __restrict__ x, int64_t R, int 
         }
         *reinterpret_cast<uint4*>(out + i * 16) =
             make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-    }
-}
-
-// bf16 planes [P][Q][8] -> [Q/8][P*8][8]: every 8x8 block transposed (d loss / d logits: vocabulary-planes over token
-// rows -> token-planes over vocabulary rows).  One thread per block: 8 x 16-byte reads 16 B apart in one 128-byte line,
-// 8 x 16-byte writes likewise.
-__global__ void transpose_planes_kernel(const uint8_t* __restrict__ in, int64_t P, int64_t Q, uint8_t* __restrict__ out) {
-    const int64_t Q8 = Q / 8;
-    const int64_t total = P * Q8;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t qb = i % Q8;   // consecutive threads: consecutive row blocks of one input plane
-        const int64_t p = i / Q8;
-        uint32_t w[8][4];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const uint4 v = *reinterpret_cast<const uint4*>(in + (p * Q + qb * 8 + j) * 16);
-            w[j][0] = v.x; w[j][1] = v.y; w[j][2] = v.z; w[j][3] = v.w;
-        }
-        // in: row j (a token) holds columns 8p .. 8p+7 (vocabulary); out: row (8p + c) holds tokens 8qb .. 8qb+7
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            uint32_t o[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const uint32_t a0 = w[2 * jj][c >> 1], a1 = w[2 * jj + 1][c >> 1];
-                const uint32_t lo = (c & 1) ? (a0 >> 16) : (a0 & 0xffffu);
-                const uint32_t hi = (c & 1) ? (a1 >> 16) : (a1 & 0xffffu);
-                o[jj] = lo | (hi << 16);
-            }
-            *reinterpret_cast<uint4*>(out + (qb * (P * 8) + p * 8 + c) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-        }
     }
 }
 
@@ -807,6 +776,7 @@ static TrainPack make_train_pack(int D, int depth, int64_t V) {
 struct TrainWs {
     int64_t M, Mp, Vp;
     int nsplit, n_mse, n_lnblk, ksplit_dx;
+    int64_t split_floats;
     // fp32 rows
     int64_t t, x0, noise, hin /* depth+1 of them */, qkv, P, att, a, z1, st1, h1, f, g, z2, st2;   // last 11: per layer, + layer_stride
     int64_t layer_stride;
@@ -892,7 +862,9 @@ static TrainWs make_train_ws(int64_t B, int L, int D, int depth, int64_t V) {
     w.tgtl = take(w.M * 4);
     w.lse = take(w.M * 4);
     w.rowl = take(w.M * 4);
-    w.split = take((int64_t)w.ksplit_dx * MD);
+    w.split_floats = (int64_t)w.ksplit_dx * w.M * D;
+    if (w.split_floats < (int64_t)16 * kTrFF * D) w.split_floats = (int64_t)16 * kTrFF * D;
+    w.split = take(w.split_floats * 4);
     const int64_t widest = 3 * (int64_t)D > kTrFF ? 3 * (int64_t)D : kTrFF;
     w.pk = take(widest * w.Mp * 2);    // k-planes of an activation / gradient [C/8][Mp][8]
     w.pm2 = take(w.Mp * widest * 2);   // m-planes [Mp/8][C][8]
@@ -937,14 +909,33 @@ static int colsum(const float* x, int64_t R, int C, int64_t ld, float* out, cuda
 
 // out[M][N_valid] (fp32 rows, leading dimension ld) = A . W^T (+ bias) (+ add) (ReLU); A: bf16 planes along K with a_rows
 // rows per plane, W: bf16 planes along K with w_rows rows per plane
+struct SplitBuf {
+    float* p;
+    int64_t cap;   // floats
+};
+
 static int gemm_rows(const uint8_t* a_planes, int64_t a_rows, const uint8_t* w_planes, int64_t w_rows, const float* bias,
                      int64_t M, int64_t n_valid, int64_t K, float* out, int64_t ld, const float* add, int relu, int ksplit,
-                     float* split_buf, cudaStream_t st, const char* name) {
+                     SplitBuf split, cudaStream_t st, const char* name) {
+    float* split_buf = split.p;
     GemmArgs g{};
     g.a = a_planes; g.a_ps = a_rows * 16; g.w = w_planes; g.w_ps = w_rows * 16; g.bias = bias;
     g.M = (int)M; g.Mp = (int)a_rows; g.N = (int)w_rows; g.n_valid = (int)n_valid; g.K = (int)K; g.relu = relu;
     g.nsplit = (int)(w_rows / kBN);
     g.logits_ld = ld; g.logits_add = add;
+    if (ksplit < 0) {
+        // automatic: a long reduction on a handful of output tiles (the dW GEMMs: K = token rows; linear2 and its dX:
+        // K = 2048) leaves most SMs idle - split K until the items fill the machine, at least 4 K blocks per item,
+        // at most as many ways as the partial-sum buffer holds
+        const int items = (int)(a_rows / kBM) * g.nsplit;
+        const int kblocks = (int)(K / kBK);
+        int ks = num_sms() / items;
+        if (ks > kblocks / 4) ks = kblocks / 4;
+        if (ks > 32) ks = 32;
+        if (split.p == nullptr || M * ld <= 0) ks = 1;
+        else if (ks > split.cap / (M * ld)) ks = (int)(split.cap / (M * ld));
+        ksplit = (relu || ld != n_valid || ks < 2) ? 1 : ks;
+    }
     if (ksplit > 1) {
         TDM_CHECK_ARG(!relu && split_buf && ld == n_valid, "%s: bad K-split arguments", name);
         g.ksplit = ksplit; g.logits = split_buf; g.split_stride = M * ld;
@@ -1108,6 +1099,7 @@ extern "C" int tdm_text_train_step(const float* flat, float* grads, const int64_
         embed_noise_kernel<<<(unsigned)M, 64, 0, st>>>(e);
         TDM_CHECK_LAUNCH("embed_noise");
     }
+    const SplitBuf SP{F(W.split), W.split_floats};
     uint8_t* pk = ws + W.pk;
     uint8_t* pm = ws + W.pm2;
     uint8_t* pk2 = ws + W.pk2;
@@ -1121,13 +1113,13 @@ extern "C" int tdm_text_train_step(const float* flat, float* grads, const int64_
         float* hout = reinterpret_cast<float*>(ws + W.hin + (int64_t)(li + 1) * hin_stride);
         const uint32_t site = 16u * (uint32_t)li;
         if ((rc = pack_k(hin, M, D, D, Mp, pk, st))) return rc;
-        if ((rc = gemm_rows(pk, Mp, lw + PK.k[0], 3 * D, flat + po[TP_BQKV], M, 3 * D, D, F(W.qkv + lo), 3 * D, nullptr, 0, 0,
-                            nullptr, st, "train_qkv"))) return rc;
+        if ((rc = gemm_rows(pk, Mp, lw + PK.k[0], 3 * D, flat + po[TP_BQKV], M, 3 * D, D, F(W.qkv + lo), 3 * D, nullptr, 0, -1,
+                            SP, st, "train_qkv"))) return rc;
         if (L == 64) rc = launch_attn_train<64>(false, F(W.qkv + lo), nullptr, nullptr, D, rng, site + 1, F(W.P + lo), F(W.att + lo), B, st);
         else rc = launch_attn_train<128>(false, F(W.qkv + lo), nullptr, nullptr, D, rng, site + 1, F(W.P + lo), F(W.att + lo), B, st);
         if (rc) return rc;
         if ((rc = pack_k(F(W.att + lo), M, D, D, Mp, pk, st))) return rc;
-        if ((rc = gemm_rows(pk, Mp, lw + PK.k[1], D, flat + po[TP_BO], M, D, D, F(W.a + lo), D, nullptr, 0, 0, nullptr, st,
+        if ((rc = gemm_rows(pk, Mp, lw + PK.k[1], D, flat + po[TP_BO], M, D, D, F(W.a + lo), D, nullptr, 0, -1, SP, st,
                             "train_out_proj"))) return rc;
         res_drop_ln_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(hin, F(W.a + lo), flat + po[TP_G1], flat + po[TP_BE1], 1e-5f, M,
                                                                   D, site + 2, rng, F(W.z1 + lo),
@@ -1135,13 +1127,13 @@ extern "C" int tdm_text_train_step(const float* flat, float* grads, const int64_
         TDM_CHECK_LAUNCH("res_drop_ln1");
         if ((rc = pack_k(F(W.h1 + lo), M, D, D, Mp, pk, st))) return rc;
         if ((rc = gemm_rows(pk, Mp, lw + PK.k[2], kTrFF, flat + po[TP_B1], M, kTrFF, D, F(W.f + lo), kTrFF, nullptr, 1, 0,
-                            nullptr, st, "train_ffn1"))) return rc;
+                            SP, st, "train_ffn1"))) return rc;
         if (drop) {
             drop_inplace_kernel<<<ew_grid(M * kTrFF / 4, 256), 256, 0, st>>>(F(W.f + lo), M * kTrFF / 4, site + 3, rng);
             TDM_CHECK_LAUNCH("ffn_dropout");
         }
         if ((rc = pack_k(F(W.f + lo), M, kTrFF, kTrFF, Mp, pk, st))) return rc;
-        if ((rc = gemm_rows(pk, Mp, lw + PK.k[3], D, flat + po[TP_B2], M, D, kTrFF, F(W.g + lo), D, nullptr, 0, 0, nullptr, st,
+        if ((rc = gemm_rows(pk, Mp, lw + PK.k[3], D, flat + po[TP_B2], M, D, kTrFF, F(W.g + lo), D, nullptr, 0, -1, SP, st,
                             "train_ffn2"))) return rc;
         res_drop_ln_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(F(W.h1 + lo), F(W.g + lo), flat + po[TP_G2], flat + po[TP_BE2],
                                                                   1e-5f, M, D, site + 4, rng, F(W.z2 + lo),
@@ -1168,18 +1160,16 @@ extern "C" int tdm_text_train_step(const float* flat, float* grads, const int64_
 
     // ---------------- rounding head: backward ----------------
     g.lse = F(W.lse); g.dev_scale = rounding_weight_dev; g.scale = 1.0f / (float)M;
-    g.out_bf16 = ws + W.dl; g.ob_ps = Mp * 16;
+    g.out_bf16 = ws + W.dl; g.ob_ps = Mp * 16; g.out_bf16_t = ws + W.dlT; g.obt_rows = Vp;
     if ((rc = launch_gemm<GE_DLOGITS>(g, st, "round_dlogits"))) return rc;
     plane_colsum_kernel<<<ew_grid(Vp / 8 * 32, 256), 256, 0, st>>>(ws + W.dl, Vp / 8, Mp, V, grads + tail[TP_DECB]);
     TDM_CHECK_LAUNCH("decoder_bias_grad");
     // d x0 (rounding) = dlogits . W   [M][D], reduction over the vocabulary
-    if ((rc = gemm_rows(ws + W.dl, Mp, wp + PK.dec_t, D, nullptr, M, D, Vp, F(W.dx0b), D, nullptr, 0, W.ksplit_dx, F(W.split), st,
+    if ((rc = gemm_rows(ws + W.dl, Mp, wp + PK.dec_t, D, nullptr, M, D, Vp, F(W.dx0b), D, nullptr, 0, W.ksplit_dx, SP, st,
                         "round_dx0"))) return rc;
-    // d W = dlogits^T . x0   [V][D], reduction over the token rows
-    transpose_planes_kernel<<<ew_grid(Vp / 8 * (Mp / 8), 256), 256, 0, st>>>(ws + W.dl, Vp / 8, Mp, ws + W.dlT);
-    TDM_CHECK_LAUNCH("transpose_dlogits");
+    // d W = dlogits^T . x0   [V][D], reduction over the token rows (the transposed planes came out of the same epilogue)
     if ((rc = pack_m(F(W.x0), M, D, D, Mp, D, pm, st))) return rc;
-    if ((rc = gemm_rows(ws + W.dlT, Vp, pm, D, nullptr, V, D, Mp, grads + tail[TP_DECW], D, nullptr, 0, 0, nullptr, st,
+    if ((rc = gemm_rows(ws + W.dlT, Vp, pm, D, nullptr, V, D, Mp, grads + tail[TP_DECW], D, nullptr, 0, -1, SP, st,
                         "round_dw"))) return rc;
 
     // ---------------- encoder backward ----------------
@@ -1200,21 +1190,21 @@ extern "C" int tdm_text_train_step(const float* flat, float* grads, const int64_
         // linear2: d f = dg . W2, dW2 = dg^T f, db2
         if ((rc = colsum(dtmp, M, D, D, grads + po[TP_B2], st))) return rc;
         if ((rc = pack_k(dtmp, M, D, D, Mp, pk, st))) return rc;
-        if ((rc = gemm_rows(pk, Mp, lw + PK.t[3], kTrFF, nullptr, M, kTrFF, D, F(W.dbig), kTrFF, nullptr, 0, 0, nullptr, st,
+        if ((rc = gemm_rows(pk, Mp, lw + PK.t[3], kTrFF, nullptr, M, kTrFF, D, F(W.dbig), kTrFF, nullptr, 0, -1, SP, st,
                             "train_dffn2_x"))) return rc;
         if ((rc = pack_m(dtmp, M, D, D, Mp, D, pm, st))) return rc;
         if ((rc = pack_m(F(W.f + lo), M, kTrFF, kTrFF, Mp, kTrFF, pk2, st))) return rc;
-        if ((rc = gemm_rows(pm, D, pk2, kTrFF, nullptr, D, kTrFF, Mp, grads + po[TP_W2], kTrFF, nullptr, 0, 0, nullptr, st,
+        if ((rc = gemm_rows(pm, D, pk2, kTrFF, nullptr, D, kTrFF, Mp, grads + po[TP_W2], kTrFF, nullptr, 0, -1, SP, st,
                             "train_dffn2_w"))) return rc;
         relu_drop_bwd_kernel<<<ew_grid(M * kTrFF / 4, 256), 256, 0, st>>>(F(W.dbig), F(W.f + lo), M * kTrFF / 4, rng.keep_scale);
         TDM_CHECK_LAUNCH("relu_drop_bwd");
         // linear1: d h1 += d pre . W1, dW1 = d pre^T h1, db1
         if ((rc = colsum(F(W.dbig), M, kTrFF, kTrFF, grads + po[TP_B1], st))) return rc;
         if ((rc = pack_k(F(W.dbig), M, kTrFF, kTrFF, Mp, pk, st))) return rc;
-        if ((rc = gemm_rows(pk, Mp, lw + PK.t[2], D, nullptr, M, D, kTrFF, dcur, D, dres, 0, 0, nullptr, st, "train_dffn1_x"))) return rc;
+        if ((rc = gemm_rows(pk, Mp, lw + PK.t[2], D, nullptr, M, D, kTrFF, dcur, D, dres, 0, -1, SP, st, "train_dffn1_x"))) return rc;
         if ((rc = pack_m(F(W.dbig), M, kTrFF, kTrFF, Mp, kTrFF, pm, st))) return rc;
         if ((rc = pack_m(F(W.h1 + lo), M, D, D, Mp, D, pk2, st))) return rc;
-        if ((rc = gemm_rows(pm, kTrFF, pk2, D, nullptr, kTrFF, D, Mp, grads + po[TP_W1], D, nullptr, 0, 0, nullptr, st,
+        if ((rc = gemm_rows(pm, kTrFF, pk2, D, nullptr, kTrFF, D, Mp, grads + po[TP_W1], D, nullptr, 0, -1, SP, st,
                             "train_dffn1_w"))) return rc;
         // LN1: dcur (= d h1) -> dres (= d h_in through the residual), dtmp (= d a through the dropout)
         if ((rc = launch_ln_bwd(dcur, F(W.z1 + lo), reinterpret_cast<const float2*>(ws + W.st1 + lo), flat + po[TP_G1], M, D, site + 2,
@@ -1224,10 +1214,10 @@ extern "C" int tdm_text_train_step(const float* flat, float* grads, const int64_
         // out_proj: d att = da . Wo, dWo = da^T att, dbo
         if ((rc = colsum(dtmp, M, D, D, grads + po[TP_BO], st))) return rc;
         if ((rc = pack_k(dtmp, M, D, D, Mp, pk, st))) return rc;
-        if ((rc = gemm_rows(pk, Mp, lw + PK.t[1], D, nullptr, M, D, D, dcur, D, nullptr, 0, 0, nullptr, st, "train_dout_x"))) return rc;
+        if ((rc = gemm_rows(pk, Mp, lw + PK.t[1], D, nullptr, M, D, D, dcur, D, nullptr, 0, -1, SP, st, "train_dout_x"))) return rc;
         if ((rc = pack_m(dtmp, M, D, D, Mp, D, pm, st))) return rc;
         if ((rc = pack_m(F(W.att + lo), M, D, D, Mp, D, pk2, st))) return rc;
-        if ((rc = gemm_rows(pm, D, pk2, D, nullptr, D, D, Mp, grads + po[TP_WO], D, nullptr, 0, 0, nullptr, st, "train_dout_w"))) return rc;
+        if ((rc = gemm_rows(pm, D, pk2, D, nullptr, D, D, Mp, grads + po[TP_WO], D, nullptr, 0, -1, SP, st, "train_dout_w"))) return rc;
         // attention: dcur (= d att) -> dqkv
         if (L == 64) rc = launch_attn_train<64>(true, F(W.qkv + lo), F(W.P + lo), dcur, D, rng, site + 1, nullptr, F(W.dqkv), B, st);
         else rc = launch_attn_train<128>(true, F(W.qkv + lo), F(W.P + lo), dcur, D, rng, site + 1, nullptr, F(W.dqkv), B, st);
@@ -1235,10 +1225,10 @@ extern "C" int tdm_text_train_step(const float* flat, float* grads, const int64_
         // in_proj: d h_in = dres + dqkv . Wqkv, dWqkv = dqkv^T h_in, dbqkv
         if ((rc = colsum(F(W.dqkv), M, 3 * D, 3 * D, grads + po[TP_BQKV], st))) return rc;
         if ((rc = pack_k(F(W.dqkv), M, 3 * D, 3 * D, Mp, pk, st))) return rc;
-        if ((rc = gemm_rows(pk, Mp, lw + PK.t[0], D, nullptr, M, D, 3 * D, dcur, D, dres, 0, 0, nullptr, st, "train_dqkv_x"))) return rc;
+        if ((rc = gemm_rows(pk, Mp, lw + PK.t[0], D, nullptr, M, D, 3 * D, dcur, D, dres, 0, -1, SP, st, "train_dqkv_x"))) return rc;
         if ((rc = pack_m(F(W.dqkv), M, 3 * D, 3 * D, Mp, 3 * D, pm, st))) return rc;
         if ((rc = pack_m(hin, M, D, D, Mp, D, pk2, st))) return rc;
-        if ((rc = gemm_rows(pm, 3 * D, pk2, D, nullptr, 3 * D, D, Mp, grads + po[TP_WQKV], D, nullptr, 0, 0, nullptr, st,
+        if ((rc = gemm_rows(pm, 3 * D, pk2, D, nullptr, 3 * D, D, Mp, grads + po[TP_WQKV], D, nullptr, 0, -1, SP, st,
                             "train_dqkv_w"))) return rc;
     }
     // ---------------- input side ----------------
