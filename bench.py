@@ -318,6 +318,9 @@ def run_ours(args) -> None:
     text2048 = (bench_text(dev, rank, world, max(64, args.text_batch // 4), barrier, peaks_all, dim=2048)
                 if not (args.no_text or args.no_extras) else None)
 
+    # ---- row f2: the Shakespeare training step (src/shakespeare.py:221-250) at the reference CLI's batch 32 x 64 ----
+    text_train = None if (args.no_text or args.no_extras) else bench_text_train(dev, rank, world, 32, barrier, peaks_all)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -337,6 +340,8 @@ def run_ours(args) -> None:
                 text["cpu_baseline"] = cpu_text_baseline(cores, 256)
             if text2048 is not None:
                 text2048["cpu_baseline"] = cpu_text_baseline(cores, 2048)
+            if text_train is not None:
+                text_train["cpu_baseline"] = cpu_text_train_baseline(cores)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -359,6 +364,7 @@ def run_ours(args) -> None:
         "train_global512_per8": train64,
         "text": text,
         "text_dim2048": text2048,
+        "text_train": text_train,
         "sweep": sweep,
         "gpu_eager_baseline": gpu_eager,
     }
@@ -521,6 +527,118 @@ def cpu_text_baseline(cores: int, dim: int) -> dict:
     return {"value": n / (dt * T_STEPS), "unit": "sequences/s", "cores": cores, "kind": "port",
             "sample": f"{nsteps} of 1000 reverse steps at n={n}, L={L}, dim={dim} (oracle port of src/shakespeare.py:343-352), "
                       f"extrapolated; rounding not included"}
+
+
+def cpu_text_train_baseline(cores: int, batch: int = 8, vocab: int = 256_000, dim: int = 256) -> dict:
+    """One reference training step (src/shakespeare.py:221-250: forward in train mode, both losses, backward, AdamW over
+    all three modules) on the host cores through the oracle port, at a bounded batch of 8 x 64 tokens (the (tokens, V)
+    fp32 logits and their gradient are 0.5 GB each at this size; the reference CLI's 32 x 64 needs 4 x that)."""
+    import torch
+    from oracle import ddpm_oracle as O
+    from oracle import text_train_oracle as TO
+    from tinydiffusionmodels_b200.shakespeare import TinyTransformer
+
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    L = 64
+    sd = {k: v.detach().clone() for k, v in TinyTransformer(dim).state_dict().items()}
+    dec_w, dec_b, emb = torch.randn(vocab, dim) * 0.05, torch.zeros(vocab), torch.randn(vocab, dim) * 0.5
+    tab = O.make_tables()
+    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in (("w", dec_w), ("b", dec_b), ("e", emb))}
+
+    def step(k):
+        nonlocal dec_w, dec_b, emb
+        ids = torch.randint(0, vocab, (batch, L))
+        t = torch.randint(0, 1000, (batch,))
+        noise = torch.randn(batch, L, dim)
+        _, g = TO.text_losses_and_grads(sd, dec_w, dec_b, emb, ids, t, noise, tab, dropout=0.1, seed=1, step=k)
+        dec_w, *mv = O.adamw_step(dec_w, g["decoder.weight"], *state["w"], k, lr=1e-4, wd=1e-4); state["w"] = tuple(mv)
+        dec_b, *mv = O.adamw_step(dec_b, g["decoder.bias"], *state["b"], k, lr=1e-4, wd=1e-4); state["b"] = tuple(mv)
+        emb, *mv = O.adamw_step(emb, g["embeddings.weight"], *state["e"], k, lr=1e-4, wd=1e-4); state["e"] = tuple(mv)
+
+    step(1)
+    t0 = time.perf_counter()
+    n = 2
+    for k in range(n):
+        step(2 + k)
+    dt = (time.perf_counter() - t0) / n
+    return {"value": batch / dt, "unit": "sequences/s", "cores": cores, "kind": "port",
+            "sample": f"{n} training steps at batch {batch} x {L} tokens, V={vocab}, dim={dim}, fp32 (oracle port of "
+                      f"src/shakespeare.py:221-250 incl. AdamW on the embedding / decoder matrices; the 3.2 M encoder "
+                      f"parameters' update is not included); {dt:.2f} s per step"}
+
+
+def bench_text_train(dev, rank, world, batch, barrier, peaks, steps: int = 20, warmup: int = 4, vocab: int = 256_000,
+                     dim: int = 256) -> dict:
+    """Row f2: one optimisation step of the Shakespeare model (src/shakespeare.py:221-250) at the reference CLI's batch
+    (32 sequences x 64 tokens per GPU), V = 256,000, width 256, depth 3, dropout 0.1, learned embeddings: forward,
+    both losses, backward, [NCCL all-reduce of the 131.6 M-float gradient when data parallel], AdamW, weight re-pack -
+    one replayed CUDA graph on one GPU.  Token ids come from pinned host memory every step (the e2e figure)."""
+    import torch
+    import torch.distributed as dist
+
+    from tinydiffusionmodels_b200 import _lib
+    from tinydiffusionmodels_b200.shakespeare import LearnedEmbedding, LearnedRounding, TinyTransformer
+    from tinydiffusionmodels_b200.text_train import TextTrainer
+
+    torch.manual_seed(0)
+    L = 64
+    m, r, e = TinyTransformer(dim).to(dev), LearnedRounding(dim, vocab).to(dev), LearnedEmbedding(vocab, dim).to(dev)
+    tr = TextTrainer(m, r, e, dev, batch, L, lr=1e-4, weight_decay=1e-4, seed=11)
+    ids_dev = torch.randint(0, vocab, (batch, L), device=dev)
+    ids_host = ids_dev.cpu().pin_memory()
+    n0 = _lib.launch_count()
+    tr.step(ids_dev)
+    launches = _lib.launch_count() - n0
+    for _ in range(warmup):
+        tr.step(ids_dev)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        tr.step(ids_dev)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    barrier()
+    e0.record()
+    for k in range(steps):
+        loss = tr.step(ids_host, lr=1e-4, rounding_weight=1.0)   # H2D of the ids + scalar updates inside the timed region
+        if k % 10 == 9:
+            loss.tolist()                                        # the reference reads its losses (.item()) for logging
+    final = tr.losses.tolist()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+    ms, mse = float(ms_t.item()), float(ms_e.item())
+    tokens = batch * L
+    # algorithmic FLOP per token: forward + dX + dW of the encoder (3 x 8,060,928, BASELINE.md section 3) and of the rounding
+    # head (3 x 2*dim*V); the recomputation of the logits in the gradient pass is NOT counted
+    flop_tok = 3 * (8_060_928 + 2.0 * dim * vocab)
+    tf = flop_tok * tokens / (ms * 1e-3) / 1e12
+    adam_bytes = 28.0 * tr.n
+    out = {
+        "metric": "shakespeare_train_sequences_per_sec", "unit": "sequences/s", "value": world * batch / (ms * 1e-3),
+        "e2e": {"value": world * batch / (mse * 1e-3), "unit": "sequences/s", "h2d_bytes_per_step": batch * L * 8 + 8,
+                "d2h_bytes_per_step": 12 / 10, "what": "TextTrainer.step from pinned host token ids, learning rate and "
+                "rounding weight rewritten every step, losses read back every 10th step"},
+        "ms_per_step": ms, "gpu_launches_per_step": int(launches), "losses_after": final,
+        "config": {"workload": f"Shakespeare training step, {batch} x {L} tokens per GPU, V={vocab}, TinyTransformer({dim}), "
+                               f"dropout 0.1, learned embeddings + learned rounding, AdamW over {tr.n:,} parameters; "
+                               f"synthetic token ids, random-init weights", "parallelism": f"dp{world}"},
+        "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+                     "frac": tf / peaks["tf_sustained"], "traffic": None,
+                     "what": "whole step: 3 x (encoder 8.06 MFLOP + rounding head 2*dim*V) FLOP per token x tokens / step time; "
+                             "the step also streams 28 B per parameter through AdamW "
+                             f"({adam_bytes / 1e9:.2f} GB = {adam_bytes / peaks['hbm_gbs'] / 1e6:.2f} ms at the HBM copy peak)"},
+        "dtype": "bf16 operands, fp32 accumulation / activations / master weights / optimiser state",
+    }
+    del tr, m, r, e
+    torch.cuda.empty_cache()
+    return out
 
 
 def bench_train(dev, rank, world, batch, barrier, peaks, steps: int = 30, warmup: int = 5, pipeline: bool = True) -> dict:

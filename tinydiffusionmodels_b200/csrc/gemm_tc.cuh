@@ -89,6 +89,13 @@ struct GemmArgs {
     int64_t obt_rows;        //             (the A operand of dW = dlogits^T . X), or null
 };
 
+// 2^x on the MUFU (ex2.approx.ftz: 2^-inf = +0, no range fix-up code)
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // one work item of the persistent loop: a row tile, a range of column tiles and a range of K blocks
 struct GemmItem {
     int mt, sp, ks, n0, n1, kb0, kb1;
@@ -229,8 +236,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                 if (rvalid) tgt = (int)__ldg(a.target + row);
             }
             if constexpr (EPI == GE_DLOGITS) {
-                if (rvalid) row_lse = __ldg(a.lse + row);
+                // row_lse: the exponent's per-row constant log2(scale) - lse * log2 e (-inf for padding rows and for a zero
+                // scale: every gradient of the row is then exactly zero)
                 gscale = a.scale * (a.dev_scale ? __ldg(a.dev_scale) : 1.0f);
+                row_lse = (rvalid && gscale > 0.f) ? log2f(gscale) - __ldg(a.lse + row) * 1.4426950408889634f : -INFINITY;
+                if (!rvalid) gscale = 0.f;
             }
             // four independent running maxima (columns k % 4): one serial compare/select chain over all
             // 256 columns of a tile is a ~2000-cycle dependency chain per thread
@@ -374,34 +384,46 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                             }
                         }
                     } else if constexpr (EPI == GE_LSE) {
-                        // logits of this row x these 32 columns (padding columns -> -inf): fold into the running
-                        // (max, sum exp) pair, keep the target's logit when it falls in this chunk
-                        const bool full = nb + 32 <= a.n_valid;
+                        // logits of this row x these 32 columns in the base-2 domain (v2 = (acc + bias) * log2 e): fold into
+                        // the running (max, sum 2^(v2 - max)) pair.  Padding columns (last vocabulary tile only) and the
+                        // target's logit are handled on rarely-taken branches, not per element.
+                        constexpr float kLog2e = 1.4426950408889634f;
+                        const float bias2_l = bias_l * kLog2e;
                         float v[32];
-                        float cmax = -INFINITY;
 #pragma unroll
-                        for (int k = 0; k < 32; ++k) {
-                            v[k] = __uint_as_float(r[k]) + __shfl_sync(0xffffffffu, bias_l, k);
-                            if (!full && nb + k >= a.n_valid) v[k] = -INFINITY;
-                            cmax = fmaxf(cmax, v[k]);
-                            if (nb + k == tgt) {
-                                tgt_v = v[k];
-                                tgt_hit = true;
-                            }
+                        for (int k = 0; k < 32; ++k) v[k] = fmaf(__uint_as_float(r[k]), kLog2e, __shfl_sync(0xffffffffu, bias2_l, k));
+                        if (nb + 32 > a.n_valid) {
+#pragma unroll
+                            for (int k = 0; k < 32; ++k)
+                                if (nb + k >= a.n_valid) v[k] = -INFINITY;
                         }
+                        if ((unsigned)(tgt - nb) < 32u) {
+#pragma unroll
+                            for (int k = 0; k < 32; ++k)
+                                if (nb + k == tgt) tgt_v = v[k];
+                            tgt_hit = true;
+                        }
+                        float c4[4] = {v[0], v[1], v[2], v[3]};
+#pragma unroll
+                        for (int k = 4; k < 32; ++k) c4[k & 3] = fmaxf(c4[k & 3], v[k]);
+                        const float cmax = fmaxf(fmaxf(c4[0], c4[1]), fmaxf(c4[2], c4[3]));
                         if (cmax > -INFINITY) {
                             if (cmax > lse_m) {
-                                lse_s *= __expf(lse_m - cmax);   // exp(-inf) = 0 on the first chunk
+                                lse_s *= ex2_approx(lse_m - cmax);   // 2^(-inf) = 0 on the first chunk
                                 lse_m = cmax;
                             }
                             float s4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                            for (int k = 0; k < 32; ++k) s4[k & 3] += __expf(v[k] - lse_m);
+                            for (int k = 0; k < 32; ++k) s4[k & 3] += ex2_approx(v[k] - lse_m);
                             lse_s += (s4[0] + s4[1]) + (s4[2] + s4[3]);
                         }
                     } else if constexpr (EPI == GE_DLOGITS) {
                         // d loss / d logits = (softmax - onehot) * scale, zero for padding rows and columns (both are
-                        // reduction indices of the gradient GEMMs that read these planes)
+                        // reduction indices of the gradient GEMMs that read these planes).  softmax * scale =
+                        // 2^((acc + bias) log2 e - lse log2 e + log2 scale): one FMA, one add and one MUFU per element; the
+                        // onehot and the padding columns are fixed up on rarely-taken branches.
+                        constexpr float kLog2e = 1.4426950408889634f;
+                        const float bias2_l = bias_l * kLog2e;
                         const bool full = nb + 32 <= a.n_valid;
                         float* art = reinterpret_cast<float*>(smem + kGemmSmemBase) + (warp - 2) * kArTileFloats;
                         if (a.out_bf16_t) __syncwarp();   // the previous chunk's reads of the tile are done
@@ -409,12 +431,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                         for (int pj = 0; pj < 4; ++pj) {
                             float gk[8];
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const int n = nb + pj * 8 + k;
-                                const float v = __uint_as_float(r[pj * 8 + k]) + __shfl_sync(0xffffffffu, bias_l, pj * 8 + k);
-                                float p = __expf(v - row_lse);
-                                if (n == tgt) p -= 1.0f;
-                                gk[k] = (rvalid && (full || n < a.n_valid)) ? p * gscale : 0.f;
+                            for (int k = 0; k < 8; ++k)
+                                gk[k] = ex2_approx(fmaf(__uint_as_float(r[pj * 8 + k]), kLog2e, __shfl_sync(0xffffffffu, bias2_l, pj * 8 + k)) + row_lse);
+                            if ((unsigned)(tgt - (nb + pj * 8)) < 8u) {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k)
+                                    if (nb + pj * 8 + k == tgt) gk[k] -= gscale;
+                            }
+                            if (!full) {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k)
+                                    if (nb + pj * 8 + k >= a.n_valid) gk[k] = 0.f;
                             }
                             const uint4 o = make_uint4(pack_bf16x2(gk[0], gk[1]), pack_bf16x2(gk[2], gk[3]),
                                                        pack_bf16x2(gk[4], gk[5]), pack_bf16x2(gk[6], gk[7]));
@@ -526,9 +553,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
             }
             if constexpr (EPI == GE_LSE) {
                 const int64_t slot = (int64_t)(sp * 2 + grp) * a.Mp + row;
-                a.part_val[slot] = lse_m;
+                a.part_val[slot] = lse_m * 0.6931471805599453f;   // back to natural-log units (the sum is unit-free)
                 a.part_sum[slot] = lse_s;
-                if (tgt_hit) a.tgt_logit[row] = tgt_v;
+                if (tgt_hit) a.tgt_logit[row] = tgt_v * 0.6931471805599453f;
             }
             if constexpr (EPI == GE_ARGMAX) {
                 float best = best4[0];

@@ -136,7 +136,7 @@ class TextTrainer:
         self.pack()
 
     def _check_ids(self, token_ids) -> torch.Tensor:
-        ids = token_ids.to(device=self.device, dtype=torch.int64)
+        ids = token_ids.to(device=self.device, dtype=torch.int64, non_blocking=True)
         if tuple(ids.shape) != (self.batch, self.seq_len):
             raise _lib.TdmError(f"token batch {tuple(ids.shape)} does not match the trainer's ({self.batch}, {self.seq_len})")
         return ids.contiguous()
