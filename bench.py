@@ -587,9 +587,8 @@ def bench_text_train(dev, rank, world, batch, barrier, peaks, steps: int = 20, w
     tr = TextTrainer(m, r, e, dev, batch, L, lr=1e-4, weight_decay=1e-4, seed=11)
     ids_dev = torch.randint(0, vocab, (batch, L), device=dev)
     ids_host = ids_dev.cpu().pin_memory()
-    n0 = _lib.launch_count()
     tr.step(ids_dev)
-    launches = _lib.launch_count() - n0
+    launches = tr.launches_per_step
     for _ in range(warmup):
         tr.step(ids_dev)
     barrier()

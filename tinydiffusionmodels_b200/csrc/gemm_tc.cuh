@@ -281,6 +281,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
             for (int nt = n0; nt < n1; ++nt, ++it) {
                 if ((it & 1) != grp) continue;
                 const uint32_t aph = (n_mine++) & 1;
+                // The tile's 256 bias values, one 128-byte line per 32-column chunk (lane l <-> column 32 c + l), are fetched
+                // BEFORE the accumulator wait: loaded chunk by chunk they put one L2 / HBM latency into every chunk's
+                // dependent chain - eight per tile, which was most of a single-tile GEMM's 16-18 us.  The chunk loop is
+                // not unrolled, so the eight registers are consumed by rotation (static indices).
+                float bl[8];
+                {
+                    const bool with_bias = a.bias && (EPI != GE_LOGITS || w.ks == 0);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) bl[c] = with_bias ? __ldg(a.bias + nt * kBN + c * 32 + lane) : 0.f;
+                }
                 mbar_wait(bar_accf + grp, aph);
                 tc_fence_after_sync();
                 float ln_sum = 0.f, ln_sq = 0.f;
@@ -291,8 +301,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                     const int c0 = c00 + 32 * hsub;
                     uint32_t r[32];
                     tmem_ld32(taddr + c0, r);
-                    // lane l fetches the bias of column c0 + l (one coalesced 128 B load); columns get it by shuffle
-                    const float bias_l = (a.bias && (EPI != GE_LOGITS || w.ks == 0)) ? __ldg(a.bias + nt * kBN + c0 + lane) : 0.f;
+                    // lane l holds the bias of column c0 + l; columns get it by shuffle
+                    const float bias_l = bl[0];
+#pragma unroll
+                    for (int c = 0; c < 7; ++c) bl[c] = bl[c + 1];
                     tmem_ld_wait();
                     if (EPI != GE_RES_LN && c0 + 32 == kBN) {
                         tc_fence_before_sync();

@@ -106,6 +106,7 @@ class TextTrainer:
         self.ids = torch.zeros(self.batch, self.seq_len, dtype=torch.int64, device=self.device)
         self.sample_offset = self.rank * self.batch
         self._graph = None
+        self.launches_per_step = 0
         self.pack()
 
     # ---- pieces ----------------------------------------------------------------------------------------------
@@ -167,7 +168,9 @@ class TextTrainer:
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(side):
+                n0 = _lib.launch_count()
                 self._one()                                   # warm-up (a real step) outside capture
+                self.launches_per_step = _lib.launch_count() - n0
             torch.cuda.current_stream(self.device).wait_stream(side)
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
