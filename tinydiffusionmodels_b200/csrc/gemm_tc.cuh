@@ -96,6 +96,23 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+#ifdef TDM_EXP_TIMELINE
+// development aid (tools/gemm_timeline.py): globaltimer stamps of block 0's phases
+__device__ unsigned long long g_gemm_tl[16];
+__device__ __forceinline__ void tl_stamp(int i) {
+    if (blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_gemm_tl[i] = t;
+    }
+}
+#define TL(i) tl_stamp(i)
+#define TL0(i) do { if (lane == 0) tl_stamp(i); } while (0)
+#else
+#define TL(i)
+#define TL0(i)
+#endif
+
 // one work item of the persistent loop: a row tile, a range of column tiles and a range of K blocks
 struct GemmItem {
     int mt, sp, ks, n0, n1, kb0, kb1;
@@ -125,6 +142,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acce + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) TL(0);
     if (threadIdx.x == 0) {
         for (int i = 0; i < kGemmStages; ++i) {
             mbar_init(bar_full + i, 1);
@@ -140,8 +158,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+    if (threadIdx.x == 0) TL(1);
     pdl_wait();                 // PDL (common.cuh): nothing above touches global memory
     pdl_launch_dependents();
+    if (threadIdx.x == 0) TL(2);
     const uint32_t tmem_base = *s_tmem;
 
     const int m_tiles = a.Mp / kBM;
@@ -180,6 +200,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                         bulk_g2s(st + kGemmStageA + j * (kBN * 16),
                                  a.w + (int64_t)(kb * 8 + j) * a.w_ps + (int64_t)nt * (kBN * 16), kBN * 16, bar_full + s);
                     }
+                    if (kit == 0) TL0(3);
                 }
             }
         }
@@ -201,6 +222,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                     const uint32_t ph = (kit / kGemmStages) & 1;
                     mbar_wait(bar_full + s, ph);
                     tc_fence_after_sync();
+                    if (kit == 0) TL(4);
                     const uint32_t a_addr = smem_u32(smem + s * kGemmStage);
                     const uint64_t a_base = make_smem_desc(a_addr, kBM * 16, 128);
                     const uint64_t b_base = make_smem_desc(a_addr + kGemmStageA, kBN * 16, 128);
@@ -212,6 +234,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                     umma_commit(bar_empty + s);
                 }
                 umma_commit(bar_accf + acc);
+                if (it == 0) TL(5);
             }
         }
         }
@@ -293,6 +316,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                 }
                 mbar_wait(bar_accf + grp, aph);
                 tc_fence_after_sync();
+                if (warp == 2 && n_mine == 1) TL0(6);
                 float ln_sum = 0.f, ln_sq = 0.f;
 #pragma unroll 1
                 for (int c00 = 0; c00 < kBN; c00 += 32 * kSub) {
@@ -306,55 +330,64 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
 #pragma unroll
                     for (int c = 0; c < 7; ++c) bl[c] = bl[c + 1];
                     tmem_ld_wait();
+                    if (warp == 2 && n_mine == 1 && c0 == 0) TL0(11);
+                    if (warp == 2 && n_mine == 1 && c0 == 32) TL0(13);
+                    if (warp == 2 && n_mine == 1 && c0 == 64) TL0(3);
                     if (EPI != GE_RES_LN && c0 + 32 == kBN) {
                         tc_fence_before_sync();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_acce + grp);
                     }
                     const int nb = nt * kBN + c0;
+                    if (warp == 2 && n_mine == 1 && c0 == 0) TL0(12);
+                    if (warp == 2 && n_mine == 1 && c0 == 32) TL0(14);
                     if constexpr (EPI == GE_BF16) {
+                        float vv[32];   // shuffles in straight-line code, stores under ONE row-validity branch (see GE_LOGITS)
 #pragma unroll
-                        for (int pj = 0; pj < 4; ++pj) {
-                            float v[8];
+                        for (int k = 0; k < 32; ++k) {
+                            vv[k] = __uint_as_float(r[k]) + __shfl_sync(0xffffffffu, bias_l, k);
+                            if (a.relu) vv[k] = fmaxf(vv[k], 0.f);
+                        }
+                        if (rvalid) {
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                v[k] = __uint_as_float(r[pj * 8 + k]) + __shfl_sync(0xffffffffu, bias_l, pj * 8 + k);
-                                if (a.relu) v[k] = fmaxf(v[k], 0.f);
-                            }
-                            if (rvalid) {
+                            for (int pj = 0; pj < 4; ++pj) {
+                                const float* v = vv + pj * 8;
                                 uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]),
                                                      pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
                                 *reinterpret_cast<uint4*>(a.out_bf16 + (int64_t)(nb / 8 + pj) * a.ob_ps + (int64_t)row * 16) = o;
                             }
                         }
                     } else if constexpr (EPI == GE_RES_F32) {
+                        float vv[32];   // shuffles in straight-line code; residual loads batched under one branch
 #pragma unroll
-                        for (int pj = 0; pj < 8; ++pj) {
-                            float bq[4];   // shuffles stay outside the row-validity branch (all lanes take part)
+                        for (int k = 0; k < 32; ++k) vv[k] = __uint_as_float(r[k]) + __shfl_sync(0xffffffffu, bias_l, k);
+                        if (rvalid) {
+                            float4 rv[8];
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) bq[k] = __shfl_sync(0xffffffffu, bias_l, pj * 4 + k);
-                            if (rvalid) {
-                                const int64_t pl = nb / 4 + pj;
-                                const float4 rv = *reinterpret_cast<const float4*>(a.res + pl * a.res_ps + (int64_t)row * 16);
-                                float4 o;
-                                o.x = __uint_as_float(r[pj * 4 + 0]) + bq[0] + rv.x;
-                                o.y = __uint_as_float(r[pj * 4 + 1]) + bq[1] + rv.y;
-                                o.z = __uint_as_float(r[pj * 4 + 2]) + bq[2] + rv.z;
-                                o.w = __uint_as_float(r[pj * 4 + 3]) + bq[3] + rv.w;
-                                *reinterpret_cast<float4*>(a.out_f32 + pl * a.of_ps + (int64_t)row * 16) = o;
-                            }
+                            for (int pj = 0; pj < 8; ++pj)
+                                rv[pj] = *reinterpret_cast<const float4*>(a.res + (int64_t)(nb / 4 + pj) * a.res_ps + (int64_t)row * 16);
+#pragma unroll
+                            for (int pj = 0; pj < 8; ++pj)
+                                *reinterpret_cast<float4*>(a.out_f32 + (int64_t)(nb / 4 + pj) * a.of_ps + (int64_t)row * 16) =
+                                    make_float4(vv[pj * 4 + 0] + rv[pj].x, vv[pj * 4 + 1] + rv[pj].y, vv[pj * 4 + 2] + rv[pj].z,
+                                                vv[pj * 4 + 3] + rv[pj].w);
                         }
                     } else if constexpr (EPI == GE_RES_LN) {
                         // pass 1 of 2: v = acc + bias + residual; row statistics; park v in TMEM
+                        // (shuffles in straight-line code, the eight residual loads issued together)
                         uint32_t vb[32];
+                        float4 rv[8];
 #pragma unroll
                         for (int pj = 0; pj < 8; ++pj) {
-                            float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (rvalid) rv = *reinterpret_cast<const float4*>(a.res + (int64_t)(nb / 4 + pj) * a.res_ps + (int64_t)row * 16);
-                            const float v0 = __uint_as_float(r[pj * 4 + 0]) + __shfl_sync(0xffffffffu, bias_l, pj * 4 + 0) + rv.x;
-                            const float v1 = __uint_as_float(r[pj * 4 + 1]) + __shfl_sync(0xffffffffu, bias_l, pj * 4 + 1) + rv.y;
-                            const float v2 = __uint_as_float(r[pj * 4 + 2]) + __shfl_sync(0xffffffffu, bias_l, pj * 4 + 2) + rv.z;
-                            const float v3 = __uint_as_float(r[pj * 4 + 3]) + __shfl_sync(0xffffffffu, bias_l, pj * 4 + 3) + rv.w;
+                            rv[pj] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (rvalid) rv[pj] = *reinterpret_cast<const float4*>(a.res + (int64_t)(nb / 4 + pj) * a.res_ps + (int64_t)row * 16);
+                        }
+#pragma unroll
+                        for (int pj = 0; pj < 8; ++pj) {
+                            const float v0 = __uint_as_float(r[pj * 4 + 0]) + __shfl_sync(0xffffffffu, bias_l, pj * 4 + 0) + rv[pj].x;
+                            const float v1 = __uint_as_float(r[pj * 4 + 1]) + __shfl_sync(0xffffffffu, bias_l, pj * 4 + 1) + rv[pj].y;
+                            const float v2 = __uint_as_float(r[pj * 4 + 2]) + __shfl_sync(0xffffffffu, bias_l, pj * 4 + 2) + rv[pj].z;
+                            const float v3 = __uint_as_float(r[pj * 4 + 3]) + __shfl_sync(0xffffffffu, bias_l, pj * 4 + 3) + rv[pj].w;
                             ln_sum += (v0 + v1) + (v2 + v3);
                             ln_sq = fmaf(v0, v0, fmaf(v1, v1, fmaf(v2, v2, fmaf(v3, v3, ln_sq))));
                             vb[pj * 4 + 0] = __float_as_uint(v0);
@@ -364,37 +397,40 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                         }
                         tmem_st32(taddr + c0, vb);
                     } else if constexpr (EPI == GE_LOGITS) {
+                        // all 32 shuffles first, in straight-line code: interleaved with the row / column validity branches
+                        // every group of four sat inside its own convergence region (BSSY / BRA.DIV / BSYNC around each
+                        // SHFL quartet) and one chunk of one warp took ~1,900 cycles
+                        float v[32];
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) {
+                            v[k] = fmaf(__uint_as_float(r[k]), rs, __shfl_sync(0xffffffffu, bias_l, k));
+                            if (a.relu) v[k] = fmaxf(v[k], 0.f);
+                        }
+                        if (warp == 2 && n_mine == 1 && c0 == 32 && __float_as_uint(v[31]) != 0x7fc12345u) TL0(15);
                         float* orow = a.logits + (int64_t)w.ks * a.split_stride + (int64_t)row * a.logits_ld + nb;
                         const float* arow = (a.logits_add && w.ks == 0) ? a.logits_add + (int64_t)row * a.logits_ld + nb : nullptr;
                         const bool vec = (a.logits_ld & 3) == 0 && nb + 32 <= a.n_valid;   // 16-byte aligned, whole chunk valid
+                        if (rvalid) {
+                            if (vec) {
+                                if (arow) {
+                                    float4 ad[8];
 #pragma unroll
-                        for (int k4 = 0; k4 < 8; ++k4) {
-                            float v[4];   // shuffles stay outside the row-validity branch (all lanes take part)
+                                    for (int k4 = 0; k4 < 8; ++k4) ad[k4] = __ldg(reinterpret_cast<const float4*>(arow) + k4);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                v[k] = __uint_as_float(r[k4 * 4 + k]) * rs + __shfl_sync(0xffffffffu, bias_l, k4 * 4 + k);
-                                if (a.relu) v[k] = fmaxf(v[k], 0.f);
-                            }
-                            if (rvalid && arow) {
-                                if (vec) {
-                                    const float4 ad = __ldg(reinterpret_cast<const float4*>(arow + k4 * 4));
-                                    v[0] += ad.x; v[1] += ad.y; v[2] += ad.z; v[3] += ad.w;
-                                } else {
-#pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-                                        if (nb + k4 * 4 + k < a.n_valid) v[k] += __ldg(arow + k4 * 4 + k);
+                                    for (int k4 = 0; k4 < 8; ++k4) {
+                                        v[4 * k4] += ad[k4].x; v[4 * k4 + 1] += ad[k4].y; v[4 * k4 + 2] += ad[k4].z; v[4 * k4 + 3] += ad[k4].w;
+                                    }
                                 }
-                            }
-                            if (rvalid) {
-                                if (vec) {
-                                    *reinterpret_cast<float4*>(orow + k4 * 4) = make_float4(v[0], v[1], v[2], v[3]);
-                                } else {
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-                                        if (nb + k4 * 4 + k < a.n_valid) orow[k4 * 4 + k] = v[k];
-                                }
+                                for (int k4 = 0; k4 < 8; ++k4)
+                                    reinterpret_cast<float4*>(orow)[k4] = make_float4(v[4 * k4], v[4 * k4 + 1], v[4 * k4 + 2], v[4 * k4 + 3]);
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 32; ++k)
+                                    if (nb + k < a.n_valid) orow[k] = arow ? v[k] + __ldg(arow + k) : v[k];
                             }
                         }
+                        if (warp == 2 && n_mine == 1 && c0 == 32) TL0(10);
                     } else if constexpr (EPI == GE_LSE) {
                         // logits of this row x these 32 columns in the base-2 domain (v2 = (acc + bias) * log2 e): fold into
                         // the running (max, sum 2^(v2 - max)) pair.  Padding columns (last vocabulary tile only) and the
@@ -439,22 +475,23 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                         const bool full = nb + 32 <= a.n_valid;
                         float* art = reinterpret_cast<float*>(smem + kGemmSmemBase) + (warp - 2) * kArTileFloats;
                         if (a.out_bf16_t) __syncwarp();   // the previous chunk's reads of the tile are done
+                        float gv[32];
+#pragma unroll
+                        for (int k = 0; k < 32; ++k)
+                            gv[k] = ex2_approx(fmaf(__uint_as_float(r[k]), kLog2e, __shfl_sync(0xffffffffu, bias2_l, k)) + row_lse);
+                        if ((unsigned)(tgt - nb) < 32u) {
+#pragma unroll
+                            for (int k = 0; k < 32; ++k)
+                                if (nb + k == tgt) gv[k] -= gscale;
+                        }
+                        if (!full) {
+#pragma unroll
+                            for (int k = 0; k < 32; ++k)
+                                if (nb + k >= a.n_valid) gv[k] = 0.f;
+                        }
 #pragma unroll
                         for (int pj = 0; pj < 4; ++pj) {
-                            float gk[8];
-#pragma unroll
-                            for (int k = 0; k < 8; ++k)
-                                gk[k] = ex2_approx(fmaf(__uint_as_float(r[pj * 8 + k]), kLog2e, __shfl_sync(0xffffffffu, bias2_l, pj * 8 + k)) + row_lse);
-                            if ((unsigned)(tgt - (nb + pj * 8)) < 8u) {
-#pragma unroll
-                                for (int k = 0; k < 8; ++k)
-                                    if (nb + pj * 8 + k == tgt) gk[k] -= gscale;
-                            }
-                            if (!full) {
-#pragma unroll
-                                for (int k = 0; k < 8; ++k)
-                                    if (nb + pj * 8 + k >= a.n_valid) gk[k] = 0.f;
-                            }
+                            const float* gk = gv + pj * 8;
                             const uint4 o = make_uint4(pack_bf16x2(gk[0], gk[1]), pack_bf16x2(gk[2], gk[3]),
                                                        pack_bf16x2(gk[4], gk[5]), pack_bf16x2(gk[6], gk[7]));
                             *reinterpret_cast<uint4*>(a.out_bf16 + (int64_t)(nb / 8 + pj) * a.ob_ps + (int64_t)row * 16) = o;
@@ -585,11 +622,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
             }
         }
     }
+    if (warp == 2) TL0(7);
     __syncwarp();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
+    if (threadIdx.x == 0) TL(8);
     if (warp == 2) tmem_dealloc<512>(tmem_base);
+    if (warp == 2) TL0(9);
 }
 
 template <int EPI>

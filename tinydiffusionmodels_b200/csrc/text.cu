@@ -791,3 +791,9 @@ extern "C" int tdm_embedding_gather(const float* table, int64_t vocab, int dim, 
     TDM_CHECK_LAUNCH("tdm_embedding_gather");
     return TDM_OK;
 }
+
+#ifdef TDM_EXP_TIMELINE
+extern "C" int tdm_debug_gemm_timeline(unsigned long long* host16) {
+    return cudaMemcpyFromSymbol(host16, tdm::g_gemm_tl, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : 2;
+}
+#endif
