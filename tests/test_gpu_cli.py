@@ -39,3 +39,18 @@ def test_shakespeare_guided_cli(cuda, in_tmp):
     from tinydiffusionmodels_b200 import shakespeare
     shakespeare.main(["--guided_sample", "--synthetic", "--vocab_size", "4096", "--n", "2", "--alpha", "0.3"])
     assert (in_tmp / "samples" / "guided_sample_1.txt").exists()
+
+
+@pytest.mark.parametrize("extra", [["--use_learned_embeddings", "--embed_dim", "256"], []])
+def test_shakespeare_train_then_sample_cli(cuda, in_tmp, extra):
+    """`python -m src.shakespeare --train` (row f2) with learned 256-wide embeddings and with the frozen pre-trained
+    table at the base LM's width (2048, the reference CLI's default), then `--sample` from the checkpoint it wrote."""
+    from tinydiffusionmodels_b200 import shakespeare
+    ck = str(in_tmp / "text_ckpt.pth")
+    shakespeare.main(["--train", "--synthetic", "--vocab_size", "1024", "--epochs", "1", "--batch_size", "4", "--warmup_steps", "2",
+                      "--seed", "3", "--ckpt", ck, *extra])
+    saved = torch.load(ck, map_location="cpu")
+    assert saved["final_training"] is True and ("embedding_fn" in saved) == bool(extra)
+    assert all(torch.isfinite(v).all() for v in saved["diffusion_model"].values())
+    shakespeare.main(["--sample", "--synthetic", "--vocab_size", "1024", "--n", "2", "--ckpt", ck, *extra])
+    assert (in_tmp / "samples" / "sample_1.txt").exists()

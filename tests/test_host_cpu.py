@@ -167,3 +167,33 @@ def test_public_surface_matches_the_live_reference():
     for e in range(0, 11):
         assert ref_t.dynamic_rounding_weight_schedule(e, 10, 0.7, 0.05) == our_t.dynamic_rounding_weight_schedule(e, 10, 0.7, 0.05)
     assert math.isclose(our_t.dynamic_rounding_weight_schedule(3, 10), 0.73)
+
+
+def test_training_learning_rates_equal_what_lambda_lr_would_set():
+    """shakespeare.train writes lr * cosine_warmup_factor(k) to the device for optimiser step k; the reference steps a
+    LambdaLR after every optim.step() (src/shakespeare.py:199-200, 250) - the same sequence."""
+    import torch
+
+    from src.shakespeare import cosine_warmup_factor, get_cosine_schedule_with_warmup
+
+    lr, warm, total = 3e-4, 5, 23
+    opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=lr)
+    sched = get_cosine_schedule_with_warmup(opt, warm, total)
+    for k in range(total):
+        assert opt.param_groups[0]["lr"] == pytest.approx(lr * cosine_warmup_factor(k, warm, total), rel=1e-12, abs=0)
+        opt.step()
+        sched.step()
+
+
+def test_text_training_refuses_to_run_without_cuda():
+    import torch
+
+    from src.shakespeare import LearnedEmbedding, LearnedRounding, TinyTransformer
+    from tinydiffusionmodels_b200._lib import TdmError
+    from tinydiffusionmodels_b200.text_train import TextTrainer
+
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    m, r, e = TinyTransformer(256, depth=1), LearnedRounding(256, 64), LearnedEmbedding(64, 256)
+    with pytest.raises(TdmError, match="no CPU fallback"):
+        TextTrainer(m, r, e, "cpu", 2, 64)

@@ -34,18 +34,19 @@ HF_TOKEN = os.getenv("HF_TOKEN")
 
 
 # ---- host-side training schedules (ref src/shakespeare.py:159-172) ---------------------------------------------
+def cosine_warmup_factor(step, num_warmup_steps, num_training_steps, eta_min=0):
+    """Learning-rate factor at optimiser step ``step`` (0-based): linear ramp 0 -> 1 over the warm-up steps, then half a
+    cosine down to ``eta_min`` (the lambda of ref :159-167)."""
+    if step < num_warmup_steps:
+        return float(step) / float(max(1, num_warmup_steps))
+    progress = float(step - num_warmup_steps) / float(max(1, num_training_steps - num_warmup_steps))
+    return max(eta_min, 0.5 * (1.0 + math.cos(math.pi * progress)))
+
+
 def get_cosine_schedule_with_warmup(optimizer, num_warmup_steps, num_training_steps, eta_min=0):
-    """``LambdaLR`` factor: linear ramp 0 -> 1 over the warm-up steps, then half a cosine down to ``eta_min``."""
-    warm = float(max(1, num_warmup_steps))
-    span = float(max(1, num_training_steps - num_warmup_steps))
-
-    def factor(step):
-        if step < num_warmup_steps:
-            return float(step) / warm
-        progress = float(step - num_warmup_steps) / span
-        return max(eta_min, 0.5 * (1.0 + math.cos(math.pi * progress)))
-
-    return torch.optim.lr_scheduler.LambdaLR(optimizer, factor)
+    """``LambdaLR`` over ``cosine_warmup_factor`` (ref :159-167)."""
+    return torch.optim.lr_scheduler.LambdaLR(
+        optimizer, lambda step: cosine_warmup_factor(step, num_warmup_steps, num_training_steps, eta_min))
 
 
 def dynamic_rounding_weight_schedule(epoch, total_epochs, initial_weight=1.0, final_weight=0.1):
@@ -202,15 +203,9 @@ def train(model, rounding_fn, embedding_fn, data_loader, val_loader, device, ckp
     tr = TextTrainer(model, rounding_fn, embedding_fn, device, batch, seq_len, lr=lr, weight_decay=weight_decay,
                      use_learned_embeddings=use_learned_embeddings, seed=_fresh_seed() if seed is None else seed)
     total_steps = len(data_loader) * epochs
-    warm = float(max(1, warmup_steps))
-    span = float(max(1, total_steps - warmup_steps))
 
-    def lr_at(k):   # LambdaLR factor of get_cosine_schedule_with_warmup, evaluated for optimiser step k (0-based)
-        if not use_lr_scheduling:
-            return lr
-        if k < warmup_steps:
-            return lr * float(k) / warm
-        return lr * max(0, 0.5 * (1.0 + math.cos(math.pi * float(k - warmup_steps) / span)))
+    def lr_at(k):   # what LambdaLR leaves in param_groups[0]["lr"] for optimiser step k (0-based; ref :199-200, :250)
+        return lr * cosine_warmup_factor(k, warmup_steps, total_steps) if use_lr_scheduling else lr
 
     best_val, bad_epochs, k = float("inf"), 0, 0
     for epoch in range(epochs):
