@@ -122,8 +122,13 @@ __device__ __forceinline__ GemmItem gemm_item(const GemmArgs& a, int item, int n
     const int ksplit = a.ksplit > 1 ? a.ksplit : 1;
     const int rest = item / ksplit;
     w.ks = item - rest * ksplit;
-    w.mt = rest / a.nsplit;
-    w.sp = rest - w.mt * a.nsplit;
+    // column-split major, row tile minor: the CTAs that run at the same time work on DIFFERENT row tiles of the SAME column
+    // range, so that range of W (V / nsplit rows: 8.5 MB of the 131 MB rounding matrix at nsplit = 15) stays in L2 while
+    // every row tile passes over it.  Row-tile major, the ~10 row tiles in flight streamed all of W concurrently and
+    // ncu counted 4.5 GB of DRAM reads for 147 MB of operands (profiles/r02_ncu_text_gemm_metrics.csv).
+    const int m_tiles = a.Mp / kBM;
+    w.sp = rest / m_tiles;
+    w.mt = rest - w.sp * m_tiles;
     w.n0 = (int)((int64_t)w.sp * n_tiles / a.nsplit);
     w.n1 = (int)((int64_t)(w.sp + 1) * n_tiles / a.nsplit);
     w.kb0 = (int)((int64_t)w.ks * kblocks / ksplit);
