@@ -85,6 +85,7 @@ struct GemmArgs {
     const float* lse;        // GE_DLOGITS: [M] log-sum-exp per row
     const float* dev_scale;  // GE_DLOGITS: device scalar multiplying the gradient (the rounding-loss weight), or null
     float scale;             // GE_DLOGITS: host factor (1 / rows)
+    int pair;                // set by launch_gemm: CTAs run as clusters of two that share one multicast W stream
     uint8_t* out_bf16_t;     // GE_DLOGITS: the same values transposed, bf16 planes along the ROW index [Mp/8][obt_rows][8]
     int64_t obt_rows;        //             (the A operand of dW = dlogits^T . X), or null
 };
@@ -151,7 +152,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
     if (threadIdx.x == 0) {
         for (int i = 0; i < kGemmStages; ++i) {
             mbar_init(bar_full + i, 1);
-            mbar_init(bar_empty + i, 1);
+            mbar_init(bar_empty + i, a.pair ? 2 : 1);   // paired: one commit from each CTA of the cluster
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_accf + i, 1);
@@ -162,10 +163,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
     if (warp == 2) tmem_alloc<512>(s_tmem);
     tc_fence_before_sync();
     __syncthreads();
+    // Paired launch (launch_gemm): the two CTAs of a cluster take consecutive work items - with the column-split-major item
+    // order these are two row tiles over the SAME columns and K range - and walk one W stream in lock step: each CTA fetches
+    // half of every K block's W planes as a cluster MULTICAST (both receive all eight), and a ring slot is released only
+    // when both CTAs' MMAs have consumed it (commit multicast onto both empty barriers).  One L2 read of W feeds two SMs:
+    // with A resident a vocabulary tile then costs 64 KB of L2 reads instead of 128 KB (the protocol of ffn_tc.cuh).
+    if (a.pair) cluster_sync_all();   // every CTA's mbarriers exist before a peer multicasts into / arrives on them
     tc_fence_after_sync();
     if (threadIdx.x == 0) TL(1);
     pdl_wait();                 // PDL (common.cuh): nothing above touches global memory
     pdl_launch_dependents();
+    const uint32_t crank = a.pair ? cluster_ctarank() : 0u;
     if (threadIdx.x == 0) TL(2);
     const uint32_t tmem_base = *s_tmem;
 
@@ -202,8 +210,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                                  kBM * 16, bar_full + s);
                     } else if (lane < 16) {
                         const int j = lane - 8;
-                        bulk_g2s(st + kGemmStageA + j * (kBN * 16),
-                                 a.w + (int64_t)(kb * 8 + j) * a.w_ps + (int64_t)nt * (kBN * 16), kBN * 16, bar_full + s);
+                        if (!a.pair)
+                            bulk_g2s(st + kGemmStageA + j * (kBN * 16),
+                                     a.w + (int64_t)(kb * 8 + j) * a.w_ps + (int64_t)nt * (kBN * 16), kBN * 16, bar_full + s);
+                        else if ((uint32_t)(j & 1) == crank)   // this CTA's half of the planes, to both CTAs
+                            bulk_g2s_multicast(st + kGemmStageA + j * (kBN * 16),
+                                               a.w + (int64_t)(kb * 8 + j) * a.w_ps + (int64_t)nt * (kBN * 16), kBN * 16,
+                                               bar_full + s, (uint16_t)3);
                     }
                     if (kit == 0) TL0(3);
                 }
@@ -236,7 +249,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                     for (int ks = 0; ks < kBK / 16; ++ks)
                         umma_bf16(d, desc_add(a_base, (2 * ks) * (kBM * 16)), desc_add(b_base, (2 * ks) * (kBN * 16)), idesc,
                                         ks != 0 ? 1u : acc_flag);
-                    umma_commit(bar_empty + s);
+                    if (a.pair) umma_commit_multicast(bar_empty + s, (uint16_t)3);
+                    else umma_commit(bar_empty + s);
                 }
                 umma_commit(bar_accf + acc);
                 if (it == 0) TL(5);
@@ -631,6 +645,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
     __syncwarp();
     tc_fence_before_sync();
     __syncthreads();
+    if (a.pair) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it or arrive on its barriers
     tc_fence_after_sync();
     if (threadIdx.x == 0) TL(8);
     if (warp == 2) tmem_dealloc<512>(tmem_base);
@@ -638,16 +653,47 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
 }
 
 template <int EPI>
-static int launch_gemm(const GemmArgs& a, cudaStream_t st, const char* name) {
+static int launch_gemm(const GemmArgs& a_in, cudaStream_t st, const char* name) {
+    GemmArgs a = a_in;
     auto kern = gemm_tc_kernel<EPI>;
     TDM_SET_MAX_DYN_SMEM(kern, kGemmSmem);
     TDM_CHECK_ARG(EPI != GE_RES_LN || a.N == kBN, "%s: fused LayerNorm needs N == 256", name);
     TDM_CHECK_ARG(a.Mp % kBM == 0 && a.N % kBN == 0 && a.K % kBK == 0 && a.K > 0 && a.nsplit > 0,
                   "%s: bad GEMM shape M=%d Mp=%d N=%d K=%d", name, a.M, a.Mp, a.N, a.K);
     TDM_CHECK_ARG(a.ksplit <= 1 || EPI == GE_LOGITS, "%s: the K split exists for the fp32 row-major epilogue only", name);
-    const int items = (a.Mp / kBM) * a.nsplit * (a.ksplit > 1 ? a.ksplit : 1);
-    const int grid = items < num_sms() ? items : num_sms();
-    launch_pdl(kern, dim3(grid), dim3(kGemmThreads), kGemmSmem, st, a);
+    const int m_tiles = a.Mp / kBM;
+    const int items = m_tiles * a.nsplit * (a.ksplit > 1 ? a.ksplit : 1);
+    int grid = items < num_sms() ? items : num_sms();
+    // pairs: consecutive items must be two row tiles of one column range (even row-tile count, no K split), and both CTAs
+    // of a cluster must run the same number of items (even item count and grid)
+    static const bool pair_ok = [] {
+        const char* e = std::getenv("TDM_NO_PAIR");
+        return !(e && e[0] == '1');
+    }();
+    a.pair = (pair_ok && m_tiles % 2 == 0 && a.ksplit <= 1 && grid >= 2) ? 1 : 0;
+    cudaLaunchConfig_t cfg{};
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (a.pair) {
+        grid -= grid % 2;
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
+    }
+    if (pdl_enabled()) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = kGemmSmem;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    TDM_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     TDM_CHECK_LAUNCH(name);
     return TDM_OK;
 }
