@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
     if (threadIdx.x == 0) {
         for (int i = 0; i < kGemmStages; ++i) {
             mbar_init(bar_full + i, 1);
-            mbar_init(bar_empty + i, a.pair ? 2 : 1);   // paired: one commit from each CTA of the cluster
+            mbar_init(bar_empty + i, a.pair ? a.pair : 1);   // clustered: one commit from each CTA of the cluster
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(bar_accf + i, 1);
@@ -213,10 +213,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                         if (!a.pair)
                             bulk_g2s(st + kGemmStageA + j * (kBN * 16),
                                      a.w + (int64_t)(kb * 8 + j) * a.w_ps + (int64_t)nt * (kBN * 16), kBN * 16, bar_full + s);
-                        else if ((uint32_t)(j & 1) == crank)   // this CTA's half of the planes, to both CTAs
+                        else if ((uint32_t)(j & (a.pair - 1)) == crank)   // this CTA's share of the planes, to all CTAs
                             bulk_g2s_multicast(st + kGemmStageA + j * (kBN * 16),
                                                a.w + (int64_t)(kb * 8 + j) * a.w_ps + (int64_t)nt * (kBN * 16), kBN * 16,
-                                               bar_full + s, (uint16_t)3);
+                                               bar_full + s, (uint16_t)((1u << a.pair) - 1));
                     }
                     if (kit == 0) TL0(3);
                 }
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_tc_kernel(const GemmArgs
                     for (int ks = 0; ks < kBK / 16; ++ks)
                         umma_bf16(d, desc_add(a_base, (2 * ks) * (kBM * 16)), desc_add(b_base, (2 * ks) * (kBN * 16)), idesc,
                                         ks != 0 ? 1u : acc_flag);
-                    if (a.pair) umma_commit_multicast(bar_empty + s, (uint16_t)3);
+                    if (a.pair) umma_commit_multicast(bar_empty + s, (uint16_t)((1u << a.pair) - 1));
                     else umma_commit(bar_empty + s);
                 }
                 umma_commit(bar_accf + acc);
@@ -670,14 +670,19 @@ static int launch_gemm(const GemmArgs& a_in, cudaStream_t st, const char* name) 
         const char* e = std::getenv("TDM_NO_PAIR");
         return !(e && e[0] == '1');
     }();
-    a.pair = (pair_ok && m_tiles % 2 == 0 && a.ksplit <= 1 && grid >= 2) ? 1 : 0;
+    static const int csize_env = [] {
+        const char* e = std::getenv("TDM_GEMM_CLUSTER");
+        return e ? std::atoi(e) : 2;
+    }();
+    int cs = (csize_env == 4 && m_tiles % 4 == 0) ? 4 : 2;
+    a.pair = (pair_ok && m_tiles % cs == 0 && a.ksplit <= 1 && grid >= cs) ? cs : 0;
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[2];
     int na = 0;
     if (a.pair) {
-        grid -= grid % 2;
+        grid -= grid % cs;
         attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.x = cs;
         attr[na].val.clusterDim.y = 1;
         attr[na].val.clusterDim.z = 1;
         ++na;
