@@ -106,6 +106,7 @@ class TextTrainer:
         self.ids = torch.zeros(self.batch, self.seq_len, dtype=torch.int64, device=self.device)
         self.sample_offset = self.rank * self.batch
         self._graph = None
+        self._eval_calls = 0
         self.launches_per_step = 0
         self.pack()
 
@@ -117,14 +118,15 @@ class TextTrainer:
         _lib.check(self.lib.tdm_text_train_pack(self.flat.data_ptr(), self.offsets, self.dim, self.depth, self.vocab,
                                                 self.wpack.data_ptr(), self.wpack_bytes, self._st()), "tdm_text_train_pack")
 
-    def _objective(self, ids, grads, t=None, noise=None, dropout=None) -> None:
+    def _objective(self, ids, grads, t=None, noise=None, dropout=None, sample_offset=None) -> None:
         s = self.sched
         p = self.dropout if dropout is None else dropout
+        off = self.sample_offset if sample_offset is None else sample_offset
         _lib.check(self.lib.tdm_text_train_step(
             self.flat.data_ptr(), _lib.ptr(grads), self.offsets, self.wpack.data_ptr(), _lib.ptr(self.emb_table),
             ids.data_ptr(), _lib.ptr(t), _lib.ptr(noise), s.sqrt_alphas_cumprod.data_ptr(),
             s.sqrt_one_minus_alphas_cumprod.data_ptr(), self.ws.data_ptr(), self.ws_bytes, self.batch, self.seq_len,
-            self.dim, self.depth, self.vocab, float(p), self.rw_dev.data_ptr(), self.seed, self.sample_offset,
+            self.dim, self.depth, self.vocab, float(p), self.rw_dev.data_ptr(), self.seed, off,
             self.step_dev.data_ptr(), self.losses.data_ptr(), self._st()), "tdm_text_train_step")
 
     def _update(self) -> None:
@@ -190,7 +192,10 @@ class TextTrainer:
         """Losses in eval mode (no dropout, no backward): the validation pass (ref :268-287).  A batch smaller than the
         trainer's (the last one of a loader) is evaluated by a throw-away trainer-shaped call on its own workspace."""
         ids = self._check_ids(token_ids)
-        self._objective(ids, None)
+        # the optimiser step does not advance during validation: successive batches draw their timesteps and noise from
+        # successive blocks of the global sequence index instead (the reference draws fresh ones per batch, ref :276-277)
+        self._eval_calls += 1
+        self._objective(ids, None, sample_offset=self.sample_offset + self._eval_calls * self.batch * self.world)
         return self.losses
 
     def sync_modules(self) -> None:
