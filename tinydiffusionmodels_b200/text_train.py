@@ -108,7 +108,8 @@ class TextTrainer:
         self._graph = None
         self._eval_calls = 0
         self.launches_per_step = 0
-        self.pack()
+        with torch.cuda.device(self.device):
+            self.pack()
 
     # ---- pieces ----------------------------------------------------------------------------------------------
     def _st(self):
@@ -148,6 +149,10 @@ class TextTrainer:
     def loss_and_grads(self, token_ids, t=None, noise=None, dropout=None):
         """Forward + backward only (no update): the flat gradient is left in ``self.grads``.  ``t`` / ``noise``
         injected (parity tests) or drawn in-kernel.  Uses the current optimiser step counter for the RNG."""
+        with torch.cuda.device(self.device):
+            return self._loss_and_grads(token_ids, t, noise, dropout)
+
+    def _loss_and_grads(self, token_ids, t, noise, dropout):
         ids = self._check_ids(token_ids)
         t = None if t is None else t.to(self.device, torch.int64).contiguous()
         noise = None if noise is None else noise.to(self.device, torch.float32).contiguous()
@@ -158,6 +163,10 @@ class TextTrainer:
     def step(self, token_ids, *, lr: float | None = None, rounding_weight: float | None = None) -> torch.Tensor:
         """One optimisation step (ref :224-248).  Returns the device tensor (diffusion, rounding, total) - reading it
         synchronises, so callers that log every step pay that; callers that do not, do not."""
+        with torch.cuda.device(self.device):
+            return self._step(token_ids, lr, rounding_weight)
+
+    def _step(self, token_ids, lr, rounding_weight) -> torch.Tensor:
         self.ids.copy_(self._check_ids(token_ids), non_blocking=True)
         if lr is not None:
             self.lr_dev.fill_(float(lr))
@@ -189,8 +198,12 @@ class TextTrainer:
 
     @torch.no_grad()
     def evaluate(self, token_ids) -> torch.Tensor:
-        """Losses in eval mode (no dropout, no backward): the validation pass (ref :268-287).  A batch smaller than the
-        trainer's (the last one of a loader) is evaluated by a throw-away trainer-shaped call on its own workspace."""
+        """Losses in eval mode (no dropout, no backward): the validation pass (ref :268-287).  The batch must have the
+        trainer's shape (``shakespeare.train`` skips a ragged last batch)."""
+        with torch.cuda.device(self.device):
+            return self._evaluate(token_ids)
+
+    def _evaluate(self, token_ids) -> torch.Tensor:
         ids = self._check_ids(token_ids)
         # the optimiser step does not advance during validation: successive batches draw their timesteps and noise from
         # successive blocks of the global sequence index instead (the reference draws fresh ones per batch, ref :276-277)
