@@ -220,6 +220,11 @@ int tdm_adamw_flat_peer(float* params, float* exp_avg, float* exp_avg_sq, int64_
  * zero.  n_padded must be a multiple of 256 for use as a GEMM / rounding operand. */
 int tdm_pack_linear(const float* w, int n, int k, int n_padded, void* out_planes, void* stream);
 
+/* Width 256 only: linear1.weight (2048, 256) and linear2.weight (256, 2048), fp32 row-major, in the stage order the
+ * fused feed-forward kernel streams them (1 MB each) - these two replace the tdm_pack_linear images in entries 4 and 6 of
+ * tdm_text_forward's per-layer pointer table when dim == 256. */
+int tdm_pack_ffn_weights(const float* w1, const float* w2, void* out1, void* out2, void* stream);
+
 int64_t tdm_text_workspace_bytes(int64_t batch, int seq_len, int dim);
 
 /* Put x_t (batch, seq_len, dim) fp32 into the workspace as the sampler state and prepare the first

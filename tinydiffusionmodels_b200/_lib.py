@@ -54,6 +54,7 @@ SIGNATURES: dict[str, tuple] = {
     "tdm_adamw_flat_peer": (c_int, [_P, _P, _P, c_int64, c_float, c_float, c_float, c_float, c_float, c_float, _P,
                                     ctypes.POINTER(_P), c_int, c_int, _P]),
     "tdm_pack_linear": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "tdm_pack_ffn_weights": (c_int, [_P, _P, _P, _P, _P]),
     "tdm_text_workspace_bytes": (c_int64, [c_int64, c_int, c_int]),
     "tdm_text_load_state": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64, c_int, c_int, _P]),
     "tdm_text_read": (c_int, [_P, c_int64, c_int, _P, c_int64, c_int, c_int, _P]),

@@ -38,9 +38,9 @@ constexpr int kFfnCluster = 2;    // CTAs sharing one multicast weight stream
 
 struct FfnArgs {
     const uint8_t* a;       // bf16 planes [32][Mp][8] (LayerNorm-1 output)
-    const uint8_t* w1;      // bf16 planes [32][2048][8]   linear1.weight (2048, 256)
+    const uint8_t* w1;      // linear1.weight (2048, 256) as bf16 STAGES [chunk 16][K block 4][plane 8][128 rows][8] (tdm_pack_ffn_weights)
     const float* b1;        // [2048]
-    const uint8_t* w2;      // bf16 planes [256][256][8]   linear2.weight (256, 2048)
+    const uint8_t* w2;      // linear2.weight (256, 2048) as bf16 STAGES [chunk 16][K block 2][plane 8][256 rows][8]
     const float* b2;        // [256]
     const uint8_t* res;     // fp32 planes [64][Mp][4] residual (same tensor as `a`, in fp32)
     const float* gamma;     // norm2
@@ -116,8 +116,6 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
     const uint32_t t_acc1 = tmem_base;           // two buffers of 128 columns
     const uint32_t t_acc2 = tmem_base + 256;     // 256 columns
     const int m_tiles = a.Mp / 128;
-    const int64_t w1_ps = (int64_t)kFfnH * 16;   // W1 planes: 2048 rows
-    const int64_t w2_ps = (int64_t)kFfnD * 16;   // W2 planes: 256 rows
 
     if (warp == 0) {
         // ===== producer: A once per tile, then the weight K-blocks in the order the MMA thread consumes them =====
@@ -132,13 +130,19 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
             }
             __syncwarp();
             uint8_t* st = sR + s * kFfnStage;
-            if (lane < 8 && (lane % kFfnCluster) == (int)crank) {   // this CTA's share of the planes, to everyone
-                if (is_w2)   // K index = hidden unit 128c + 64kb + 8*lane .. ; all 256 output rows
-                    bulk_g2s_multicast(st + lane * 4096, a.w2 + (int64_t)(16 * c + 8 * kb + lane) * w2_ps, 4096,
-                                       bar_full + s, kAll);
-                else         // K index = model channel 64kb + 8*lane .. ; rows 128c .. 128c+127 of W1
-                    bulk_g2s_multicast(st + lane * 2048, a.w1 + (int64_t)(8 * kb + lane) * w1_ps + (int64_t)c * (kFfnC * 16),
-                                       2048, bar_full + s, kAll);
+            // The weights are stored stage by stage (tdm_pack_ffn_weights): K block kb of chunk c is ONE contiguous 16 KB (W1) or
+            // 32 KB (W2) block in exactly the order the ring slot holds it (eight planes), so each CTA of the pair fetches
+            // its contiguous half with a single multicast copy.  In the plane layout a stage was eight 2-4 KB copies, 24 per
+            // chunk and CTA, and the copy engine's issue rate (one small bulk copy per ~50-150 ns) - not its bandwidth -
+            // paced the weight stream.
+            if (lane == 0) {
+                if (is_w2) {
+                    const uint32_t half = 32768 / kFfnCluster;
+                    bulk_g2s_multicast(st + crank * half, a.w2 + ((int64_t)(c * 2 + kb) * 32768) + crank * half, half, bar_full + s, kAll);
+                } else {
+                    const uint32_t half = 16384 / kFfnCluster;
+                    bulk_g2s_multicast(st + crank * half, a.w1 + ((int64_t)(c * 4 + kb) * 16384) + crank * half, half, bar_full + s, kAll);
+                }
             }
         };
         for (int mt = cluster_id * kFfnCluster + (int)crank; mt < m_tiles; mt += n_clusters * kFfnCluster, ++ti) {

@@ -37,6 +37,33 @@ __global__ void pack_linear_kernel(const float* __restrict__ w, int N, int K, in
     }
 }
 
+// linear1.weight (2048, 256) and linear2.weight (256, 2048) in the order the fused FFN kernel's ring consumes them
+// (ffn_tc.cuh): per hidden chunk c of 128 units and K block kb of 64, eight 16-byte-row planes -
+//   W1 stage (c, kb): [plane j][row r < 128][8]  = W1[128c + r][64kb + 8j .. +8]        16 KB
+//   W2 stage (c, kb): [plane j][row r < 256][8]  = W2[r][128c + 64kb + 8j .. +8]        32 KB
+__global__ void pack_ffn_weights_kernel(const float* __restrict__ w1, const float* __restrict__ w2,
+                                        __nv_bfloat16* __restrict__ o1, __nv_bfloat16* __restrict__ o2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // one 16-byte row of either output
+    constexpr int kRows1 = 16 * 4 * 8 * 128, kRows2 = 16 * 2 * 8 * 256;
+    const float* src;
+    __nv_bfloat16* dst;
+    if (i < kRows1) {
+        const int r = i % 128, j = (i / 128) % 8, kb = (i / 1024) % 4, c = i / 4096;
+        src = w1 + (int64_t)(128 * c + r) * 256 + 64 * kb + 8 * j;
+        dst = o1 + (int64_t)i * 8;
+    } else if (i < kRows1 + kRows2) {
+        const int t = i - kRows1;
+        const int r = t % 256, j = (t / 256) % 8, kb = (t / 2048) % 2, c = t / 4096;
+        src = w2 + (int64_t)r * 2048 + 128 * c + 64 * kb + 8 * j;
+        dst = o2 + (int64_t)t * 8;
+    } else {
+        return;
+    }
+    const float4 lo = *reinterpret_cast<const float4*>(src);
+    const float4 hi = *reinterpret_cast<const float4*>(src + 4);
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(lo.x, lo.y), pack_bf16x2(lo.z, lo.w), pack_bf16x2(hi.x, hi.y), pack_bf16x2(hi.z, hi.w));
+}
+
 // ---------------------------------------------------------------------------------------------
 // rows <-> planes
 // ---------------------------------------------------------------------------------------------
@@ -615,6 +642,15 @@ extern "C" int tdm_pack_linear(const float* w, int n, int k, int n_padded, void*
     const unsigned grid = (unsigned)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
     pack_linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(w, n, k, n_padded, reinterpret_cast<__nv_bfloat16*>(out_planes));
     TDM_CHECK_LAUNCH("tdm_pack_linear");
+    return TDM_OK;
+}
+
+extern "C" int tdm_pack_ffn_weights(const float* w1, const float* w2, void* out1, void* out2, void* stream) {
+    TDM_CHECK_ARG(w1 && w2 && out1 && out2, "tdm_pack_ffn_weights: null pointer");
+    constexpr int kRows = 16 * 4 * 8 * 128 + 16 * 2 * 8 * 256;
+    pack_ffn_weights_kernel<<<(kRows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w1, w2, reinterpret_cast<__nv_bfloat16*>(out1),
+                                                                                 reinterpret_cast<__nv_bfloat16*>(out2));
+    TDM_CHECK_LAUNCH("tdm_pack_ffn_weights");
     return TDM_OK;
 }
 

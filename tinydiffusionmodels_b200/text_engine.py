@@ -47,10 +47,18 @@ class TextEngine:
             p = f"encoder.layers.{i}."
             if sd[p + "linear1.weight"].shape[0] != FF:
                 raise _lib.TdmError("only dim_feedforward=2048 (the reference's default) is supported")
+            if self.dim == 256:
+                # the fused feed-forward kernel streams its weights stage by stage: one contiguous copy per ring slot
+                w1p = torch.empty(FF * 256 * 2, dtype=torch.uint8, device=self.device)
+                w2p = torch.empty(FF * 256 * 2, dtype=torch.uint8, device=self.device)
+                _lib.check(self.lib.tdm_pack_ffn_weights(sd[p + "linear1.weight"].data_ptr(), sd[p + "linear2.weight"].data_ptr(),
+                                                         w1p.data_ptr(), w2p.data_ptr(), _lib.stream_ptr(self.device)),
+                           "tdm_pack_ffn_weights")
+            else:
+                w1p, w2p = pack_linear(sd[p + "linear1.weight"]), pack_linear(sd[p + "linear2.weight"])
             items = [pack_linear(sd[p + "self_attn.in_proj_weight"]), sd[p + "self_attn.in_proj_bias"],
                      pack_linear(sd[p + "self_attn.out_proj.weight"]), sd[p + "self_attn.out_proj.bias"],
-                     pack_linear(sd[p + "linear1.weight"]), sd[p + "linear1.bias"],
-                     pack_linear(sd[p + "linear2.weight"]), sd[p + "linear2.bias"],
+                     w1p, sd[p + "linear1.bias"], w2p, sd[p + "linear2.bias"],
                      sd[p + "norm1.weight"], sd[p + "norm1.bias"], sd[p + "norm2.weight"], sd[p + "norm2.bias"]]
             keep += items
             ptrs += [t.data_ptr() for t in items]
