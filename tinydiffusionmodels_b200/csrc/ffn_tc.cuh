@@ -65,6 +65,19 @@ struct FfnArgs {
     uint32_t step_id;
 };
 
+#ifdef TDM_EXP_TIMELINE
+// development aid (tools/ffn_timeline.py): globaltimer stamps of block 0, second tile: [what][chunk]
+__device__ unsigned long long g_ffn_tl[9][16];
+__device__ __forceinline__ void ffn_stamp(int what, int c) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_ffn_tl[what][c] = t;
+}
+#define FTL(what, c) do { if (blockIdx.x == 0 && ti == 1) ffn_stamp(what, c); } while (0)
+#else
+#define FTL(what, c)
+#endif
+
 __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* sA = smem;
@@ -195,8 +208,10 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
             for (int c = 0; c < kFfnChunks; ++c) {
                 const int cg = cg0 + c;
                 if (c == 0) mbar_wait(bar_acc2_empty, (ti & 1) ^ 1);
+                FTL(0, c);                       // MMA thread: about to wait for P(c)
                 mbar_wait(bar_p_full, cg & 1);
                 tc_fence_after_sync();
+                FTL(1, c);                       // MMA thread: P(c) seen, G2(c) starts
                 for (int kb = 0; kb < 2; ++kb, ++kit) {
                     const int s = kit % kFfnStages;
                     mbar_wait(bar_full + s, (kit / kFfnStages) & 1);
@@ -209,10 +224,12 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
                                         ks != 0 ? 1u : acc_flag);
                     umma_commit_multicast(bar_empty + s, kAll);
                 }
+                FTL(2, c);                       // MMA thread: G2(c) issued
                 umma_commit(bar_p_empty);                 // P may be overwritten once these MMAs retire
                 if (c == kFfnChunks - 1) umma_commit(bar_acc2_full);
                 if (c + 2 < kFfnChunks) {
                     g1(cg + 2);
+                    FTL(3, c);                   // MMA thread: G1(c+2) issued
                     if (c + 2 == kFfnChunks - 1) umma_commit(bar_a_empty);   // last G1 of the tile: A may be reloaded
                 }
             }
@@ -232,6 +249,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
                 const int cg = ti * kFfnChunks + c;
                 mbar_wait(bar_acc1_full + grp, (cg >> 1) & 1);
                 tc_fence_after_sync();
+                if (q == 0 && lane == 0) FTL(4, c);   // E1: G1(c) result seen
                 uint4 pk[kFfnC / 8];
 #pragma unroll
                 for (int c0 = 0; c0 < kFfnC; c0 += 32) {
@@ -254,20 +272,25 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
                                                      pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
                     }
                 }
+                if (q == 0 && lane == 0) FTL(5, c);   // E1: converted, about to wait for P to be free
                 mbar_wait(bar_p_empty, (cg & 1) ^ 1);          // G2 of the previous chunk has consumed P
+                if (q == 0 && lane == 0) FTL(6, c);   // E1: P free
 #pragma unroll
                 for (int pl = 0; pl < kFfnC / 8; ++pl)
                     *reinterpret_cast<uint4*>(sP + pl * 2048 + (q * 32 + lane) * 16) = pk[pl];
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_p_full);
+                if (q == 0 && lane == 0) FTL(7, c);   // E1: P(c) written
             }
             // ---- tile epilogue: bias + residual, LayerNorm, optional reverse step.  The two groups split the
             //      256 columns (same TMEM lanes, i.e. rows; disjoint columns) and exchange the row statistics
             //      through smem: with one group the last layer's Philox + reverse-step epilogue was 67 us
             //      of a 184 us kernel (profiles/r01_ncu_launches_text_B512.csv). ----
+            if (q == 0 && lane == 0) FTL(8, 0 + 8 * grp);   // tile epilogue: E1 work of this group done, waiting for acc2
             mbar_wait(bar_acc2_full, ti & 1);
             tc_fence_after_sync();
+            if (q == 0 && lane == 0) FTL(8, 1 + 8 * grp);   // acc2 complete
             const uint32_t taddr = t_acc2 + lane_base;
             const int col_lo = grp * (kFfnD / 2), col_hi = col_lo + kFfnD / 2;
             float ln_sum = 0.f, ln_sq = 0.f;
@@ -295,8 +318,10 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
                 tmem_st32(taddr + c0, vb);
             }
             tmem_st_wait();
+            if (q == 0 && lane == 0) FTL(8, 2 + 8 * grp);   // pass 1 done
             s_ln[grp * 128 + q * 32 + lane] = make_float2(ln_sum, ln_sq);
             asm volatile("bar.sync 1, 256;" ::: "memory");   // the eight epilogue warps
+            if (q == 0 && lane == 0) FTL(8, 3 + 8 * grp);   // statistics exchanged
             {
                 const float2 o = s_ln[(grp ^ 1) * 128 + q * 32 + lane];
                 ln_sum += o.x;
@@ -368,6 +393,7 @@ __global__ void __launch_bounds__(kFfnThreads, 1) ffn_tc_kernel(const FfnArgs a)
                         make_uint4(pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
                 }
             }
+            if (q == 0 && lane == 0) FTL(8, 4 + 8 * grp);   // pass 2 done
         }
     }
     __syncwarp();

@@ -832,4 +832,7 @@ extern "C" int tdm_embedding_gather(const float* table, int64_t vocab, int dim, 
 extern "C" int tdm_debug_gemm_timeline(unsigned long long* host16) {
     return cudaMemcpyFromSymbol(host16, tdm::g_gemm_tl, sizeof(unsigned long long) * 16) == cudaSuccess ? 0 : 2;
 }
+extern "C" int tdm_debug_ffn_timeline(unsigned long long* host128) {
+    return cudaMemcpyFromSymbol(host128, tdm::g_ffn_tl, sizeof(unsigned long long) * 144) == cudaSuccess ? 0 : 2;
+}
 #endif
