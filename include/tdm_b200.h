@@ -242,8 +242,8 @@ int tdm_text_read(const void* workspace, int64_t workspace_bytes, int which, flo
  * host_ptrs: HOST array of DEVICE pointers, 12 per encoder layer in this order —
  *   in_proj_weight*, in_proj_bias, out_proj.weight*, out_proj.bias, linear1.weight*, linear1.bias,
  *   linear2.weight*, linear2.bias, norm1.weight, norm1.bias, norm2.weight, norm2.bias
- * (* = packed with tdm_pack_linear; the rest fp32 vectors) — followed by time_emb.weight [dim] and
- * time_emb.bias [dim] (fp32). */
+ * (* = packed with tdm_pack_linear - except linear1 / linear2 at dim == 256, which are the two images written by
+ * tdm_pack_ffn_weights; the rest fp32 vectors) — followed by time_emb.weight [dim] and time_emb.bias [dim] (fp32). */
 int tdm_text_forward(const void* const* host_ptrs, int depth, void* workspace, int64_t workspace_bytes,
                      const int64_t* t, int64_t batch, int seq_len, int dim, void* stream);
 
