@@ -323,7 +323,8 @@ int tdm_adamw_flat_lr(float* params, const float* grads, float* exp_avg, float* 
                       const float* lr_dev, double beta1, double beta2, float eps, float weight_decay, float grad_scale,
                       const int64_t* step_dev, void* stream);
 
-/* Test aid: byte offsets of the training workspace's tensors (24 values, see text_train.cu). */
+/* Test aid: byte offsets of the training workspace's tensors (25 values, see text_train.cu; the last one is the int32
+ * flag an out-of-range token id sets - nn.Embedding would raise IndexError). */
 int tdm_text_train_debug_layout(int64_t batch, int seq_len, int dim, int depth, int64_t vocab, int64_t* out);
 
 /* Measurement aid (bench.py roofline): one fused p_sample with CUDA events recorded on `stream`

@@ -144,7 +144,7 @@ def test_in_kernel_timesteps_noise_and_input_dropout(cuda):
     tr = TextTrainer(m, r, e, cuda, batch, seq, dropout=p, seed=123456789012345, use_graph=False)
     tr.step_dev.fill_(9)
     tr.loss_and_grads(ids)
-    lay = (ctypes.c_int64 * 24)()
+    lay = (ctypes.c_int64 * 25)()
     _lib.check(tr.lib.tdm_text_train_debug_layout(batch, seq, dim, 1, vocab, lay), "layout")
     n = batch * seq * dim
     t_dev = tr.ws[lay[1]:lay[1] + batch * 8].view(torch.int64).cpu()
@@ -250,3 +250,17 @@ def test_train_loop_writes_reference_format_checkpoints_and_samplers_see_new_wei
     assert rel_rms(after.cpu(), before.cpu()) > 1e-4          # the sampler's packed weights were refreshed
     want = O.transformer_forward({k: v.float() for k, v in saved["diffusion_model"].items()}, x.cpu(), t.cpu())
     assert rel_rms(after.cpu(), want) < 1e-2
+
+
+def test_out_of_range_token_ids_are_reported(cuda):
+    m, r, e = _modules(256, 300, 1, 0.0)
+    m.to(cuda); r.to(cuda); e.to(cuda)
+    tr = TextTrainer(m, r, e, cuda, 2, 64, use_graph=False)
+    ids = torch.randint(0, 300, (2, 64))
+    tr.loss_and_grads(ids)
+    tr.check_token_ids()                       # clean batch: no error
+    ids[1, 7] = 300
+    tr.loss_and_grads(ids)
+    with pytest.raises(IndexError):
+        tr.check_token_ids()
+    tr.check_token_ids()                       # the flag was cleared

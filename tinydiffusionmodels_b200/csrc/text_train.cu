@@ -1000,7 +1000,7 @@ extern "C" int tdm_text_train_debug_layout(int64_t batch, int seq_len, int dim, 
     TDM_CHECK_ARG(out, "tdm_text_train_debug_layout: null pointer");
     const TrainWs w = make_train_ws(batch, seq_len, dim, depth, vocab);
     const int64_t v[] = {w.total, w.t, w.x0, w.noise, w.hin, up256(w.M * dim * 4), w.qkv, w.P, w.att, w.a, w.z1, w.h1, w.f,
-                         w.g, w.z2, w.layer_stride, w.dx0a, w.dx0b, w.lse, w.rowl, w.dl, w.dlT, w.Mp, w.Vp};
+                         w.g, w.z2, w.layer_stride, w.dx0a, w.dx0b, w.lse, w.rowl, w.dl, w.dlT, w.Mp, w.Vp, w.bad};
     for (size_t i = 0; i < sizeof(v) / sizeof(v[0]); ++i) out[i] = v[i];
     return TDM_OK;
 }

@@ -221,6 +221,7 @@ def train(model, rounding_fn, embedding_fn, data_loader, val_loader, device, ckp
             if log_every and n_tr % log_every == 0:
                 d, r, t_ = (acc / n_tr).tolist()
                 print(f"Epoch {epoch + 1}/{epochs} step {n_tr}: diff={d:.4f} round={r:.4f} total={t_:.4f} rw={rw:.3f} lr={lr_at(k):.2e}")
+        tr.check_token_ids()
         train_losses = _mean_losses((acc / max(n_tr, 1)).tolist(), 1)
         model.eval(); rounding_fn.eval()
         vacc = torch.zeros(3, device=tr.device)
@@ -230,6 +231,7 @@ def train(model, rounding_fn, embedding_fn, data_loader, val_loader, device, ckp
                 continue
             vacc += tr.evaluate(token_ids)
             n_val += 1
+        tr.check_token_ids()
         val_losses = _mean_losses((vacc / max(n_val, 1)).tolist(), 1)
         print(f"Epoch {epoch + 1}/{epochs}:")
         print(f"  Train: diff={train_losses['diff']:.4f}, round={train_losses['round']:.4f}, total={train_losses['total']:.4f}")

@@ -98,6 +98,10 @@ class TextTrainer:
                                 f"({_lib.load().tdm_last_error().decode(errors='replace')})")
         self.wpack = torch.empty(self.wpack_bytes, dtype=torch.uint8, device=self.device)
         self.ws = torch.zeros(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        lay = (ctypes.c_int64 * 25)()
+        _lib.check(self.lib.tdm_text_train_debug_layout(self.batch, self.seq_len, self.dim, self.depth, self.vocab, lay),
+                   "tdm_text_train_debug_layout")
+        self._bad_flag = self.ws[lay[24]:lay[24] + 4].view(torch.int32)
         self.sched = schedule_on(self.device)
         self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.device)
         self.rw_dev = torch.ones(1, dtype=torch.float32, device=self.device)
@@ -210,6 +214,14 @@ class TextTrainer:
         self._eval_calls += 1
         self._objective(ids, None, sample_offset=self.sample_offset + self._eval_calls * self.batch * self.world)
         return self.losses
+
+    def check_token_ids(self) -> None:
+        """Raise IndexError if any batch since the last check held a token id outside [0, vocab) - what nn.Embedding
+        does immediately (ref :226); here the kernels flag it on the device and this read synchronises, so callers
+        check once per epoch rather than once per step."""
+        if int(self._bad_flag.item()):
+            self._bad_flag.zero_()
+            raise IndexError("index out of range in the token ids of a training / validation batch")
 
     def sync_modules(self) -> None:
         """Invalidate the samplers' packed copies of the weights (they key on tensor versions, which raw-pointer
