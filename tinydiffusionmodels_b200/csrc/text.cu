@@ -549,7 +549,10 @@ static int text_forward_impl(const void* const* ptrs, int depth, uint8_t* ws, in
         // QKV
         g.a = ws + W.h16; g.a_ps = W.ps; g.w = (const uint8_t*)p[LW_QKV]; g.w_ps = (int64_t)3 * D * 16;
         g.bias = (const float*)p[LB_QKV]; g.M = W.M; g.Mp = W.Mp; g.N = 3 * D; g.n_valid = 3 * D; g.K = D;
-        g.out_bf16 = ws + W.qkv; g.ob_ps = W.ps; g.nsplit = g.N / kBN;
+        g.out_bf16 = ws + W.qkv; g.ob_ps = W.ps;
+        // enough row tiles to fill the GPU: one item per row tile walks all three column tiles with its A tile resident
+        // (gemm_tc.cuh); fewer: one item per (row tile, column tile) for parallelism
+        g.nsplit = (D == kBN && W.Mp / kBM >= num_sms()) ? 1 : g.N / kBN;
         if ((rc = launch_gemm<GE_BF16>(g, st, "gemm_qkv"))) return rc;
         // attention
         if (L == 64 && HD == 64) rc = launch_attn<64, 64>(ws + W.qkv, W.ps, D, heads, B, ws + W.att, st);
