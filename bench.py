@@ -613,6 +613,15 @@ def bench_text_train(dev, rank, world, batch, barrier, peaks, steps: int = 20, w
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
         dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
     ms, mse = float(ms_t.item()), float(ms_e.item())
+    # the step's HBM-bound part on its own: AdamW over every parameter (28 B per parameter: p, g, m, v read; p, m, v written)
+    e0.record()
+    for _ in range(5):
+        _lib.check(tr.lib.tdm_adamw_flat_lr(tr.flat.data_ptr(), tr.grads.data_ptr(), tr.exp_avg.data_ptr(), tr.exp_avg_sq.data_ptr(),
+                                            tr.n, tr.lr_dev.data_ptr(), 0.9, 0.999, 1e-8, 1e-4, 1.0, tr.step_dev.data_ptr(),
+                                            _lib.stream_ptr(dev)), "tdm_adamw_flat_lr")
+    e1.record()
+    torch.cuda.synchronize()
+    ms_adam = e0.elapsed_time(e1) / 5
     tokens = batch * L
     # algorithmic FLOP per token: forward + dX + dW of the encoder (3 x 8,060,928) and of the rounding
     # head (3 x 2*dim*V); the recomputation of the logits in the gradient pass is NOT counted
@@ -635,6 +644,9 @@ def bench_text_train(dev, rank, world, batch, barrier, peaks, steps: int = 20, w
                              f"({adam_bytes / 1e9:.2f} GB = {adam_bytes / peaks['hbm_gbs'] / 1e6:.2f} ms at the HBM copy peak)"},
         "dtype": "bf16 operands, fp32 accumulation / activations / master weights / optimiser state",
     }
+    out["roofline"]["adamw"] = {"bound": "hbm", "achieved": adam_bytes / (ms_adam * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                "frac": adam_bytes / (ms_adam * 1e-3) / 1e9 / peaks["hbm_gbs"], "ms": ms_adam,
+                                "what": f"AdamW over {tr.n:,} parameters timed alone, 28 B per parameter"}
     del tr, m, r, e
     torch.cuda.empty_cache()
     return out
