@@ -441,8 +441,9 @@ __global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ pred
 // dropout(P) v -> att.  fp32 SIMT: 4*L*D FLOP per token, ~2 % of an encoder layer.  The head dimension is walked in
 // chunks of 64 so that any width fits: smem = S [L][L+1] + two [L][65] operand tiles.
 // ---------------------------------------------------------------------------------------------
+constexpr int kAttnThreads = 512;   // one block per (sequence, head): with 128 blocks on 148 SMs at the reference batch, warps per block are the only parallelism
 template <int L>
-__global__ void __launch_bounds__(256) attn_train_fwd_kernel(const float* __restrict__ qkv, int D, Rng rng, uint32_t site,
+__global__ void __launch_bounds__(kAttnThreads) attn_train_fwd_kernel(const float* __restrict__ qkv, int D, Rng rng, uint32_t site,
                                                              float* __restrict__ P, float* __restrict__ att) {
     extern __shared__ float sm[];
     float* sS = sm;                    // [L][L+1]
@@ -453,16 +454,16 @@ __global__ void __launch_bounds__(256) attn_train_fwd_kernel(const float* __rest
     const int h = blockIdx.x % kTrHeads;
     const float* base = qkv + b * L * (int64_t)(3 * D) + h * HD;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int e = tid; e < L * (L + 1); e += 256) sS[e] = 0.f;
+    for (int e = tid; e < L * (L + 1); e += kAttnThreads) sS[e] = 0.f;
     for (int d0 = 0; d0 < HD; d0 += 64) {
         __syncthreads();
-        for (int e = tid; e < L * 64; e += 256) {
+        for (int e = tid; e < L * 64; e += kAttnThreads) {
             const int i = e >> 6, d = e & 63;
             sA[i * 65 + d] = base[(int64_t)i * 3 * D + d0 + d];
             sB[i * 65 + d] = base[(int64_t)i * 3 * D + D + d0 + d];
         }
         __syncthreads();
-        for (int e = tid; e < L * L; e += 256) {
+        for (int e = tid; e < L * L; e += kAttnThreads) {
             const int i = e / L, j = e % L;
             float acc = 0.f;
 #pragma unroll 16
@@ -473,7 +474,7 @@ __global__ void __launch_bounds__(256) attn_train_fwd_kernel(const float* __rest
     __syncthreads();
     const float scale = rsqrtf((float)HD);
     const uint32_t step = rng_step(rng);
-    for (int i = warp; i < L; i += 8) {
+    for (int i = warp; i < L; i += kAttnThreads / 32) {
         float v[L / 32];
         float mx = -INFINITY;
 #pragma unroll
@@ -503,12 +504,12 @@ __global__ void __launch_bounds__(256) attn_train_fwd_kernel(const float* __rest
     }
     for (int d0 = 0; d0 < HD; d0 += 64) {
         __syncthreads();
-        for (int e = tid; e < L * 64; e += 256) {
+        for (int e = tid; e < L * 64; e += kAttnThreads) {
             const int j = e >> 6, d = e & 63;
             sB[j * 65 + d] = base[(int64_t)j * 3 * D + 2 * D + d0 + d];
         }
         __syncthreads();
-        for (int e = tid; e < L * 64; e += 256) {
+        for (int e = tid; e < L * 64; e += kAttnThreads) {
             const int i = e >> 6, d = e & 63;
             float acc = 0.f;
 #pragma unroll 16
@@ -520,7 +521,7 @@ __global__ void __launch_bounds__(256) attn_train_fwd_kernel(const float* __rest
 
 // backward of the above: datt [M][D] -> dqkv [M][3D]
 template <int L>
-__global__ void __launch_bounds__(256) attn_train_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
+__global__ void __launch_bounds__(kAttnThreads) attn_train_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
                                                              const float* __restrict__ datt, int D, Rng rng, uint32_t site,
                                                              float* __restrict__ dqkv) {
     extern __shared__ float sm[];
@@ -538,7 +539,7 @@ __global__ void __launch_bounds__(256) attn_train_bwd_kernel(const float* __rest
     const float* Pb = P + (int64_t)blockIdx.x * L * L;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t step = rng_step(rng);
-    for (int e = tid; e < L * L; e += 256) {
+    for (int e = tid; e < L * L; e += kAttnThreads) {
         const int i = e / L, j = e % L;
         const float p = Pb[e];
         sP[i * (L + 1) + j] = drop_keep1(rng, step, site, (uint64_t)((int64_t)blockIdx.x * L * L + e)) ? p * rng.keep_scale : 0.f;
@@ -547,20 +548,20 @@ __global__ void __launch_bounds__(256) attn_train_bwd_kernel(const float* __rest
     // phase A: d dropout(P) = dO v^T (accumulated over head-dimension chunks), dv = dropout(P)^T dO
     for (int d0 = 0; d0 < HD; d0 += 64) {
         __syncthreads();
-        for (int e = tid; e < L * 64; e += 256) {
+        for (int e = tid; e < L * 64; e += kAttnThreads) {
             const int i = e >> 6, d = e & 63;
             sA[i * 65 + d] = dobase[(int64_t)i * D + d0 + d];
             sB[i * 65 + d] = base[(int64_t)i * ld + 2 * D + d0 + d];
         }
         __syncthreads();
-        for (int e = tid; e < L * L; e += 256) {
+        for (int e = tid; e < L * L; e += kAttnThreads) {
             const int i = e / L, j = e % L;
             float acc = 0.f;
 #pragma unroll 16
             for (int d = 0; d < 64; ++d) acc = fmaf(sA[i * 65 + d], sB[j * 65 + d], acc);
             sS[i * (L + 1) + j] += acc;
         }
-        for (int e = tid; e < L * 64; e += 256) {
+        for (int e = tid; e < L * 64; e += kAttnThreads) {
             const int j = e >> 6, d = e & 63;
             float acc = 0.f;
 #pragma unroll 16
@@ -571,7 +572,7 @@ __global__ void __launch_bounds__(256) attn_train_bwd_kernel(const float* __rest
     __syncthreads();
     // softmax backward per row, with the 1/sqrt(hd) of the scores folded in
     const float scale = rsqrtf((float)HD);
-    for (int i = warp; i < L; i += 8) {
+    for (int i = warp; i < L; i += kAttnThreads / 32) {
         float p[L / 32], dp[L / 32];
         float rs = 0.f;
 #pragma unroll
@@ -589,13 +590,13 @@ __global__ void __launch_bounds__(256) attn_train_bwd_kernel(const float* __rest
     // phase B: dq = dS k, dk = dS^T q
     for (int d0 = 0; d0 < HD; d0 += 64) {
         __syncthreads();
-        for (int e = tid; e < L * 64; e += 256) {
+        for (int e = tid; e < L * 64; e += kAttnThreads) {
             const int i = e >> 6, d = e & 63;
             sA[i * 65 + d] = base[(int64_t)i * ld + D + d0 + d];   // k
             sB[i * 65 + d] = base[(int64_t)i * ld + d0 + d];       // q
         }
         __syncthreads();
-        for (int e = tid; e < L * 64; e += 256) {
+        for (int e = tid; e < L * 64; e += kAttnThreads) {
             const int i = e >> 6, d = e & 63;
             float aq = 0.f, ak = 0.f;
 #pragma unroll 8
@@ -977,13 +978,13 @@ static int launch_attn_train(bool bwd, const float* qkv, const float* P, const f
         constexpr int smem = (L * (L + 1) + 2 * L * 65) * 4;
         auto kern = attn_train_fwd_kernel<L>;
         TDM_SET_MAX_DYN_SMEM(kern, smem);
-        kern<<<(unsigned)(B * kTrHeads), 256, smem, st>>>(qkv, D, rng, site, Pout, out);
+        kern<<<(unsigned)(B * kTrHeads), kAttnThreads, smem, st>>>(qkv, D, rng, site, Pout, out);
         TDM_CHECK_LAUNCH("attn_train_fwd");
     } else {
         constexpr int smem = (2 * L * (L + 1) + 2 * L * 65) * 4;
         auto kern = attn_train_bwd_kernel<L>;
         TDM_SET_MAX_DYN_SMEM(kern, smem);
-        kern<<<(unsigned)(B * kTrHeads), 256, smem, st>>>(qkv, P, datt, D, rng, site, out);
+        kern<<<(unsigned)(B * kTrHeads), kAttnThreads, smem, st>>>(qkv, P, datt, D, rng, site, out);
         TDM_CHECK_LAUNCH("attn_train_bwd");
     }
     return TDM_OK;
